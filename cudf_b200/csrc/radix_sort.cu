@@ -1,0 +1,892 @@
+// radix_sort.cu — LSD one-sweep radix sort for sm_100a (no thrust / cub).
+//
+// Replaces the cub::DeviceRadixSort / DeviceMergeSort call sites of the reference:
+//   cpp/src/sort/sorted_order_radix.cu:57-180  (SortPairs over (key, row index))
+//   cpp/src/sort/sort_radix.cu:59-161          (SortKeys fast path of cudf::sort)
+//   cpp/src/sort/sort_column_impl.cuh:35-97    (nullable single column; comparator semantics)
+//   cpp/src/sort/sort_impl.cuh:31-96           (table dispatch, defaults, multi-column lexicographic)
+//
+// Design (one GPU, N rows, key type of W bytes => W passes of 8 bits):
+//   1. histogram kernel: one streaming read of the keys, W x 256 digit counts (smem atomics with a
+//      warp match_all shortcut for constant digits).
+//   2. plan kernel (1 CTA): exclusive scan of each histogram -> global digit bases; passes whose
+//      digit is constant over all keys are marked trivial and skipped on the device (no host sync);
+//      ping-pong buffer roles are chosen so that the last executed pass writes the output buffer.
+//   3. one-sweep pass kernel per digit: dynamic tile ids, warp-level MATCH.ANY ranking (stable),
+//      per-digit decoupled look-back over 32-bit {flag,count} words, keys and row indices staged
+//      through shared memory in tile-sorted order and written as coalesced per-digit runs.
+//      Pass 1 generates row indices on the fly; the last pass of sorted_order writes indices only.
+//   4. nullable column: warp-ballot/popc compaction splits valid rows (twiddled key, row index) from
+//      null rows (row index in input order), then 3. runs on the valid part only.
+// Keys are twiddled to unsigned order-preserving bits on first load (device_utils.cuh) and inverted
+// for descending order, which keeps the sort stable like cub's Descending variants.
+#include "common.cuh"
+#include "device_utils.cuh"
+
+#include <algorithm>
+#include <cstdlib>
+
+namespace b2 {
+namespace {
+
+constexpr int RADIX_BITS = 8;
+constexpr int RADIX      = 256;
+constexpr uint32_t FLAG_AGG  = 1u << 30;
+constexpr uint32_t FLAG_INCL = 2u << 30;
+constexpr uint32_t VAL_MASK  = (1u << 30) - 1;
+
+struct pass_plan {
+  int32_t trivial;  // 1: every key has the same digit -> pass skipped
+  int32_t key_src;  // 0 raw input, 1 buffer A, 2 buffer B
+  int32_t key_dst;  // 1 / 2 (unused when last && pairs)
+  int32_t idx_src;  // -1 implicit iota, 0 buffer X (output), 1 buffer Y (temp)
+  int32_t idx_dst;  // 0 / 1
+  int32_t last;     // 1: last executed pass
+  int32_t pad[2];
+};
+
+struct sort_ctl {
+  pass_plan plan[8];
+  uint32_t base[2][8][RADIX];  // [portion parity][pass][digit] global start offset of digit
+  int32_t any_pass;            // number of executed passes
+  uint32_t nan_count;          // FLOAT keys only
+};
+
+template <typename UK>
+__device__ __forceinline__ UK twiddle_rt(UK bits, int kind, UK desc_mask)
+{
+  UK k;
+  if (kind == (int)key_kind::SIGNED) k = twiddle_in<UK, key_kind::SIGNED>(bits);
+  else if (kind == (int)key_kind::FLOAT) {
+    if constexpr (sizeof(UK) >= 4) k = twiddle_in<UK, key_kind::FLOAT>(bits);
+    else k = bits;
+  } else k = bits;
+  return k ^ desc_mask;
+}
+// inverse for integer kinds (float keys never take the keys-only path)
+template <typename UK>
+__device__ __forceinline__ UK untwiddle_rt(UK k, int kind, UK desc_mask)
+{
+  k ^= desc_mask;
+  if (kind == (int)key_kind::SIGNED) k ^= (UK(1) << (sizeof(UK) * 8 - 1));
+  return k;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 1. histogram
+// ------------------------------------------------------------------------------------------------
+template <typename UK>
+__global__ void __launch_bounds__(512) histogram_kernel(const UK* __restrict__ keys, int64_t n, int raw, int kind,
+                                                       UK desc_mask, uint32_t* __restrict__ ghist,
+                                                       uint32_t* __restrict__ nan_count)
+{
+  constexpr int NP = sizeof(UK);
+  __shared__ uint32_t sh[NP][RADIX];
+  for (int i = threadIdx.x; i < NP * RADIX; i += blockDim.x) (&sh[0][0])[i] = 0;
+  __syncthreads();
+  uint32_t nans = 0;
+  constexpr int VEC = 16 / sizeof(UK);
+  // head (unaligned prefix), vector body, tail
+  const uintptr_t addr = reinterpret_cast<uintptr_t>(keys);
+  int64_t head = ((16 - (addr & 15)) & 15) / sizeof(UK);
+  if (head > n) head = n;
+  const int64_t nvec = (n - head) / VEC;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+
+  auto account = [&](UK rawbits, bool active) {
+    UK k = raw ? twiddle_rt<UK>(rawbits, kind, desc_mask) : rawbits;
+    if (active && raw && kind == (int)key_kind::FLOAT && (UK)(k ^ desc_mask) == (UK)~UK(0)) nans++;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      unsigned d = (unsigned)(k >> (p * 8)) & 255u;
+      unsigned amask = __ballot_sync(0xffffffffu, active);
+      if (amask == 0) continue;
+      int pred = 0;
+      // constant-digit shortcut: one add per warp instead of 32 same-address atomics
+      if (amask == 0xffffffffu) __match_all_sync(0xffffffffu, d, &pred);
+      if (pred) {
+        if (lane_id() == 0) atomicAdd(&sh[p][d], 32u);
+      } else if (active) {
+        atomicAdd(&sh[p][d], 1u);
+      }
+    }
+  };
+
+  const int4* vkeys = reinterpret_cast<const int4*>(keys + head);
+  const int64_t nvec_round = (nvec + 31) / 32 * 32;  // keep warps converged for the ballots
+  for (int64_t v = tid; v < nvec_round; v += nthreads) {
+    bool act = v < nvec;
+    int4 q = act ? ld_nc_v4(vkeys + v) : make_int4(0, 0, 0, 0);
+    UK tmp[VEC];
+    memcpy(tmp, &q, 16);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) account(tmp[j], act);
+  }
+  // head + tail scalars handled by block 0 warp 0
+  if (blockIdx.x == 0 && threadIdx.x < 32) {
+    int64_t tail_start = head + nvec * VEC;
+    int64_t nscalar = head + (n - tail_start);
+    for (int64_t b = 0; b < nscalar; b += 32) {
+      int64_t j = b + threadIdx.x;
+      bool act = j < nscalar;
+      int64_t e = j < head ? j : tail_start + (j - head);
+      UK rb = act ? keys[e] : UK(0);
+      account(rb, act);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NP * RADIX; i += blockDim.x) {
+    uint32_t c = (&sh[0][0])[i];
+    if (c) atomicAdd(&ghist[i], c);
+  }
+  if (nan_count) {
+    nans = warp_sum(nans);
+    if (lane_id() == 0 && nans) atomicAdd(nan_count, nans);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 2. plan
+// ------------------------------------------------------------------------------------------------
+// mode_pairs: 1 sorted_order (indices), 0 keys-only.  raw: 1 keys come from the user's column
+// (implicit indices), 0 keys already twiddled in buffer A with explicit indices in idx buffer
+// `pre_idx_buf`.
+__global__ void plan_kernel(const uint32_t* __restrict__ ghist, int npass, uint32_t n, int raw, int pre_idx_buf,
+                            sort_ctl* ctl)
+{
+  __shared__ uint32_t warp_tot[8];
+  __shared__ int triv[8];
+  const int d = threadIdx.x;  // 256 threads
+  for (int p = 0; p < npass; ++p) {
+    uint32_t c = ghist[p * RADIX + d];
+    if (d == 0) triv[p] = 0;
+    __syncthreads();
+    if (c == n) triv[p] = 1;
+    uint32_t inc = warp_inclusive_sum(c);
+    if ((d & 31) == 31) warp_tot[d >> 5] = inc;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (int w = 0; w < (d >> 5); ++w) woff += warp_tot[w];
+    ctl->base[0][p][d] = woff + inc - c;
+    __syncthreads();
+  }
+  if (d == 0) {
+    int nexec = 0;
+    for (int p = 0; p < npass; ++p) nexec += triv[p] ? 0 : 1;
+    // idx buffers: 0 = output, 1 = temp. the last executed pass must write 0.
+    // key buffers: 1 = A, 2 = B (keys-only: 1 = output, 2 = temp; last executed pass must write 1)
+    int k = 0;
+    int key_cur = raw ? 0 : 1;
+    int idx_cur = raw ? -1 : pre_idx_buf;
+    for (int p = 0; p < npass; ++p) {
+      pass_plan pl{};
+      pl.trivial = triv[p];
+      if (!triv[p]) {
+        int remaining_after = nexec - 1 - k;  // passes after this one
+        pl.key_src = key_cur;
+        pl.idx_src = idx_cur;
+        // destination chosen so that the final pass lands in buffer 1 (keys) / 0 (idx)
+        pl.key_dst = (remaining_after % 2 == 0) ? 1 : 2;
+        pl.idx_dst = (remaining_after % 2 == 0) ? 0 : 1;
+        pl.last    = remaining_after == 0;
+        key_cur = pl.key_dst;
+        idx_cur = pl.idx_dst;
+        ++k;
+      }
+      ctl->plan[p] = pl;
+    }
+    ctl->any_pass = nexec;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3. one-sweep pass
+// ------------------------------------------------------------------------------------------------
+struct pass_args {
+  const void* key_bufs[3];  // [0] raw input column data (already offset), [1], [2]
+  int32_t* idx_bufs[2];
+  sort_ctl* ctl;
+  uint32_t* status;         // [num_tiles][256] for this (pass, portion)
+  uint32_t* tile_counter;   // for this (pass, portion)
+  int64_t portion_start;    // element offset of this portion
+  uint32_t portion_n;       // elements in this portion
+  int32_t pass;
+  int32_t portion_parity;   // which base[] copy to read; the other is written for the next portion
+  int32_t has_next_portion;
+  int32_t kind;             // key_kind for raw loads / keys-only untwiddle
+  int32_t pairs;            // 1: (key, idx) ; 0: keys only
+  uint64_t desc_mask;
+  int32_t pre_n_is_dynamic; // unused
+};
+
+template <typename UK, int THREADS, int IPT>
+__global__ void __launch_bounds__(THREADS, (THREADS <= 384 ? 2 : 1)) onesweep_kernel(pass_args a)
+{
+  constexpr int TILE   = THREADS * IPT;
+  constexpr int NWARPS = THREADS / 32;
+  static_assert(THREADS >= RADIX, "need one thread per digit");
+
+  const pass_plan pl = a.ctl->plan[a.pass];
+  if (pl.trivial) return;
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  UK* s_keys          = reinterpret_cast<UK*>(smem_raw);
+  uint32_t* s_vals    = reinterpret_cast<uint32_t*>(smem_raw);
+  constexpr int STAGE_W = sizeof(UK) > 4 ? sizeof(UK) : 4;  // staging holds keys, then 32-bit row ids
+  uint32_t* s_whist   = reinterpret_cast<uint32_t*>(smem_raw + (size_t)STAGE_W * TILE);  // [NWARPS][256]
+  uint32_t* s_off     = s_whist + NWARPS * RADIX;                                    // [256] global offset - tile start
+  uint32_t* s_start   = s_off + RADIX;                                               // [256] tile-local start
+  uint32_t* s_misc    = s_start + RADIX;                                             // [16]
+
+  const int tid  = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+
+  if (tid == 0) s_misc[0] = atomicAdd(a.tile_counter, 1u);
+  // zero this warp's histogram while waiting
+#pragma unroll
+  for (int j = 0; j < RADIX / 32; ++j) s_whist[warp * RADIX + j * 32 + lane] = 0;
+  __syncthreads();
+  const uint32_t tile = s_misc[0];
+  const uint32_t tile_base = tile * (uint32_t)TILE;       // within portion
+  const uint32_t tile_n = min((uint32_t)TILE, a.portion_n - tile_base);
+  const bool full = tile_n == (uint32_t)TILE;
+  const int shift = a.pass * RADIX_BITS;
+  const UK desc = (UK)a.desc_mask;
+
+  // ---- load (warp-striped: item i of lane l in warp w = w*32*IPT + i*32 + l) -------------------
+  UK key[IPT];
+  uint32_t idx[IPT];
+  const uint32_t wbase = tile_base + warp * (32 * IPT) + lane;
+  {
+    const UK* src = static_cast<const UK*>(pl.key_src == 0 ? a.key_bufs[0] : (pl.key_src == 1 ? a.key_bufs[1] : a.key_bufs[2])) + a.portion_start;
+    const bool raw = pl.key_src == 0;
+    if (full) {
+#pragma unroll
+      for (int i = 0; i < IPT; ++i) key[i] = ld_stream(src + wbase + i * 32);
+    } else {
+#pragma unroll
+      for (int i = 0; i < IPT; ++i) {
+        uint32_t e = wbase + i * 32;
+        key[i] = e < a.portion_n ? ld_stream(src + e) : UK(0);
+      }
+    }
+    if (raw) {
+#pragma unroll
+      for (int i = 0; i < IPT; ++i) key[i] = twiddle_rt<UK>(key[i], a.kind, desc);
+    }
+    if (!full) {
+      // padding items take the maximum key so that they rank last in the tile
+#pragma unroll
+      for (int i = 0; i < IPT; ++i)
+        if (wbase + i * 32 >= a.portion_n) key[i] = ~UK(0);
+    }
+    if (a.pairs) {
+      if (pl.idx_src < 0) {
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) idx[i] = (uint32_t)(a.portion_start + wbase + i * 32);
+      } else {
+        const uint32_t* isrc = reinterpret_cast<const uint32_t*>(pl.idx_src == 0 ? a.idx_bufs[0] : a.idx_bufs[1]) + a.portion_start;
+        if (full) {
+#pragma unroll
+          for (int i = 0; i < IPT; ++i) idx[i] = ld_stream(isrc + wbase + i * 32);
+        } else {
+#pragma unroll
+          for (int i = 0; i < IPT; ++i) {
+            uint32_t e = wbase + i * 32;
+            idx[i] = e < a.portion_n ? ld_stream(isrc + e) : 0u;
+          }
+        }
+      }
+    }
+  }
+
+  // ---- rank within warp (stable): MATCH.ANY peers + per-warp digit counters -------------------
+  uint32_t rank[IPT];
+  uint32_t* my_hist = s_whist + warp * RADIX;
+#pragma unroll
+  for (int i = 0; i < IPT; ++i) {
+    const unsigned d = (unsigned)(key[i] >> shift) & 255u;
+    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    const unsigned lt = __popc(peers & lanemask_lt());
+    uint32_t prev = 0;
+    if (lt == 0) {
+      prev = my_hist[d];
+      my_hist[d] = prev + __popc(peers);
+    }
+    __syncwarp();
+    prev = __shfl_sync(0xffffffffu, prev, __ffs(peers) - 1);
+    rank[i] = prev + lt;
+  }
+  __syncthreads();
+
+  // ---- per-digit: counts across warps -> warp offsets, tile count -------------------------------
+  uint32_t count = 0;
+  if (tid < RADIX) {
+#pragma unroll
+    for (int w = 0; w < NWARPS; ++w) {
+      uint32_t c = s_whist[w * RADIX + tid];
+      s_whist[w * RADIX + tid] = count;
+      count += c;
+    }
+    if (!full && tid == RADIX - 1) count -= ((uint32_t)TILE - tile_n);  // padding sits in digit 255
+    // publish the tile aggregate as early as possible
+    uint32_t* st = a.status + (size_t)tile * RADIX + tid;
+    uint32_t word = (tile == 0 ? FLAG_INCL : FLAG_AGG) | count;
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(st), "r"(word) : "memory");
+    // exclusive scan of counts over digits (8 warps of 32 digits)
+    uint32_t padded = count + ((!full && tid == RADIX - 1) ? ((uint32_t)TILE - tile_n) : 0u);
+    uint32_t inc = warp_inclusive_sum(padded);
+    if (lane == 31) s_misc[1 + warp] = inc;
+    s_start[tid] = inc - padded;  // completed below
+  }
+  __syncthreads();
+  if (tid < RADIX) {
+    uint32_t woff = 0;
+#pragma unroll
+    for (int w = 0; w < RADIX / 32; ++w) woff += (w < warp) ? s_misc[1 + w] : 0u;
+    const uint32_t tstart = s_start[tid] + woff;
+    s_start[tid] = tstart;
+    // ---- decoupled look-back for digit `tid` ----------------------------------------------------
+    uint32_t excl = 0;
+    if (tile > 0) {
+      int64_t t = (int64_t)tile - 1;
+      while (true) {
+        const uint32_t* pst = a.status + (size_t)t * RADIX + tid;
+        uint32_t v;
+        do {
+          asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(pst) : "memory");
+        } while ((v >> 30) == 0);
+        excl += v & VAL_MASK;
+        if (v & FLAG_INCL) break;
+        --t;
+      }
+      uint32_t* st = a.status + (size_t)tile * RADIX + tid;
+      uint32_t word = FLAG_INCL | (excl + count);
+      asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(st), "r"(word) : "memory");
+    }
+    const uint32_t gbase = a.ctl->base[a.portion_parity][a.pass][tid];
+    s_off[tid] = gbase + excl - tstart;
+    if (a.has_next_portion && tile_base + tile_n == a.portion_n) {
+      // last tile of the portion: digit bases for the next portion
+      a.ctl->base[a.portion_parity ^ 1][a.pass][tid] = gbase + excl + count;
+    }
+  }
+  __syncthreads();
+
+  // ---- scatter through shared memory in tile-sorted order ------------------------------------
+  uint32_t pos[IPT];
+#pragma unroll
+  for (int i = 0; i < IPT; ++i) {
+    const unsigned d = (unsigned)(key[i] >> shift) & 255u;
+    pos[i] = s_start[d] + my_hist[d] + rank[i];
+    s_keys[pos[i]] = key[i];
+  }
+  __syncthreads();
+
+  const bool write_keys = !(a.pairs && pl.last);
+  UK* kdst = static_cast<UK*>(const_cast<void*>(pl.key_dst == 1 ? a.key_bufs[1] : a.key_bufs[2]));
+  uint32_t dst[IPT];
+#pragma unroll
+  for (int j = 0; j < IPT; ++j) {
+    const uint32_t q = j * THREADS + tid;
+    UK k = s_keys[q];
+    const unsigned d = (unsigned)(k >> shift) & 255u;
+    dst[j] = s_off[d] + q;
+    if (write_keys && q < tile_n) {
+      if (!a.pairs && pl.last) k = untwiddle_rt<UK>(k, a.kind, desc);
+      kdst[dst[j]] = k;
+    }
+  }
+  if (a.pairs) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) s_vals[pos[i]] = idx[i];
+    __syncthreads();
+    uint32_t* idst = reinterpret_cast<uint32_t*>(pl.idx_dst == 0 ? a.idx_bufs[0] : a.idx_bufs[1]);
+#pragma unroll
+    for (int j = 0; j < IPT; ++j) {
+      const uint32_t q = j * THREADS + tid;
+      if (q < tile_n) idst[dst[j]] = s_vals[q];
+    }
+  }
+}
+
+// all passes trivial: the sorted order is the input order
+template <typename UK>
+__global__ void finalize_kernel(pass_args a, int64_t n, int raw, int pre_idx_buf)
+{
+  if (a.ctl->any_pass != 0) return;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    if (a.pairs) {
+      if (raw) a.idx_bufs[0][i] = (int32_t)i;
+      else if (pre_idx_buf != 0) a.idx_bufs[0][i] = a.idx_bufs[1][i];
+    } else {
+      // keys-only (always raw): copy input to output
+      static_cast<UK*>(const_cast<void*>(a.key_bufs[1]))[i] = static_cast<const UK*>(a.key_bufs[0])[i];
+    }
+  }
+}
+
+// descending float keys: cub sorts the (nan_bias, value) tuple descending, i.e. NaNs come first in
+// DESCENDING row order (sorted_order_radix.cu:41-50,121-131). The stable pass above leaves them
+// ascending; reverse that prefix.
+__global__ void reverse_nan_prefix_kernel(int32_t* idx, const uint32_t* nan_count)
+{
+  const uint32_t m = *nan_count;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m / 2; i += stride) {
+    int32_t x = idx[i], y = idx[m - 1 - i];
+    idx[i] = y;
+    idx[m - 1 - i] = x;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 4. null compaction (single nullable column)
+// ------------------------------------------------------------------------------------------------
+constexpr int CP_THREADS = 256;
+constexpr int CP_ROWS    = 2048;  // rows per CTA = 64 mask words
+
+__global__ void __launch_bounds__(CP_THREADS) valid_count_kernel(const uint32_t* __restrict__ mask, int64_t bit_offset,
+                                                                  int64_t n, uint32_t* __restrict__ tile_valid)
+{
+  // each warp counts one tile of CP_ROWS rows
+  const int64_t tile = (int64_t)blockIdx.x * (CP_THREADS / 32) + (threadIdx.x >> 5);
+  const int64_t ntiles = (n + CP_ROWS - 1) / CP_ROWS;
+  if (tile >= ntiles) return;
+  const int64_t row0 = tile * CP_ROWS;
+  const int64_t last_word = (bit_offset + n - 1) >> 5;
+  uint32_t c = 0;
+  for (int w = lane_id(); w < CP_ROWS / 32; w += 32) {
+    int64_t r = row0 + (int64_t)w * 32;
+    if (r < n) {
+      uint32_t bits = load_mask_word_unaligned(mask, bit_offset + r, last_word);
+      int64_t rem = n - r;
+      if (rem < 32) bits &= (1u << rem) - 1u;
+      c += __popc(bits);
+    }
+  }
+  c = warp_sum(c);
+  if (lane_id() == 0) tile_valid[tile] = c;
+}
+
+// single-CTA exclusive scan over tile counts (ntiles <= ~1M); also writes total
+__global__ void __launch_bounds__(1024) scan_tiles_kernel(uint32_t* __restrict__ tile_valid, int64_t ntiles,
+                                                          uint32_t* __restrict__ total)
+{
+  __shared__ uint32_t wsum[32];
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int64_t b = 0; b < ntiles; b += 1024) {
+    int64_t i = b + threadIdx.x;
+    uint32_t v = i < ntiles ? tile_valid[i] : 0;
+    uint32_t inc = warp_inclusive_sum(v);
+    if (lane_id() == 31) wsum[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) woff += wsum[w];
+    uint32_t c = carry;
+    if (i < ntiles) tile_valid[i] = c + woff + inc - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = c + woff + inc;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry;
+}
+
+template <typename UK>
+__global__ void __launch_bounds__(CP_THREADS) compact_kernel(const UK* __restrict__ keys, const uint32_t* __restrict__ mask,
+                                                             int64_t bit_offset, int64_t n, int kind, UK desc_mask,
+                                                             const uint32_t* __restrict__ tile_valid_excl,
+                                                             UK* __restrict__ out_keys, int32_t* __restrict__ out_valid_idx,
+                                                             int32_t* __restrict__ out_null_idx)
+{
+  __shared__ uint32_t wcount[CP_ROWS / 32];  // valid count per 32-row word
+  const int64_t tile = blockIdx.x;
+  const int64_t row0 = tile * CP_ROWS;
+  const int64_t last_word = (bit_offset + n - 1) >> 5;
+  const uint32_t vbase = tile_valid_excl[tile];
+  const uint32_t nbase = (uint32_t)row0 - vbase;
+  // 64 words per tile; thread t<64 loads word t
+  uint32_t bits = 0;
+  if (threadIdx.x < CP_ROWS / 32) {
+    int64_t r = row0 + (int64_t)threadIdx.x * 32;
+    if (r < n) {
+      bits = load_mask_word_unaligned(mask, bit_offset + r, last_word);
+      int64_t rem = n - r;
+      if (rem < 32) bits &= (1u << rem) - 1u;
+    }
+    wcount[threadIdx.x] = __popc(bits);
+  }
+  __syncthreads();
+  // each warp handles words warp, warp+8, ... ; prefix of earlier words by summing smem (<=64 adds)
+  for (int w = threadIdx.x >> 5; w < CP_ROWS / 32; w += CP_THREADS / 32) {
+    int64_t r = row0 + (int64_t)w * 32 + lane_id();
+    uint32_t before = 0;
+    for (int j = lane_id(); j < w; j += 32) before += wcount[j];
+    before = warp_sum(before);
+    bool in = r < n;
+    bool valid = false;
+    if (in) {
+      // recompute this word's bits (cheap, L1-resident)
+      uint32_t wb = load_mask_word_unaligned(mask, bit_offset + row0 + (int64_t)w * 32, last_word);
+      valid = (wb >> lane_id()) & 1u;
+    }
+    unsigned vb = __ballot_sync(0xffffffffu, valid);
+    unsigned nb = __ballot_sync(0xffffffffu, in && !valid);
+    if (valid) {
+      uint32_t o = vbase + before + __popc(vb & lanemask_lt());
+      out_keys[o]      = twiddle_rt<UK>(keys[r], kind, desc_mask);
+      out_valid_idx[o] = (int32_t)r;
+    } else if (in) {
+      uint32_t o = nbase + ((uint32_t)w * 32 - before) + __popc(nb & lanemask_lt());
+      out_null_idx[o] = (int32_t)r;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host driver
+// ------------------------------------------------------------------------------------------------
+struct tile_cfg { int threads; int ipt; };
+
+template <typename UK> struct cfg_for;
+template <> struct cfg_for<uint8_t>  { static constexpr int T = 512, I = 16; };
+template <> struct cfg_for<uint16_t> { static constexpr int T = 512, I = 16; };
+template <> struct cfg_for<uint32_t> { static constexpr int T = 512, I = 16; };
+template <> struct cfg_for<uint64_t> { static constexpr int T = 384, I = 16; };
+
+template <typename UK, int T, int I>
+size_t onesweep_smem()
+{
+  return (sizeof(UK) > 4 ? sizeof(UK) : 4) * (size_t)T * I + sizeof(uint32_t) * ((T / 32) * RADIX + 2 * RADIX + 16);
+}
+
+int64_t portion_limit()
+{
+  static int64_t lim = [] {
+    const char* e = std::getenv("B2_SORT_PORTION");
+    int64_t v = e ? std::atoll(e) : 0;
+    if (v <= 0) v = (int64_t(1) << 30) - 16384;
+    return v;
+  }();
+  return lim;
+}
+
+// Sort `n` keys.
+//  raw_keys != nullptr : keys are the user's raw column (twiddled on load, implicit row ids)
+//  raw_keys == nullptr : keys are pre-twiddled in bufA with explicit row ids in idx buffer pre_idx_buf
+//  pairs: idx_out receives the permutation ; keys-only: bufA is the OUTPUT, bufB the temp.
+template <typename UK>
+void run_radix(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int32_t* idx_tmp, int pre_idx_buf, int64_t n,
+               int kind, bool descending, bool pairs, cudaStream_t stream)
+{
+  constexpr int NP = sizeof(UK);
+  constexpr int T = cfg_for<UK>::T, I = cfg_for<UK>::I;
+  constexpr int TILE = T * I;
+  const bool raw = raw_keys != nullptr;
+  const UK desc_mask = descending ? ~UK(0) : UK(0);
+
+  const int64_t plim = std::max<int64_t>(TILE, portion_limit() / TILE * TILE);
+  const int64_t nportions = (n + plim - 1) / plim;
+  const int64_t tiles_per_portion = (std::min(n, plim) + TILE - 1) / TILE;
+
+  // control block + histograms + status words + tile counters in one zeroed allocation
+  const size_t ctl_bytes   = (sizeof(sort_ctl) + 255) / 256 * 256;
+  const size_t hist_bytes  = sizeof(uint32_t) * NP * RADIX;
+  const size_t cnt_bytes   = (sizeof(uint32_t) * NP * nportions + 255) / 256 * 256;
+  const size_t status_per  = sizeof(uint32_t) * RADIX * (size_t)tiles_per_portion;
+  const size_t status_bytes = status_per * NP * nportions;
+  dbuf work(ctl_bytes + hist_bytes + cnt_bytes + status_bytes, stream);
+  B2_CUDA_TRY(cudaMemsetAsync(work.ptr, 0, work.bytes, stream));
+  auto* ctl       = reinterpret_cast<sort_ctl*>(work.ptr);
+  auto* ghist     = reinterpret_cast<uint32_t*>(static_cast<char*>(work.ptr) + ctl_bytes);
+  auto* counters  = reinterpret_cast<uint32_t*>(static_cast<char*>(work.ptr) + ctl_bytes + hist_bytes);
+  auto* status    = reinterpret_cast<uint32_t*>(static_cast<char*>(work.ptr) + ctl_bytes + hist_bytes + cnt_bytes);
+
+  {
+    int grid = (int)std::min<int64_t>((n + 512 * 16 - 1) / (512 * 16), NUM_SMS_B200 * 4);
+    grid = std::max(grid, 1);
+    B2_LAUNCH((histogram_kernel<UK>), grid, 512, 0, stream, raw ? raw_keys : bufA, n, raw ? 1 : 0, kind, desc_mask, ghist,
+              (raw && kind == (int)key_kind::FLOAT) ? &ctl->nan_count : nullptr);
+  }
+  B2_LAUNCH(plan_kernel, 1, RADIX, 0, stream, ghist, NP, (uint32_t)n, raw ? 1 : 0, pre_idx_buf, ctl);
+
+  static bool attr_set = [] {
+    cudaFuncSetAttribute(onesweep_kernel<UK, T, I>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)onesweep_smem<UK, T, I>());
+    return true;
+  }();
+  (void)attr_set;
+
+  pass_args a{};
+  a.key_bufs[0] = raw_keys;
+  a.key_bufs[1] = bufA;
+  a.key_bufs[2] = bufB;
+  a.idx_bufs[0] = idx_out;
+  a.idx_bufs[1] = idx_tmp;
+  a.ctl = ctl;
+  a.kind = kind;
+  a.pairs = pairs ? 1 : 0;
+  a.desc_mask = (uint64_t)desc_mask;
+  for (int p = 0; p < NP; ++p) {
+    for (int64_t q = 0; q < nportions; ++q) {
+      const int64_t start = q * plim;
+      const int64_t pn = std::min(plim, n - start);
+      a.pass = p;
+      a.portion_start = start;
+      a.portion_n = (uint32_t)pn;
+      a.portion_parity = (int)(q & 1);
+      a.has_next_portion = q + 1 < nportions;
+      a.status = status + (size_t)(p * nportions + q) * RADIX * (size_t)tiles_per_portion;
+      a.tile_counter = counters + p * nportions + q;
+      const int64_t ntiles = (pn + TILE - 1) / TILE;
+      const size_t smem_bytes = onesweep_smem<UK, T, I>();
+      B2_LAUNCH((onesweep_kernel<UK, T, I>), (unsigned)ntiles, T, smem_bytes, stream, a);
+    }
+  }
+  {
+    int grid = (int)std::min<int64_t>((n + 255) / 256, NUM_SMS_B200 * 8);
+    B2_LAUNCH((finalize_kernel<UK>), std::max(grid, 1), 256, 0, stream, a, n, raw ? 1 : 0, pre_idx_buf);
+  }
+  if (pairs && raw && kind == (int)key_kind::FLOAT && descending) {
+    B2_LAUNCH(reverse_nan_prefix_kernel, NUM_SMS_B200 * 4, 256, 0, stream, idx_out, &ctl->nan_count);
+  }
+}
+
+int kind_of(int32_t storage_id)
+{
+  if (is_float_id(storage_id)) return (int)key_kind::FLOAT;
+  if (is_signed_id(storage_id)) return (int)key_kind::SIGNED;
+  return (int)key_kind::UNSIGNED;  // unsigned ints and BOOL8
+}
+
+template <typename UK>
+column_ptr sorted_order_single(const b2_column_view& col, bool ascending, bool nulls_before, cudaStream_t stream)
+{
+  const int64_t n = col.size;
+  const int sid   = storage_type(col.type_id);
+  const int kind  = kind_of(sid);
+  auto out = make_column(B2_INT32, col.size, false, stream);
+  const UK* data = static_cast<const UK*>(col.data) + col.offset;
+  int32_t* out_idx = out->data.as<int32_t>();
+
+  if (!has_nulls(col)) {
+    dbuf a(sizeof(UK) * n, stream), b(sizeof(UK) > 1 ? sizeof(UK) * n : 0, stream), it(sizeof(int32_t) * n, stream);
+    run_radix<UK>(data, a.as<UK>(), b.as<UK>(), out_idx, it.as<int32_t>(), 0, n, kind, !ascending, true, stream);
+    return out;
+  }
+  // nullable: nulls first iff (null_order == BEFORE) xor descending (sort_column_impl.cuh:35-57)
+  const bool nulls_first = nulls_before != !ascending;
+  const int64_t n_null  = col.null_count;
+  const int64_t n_valid = n - n_null;
+  const int64_t ntiles = (n + CP_ROWS - 1) / CP_ROWS;
+  dbuf tv(sizeof(uint32_t) * (ntiles + 1), stream);
+  B2_LAUNCH(valid_count_kernel, (unsigned)((ntiles + 7) / 8), CP_THREADS, 0, stream, col.null_mask, (int64_t)col.offset, n,
+            tv.as<uint32_t>());
+  B2_LAUNCH(scan_tiles_kernel, 1, 1024, 0, stream, tv.as<uint32_t>(), ntiles, tv.as<uint32_t>() + ntiles);
+  dbuf a(sizeof(UK) * std::max<int64_t>(n_valid, 1), stream), b(sizeof(UK) * std::max<int64_t>(n_valid, 1), stream);
+  dbuf it(sizeof(int32_t) * std::max<int64_t>(n_valid, 1), stream);
+  int32_t* valid_out = out_idx + (nulls_first ? n_null : 0);
+  int32_t* null_out  = out_idx + (nulls_first ? 0 : n_valid);
+  const UK desc_mask = ascending ? UK(0) : ~UK(0);
+  // compaction writes explicit row ids into the TEMP idx buffer (buffer 1); the plan then makes the
+  // last executed pass land in buffer 0 = valid_out.
+  B2_LAUNCH((compact_kernel<UK>), (unsigned)ntiles, CP_THREADS, 0, stream, data, col.null_mask, (int64_t)col.offset, n,
+            kind, desc_mask, tv.as<uint32_t>(), a.as<UK>(), it.as<int32_t>(), null_out);
+  if (n_valid > 0)
+    run_radix<UK>(nullptr, a.as<UK>(), b.as<UK>(), valid_out, it.as<int32_t>(), 1, n_valid, kind, !ascending, true, stream);
+  return out;
+}
+
+}  // namespace
+
+bool is_radix_sortable(const b2_column_view& c) { return !has_nulls(c) && is_fixed_width(c.type_id); }
+
+// cudf::detail::sorted_order(column_view) — cpp/src/sort/sort_column.cu:22-44
+static column_ptr sorted_order_column(const b2_column_view& col, bool ascending, bool nulls_before, cudaStream_t stream)
+{
+  switch (type_width(col.type_id)) {
+    case 1: return sorted_order_single<uint8_t>(col, ascending, nulls_before, stream);
+    case 2: return sorted_order_single<uint16_t>(col, ascending, nulls_before, stream);
+    case 4: return sorted_order_single<uint32_t>(col, ascending, nulls_before, stream);
+    case 8: return sorted_order_single<uint64_t>(col, ascending, nulls_before, stream);
+    default: B2_FAIL(B2_ERR_DATA_TYPE, "sorted_order: unsupported (non fixed-width) key type");
+  }
+}
+
+// ---- multi-column lexicographic order (sort_impl.cuh:61-93): LSD over columns, last to first ----
+namespace {
+template <typename UK>
+__global__ void gather_twiddle_kernel(const UK* __restrict__ keys, const uint32_t* __restrict__ mask, int64_t bit_offset,
+                                      const int32_t* __restrict__ perm, int64_t n, int kind, UK desc_mask,
+                                      UK* __restrict__ out_keys, uint8_t* __restrict__ out_null)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    int32_t r = perm ? perm[i] : (int32_t)i;
+    bool valid = mask == nullptr || bit_is_set(mask, bit_offset + r);
+    out_keys[i] = valid ? twiddle_rt<UK>(keys[r], kind, desc_mask) : UK(0);
+    if (out_null) out_null[i] = valid ? 0 : 1;
+  }
+}
+// stable 2-way partition of perm by flag (0 first when zero_first) — used for the null "digit"
+__global__ void flag_count_kernel(const uint8_t* __restrict__ flag, int64_t n, uint32_t* __restrict__ tile_ones)
+{
+  // one warp per 1024 elements
+  const int64_t tile = (int64_t)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+  const int64_t ntiles = (n + 1023) / 1024;
+  if (tile >= ntiles) return;
+  uint32_t c = 0;
+  for (int j = 0; j < 32; ++j) {
+    int64_t i = tile * 1024 + j * 32 + lane_id();
+    c += (i < n && flag[i]) ? 1u : 0u;
+  }
+  c = warp_sum(c);
+  if (lane_id() == 0) tile_ones[tile] = c;
+}
+__global__ void flag_partition_kernel(const uint8_t* __restrict__ flag, const int32_t* __restrict__ perm_in, int64_t n,
+                                      const uint32_t* __restrict__ tile_ones_excl, const uint32_t* __restrict__ total_ones,
+                                      int ones_first, int32_t* __restrict__ perm_out)
+{
+  const int64_t tile = (int64_t)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+  const int64_t ntiles = (n + 1023) / 1024;
+  if (tile >= ntiles) return;
+  const uint32_t tot1 = *total_ones;
+  const uint32_t tot0 = (uint32_t)n - tot1;
+  uint32_t ones_before = tile_ones_excl[tile];
+  uint32_t zeros_before = (uint32_t)(tile * 1024) - ones_before;
+  for (int j = 0; j < 32; ++j) {
+    int64_t i = tile * 1024 + j * 32 + lane_id();
+    bool in = i < n;
+    bool f = in && flag[i];
+    unsigned b1 = __ballot_sync(0xffffffffu, f);
+    unsigned b0 = __ballot_sync(0xffffffffu, in && !f);
+    if (in) {
+      uint32_t o = f ? (ones_first ? 0u : tot0) + ones_before + __popc(b1 & lanemask_lt())
+                     : (ones_first ? tot1 : 0u) + zeros_before + __popc(b0 & lanemask_lt());
+      perm_out[o] = perm_in[i];
+    }
+    ones_before += __popc(b1);
+    zeros_before += __popc(b0);
+  }
+}
+__global__ void compose_perm_kernel(const int32_t* __restrict__ perm, const int32_t* __restrict__ order, int64_t n,
+                                    int32_t* __restrict__ out)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = perm[order[i]];
+}
+
+template <typename UK>
+void lex_step(const b2_column_view& col, bool ascending, bool nulls_before, int32_t*& perm, int32_t*& perm_alt,
+              bool& have_perm, dbuf& ka, dbuf& kb, dbuf& kc, dbuf& ord, dbuf& otmp, dbuf& nullflag, dbuf& tiles, cudaStream_t stream)
+{
+  const int64_t n = col.size;
+  const int kind  = kind_of(storage_type(col.type_id));
+  const UK desc_mask = ascending ? UK(0) : ~UK(0);
+  const bool nullable = has_nulls(col);
+  const int grid = (int)std::min<int64_t>((n + 255) / 256, NUM_SMS_B200 * 16);
+  B2_LAUNCH((gather_twiddle_kernel<UK>), grid, 256, 0, stream, static_cast<const UK*>(col.data) + col.offset,
+            nullable ? col.null_mask : nullptr, (int64_t)col.offset, have_perm ? perm : nullptr, n, kind, desc_mask,
+            ka.as<UK>(), nullable ? nullflag.as<uint8_t>() : nullptr);
+  // sort positions 0..n-1 by the gathered key: explicit ids = iota in buffer 1 (otmp), result in ord
+  // (raw=false path wants explicit ids; generate iota cheaply through the same compose kernel is
+  // not possible, so run with pre-twiddled keys + implicit ids by treating them as UNSIGNED raw.)
+  run_radix<UK>(ka.as<UK>(), kb.as<UK>(), kc.as<UK>(), ord.as<int32_t>(), otmp.as<int32_t>(), 0, n,
+                (int)key_kind::UNSIGNED, false, true, stream);
+  // perm' = perm ∘ ord
+  if (have_perm) {
+    B2_LAUNCH(compose_perm_kernel, grid, 256, 0, stream, perm, ord.as<int32_t>(), n, perm_alt);
+    std::swap(perm, perm_alt);
+  } else {
+    B2_CUDA_TRY(cudaMemcpyAsync(perm, ord.ptr, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, stream));
+    have_perm = true;
+  }
+  if (nullable) {
+    // null flag of the rows in the new order, then a stable partition (the null "digit")
+    const bool nulls_first = nulls_before != !ascending;
+    const int64_t ntiles = (n + 1023) / 1024;
+    // flags in new order: gather nullflag (indexed by old position) through ord
+    // reuse kb as byte scratch
+    uint8_t* f2 = kb.as<uint8_t>();
+    // f2[i] = nullflag[ord[i]]
+    B2_LAUNCH((gather_twiddle_kernel<uint8_t>), grid, 256, 0, stream, nullflag.as<uint8_t>(), (const uint32_t*)nullptr,
+              (int64_t)0, ord.as<int32_t>(), n, (int)key_kind::UNSIGNED, (uint8_t)0, f2, (uint8_t*)nullptr);
+    B2_LAUNCH(flag_count_kernel, (unsigned)((ntiles + 7) / 8), 256, 0, stream, f2, n, tiles.as<uint32_t>());
+    B2_LAUNCH(scan_tiles_kernel, 1, 1024, 0, stream, tiles.as<uint32_t>(), ntiles, tiles.as<uint32_t>() + ntiles);
+    B2_LAUNCH(flag_partition_kernel, (unsigned)((ntiles + 7) / 8), 256, 0, stream, f2, perm, n, tiles.as<uint32_t>(),
+              tiles.as<uint32_t>() + ntiles, nulls_first ? 1 : 0, perm_alt);
+    std::swap(perm, perm_alt);
+  }
+}
+}  // namespace
+
+// cudf::detail::sorted_order(table_view) — cpp/src/sort/sort_impl.cuh:31-96
+column_ptr sorted_order(const std::vector<b2_column_view>& keys, const std::vector<uint8_t>& order,
+                        const std::vector<uint8_t>& null_prec, bool /*stable: every path here is stable*/,
+                        cudaStream_t stream)
+{
+  if (keys.empty() || keys[0].size == 0) return make_column(B2_INT32, 0, false, stream);
+  B2_EXPECTS(order.empty() || order.size() == keys.size(), B2_ERR_LOGIC,
+             "Mismatch between number of columns and column order.");
+  B2_EXPECTS(null_prec.empty() || null_prec.size() == keys.size(), B2_ERR_LOGIC,
+             "Mismatch between number of columns and null_precedence size.");
+  auto asc = [&](size_t i) { return order.empty() ? true : order[i] == B2_ASCENDING; };
+  auto before = [&](size_t i) { return null_prec.empty() ? true : null_prec[i] == B2_NULL_BEFORE; };
+  if (keys.size() == 1) return sorted_order_column(keys[0], asc(0), before(0), stream);
+
+  const int64_t n = keys[0].size;
+  auto out = make_column(B2_INT32, (int32_t)n, false, stream);
+  dbuf alt(sizeof(int32_t) * n, stream), ka(8 * n, stream), kb(8 * n, stream), kc(8 * n, stream), ord(sizeof(int32_t) * n, stream),
+    otmp(sizeof(int32_t) * n, stream), nullflag(n, stream), tiles(sizeof(uint32_t) * ((n + 1023) / 1024 + 1), stream);
+  int32_t* perm = out->data.as<int32_t>();
+  int32_t* perm_alt = alt.as<int32_t>();
+  bool have_perm = false;
+  for (size_t c = keys.size(); c-- > 0;) {
+    const auto& col = keys[c];
+    switch (type_width(col.type_id)) {
+      case 1: lex_step<uint8_t>(col, asc(c), before(c), perm, perm_alt, have_perm, ka, kb, kc, ord, otmp, nullflag, tiles, stream); break;
+      case 2: lex_step<uint16_t>(col, asc(c), before(c), perm, perm_alt, have_perm, ka, kb, kc, ord, otmp, nullflag, tiles, stream); break;
+      case 4: lex_step<uint32_t>(col, asc(c), before(c), perm, perm_alt, have_perm, ka, kb, kc, ord, otmp, nullflag, tiles, stream); break;
+      case 8: lex_step<uint64_t>(col, asc(c), before(c), perm, perm_alt, have_perm, ka, kb, kc, ord, otmp, nullflag, tiles, stream); break;
+      default: B2_FAIL(B2_ERR_DATA_TYPE, "sorted_order: unsupported (non fixed-width) key type");
+    }
+  }
+  if (perm != out->data.as<int32_t>()) {
+    B2_CUDA_TRY(cudaMemcpyAsync(out->data.ptr, perm, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, stream));
+    // `alt` now aliases the live result until the copy has run; it is freed stream-ordered after it.
+  }
+  return out;
+}
+
+// cudf::detail::sort_radix — cpp/src/sort/sort_radix.cu:151-161 (integer / chrono / bool keys;
+// float columns go through sorted_order + gather so that NaN payloads and -0/+0 survive)
+column_ptr sort_single_column(const b2_column_view& col, bool ascending, cudaStream_t stream)
+{
+  const int64_t n = col.size;
+  auto out = make_column(col.type_id, col.size, false, stream);
+  if (n == 0) return out;
+  const int kind = kind_of(storage_type(col.type_id));
+  B2_EXPECTS(kind != (int)key_kind::FLOAT, B2_ERR_LOGIC, "keys-only radix path is for integer-like keys");
+  auto run = [&](auto tag) {
+    using UK = decltype(tag);
+    dbuf tmp(sizeof(UK) > 1 ? sizeof(UK) * n : 0, stream);
+    run_radix<UK>(static_cast<const UK*>(col.data) + col.offset, out->data.as<UK>(), tmp.as<UK>(), nullptr, nullptr, 0, n, kind,
+                  !ascending, false, stream);
+  };
+  switch (type_width(col.type_id)) {
+    case 1: run(uint8_t{}); break;
+    case 2: run(uint16_t{}); break;
+    case 4: run(uint32_t{}); break;
+    case 8: run(uint64_t{}); break;
+    default: B2_FAIL(B2_ERR_DATA_TYPE, "sort: unsupported key type");
+  }
+  return out;
+}
+
+}  // namespace b2

@@ -1,0 +1,65 @@
+"""pylibcudf.sorting twin (python/pylibcudf/pylibcudf/sorting.pyx:37-79,333-520) over the C ABI."""
+from __future__ import annotations
+
+import ctypes as C
+
+from .. import _lib
+from .._lib import check, lib
+from .column import Column, Table
+
+
+def _u8(seq):
+    seq = [int(x) for x in (seq or [])]
+    arr = (C.c_uint8 * max(len(seq), 1))(*seq)
+    return arr, len(seq)
+
+
+def _sorted_order(source_table, column_order, null_precedence, stable, stream):
+    o, no = _u8(column_order)
+    p, np_ = _u8(null_precedence)
+    out = C.c_void_p()
+    tv = source_table._view()
+    check(lib.b2_sorted_order(C.byref(tv), o, no, p, np_, stable, _lib.stream_arg(stream), C.byref(out)))
+    return Column._from_handle(out.value)
+
+
+def sorted_order(source_table: Table, column_order: list, null_precedence: list, stream=None, mr=None) -> Column:
+    return _sorted_order(source_table, column_order, null_precedence, 0, stream)
+
+
+def stable_sorted_order(source_table: Table, column_order: list, null_precedence: list, stream=None, mr=None) -> Column:
+    return _sorted_order(source_table, column_order, null_precedence, 1, stream)
+
+
+def _sort(source_table, column_order, null_precedence, stable, stream):
+    o, no = _u8(column_order)
+    p, np_ = _u8(null_precedence)
+    out = C.c_void_p()
+    tv = source_table._view()
+    check(lib.b2_sort(C.byref(tv), o, no, p, np_, stable, _lib.stream_arg(stream), C.byref(out)))
+    return Table._from_handle(out.value)
+
+
+def sort(source_table: Table, column_order: list, null_precedence: list, stream=None, mr=None) -> Table:
+    return _sort(source_table, column_order, null_precedence, 0, stream)
+
+
+def stable_sort(source_table: Table, column_order: list, null_precedence: list, stream=None, mr=None) -> Table:
+    return _sort(source_table, column_order, null_precedence, 1, stream)
+
+
+def _sort_by_key(values, keys, column_order, null_precedence, stable, stream):
+    o, no = _u8(column_order)
+    p, np_ = _u8(null_precedence)
+    out = C.c_void_p()
+    vv, kv = values._view(), keys._view()
+    check(lib.b2_sort_by_key(C.byref(vv), C.byref(kv), o, no, p, np_, stable, _lib.stream_arg(stream), C.byref(out)))
+    return Table._from_handle(out.value)
+
+
+def sort_by_key(values: Table, keys: Table, column_order: list, null_precedence: list, stream=None, mr=None) -> Table:
+    return _sort_by_key(values, keys, column_order, null_precedence, 0, stream)
+
+
+def stable_sort_by_key(values: Table, keys: Table, column_order: list, null_precedence: list, stream=None, mr=None) -> Table:
+    return _sort_by_key(values, keys, column_order, null_precedence, 1, stream)

@@ -1,0 +1,132 @@
+"""Hash-groupby semantics: cpp/src/groupby/groupby.cu:40-71,220-259, hash/{groupby.cu,compute_groupby.cu,
+extract_single_pass_aggs.cpp,hash_compound_agg_finalizer.cu,output_utils.cu}, device_aggregators.cuh:428-446,
+result types cpp/include/cudf/detail/aggregation/aggregation.hpp:879-970; grouped scan:
+cpp/src/groupby/sort/{scan.cpp,group_scan_util.cuh:77-128}. Output here is canonical: groups in sorted key
+order (nulls first); the reference's order is arbitrary (groupby.hpp:148-150)."""
+from __future__ import annotations
+
+import numpy as np
+
+from . import sort as osort
+
+SUM, PRODUCT, MIN, MAX, COUNT_VALID, COUNT_ALL, MEAN = 0, 2, 3, 4, 5, 6, 10
+EXCLUDE, INCLUDE = 0, 1
+
+
+def _group_ids(key_cols, include_nulls):
+    """-> (order of rows sorted by key (stable), group id per sorted row, keep mask per row)."""
+    n = len(key_cols[0][0]) if key_cols else 0
+    keep = np.ones(n, dtype=bool)
+    if not include_nulls:
+        for _, m in key_cols:
+            if m is not None:
+                keep &= np.asarray(m, dtype=bool)
+    ranks = [osort._column_rank(v, m, osort.ASCENDING, osort.BEFORE) for v, m in key_cols]
+    rows = np.nonzero(keep)[0]
+    if len(rows) == 0:
+        return rows, np.empty(0, dtype=np.int64), keep
+    sub = [r[rows] for r in ranks]
+    o = np.lexsort(tuple(reversed(sub))) if len(sub) > 1 else np.argsort(sub[0], kind="stable")
+    rows = rows[o]
+    stacked = np.stack([r[rows] for r in ranks], axis=1)
+    new = np.ones(len(rows), dtype=bool)
+    new[1:] = (stacked[1:] != stacked[:-1]).any(axis=1)
+    gid = np.cumsum(new) - 1
+    return rows, gid, keep
+
+
+def result_dtype(kind, in_dtype):
+    in_dtype = np.dtype(in_dtype)
+    if kind == SUM or kind == PRODUCT:
+        if in_dtype.kind in "iu" or in_dtype == np.bool_:
+            return np.dtype(np.int64) if in_dtype.kind != "u" else np.dtype(np.uint64)
+        return in_dtype
+    if kind in (COUNT_VALID, COUNT_ALL):
+        return np.dtype(np.int32)
+    if kind == MEAN:
+        return np.dtype(np.float64)
+    return in_dtype
+
+
+def aggregate(key_cols, requests, null_handling=EXCLUDE):
+    """requests: list of ((values, valid), [kinds]).
+    -> (key columns [(values, valid)], results[request][kind] = (values, valid | None))."""
+    n = len(key_cols[0][0]) if key_cols else 0
+    for (vals, _), _k in requests:
+        if len(vals) != n:
+            raise RuntimeError("Size mismatch between request values and groupby keys.")
+    rows, gid, _ = _group_ids(key_cols, null_handling == INCLUDE)
+    ng = int(gid[-1]) + 1 if len(gid) else 0
+    first = np.nonzero(np.concatenate([[True], gid[1:] != gid[:-1]]))[0] if ng else np.empty(0, dtype=np.int64)
+    out_keys = []
+    for v, m in key_cols:
+        kv = np.asarray(v)[rows[first]] if ng else np.empty(0, dtype=np.asarray(v).dtype)
+        km = (np.asarray(m)[rows[first]] if m is not None else None) if ng else (None if m is None else np.empty(0, bool))
+        out_keys.append((kv, km))
+    results = []
+    for (vals, valid), kinds in requests:
+        vals = np.asarray(vals)
+        v = vals[rows]
+        m = np.ones(len(rows), bool) if valid is None else np.asarray(valid, dtype=bool)[rows]
+        has_nulls = valid is not None and not np.asarray(valid).all()
+        per = []
+        vc = np.bincount(gid[m], minlength=ng).astype(np.int64) if ng else np.empty(0, np.int64)
+        for kind in kinds:
+            rdt = result_dtype(kind, vals.dtype)
+            if kind == COUNT_ALL:
+                per.append((np.bincount(gid, minlength=ng).astype(np.int32), None))
+                continue
+            if kind == COUNT_VALID:
+                per.append((vc.astype(np.int32), None))
+                continue
+            out = np.zeros(ng, dtype=rdt)
+            xv, xg = v[m], gid[m]
+            with np.errstate(over="ignore", invalid="ignore"):
+                if kind in (SUM, MEAN):
+                    acc = np.zeros(ng, dtype=np.float64 if (rdt.kind == "f") else rdt)
+                    np.add.at(acc, xg, xv.astype(acc.dtype))
+                    out = (acc / np.maximum(vc, 1)).astype(rdt) if kind == MEAN else acc.astype(rdt)
+                elif kind == PRODUCT:
+                    acc = np.ones(ng, dtype=rdt)
+                    np.multiply.at(acc, xg, xv.astype(rdt))
+                    out = acc
+                elif kind == MIN:
+                    big = np.full(ng, np.inf if rdt.kind == "f" else (np.iinfo(rdt).max if rdt != np.bool_ else True), dtype=rdt)
+                    np.minimum.at(big, xg, xv)
+                    out = big
+                elif kind == MAX:
+                    small = np.full(ng, -np.inf if rdt.kind == "f" else (np.iinfo(rdt).min if rdt != np.bool_ else False), dtype=rdt)
+                    np.maximum.at(small, xg, xv)
+                    out = small
+                else:
+                    raise ValueError("unsupported aggregation")
+            ov = (vc > 0) if has_nulls else None
+            per.append((out, ov))
+        results.append(per)
+    return out_keys, results
+
+
+def scan(key_cols, requests, null_handling=EXCLUDE):
+    """cudf::groupby::scan: rows in stable sorted key order; inclusive scan restarted per group."""
+    from . import reduce as ored
+
+    rows, gid, _ = _group_ids(key_cols, null_handling == INCLUDE)
+    out_keys = [(np.asarray(v)[rows], None if m is None else np.asarray(m)[rows]) for v, m in key_cols]
+    starts = np.nonzero(np.concatenate([[True], gid[1:] != gid[:-1]]))[0] if len(gid) else np.empty(0, np.int64)
+    bounds = list(starts) + [len(rows)]
+    results = []
+    for (vals, valid), kinds in requests:
+        vals = np.asarray(vals)
+        v = vals[rows]
+        m = None if valid is None else np.asarray(valid, dtype=bool)[rows]
+        per = []
+        for kind in kinds:
+            rdt = result_dtype(kind, vals.dtype)
+            out = np.zeros(len(rows), dtype=rdt)
+            for b, e in zip(bounds[:-1], bounds[1:]):
+                seg = v[b:e].astype(rdt) if kind not in (COUNT_VALID, COUNT_ALL) else v[b:e]
+                r, _ = ored.scan(seg, None if m is None else m[b:e], kind, True, ored.EXCLUDE)
+                out[b:e] = r
+            per.append((out, m if kind not in (COUNT_VALID, COUNT_ALL) else None))
+        results.append(per)
+    return out_keys, results

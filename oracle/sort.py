@@ -1,0 +1,96 @@
+"""Sort semantics of cpp/src/sort/{sort.cu,sort_impl.cuh,sort_column.cu,sort_column_impl.cuh,
+sorted_order_radix.cu,sort_radix.cu,stable_sort.cu} restated with numpy (dense ranks + stable lexsort;
+deliberately NOT the radix/twiddle formulation the CUDA path uses)."""
+from __future__ import annotations
+
+import numpy as np
+
+ASCENDING, DESCENDING = 0, 1
+AFTER, BEFORE = 0, 1
+
+
+def _dense_rank(values: np.ndarray) -> tuple[np.ndarray, int]:
+    """Rank under relational_compare (cpp/include/cudf/detail/row_operator/common_utils.cuh:157-169):
+    -0 == +0, NaN greater than everything, NaN == NaN."""
+    v = np.asarray(values)
+    if v.dtype == np.bool_:
+        v = v.astype(np.uint8)
+    if v.dtype.kind == "f":
+        v = np.where(v == 0, 0.0, v).astype(v.dtype)  # -0.0 -> +0.0
+        nan = np.isnan(v)
+        uniq, inv = np.unique(v[~nan], return_inverse=True)
+        rank = np.empty(len(v), dtype=np.int64)
+        rank[~nan] = inv
+        rank[nan] = len(uniq)
+        return rank, len(uniq) + 1
+    uniq, inv = np.unique(v, return_inverse=True)
+    return inv.astype(np.int64), len(uniq)
+
+
+def _column_rank(values, valid, order, null_order) -> np.ndarray:
+    rank, k = _dense_rank(values)
+    if order == DESCENDING:
+        rank = (k - 1) - rank
+    if valid is not None and not valid.all():
+        # sort_column_impl.cuh:35-57: the null flags are swapped for DESCENDING
+        nulls_first = (null_order == BEFORE) != (order == DESCENDING)
+        rank = np.where(valid, rank, -1 if nulls_first else k)
+    return rank
+
+
+def sorted_order(columns, column_order=None, null_precedence=None) -> np.ndarray:
+    """cudf::sorted_order / stable_sorted_order (sort_impl.cuh:31-96). columns: list of (values, valid)."""
+    if not columns or len(columns[0][0]) == 0:
+        return np.empty(0, dtype=np.int32)
+    ncol = len(columns)
+    if column_order and len(column_order) != ncol:
+        raise RuntimeError("Mismatch between number of columns and column order.")  # cudf::logic_error
+    if null_precedence and len(null_precedence) != ncol:
+        raise RuntimeError("Mismatch between number of columns and null_precedence size.")
+    order = list(column_order) if column_order else [ASCENDING] * ncol
+    nprec = list(null_precedence) if null_precedence else [BEFORE] * ncol  # sort_impl.cuh:56-57
+    ranks = [_column_rank(v, m, o, p) for (v, m), o, p in zip(columns, order, nprec)]
+    n = len(ranks[0])
+    out = np.lexsort(tuple(reversed(ranks))).astype(np.int32) if ncol > 1 else np.argsort(ranks[0], kind="stable").astype(np.int32)
+    # single non-null float column, DESCENDING: the radix path sorts the tuple (isnan*(idx+1), f)
+    # descending (sorted_order_radix.cu:41-50,121-131) => NaNs come first in DESCENDING row order.
+    v0, m0 = columns[0]
+    if ncol == 1 and order[0] == DESCENDING and np.asarray(v0).dtype.kind == "f" and (m0 is None or m0.all()):
+        k = int(np.isnan(v0).sum())
+        out[:k] = out[:k][::-1]
+    assert len(out) == n
+    return out
+
+
+def gather(columns, gather_map, nullify_oob=False):
+    """cudf::gather (cpp/include/cudf/detail/gather.cuh:627-675): negative indices wrap once."""
+    out = []
+    gm = np.asarray(gather_map, dtype=np.int64)
+    for values, valid in columns:
+        n = len(values)
+        idx = np.where(gm < 0, gm + n, gm)
+        inb = (idx >= 0) & (idx < n)
+        safe = np.where(inb, idx, 0)
+        vals = np.asarray(values)[safe] if n else np.zeros(len(gm), dtype=np.asarray(values).dtype)
+        if valid is not None and not np.asarray(valid).all() or nullify_oob:
+            v = (np.asarray(valid)[safe] if valid is not None else np.ones(len(gm), dtype=bool))
+            if nullify_oob:
+                v = v & inb
+            out.append((vals, v))
+        else:
+            out.append((vals, None))
+    return out
+
+
+def sort_by_key(values, keys, column_order=None, null_precedence=None):
+    """cudf::sort_by_key (sort.cu:31-50)."""
+    nv = len(values[0][0]) if values else 0
+    nk = len(keys[0][0]) if keys else 0
+    if nv != nk:
+        raise RuntimeError("Mismatch in number of rows for values and keys")
+    return gather(values, sorted_order(keys, column_order, null_precedence))
+
+
+def sort(columns, column_order=None, null_precedence=None):
+    """cudf::sort (sort.cu:52-67)."""
+    return sort_by_key(columns, columns, column_order, null_precedence)
