@@ -107,6 +107,9 @@ _sig("b2_scalar_device_data", [vp], vp)
 _sig("b2_scalar_get", [vp, b2_stream, vp, P(i32)])
 _sig("b2_scalar_free", [vp], None)
 _sig("b2_trim_pool", [])
+_sig("b2_profile_enable", [i32], None)
+_sig("b2_profile_reset", [], None)
+_sig("b2_profile_get", [C.c_char_p, P(C.c_double), P(C.c_int64)])
 _sig("b2_bitmask_allocation_size_bytes", [i32], C.c_size_t)
 _sig("b2_create_null_mask", [i32, i32, b2_stream, P(vp)])
 _sig("b2_set_null_mask", [vp, i32, i32, i32, b2_stream])
@@ -136,7 +139,8 @@ _sig("b2_fill_splitmix64", [vp, C.c_int64, C.c_uint64, C.c_int64, i32, C.c_uint6
 
 # every symbol the header declares, for the loader test
 DECLARED_SYMBOLS = [
-    "b2_last_error", "b2_version", "b2_kernel_launch_count", "b2_trim_pool", "b2_column_view_of", "b2_column_free",
+    "b2_last_error", "b2_version", "b2_kernel_launch_count", "b2_trim_pool", "b2_profile_enable", "b2_profile_reset",
+    "b2_profile_get", "b2_column_view_of", "b2_column_free",
     "b2_table_num_columns", "b2_table_num_rows", "b2_table_column", "b2_table_release", "b2_table_free",
     "b2_buffer_data", "b2_buffer_size", "b2_buffer_free", "b2_scalar_create", "b2_scalar_type",
     "b2_scalar_device_data", "b2_scalar_get", "b2_scalar_free", "b2_bitmask_allocation_size_bytes",
@@ -170,3 +174,9 @@ def stream_arg(stream) -> C.c_void_p:
 
 def kernel_launch_count() -> int:
     return int(lib.b2_kernel_launch_count())
+
+
+def profile_get(name: str):
+    ms, cnt = C.c_double(0), C.c_int64(0)
+    check(lib.b2_profile_get(name.encode(), C.byref(ms), C.byref(cnt)))
+    return ms.value, cnt.value

@@ -32,7 +32,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     sources = sorted(CSRC.glob("*.cu"))
     headers = sorted(CSRC.glob("*.cuh")) + [HERE.parent / "include" / "cudf_b200.h"]
     OBJ.mkdir(exist_ok=True)
-    stamp = OBJ / "stamp.txt"
+    stamp = HERE / "libcudf_b200.stamp"
     digest = _digest(sources + headers)
     if not force and LIB.exists() and stamp.exists() and stamp.read_text() == digest:
         return LIB

@@ -14,6 +14,28 @@ std::atomic<uint64_t> g_launch_count{0};
 static thread_local std::string tl_error;
 void set_last_error(const char* msg) { tl_error = msg ? msg : ""; }
 
+// ---- profiler ------------------------------------------------------------------------------------
+std::atomic<int> g_profile_on{0};
+namespace {
+struct prof_rec { std::string name; cudaEvent_t e0, e1; };
+std::mutex g_prof_mu;
+std::vector<prof_rec> g_prof;
+}  // namespace
+prof_scope::prof_scope(const char* n, cudaStream_t stream) : name(n), s(stream)
+{
+  if (!g_profile_on.load(std::memory_order_relaxed)) return;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  cudaEventRecord(e0, s);
+}
+prof_scope::~prof_scope()
+{
+  if (!e0) return;
+  cudaEventRecord(e1, s);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof.push_back({name, e0, e1});
+}
+
 // ---- allocator ----------------------------------------------------------------------------------
 static void init_pool_once()
 {
@@ -131,6 +153,29 @@ extern "C" {
 const char* b2_last_error(void) { return tl_error.c_str(); }
 const char* b2_version(void) { return "cudf_b200 0.1 (sm_100a)"; }
 uint64_t b2_kernel_launch_count(void) { return g_launch_count.load(); }
+void b2_profile_enable(int32_t on) { g_profile_on.store(on ? 1 : 0); }
+void b2_profile_reset(void)
+{
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& r : g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  g_prof.clear();
+}
+b2_status b2_profile_get(const char* name, double* total_ms, int64_t* launches)
+{
+  B2_TRY_BEGIN
+  B2_EXPECTS(name && total_ms && launches, B2_ERR_INVALID_ARGUMENT, "null argument");
+  B2_CUDA_TRY(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  double t = 0; int64_t c = 0;
+  for (auto& r : g_prof) {
+    if (r.name != name) continue;
+    float ms = 0;
+    B2_CUDA_TRY(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    t += ms; ++c;
+  }
+  *total_ms = t; *launches = c;
+  B2_TRY_END
+}
 b2_status b2_trim_pool(void)
 {
   B2_TRY_BEGIN

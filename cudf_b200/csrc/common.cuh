@@ -58,6 +58,16 @@ extern std::atomic<uint64_t> g_launch_count;
     B2_CUDA_TRY(cudaGetLastError());                                     \
   } while (0)
 
+// optional event timing of a kernel family (see b2_profile_* in the C ABI)
+extern std::atomic<int> g_profile_on;
+struct prof_scope {
+  const char* name;
+  cudaStream_t s;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  prof_scope(const char* n, cudaStream_t stream);
+  ~prof_scope();
+};
+
 // ---------------------------------------------------------------------------------------------
 // device memory: stream-ordered pool (cudaMallocAsync) — stands in for rmm::device_buffer / mr
 // ---------------------------------------------------------------------------------------------

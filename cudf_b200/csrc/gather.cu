@@ -96,6 +96,7 @@ void launch_gather(const b2_column_view& src, const int32_t* map, int64_t n, boo
   const int64_t groups = (n + 3) / 4;
   int grid = (int)std::max<int64_t>(1, std::min<int64_t>((groups + 255) / 256, NUM_SMS_B200 * 16));
   const T* data = static_cast<const T*>(src.data) + src.offset;
+  prof_scope ps("gather", stream);
   if (with_mask) {
     B2_LAUNCH((gather_kernel<T, true>), grid, 256, 0, stream, data, has_nulls(src) ? src.null_mask : nullptr,
               (int64_t)src.offset, src.size, map, n, nullify, out.data.as<T>(), out.mask.as<uint32_t>(),

@@ -611,6 +611,7 @@ void run_radix(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int32_t
   {
     int grid = (int)std::min<int64_t>((n + 512 * 16 - 1) / (512 * 16), NUM_SMS_B200 * 4);
     grid = std::max(grid, 1);
+    prof_scope ps("histogram", stream);
     B2_LAUNCH((histogram_kernel<UK>), grid, 512, 0, stream, raw ? raw_keys : bufA, n, raw ? 1 : 0, kind, desc_mask, ghist,
               (raw && kind == (int)key_kind::FLOAT) ? &ctl->nan_count : nullptr);
   }
@@ -646,6 +647,7 @@ void run_radix(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int32_t
       a.tile_counter = counters + p * nportions + q;
       const int64_t ntiles = (pn + TILE - 1) / TILE;
       const size_t smem_bytes = onesweep_smem<UK, T, I>();
+      prof_scope ps("onesweep", stream);
       B2_LAUNCH((onesweep_kernel<UK, T, I>), (unsigned)ntiles, T, smem_bytes, stream, a);
     }
   }

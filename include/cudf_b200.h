@@ -109,6 +109,12 @@ B2_API const char* b2_last_error(void);
 B2_API const char* b2_version(void);
 /* Number of kernels this library has launched in this process (bench.py gpu_launches). */
 B2_API uint64_t b2_kernel_launch_count(void);
+/* Optional per-kernel-family timing with CUDA events on the caller's stream (off by default; the
+ * NVTX-range analogue of CUDF_FUNC_RANGE, used by bench.py for the live roofline figure).
+ * b2_profile_get synchronises the device and returns accumulated milliseconds and launch count. */
+B2_API void      b2_profile_enable(int32_t on);
+B2_API void      b2_profile_reset(void);
+B2_API b2_status b2_profile_get(const char* name, double* total_ms, int64_t* launches);
 /* Trim the stream-ordered pool back to the driver (rmm pool release analogue). */
 B2_API b2_status b2_trim_pool(void);
 
