@@ -113,18 +113,48 @@ __global__ void __launch_bounds__(512) histogram_kernel(const UK* __restrict__ k
     }
   };
 
+  // fast path: whole warps of full 16-byte vectors. Digits that are constant across the warp (the
+  // common case for the high bytes of real data) are detected with two REDUX ops on key ^ key(lane 0)
+  // and counted by one lane, so that skewed inputs do not serialise on same-address atomics.
+  auto account_fast = [&](UK rawbits) {
+    UK k = raw ? twiddle_rt<UK>(rawbits, kind, desc_mask) : rawbits;
+    if (raw && kind == (int)key_kind::FLOAT && (UK)(k ^ desc_mask) == (UK)~UK(0)) nans++;
+    const uint64_t k64 = (uint64_t)k;
+    const uint64_t d64 = k64 ^ __shfl_sync(0xffffffffu, k64, 0);
+    uint32_t vary_lo = __reduce_or_sync(0xffffffffu, (uint32_t)d64);
+    uint32_t vary_hi = sizeof(UK) > 4 ? __reduce_or_sync(0xffffffffu, (uint32_t)(d64 >> 32)) : 0u;
+    const uint64_t vary = ((uint64_t)vary_hi << 32) | vary_lo;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      const unsigned d = (unsigned)(k >> (p * 8)) & 255u;
+      if (((vary >> (p * 8)) & 255u) == 0) {
+        if (lane_id() == 0) atomicAdd(&sh[p][d], 32u);
+      } else {
+        atomicAdd(&sh[p][d], 1u);
+      }
+    }
+  };
   const int4* vkeys = reinterpret_cast<const int4*>(keys + head);
-  const int64_t nvec_round = (nvec + 31) / 32 * 32;  // keep warps converged for the ballots
-  for (int64_t v = tid; v < nvec_round; v += nthreads) {
-    bool act = v < nvec;
-    int4 q = act ? ld_nc_v4(vkeys + v) : make_int4(0, 0, 0, 0);
+  int64_t v = tid;
+  for (; (v | 31) < nvec; v += nthreads) {
+    int4 q = ld_nc_v4(vkeys + v);
     UK tmp[VEC];
     memcpy(tmp, &q, 16);
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) account(tmp[j], act);
+    for (int j = 0; j < VEC; ++j) account_fast(tmp[j]);
   }
-  // head + tail scalars handled by block 0 warp 0
+  // remaining (< 32) vectors of the last partial warp-row, plus head / tail scalars: block 0, warp 0
   if (blockIdx.x == 0 && threadIdx.x < 32) {
+    const int64_t vrem0 = nvec / 32 * 32;
+    {
+      const int64_t vv = vrem0 + threadIdx.x;
+      const bool act = vv < nvec;
+      int4 q = act ? ld_nc_v4(vkeys + vv) : make_int4(0, 0, 0, 0);
+      UK tmp[VEC];
+      memcpy(tmp, &q, 16);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) account(tmp[j], act);
+    }
     int64_t tail_start = head + nvec * VEC;
     int64_t nscalar = head + (n - tail_start);
     for (int64_t b = 0; b < nscalar; b += 32) {
@@ -186,9 +216,13 @@ __global__ void plan_kernel(const uint32_t* __restrict__ ghist, int npass, uint3
         int remaining_after = nexec - 1 - k;  // passes after this one
         pl.key_src = key_cur;
         pl.idx_src = idx_cur;
-        // destination chosen so that the final pass lands in buffer 1 (keys) / 0 (idx)
-        pl.key_dst = (remaining_after % 2 == 0) ? 1 : 2;
-        pl.idx_dst = (remaining_after % 2 == 0) ? 0 : 1;
+        // A pass never writes the buffer it reads. Raw input: ping-pong so that the final pass lands in
+        // key buffer 1 (the keys-only output) / idx buffer 0 (the output column). Pre-compacted input
+        // (keys in A, row ids in idx buffer 1): keys alternate A/B (their final home is irrelevant,
+        // pairs mode never returns keys); row ids go to 0 whenever an even number of passes remains,
+        // else to a non-zero buffer other than the source (third buffer only for the first pass).
+        pl.key_dst = raw ? ((remaining_after % 2 == 0) ? 1 : 2) : (key_cur == 1 ? 2 : 1);
+        pl.idx_dst = (remaining_after % 2 == 0) ? 0 : (idx_cur == 1 ? 2 : 1);
         pl.last    = remaining_after == 0;
         key_cur = pl.key_dst;
         idx_cur = pl.idx_dst;
@@ -205,7 +239,7 @@ __global__ void plan_kernel(const uint32_t* __restrict__ ghist, int npass, uint3
 // ------------------------------------------------------------------------------------------------
 struct pass_args {
   const void* key_bufs[3];  // [0] raw input column data (already offset), [1], [2]
-  int32_t* idx_bufs[2];
+  int32_t* idx_bufs[3];
   sort_ctl* ctl;
   uint32_t* status;         // [num_tiles][256] for this (pass, portion)
   uint32_t* tile_counter;   // for this (pass, portion)
@@ -220,48 +254,147 @@ struct pass_args {
   int32_t pre_n_is_dynamic; // unused
 };
 
-template <typename UK, int THREADS, int IPT>
-__global__ void __launch_bounds__(THREADS, (THREADS <= 384 ? 2 : 1)) onesweep_kernel(pass_args a)
+__device__ __forceinline__ void ranker_barrier(int nthreads)
+{
+  asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+}
+__device__ __forceinline__ uint4 ld_volatile_v4(const uint32_t* p)
+{
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
+// One CTA = THREADS ranking threads (NWARPS warps holding IPT keys per thread) + ONE look-back warp.
+// The look-back warp resolves the 256 per-digit decoupled look-backs (8 consecutive digits per lane,
+// 128-bit volatile loads, LBT predecessor tiles per round) while the ranking warps run the latency-heavy
+// MATCH ranking, so the tile's inclusive prefix is published early and nobody idles on it.
+template <typename UK, int THREADS, int IPT, int MINB>
+__global__ void __launch_bounds__(THREADS + 32, MINB) onesweep_kernel(pass_args a)
 {
   constexpr int TILE   = THREADS * IPT;
   constexpr int NWARPS = THREADS / 32;
-  static_assert(THREADS >= RADIX, "need one thread per digit");
+  static_assert(THREADS >= RADIX, "need one ranking thread per digit");
 
   const pass_plan pl = a.ctl->plan[a.pass];
   if (pl.trivial) return;
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int STAGE_W = sizeof(UK) > 4 ? sizeof(UK) : 4;  // staging holds keys, then 32-bit row ids
   UK* s_keys          = reinterpret_cast<UK*>(smem_raw);
   uint32_t* s_vals    = reinterpret_cast<uint32_t*>(smem_raw);
-  constexpr int STAGE_W = sizeof(UK) > 4 ? sizeof(UK) : 4;  // staging holds keys, then 32-bit row ids
   uint32_t* s_whist   = reinterpret_cast<uint32_t*>(smem_raw + (size_t)STAGE_W * TILE);  // [NWARPS][256]
-  uint32_t* s_off     = s_whist + NWARPS * RADIX;                                    // [256] global offset - tile start
-  uint32_t* s_start   = s_off + RADIX;                                               // [256] tile-local start
-  uint32_t* s_misc    = s_start + RADIX;                                             // [16]
+  uint32_t* s_off     = s_whist + NWARPS * RADIX;  // [256] global offset of digit - tile-local start
+  uint32_t* s_cnt     = s_off + RADIX;             // [256] tile count of digit (without padding)
+  uint32_t* s_misc    = s_cnt + RADIX;             // [16]
 
   const int tid  = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
+  const bool ranker = warp < NWARPS;
 
   if (tid == 0) s_misc[0] = atomicAdd(a.tile_counter, 1u);
-  // zero this warp's histogram while waiting
+  if (ranker) {
 #pragma unroll
-  for (int j = 0; j < RADIX / 32; ++j) s_whist[warp * RADIX + j * 32 + lane] = 0;
+    for (int j = 0; j < RADIX / 32; ++j) s_whist[warp * RADIX + j * 32 + lane] = 0;
+  }
   __syncthreads();
   const uint32_t tile = s_misc[0];
-  const uint32_t tile_base = tile * (uint32_t)TILE;       // within portion
+  const uint32_t tile_base = tile * (uint32_t)TILE;  // within portion
   const uint32_t tile_n = min((uint32_t)TILE, a.portion_n - tile_base);
   const bool full = tile_n == (uint32_t)TILE;
+  const uint32_t pad = (uint32_t)TILE - tile_n;      // padding items sit at the end of digit 255
   const int shift = a.pass * RADIX_BITS;
   const UK desc = (UK)a.desc_mask;
 
+  if (!ranker) {
+    // ================================ look-back warp =============================================
+    __syncthreads();  // (S2) tile counts are in s_cnt, aggregate already published by the rankers
+    const int d0 = lane * 8;
+    uint32_t cnt[8], excl[8];
+    {
+      const uint4 c0 = *reinterpret_cast<const uint4*>(s_cnt + d0);
+      const uint4 c1 = *reinterpret_cast<const uint4*>(s_cnt + d0 + 4);
+      cnt[0] = c0.x; cnt[1] = c0.y; cnt[2] = c0.z; cnt[3] = c0.w;
+      cnt[4] = c1.x; cnt[5] = c1.y; cnt[6] = c1.z; cnt[7] = c1.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) excl[j] = 0;
+    if (tile > 0) {
+      constexpr int LBT = 4;
+      int64_t t = (int64_t)tile - 1;  // next predecessor tile to fold (common to the 8 digits:
+      uint32_t done = 0;              // a tile publishes all its digits, usually at the same time)
+      while (done != 0xffu) {
+        uint32_t v[LBT][8];
+#pragma unroll
+        for (int r = 0; r < LBT; ++r) {
+          const int64_t tt = t - r;
+          if (tt >= 0) {
+            const uint32_t* p = a.status + (size_t)tt * RADIX + d0;
+            const uint4 x = ld_volatile_v4(p), y = ld_volatile_v4(p + 4);
+            v[r][0] = x.x; v[r][1] = x.y; v[r][2] = x.z; v[r][3] = x.w;
+            v[r][4] = y.x; v[r][5] = y.y; v[r][6] = y.z; v[r][7] = y.w;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[r][j] = FLAG_INCL;
+          }
+        }
+        // a round is folded only as far as EVERY still-open digit of this lane is ready
+        int consumed = 0;
+#pragma unroll
+        for (int r = 0; r < LBT; ++r) {
+          if (consumed == r && done != 0xffu) {
+            bool ready = true;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ready = ready && (((done >> j) & 1u) || (v[r][j] >> 30) != 0);
+            if (ready) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                if (!((done >> j) & 1u)) {
+                  excl[j] += v[r][j] & VAL_MASK;
+                  if (v[r][j] & FLAG_INCL) done |= 1u << j;
+                }
+              }
+              ++consumed;
+            }
+          }
+        }
+        t -= consumed;
+      }
+      // publish the inclusive prefix
+      uint32_t* st = a.status + (size_t)tile * RADIX + d0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t word = FLAG_INCL | (excl[j] + cnt[j]);
+        asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(st + j), "r"(word) : "memory");
+      }
+    }
+    // tile-local start of each digit (exclusive scan of the padded counts) and the scatter offsets
+    uint32_t run = 0, loc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      loc[j] = run;
+      run += cnt[j] + ((lane == 31 && j == 7) ? pad : 0u);
+    }
+    const uint32_t lane_excl = warp_inclusive_sum(run) - run;
+    const uint32_t* gb = &a.ctl->base[a.portion_parity][a.pass][d0];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t gbase = gb[j];
+      s_off[d0 + j] = gbase + excl[j] - (lane_excl + loc[j]);
+      if (a.has_next_portion && tile_base + tile_n == a.portion_n)
+        a.ctl->base[a.portion_parity ^ 1][a.pass][d0 + j] = gbase + excl[j] + cnt[j];
+    }
+    __syncthreads();  // (S4) offsets ready
+    return;
+  }
+
+  // ================================== ranking warps ================================================
   // ---- load (warp-striped: item i of lane l in warp w = w*32*IPT + i*32 + l) -------------------
   UK key[IPT];
-  uint32_t idx[IPT];
   const uint32_t wbase = tile_base + warp * (32 * IPT) + lane;
   {
     const UK* src = static_cast<const UK*>(pl.key_src == 0 ? a.key_bufs[0] : (pl.key_src == 1 ? a.key_bufs[1] : a.key_bufs[2])) + a.portion_start;
-    const bool raw = pl.key_src == 0;
     if (full) {
 #pragma unroll
       for (int i = 0; i < IPT; ++i) key[i] = ld_stream(src + wbase + i * 32);
@@ -272,7 +405,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 384 ? 2 : 1)) onesweep_ke
         key[i] = e < a.portion_n ? ld_stream(src + e) : UK(0);
       }
     }
-    if (raw) {
+    if (pl.key_src == 0) {
 #pragma unroll
       for (int i = 0; i < IPT; ++i) key[i] = twiddle_rt<UK>(key[i], a.kind, desc);
     }
@@ -282,33 +415,68 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 384 ? 2 : 1)) onesweep_ke
       for (int i = 0; i < IPT; ++i)
         if (wbase + i * 32 >= a.portion_n) key[i] = ~UK(0);
     }
-    if (a.pairs) {
-      if (pl.idx_src < 0) {
-#pragma unroll
-        for (int i = 0; i < IPT; ++i) idx[i] = (uint32_t)(a.portion_start + wbase + i * 32);
-      } else {
-        const uint32_t* isrc = reinterpret_cast<const uint32_t*>(pl.idx_src == 0 ? a.idx_bufs[0] : a.idx_bufs[1]) + a.portion_start;
-        if (full) {
-#pragma unroll
-          for (int i = 0; i < IPT; ++i) idx[i] = ld_stream(isrc + wbase + i * 32);
-        } else {
-#pragma unroll
-          for (int i = 0; i < IPT; ++i) {
-            uint32_t e = wbase + i * 32;
-            idx[i] = e < a.portion_n ? ld_stream(isrc + e) : 0u;
-          }
-        }
-      }
-    }
   }
 
-  // ---- rank within warp (stable): MATCH.ANY peers + per-warp digit counters -------------------
-  uint32_t rank[IPT];
+  // ---- early counts: warp-private digit histogram by shared-memory atomics (no dependency chain) ----
   uint32_t* my_hist = s_whist + warp * RADIX;
+#pragma unroll
+  for (int i = 0; i < IPT; ++i) atomicAdd(&my_hist[(unsigned)(key[i] >> shift) & 255u], 1u);
+  ranker_barrier(THREADS);  // (S1)
+
+  // ---- per digit: warp counts -> warp offsets; publish the aggregate ---------------------------
+  uint32_t tstart = 0;
+  if (tid < RADIX) {
+    uint32_t count = 0;
+#pragma unroll
+    for (int w = 0; w < NWARPS; ++w) {
+      uint32_t c = s_whist[w * RADIX + tid];
+      s_whist[w * RADIX + tid] = count;  // exclusive offset of warp w inside digit `tid`
+      count += c;
+    }
+    const uint32_t padded = count;
+    if (tid == RADIX - 1) count -= pad;
+    uint32_t word = (tile == 0 ? FLAG_INCL : FLAG_AGG) | count;
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(a.status + (size_t)tile * RADIX + tid), "r"(word) : "memory");
+    s_cnt[tid] = count;
+    // exclusive scan of the padded counts over digits: 8 warps of 32 digits
+    uint32_t inc = warp_inclusive_sum(padded);
+    if (lane == 31) s_misc[1 + warp] = inc;
+    tstart = inc - padded;
+  }
+  __syncthreads();  // (S2) releases the look-back warp
+  if (tid < RADIX) {
+    uint32_t woff = 0;
+#pragma unroll
+    for (int w = 0; w < RADIX / 32; ++w) woff += (w < warp) ? s_misc[1 + w] : 0u;
+    tstart += woff;
+    // fold the tile-local digit start into the warp offsets: position = s_whist[w][d] + rank in warp
+#pragma unroll
+    for (int w = 0; w < NWARPS; ++w) s_whist[w * RADIX + tid] += tstart;
+  }
+  ranker_barrier(THREADS);  // (S3)
+
+  // ---- rank within warp (stable): MATCH.ANY peers + running per-warp digit offsets --------------
+  // All MATCH ops are issued first (independent, pipelined); only the counter chain is serial.
+  // Peer masks come from 8 ballots per item rather than MATCH.ANY: on sm_100 MATCH.ANY measured at
+  // roughly one per 30-90 cycles per SM with ~30 distinct digits per warp (ncu: mio_throttle on the
+  // MATCH cluster, 33 % of the kernel), while VOTE + LOP3 stay on the ALU path.
+  uint32_t pos[IPT];
 #pragma unroll
   for (int i = 0; i < IPT; ++i) {
     const unsigned d = (unsigned)(key[i] >> shift) & 255u;
-    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    unsigned peers = 0xffffffffu;
+#pragma unroll
+    for (int b = 0; b < RADIX_BITS; ++b) {
+      const unsigned bit = (d >> b) & 1u;
+      const unsigned v = __ballot_sync(0xffffffffu, bit);
+      peers &= v ^ (bit - 1u);  // bit ? v : ~v
+    }
+    pos[i] = peers;
+  }
+#pragma unroll
+  for (int i = 0; i < IPT; ++i) {
+    const unsigned d = (unsigned)(key[i] >> shift) & 255u;
+    const unsigned peers = pos[i];
     const unsigned lt = __popc(peers & lanemask_lt());
     uint32_t prev = 0;
     if (lt == 0) {
@@ -317,73 +485,33 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 384 ? 2 : 1)) onesweep_ke
     }
     __syncwarp();
     prev = __shfl_sync(0xffffffffu, prev, __ffs(peers) - 1);
-    rank[i] = prev + lt;
+    pos[i] = prev + lt;
   }
-  __syncthreads();
-
-  // ---- per-digit: counts across warps -> warp offsets, tile count -------------------------------
-  uint32_t count = 0;
-  if (tid < RADIX) {
+  // tile-sorted staging of the keys
 #pragma unroll
-    for (int w = 0; w < NWARPS; ++w) {
-      uint32_t c = s_whist[w * RADIX + tid];
-      s_whist[w * RADIX + tid] = count;
-      count += c;
-    }
-    if (!full && tid == RADIX - 1) count -= ((uint32_t)TILE - tile_n);  // padding sits in digit 255
-    // publish the tile aggregate as early as possible
-    uint32_t* st = a.status + (size_t)tile * RADIX + tid;
-    uint32_t word = (tile == 0 ? FLAG_INCL : FLAG_AGG) | count;
-    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(st), "r"(word) : "memory");
-    // exclusive scan of counts over digits (8 warps of 32 digits)
-    uint32_t padded = count + ((!full && tid == RADIX - 1) ? ((uint32_t)TILE - tile_n) : 0u);
-    uint32_t inc = warp_inclusive_sum(padded);
-    if (lane == 31) s_misc[1 + warp] = inc;
-    s_start[tid] = inc - padded;  // completed below
-  }
-  __syncthreads();
-  if (tid < RADIX) {
-    uint32_t woff = 0;
+  for (int i = 0; i < IPT; ++i) s_keys[pos[i]] = key[i];
+  // row ids are fetched only now (their registers replace the dead key registers); the loads
+  // overlap with the key write-out below
+  uint32_t idx[IPT];
+  if (a.pairs) {
+    if (pl.idx_src < 0) {
 #pragma unroll
-    for (int w = 0; w < RADIX / 32; ++w) woff += (w < warp) ? s_misc[1 + w] : 0u;
-    const uint32_t tstart = s_start[tid] + woff;
-    s_start[tid] = tstart;
-    // ---- decoupled look-back for digit `tid` ----------------------------------------------------
-    uint32_t excl = 0;
-    if (tile > 0) {
-      int64_t t = (int64_t)tile - 1;
-      while (true) {
-        const uint32_t* pst = a.status + (size_t)t * RADIX + tid;
-        uint32_t v;
-        do {
-          asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(pst) : "memory");
-        } while ((v >> 30) == 0);
-        excl += v & VAL_MASK;
-        if (v & FLAG_INCL) break;
-        --t;
+      for (int i = 0; i < IPT; ++i) idx[i] = (uint32_t)(a.portion_start + wbase + i * 32);
+    } else {
+      const uint32_t* isrc = reinterpret_cast<const uint32_t*>(pl.idx_src == 0 ? a.idx_bufs[0] : (pl.idx_src == 1 ? a.idx_bufs[1] : a.idx_bufs[2])) + a.portion_start;
+      if (full) {
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) idx[i] = ld_stream(isrc + wbase + i * 32);
+      } else {
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) {
+          uint32_t e = wbase + i * 32;
+          idx[i] = e < a.portion_n ? ld_stream(isrc + e) : 0u;
+        }
       }
-      uint32_t* st = a.status + (size_t)tile * RADIX + tid;
-      uint32_t word = FLAG_INCL | (excl + count);
-      asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(st), "r"(word) : "memory");
-    }
-    const uint32_t gbase = a.ctl->base[a.portion_parity][a.pass][tid];
-    s_off[tid] = gbase + excl - tstart;
-    if (a.has_next_portion && tile_base + tile_n == a.portion_n) {
-      // last tile of the portion: digit bases for the next portion
-      a.ctl->base[a.portion_parity ^ 1][a.pass][tid] = gbase + excl + count;
     }
   }
-  __syncthreads();
-
-  // ---- scatter through shared memory in tile-sorted order ------------------------------------
-  uint32_t pos[IPT];
-#pragma unroll
-  for (int i = 0; i < IPT; ++i) {
-    const unsigned d = (unsigned)(key[i] >> shift) & 255u;
-    pos[i] = s_start[d] + my_hist[d] + rank[i];
-    s_keys[pos[i]] = key[i];
-  }
-  __syncthreads();
+  __syncthreads();  // (S4) keys staged, scatter offsets ready
 
   const bool write_keys = !(a.pairs && pl.last);
   UK* kdst = static_cast<UK*>(const_cast<void*>(pl.key_dst == 1 ? a.key_bufs[1] : a.key_bufs[2]));
@@ -400,11 +528,11 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 384 ? 2 : 1)) onesweep_ke
     }
   }
   if (a.pairs) {
-    __syncthreads();
+    ranker_barrier(THREADS);
 #pragma unroll
     for (int i = 0; i < IPT; ++i) s_vals[pos[i]] = idx[i];
-    __syncthreads();
-    uint32_t* idst = reinterpret_cast<uint32_t*>(pl.idx_dst == 0 ? a.idx_bufs[0] : a.idx_bufs[1]);
+    ranker_barrier(THREADS);
+    uint32_t* idst = reinterpret_cast<uint32_t*>(pl.idx_dst == 0 ? a.idx_bufs[0] : (pl.idx_dst == 1 ? a.idx_bufs[1] : a.idx_bufs[2]));
 #pragma unroll
     for (int j = 0; j < IPT; ++j) {
       const uint32_t q = j * THREADS + tid;
@@ -554,11 +682,6 @@ __global__ void __launch_bounds__(CP_THREADS) compact_kernel(const UK* __restric
 // ------------------------------------------------------------------------------------------------
 struct tile_cfg { int threads; int ipt; };
 
-template <typename UK> struct cfg_for;
-template <> struct cfg_for<uint8_t>  { static constexpr int T = 512, I = 16; };
-template <> struct cfg_for<uint16_t> { static constexpr int T = 512, I = 16; };
-template <> struct cfg_for<uint32_t> { static constexpr int T = 512, I = 16; };
-template <> struct cfg_for<uint64_t> { static constexpr int T = 384, I = 16; };
 
 template <typename UK, int T, int I>
 size_t onesweep_smem()
@@ -581,12 +704,11 @@ int64_t portion_limit()
 //  raw_keys != nullptr : keys are the user's raw column (twiddled on load, implicit row ids)
 //  raw_keys == nullptr : keys are pre-twiddled in bufA with explicit row ids in idx buffer pre_idx_buf
 //  pairs: idx_out receives the permutation ; keys-only: bufA is the OUTPUT, bufB the temp.
-template <typename UK>
-void run_radix(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int32_t* idx_tmp, int pre_idx_buf, int64_t n,
-               int kind, bool descending, bool pairs, cudaStream_t stream)
+template <typename UK, int T, int I, int MINB>
+void run_radix_cfg(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int32_t* idx_tmp, int32_t* idx_tmp2, int pre_idx_buf, int64_t n,
+                   int kind, bool descending, bool pairs, cudaStream_t stream)
 {
   constexpr int NP = sizeof(UK);
-  constexpr int T = cfg_for<UK>::T, I = cfg_for<UK>::I;
   constexpr int TILE = T * I;
   const bool raw = raw_keys != nullptr;
   const UK desc_mask = descending ? ~UK(0) : UK(0);
@@ -618,7 +740,7 @@ void run_radix(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int32_t
   B2_LAUNCH(plan_kernel, 1, RADIX, 0, stream, ghist, NP, (uint32_t)n, raw ? 1 : 0, pre_idx_buf, ctl);
 
   static bool attr_set = [] {
-    cudaFuncSetAttribute(onesweep_kernel<UK, T, I>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncSetAttribute(onesweep_kernel<UK, T, I, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)onesweep_smem<UK, T, I>());
     return true;
   }();
@@ -630,6 +752,7 @@ void run_radix(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int32_t
   a.key_bufs[2] = bufB;
   a.idx_bufs[0] = idx_out;
   a.idx_bufs[1] = idx_tmp;
+  a.idx_bufs[2] = idx_tmp2;
   a.ctl = ctl;
   a.kind = kind;
   a.pairs = pairs ? 1 : 0;
@@ -648,7 +771,7 @@ void run_radix(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int32_t
       const int64_t ntiles = (pn + TILE - 1) / TILE;
       const size_t smem_bytes = onesweep_smem<UK, T, I>();
       prof_scope ps("onesweep", stream);
-      B2_LAUNCH((onesweep_kernel<UK, T, I>), (unsigned)ntiles, T, smem_bytes, stream, a);
+      B2_LAUNCH((onesweep_kernel<UK, T, I, MINB>), (unsigned)ntiles, T + 32, smem_bytes, stream, a);
     }
   }
   {
@@ -658,6 +781,38 @@ void run_radix(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int32_t
   if (pairs && raw && kind == (int)key_kind::FLOAT && descending) {
     B2_LAUNCH(reverse_nan_prefix_kernel, NUM_SMS_B200 * 4, 256, 0, stream, idx_out, &ctl->nan_count);
   }
+}
+
+int sort_cfg_env()
+{
+  static int v = [] {
+    const char* e = std::getenv("B2_SORT_CFG");
+    return e ? std::atoi(e) : 0;
+  }();
+  return v;
+}
+
+template <typename UK>
+void run_radix(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int32_t* idx_tmp, int pre_idx_buf, int64_t n,
+               int kind, bool descending, bool pairs, cudaStream_t stream, int32_t* idx_tmp2 = nullptr)
+{
+#define B2_RUN(T, I, MINB) \
+  run_radix_cfg<UK, T, I, MINB>(raw_keys, bufA, bufB, idx_out, idx_tmp, idx_tmp2, pre_idx_buf, n, kind, descending, pairs, stream)
+  if constexpr (sizeof(UK) == 8) {
+    switch (sort_cfg_env()) {  // tuning knob (B2_SORT_CFG); 0 is the shipped default
+      case 1: B2_RUN(256, 16, 3); break;
+      case 2: B2_RUN(512, 12, 2); break;
+      case 3: B2_RUN(256, 12, 4); break;
+      case 4: B2_RUN(512, 16, 1); break;
+      case 5: B2_RUN(384, 12, 3); break;
+      case 6: B2_RUN(256, 16, 4); break;
+      case 7: B2_RUN(256, 20, 3); break;
+      default: B2_RUN(384, 16, 2); break;
+    }
+  } else {
+    B2_RUN(512, 16, 1);
+  }
+#undef B2_RUN
 }
 
 int kind_of(int32_t storage_id)
@@ -692,7 +847,7 @@ column_ptr sorted_order_single(const b2_column_view& col, bool ascending, bool n
             tv.as<uint32_t>());
   B2_LAUNCH(scan_tiles_kernel, 1, 1024, 0, stream, tv.as<uint32_t>(), ntiles, tv.as<uint32_t>() + ntiles);
   dbuf a(sizeof(UK) * std::max<int64_t>(n_valid, 1), stream), b(sizeof(UK) * std::max<int64_t>(n_valid, 1), stream);
-  dbuf it(sizeof(int32_t) * std::max<int64_t>(n_valid, 1), stream);
+  dbuf it(sizeof(int32_t) * std::max<int64_t>(n_valid, 1), stream), it2(sizeof(int32_t) * std::max<int64_t>(n_valid, 1), stream);
   int32_t* valid_out = out_idx + (nulls_first ? n_null : 0);
   int32_t* null_out  = out_idx + (nulls_first ? 0 : n_valid);
   const UK desc_mask = ascending ? UK(0) : ~UK(0);
@@ -701,7 +856,8 @@ column_ptr sorted_order_single(const b2_column_view& col, bool ascending, bool n
   B2_LAUNCH((compact_kernel<UK>), (unsigned)ntiles, CP_THREADS, 0, stream, data, col.null_mask, (int64_t)col.offset, n,
             kind, desc_mask, tv.as<uint32_t>(), a.as<UK>(), it.as<int32_t>(), null_out);
   if (n_valid > 0)
-    run_radix<UK>(nullptr, a.as<UK>(), b.as<UK>(), valid_out, it.as<int32_t>(), 1, n_valid, kind, !ascending, true, stream);
+    run_radix<UK>(nullptr, a.as<UK>(), b.as<UK>(), valid_out, it.as<int32_t>(), 1, n_valid, kind, !ascending, true, stream,
+                  it2.as<int32_t>());
   return out;
 }
 
