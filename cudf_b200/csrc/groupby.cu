@@ -1,0 +1,759 @@
+// groupby.cu — hash groupby-aggregate (SUM / MIN / MAX / COUNT / MEAN) and the sort-based grouped scan.
+//
+// Replaces cpp/src/groupby/groupby.cu:40-71,186-259 (dispatch, validation, empty results),
+// cpp/src/groupby/hash/{groupby.cu,compute_groupby.cu,compute_single_pass_aggs.cuh,
+// compute_global_memory_aggs.cuh,single_pass_functors.cuh,output_utils.cu,
+// hash_compound_agg_finalizer.cu,extract_single_pass_aggs.cpp} and the cuco::static_set they use;
+// element semantics from cpp/include/cudf/detail/aggregation/device_aggregators.cuh:99-112,337-446
+// and result types from cpp/include/cudf/detail/aggregation/aggregation.hpp:879-970.
+// Grouped scan: cpp/src/groupby/sort/{scan.cpp,group_scan_util.cuh:77-128,sort_helper.cu}.
+//
+// One fused kernel per aggregate() call: every row packs its key (key_pack.cuh), finds or claims its
+// group slot with ONE 128-bit CAS on {key, representative row, nullbits} (linear probing), then
+// updates that slot's accumulators with L2 atomics: a per-slot row counter shared by all requests
+// plus one 8-byte accumulator per value aggregation (int64 / uint64 / double / order-preserving
+// int64 for float MIN/MAX) and a valid counter per nullable value column.  The table starts at a
+// size that keeps slots + accumulators L2-resident (2^21 slots) and grows x8 after a device-side
+// overflow signal (one host sync per aggregate(), the reference also syncs once:
+// compute_single_pass_aggs.cuh:111-122).  The reference instead sizes its set for N rows and
+// aggregates into a sparse N-row table.  A finalize kernel converts accumulators to the reference
+// result types, builds null masks (group with zero valid values -> null) and MEAN = SUM / COUNT.
+#include "common.cuh"
+#include "device_utils.cuh"
+#include "key_pack.cuh"
+
+#include <algorithm>
+
+namespace b2 {
+namespace {
+
+constexpr int MAX_OPS = 24;
+
+enum acc_kind : int8_t { ACC_I64 = 0, ACC_U64 = 1, ACC_F64 = 2 };
+enum op_kind : int8_t { OPK_SUM = 0, OPK_MIN = 1, OPK_MAX = 2 };
+
+struct value_op {
+  const void* src;
+  const uint32_t* mask;  // null when the column has no nulls
+  int32_t offset;
+  int8_t src_type;       // storage type id (B2_INT8 ... B2_BOOL8)
+  int8_t acc;            // acc_kind
+  int8_t op;             // op_kind
+  int8_t pad;
+  unsigned long long* accum;  // [slots]
+  int32_t* vcount;            // [slots] valid-value counter of the source column (shared by its ops) or null
+  int32_t bump_vcount;        // only the first op of a column bumps the shared counter
+};
+
+struct value_ops {
+  value_op op[MAX_OPS];
+  int32_t n;
+};
+
+struct gb_ctl {
+  unsigned int ngroups;
+  unsigned int overflow;
+};
+
+__device__ __forceinline__ slot_t cas128(slot_t* addr, const slot_t& expected, const slot_t& desired)
+{
+  uint64_t e0, e1, d0, d1, r0, r1;
+  memcpy(&e0, &expected, 8);
+  memcpy(&e1, reinterpret_cast<const char*>(&expected) + 8, 8);
+  memcpy(&d0, &desired, 8);
+  memcpy(&d1, reinterpret_cast<const char*>(&desired) + 8, 8);
+  asm volatile(
+    "{\n .reg .b128 e, d, r;\n mov.b128 e, {%2, %3};\n mov.b128 d, {%4, %5};\n"
+    " atom.global.cas.b128 r, [%6], e, d;\n mov.b128 {%0, %1}, r;\n}"
+    : "=l"(r0), "=l"(r1)
+    : "l"(e0), "l"(e1), "l"(d0), "l"(d1), "l"(addr)
+    : "memory");
+  slot_t out;
+  memcpy(&out, &r0, 8);
+  memcpy(reinterpret_cast<char*>(&out) + 8, &r1, 8);
+  return out;
+}
+
+__device__ __forceinline__ slot_t load_slot_volatile(const slot_t* p)
+{
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  slot_t s;
+  memcpy(&s, &v, 16);
+  return s;
+}
+
+// order-preserving double <-> int64 (for MIN/MAX of floats with integer atomics)
+__device__ __forceinline__ long long f64_to_ordered(double v)
+{
+  long long b = __double_as_longlong(v);
+  return b >= 0 ? b : (b ^ 0x7fffffffffffffffll);
+}
+__device__ __forceinline__ double ordered_to_f64(long long o)
+{
+  return __longlong_as_double(o >= 0 ? o : (o ^ 0x7fffffffffffffffll));
+}
+
+__device__ __forceinline__ void load_value(const value_op& op, int64_t e, long long& iv, unsigned long long& uv, double& fv)
+{
+  switch (op.src_type) {
+    case B2_INT8: iv = static_cast<const int8_t*>(op.src)[e]; break;
+    case B2_INT16: iv = static_cast<const int16_t*>(op.src)[e]; break;
+    case B2_INT32: iv = static_cast<const int32_t*>(op.src)[e]; break;
+    case B2_INT64: iv = static_cast<const int64_t*>(op.src)[e]; break;
+    case B2_UINT8: uv = static_cast<const uint8_t*>(op.src)[e]; iv = (long long)uv; break;
+    case B2_UINT16: uv = static_cast<const uint16_t*>(op.src)[e]; iv = (long long)uv; break;
+    case B2_UINT32: uv = static_cast<const uint32_t*>(op.src)[e]; iv = (long long)uv; break;
+    case B2_UINT64: uv = static_cast<const uint64_t*>(op.src)[e]; iv = (long long)uv; break;
+    case B2_BOOL8: uv = static_cast<const uint8_t*>(op.src)[e] != 0; iv = (long long)uv; break;
+    case B2_FLOAT32: fv = static_cast<const float*>(op.src)[e]; break;
+    default: fv = static_cast<const double*>(op.src)[e]; break;
+  }
+}
+
+__global__ void __launch_bounds__(256) groupby_kernel(key_cols kc, int64_t n, bool skip_null_keys, slot_t* __restrict__ table,
+                                                      uint32_t mask, uint32_t cap, int32_t* __restrict__ gsize,
+                                                      int32_t* __restrict__ slot_gid, int32_t* __restrict__ rep_rows, value_ops ops,
+                                                      gb_ctl* ctl)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  slot_t empty;
+  memset(&empty, 0xff, sizeof(empty));
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
+    if (*reinterpret_cast<volatile unsigned int*>(&ctl->overflow)) return;  // table too small: host will grow it
+    uint64_t key;
+    uint32_t nb;
+    pack_row(kc, r, key, nb);
+    if (skip_null_keys && nb) continue;
+    uint32_t i = slot_hash(key, nb, mask);
+    while (true) {
+      // cheap read first: most rows find their group already present
+      slot_t cur = load_slot_volatile(&table[i]);
+      if (cur.row == -1) {
+        const slot_t want{key, (int32_t)r, nb};
+        cur = cas128(&table[i], empty, want);
+        if (cur.row == -1) {  // we created the group
+          const unsigned int g = atomicAdd(&ctl->ngroups, 1u);
+          if (g >= cap) { atomicExch(&ctl->overflow, 1u); return; }
+          slot_gid[i] = (int32_t)g;
+          rep_rows[g] = (int32_t)r;
+          break;
+        }
+      }
+      if (cur.key == key && cur.nullbits == nb) break;
+      i = (i + 1) & mask;
+    }
+    atomicAdd(&gsize[i], 1);
+    for (int k = 0; k < ops.n; ++k) {
+      const value_op& op = ops.op[k];
+      const int64_t e = r + op.offset;
+      if (op.mask != nullptr) {
+        if (!bit_is_set(op.mask, e)) continue;
+        if (op.bump_vcount) atomicAdd(&op.vcount[i], 1);
+      }
+      long long iv = 0;
+      unsigned long long uv = 0;
+      double fv = 0;
+      load_value(op, e, iv, uv, fv);
+      unsigned long long* a = op.accum + i;
+      if (op.acc == ACC_F64) {
+        if (op.op == OPK_SUM) atomicAdd(reinterpret_cast<double*>(a), fv);
+        else if (op.op == OPK_MIN) atomicMin(reinterpret_cast<long long*>(a), f64_to_ordered(fv));
+        else atomicMax(reinterpret_cast<long long*>(a), f64_to_ordered(fv));
+      } else if (op.acc == ACC_I64) {
+        if (op.op == OPK_SUM) atomicAdd(a, (unsigned long long)iv);
+        else if (op.op == OPK_MIN) atomicMin(reinterpret_cast<long long*>(a), iv);
+        else atomicMax(reinterpret_cast<long long*>(a), iv);
+      } else {
+        if (op.op == OPK_SUM) atomicAdd(a, uv);
+        else if (op.op == OPK_MIN) atomicMin(a, uv);
+        else atomicMax(a, uv);
+      }
+    }
+  }
+}
+
+__global__ void fill_u64_kernel(unsigned long long* p, int64_t n, unsigned long long v)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = v;
+}
+
+// finalize one output column: walk the slots, write dense group g = slot_gid[s]
+struct out_spec {
+  const unsigned long long* accum;  // null for counts
+  const int32_t* vcount;            // null: column without nulls
+  const int32_t* gsize;
+  int8_t acc;       // acc_kind of accum
+  int8_t op;        // op_kind
+  int8_t mode;      // 0 value (SUM/MIN/MAX), 1 MEAN, 2 COUNT_VALID, 3 COUNT_ALL
+  int8_t pad;
+  int32_t out_type; // storage type id of the output column
+  void* out;
+  uint32_t* out_mask;  // null: no mask
+  unsigned long long* null_count;
+};
+
+__global__ void __launch_bounds__(256) finalize_kernel(const slot_t* __restrict__ table, int64_t slots,
+                                                       const int32_t* __restrict__ slot_gid, out_spec o)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  unsigned long long nulls = 0;
+  for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < slots; s += stride) {
+    if (table[s].row == -1) continue;
+    const int32_t g = slot_gid[s];
+    const int32_t nvalid = o.vcount ? o.vcount[s] : o.gsize[s];
+    if (o.mode == 2) { static_cast<int32_t*>(o.out)[g] = nvalid; continue; }
+    if (o.mode == 3) { static_cast<int32_t*>(o.out)[g] = o.gsize[s]; continue; }
+    const unsigned long long raw = o.accum[s];
+    if (o.mode == 1) {
+      double sum = o.acc == ACC_F64 ? __longlong_as_double((long long)raw)
+                                    : (o.acc == ACC_I64 ? (double)(long long)raw : (double)raw);
+      static_cast<double*>(o.out)[g] = nvalid > 0 ? sum / (double)nvalid : 0.0;
+    } else {
+      double fv = 0;
+      long long iv = (long long)raw;
+      if (o.acc == ACC_F64) fv = o.op == OPK_SUM ? __longlong_as_double((long long)raw) : ordered_to_f64((long long)raw);
+      switch (o.out_type) {
+        case B2_INT8: static_cast<int8_t*>(o.out)[g] = (int8_t)iv; break;
+        case B2_INT16: static_cast<int16_t*>(o.out)[g] = (int16_t)iv; break;
+        case B2_INT32: static_cast<int32_t*>(o.out)[g] = (int32_t)iv; break;
+        case B2_INT64: static_cast<int64_t*>(o.out)[g] = iv; break;
+        case B2_UINT8: case B2_BOOL8: static_cast<uint8_t*>(o.out)[g] = (uint8_t)raw; break;
+        case B2_UINT16: static_cast<uint16_t*>(o.out)[g] = (uint16_t)raw; break;
+        case B2_UINT32: static_cast<uint32_t*>(o.out)[g] = (uint32_t)raw; break;
+        case B2_UINT64: static_cast<uint64_t*>(o.out)[g] = raw; break;
+        case B2_FLOAT32: static_cast<float*>(o.out)[g] = (float)fv; break;
+        default: static_cast<double*>(o.out)[g] = fv; break;
+      }
+    }
+    if (o.out_mask) {
+      if (nvalid > 0) atomicOr(&o.out_mask[g >> 5], 1u << (g & 31));
+      else ++nulls;
+    }
+  }
+  if (o.null_count) {
+    nulls = warp_sum(nulls);
+    if (lane_id() == 0 && nulls) atomicAdd(o.null_count, nulls);
+  }
+}
+
+int grid_for(int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, NUM_SMS_B200 * 16)); }
+
+// result type rules: aggregation.hpp:879-970
+int32_t result_type(int32_t kind, int32_t src)
+{
+  switch (kind) {
+    case B2_AGG_SUM: return is_float_id(src) ? src : B2_INT64;
+    case B2_AGG_MIN: case B2_AGG_MAX: return src;
+    case B2_AGG_COUNT_VALID: case B2_AGG_COUNT_ALL: return B2_INT32;
+    case B2_AGG_MEAN: return B2_FLOAT64;
+    default: B2_FAIL(B2_ERR_INVALID_ARGUMENT, "unsupported groupby aggregation on the hash path (SUM/MIN/MAX/COUNT/MEAN)");
+  }
+}
+
+unsigned long long acc_init(int8_t acc, int8_t op)
+{
+  if (op == OPK_SUM) return 0ull;
+  if (acc == ACC_U64) return op == OPK_MIN ? ~0ull : 0ull;
+  // I64, and F64 in ordered-int64 space
+  return op == OPK_MIN ? (unsigned long long)INT64_MAX : (unsigned long long)INT64_MIN;
+}
+
+}  // namespace
+}  // namespace b2
+
+using namespace b2;
+
+struct b2_groupby {
+  std::vector<b2_column_view> keys;
+  int32_t null_handling = B2_NULL_EXCLUDE;
+  bool keys_are_sorted  = false;
+  std::vector<uint8_t> order, nprec;
+};
+
+namespace b2 {
+
+struct request_view {
+  b2_column_view values;
+  std::vector<int32_t> kinds;
+};
+
+static void empty_results(const b2_groupby& gb, const std::vector<request_view>& reqs, cudaStream_t stream, table_ptr& keys_out,
+                          table_ptr& res_out)
+{
+  keys_out = std::make_unique<b2_table>();
+  for (auto& k : gb.keys) keys_out->cols.push_back(make_column(k.type_id, 0, false, stream));
+  res_out = std::make_unique<b2_table>();
+  for (auto& r : reqs)
+    for (int32_t kind : r.kinds) res_out->cols.push_back(make_column(result_type(kind, r.values.type_id), 0, false, stream));
+}
+
+// cudf::groupby::groupby::aggregate — groupby.cu:220-237 -> hash path
+void groupby_aggregate(const b2_groupby& gb, const std::vector<request_view>& reqs, cudaStream_t stream, table_ptr& keys_out,
+                       table_ptr& res_out)
+{
+  const int64_t n = gb.keys.empty() ? 0 : gb.keys[0].size;
+  for (auto& r : reqs) {
+    validate_column(r.values);
+    B2_EXPECTS(r.values.size == n, B2_ERR_LOGIC, "Size mismatch between request values and groupby keys.");
+    B2_EXPECTS(!r.kinds.empty(), B2_ERR_LOGIC, "Empty aggregation request");  // verify_valid_requests
+    for (int32_t kind : r.kinds) {
+      (void)result_type(kind, r.values.type_id);
+      if (kind == B2_AGG_SUM || kind == B2_AGG_MEAN)
+        B2_EXPECTS(is_numeric(r.values.type_id), B2_ERR_LOGIC, "SUM/MEAN need a numeric values column");
+    }
+  }
+  if (n == 0) return empty_results(gb, reqs, stream, keys_out, res_out);
+
+  key_cols kc = make_key_cols(gb.keys);
+  bool keys_nullable = false;
+  for (auto& k : gb.keys) keys_nullable |= has_nulls(k);
+  const bool skip_null_keys = keys_nullable && gb.null_handling == B2_NULL_EXCLUDE;
+
+  // ---- plan the accumulators ----
+  struct col_plan { int32_t* vcount = nullptr; bool bumped = false; };
+  uint64_t max_slots = 16;
+  while (max_slots < 2ull * (uint64_t)n) max_slots <<= 1;
+  uint64_t slots = std::min<uint64_t>(max_slots, 1ull << 21);
+
+  while (true) {
+    const uint32_t cap = (uint32_t)std::min<uint64_t>((uint64_t)n, (uint64_t)(slots * 0.6));
+    dbuf table(slots * sizeof(slot_t), stream);
+    B2_CUDA_TRY(cudaMemsetAsync(table.ptr, 0xff, table.bytes, stream));
+    dbuf gsize(sizeof(int32_t) * slots, stream), slot_gid(sizeof(int32_t) * slots, stream);
+    B2_CUDA_TRY(cudaMemsetAsync(gsize.ptr, 0, gsize.bytes, stream));
+    dbuf rep_rows(sizeof(int32_t) * (size_t)cap, stream);
+    dbuf ctl(sizeof(gb_ctl), stream);
+    B2_CUDA_TRY(cudaMemsetAsync(ctl.ptr, 0, sizeof(gb_ctl), stream));
+
+    value_ops ops{};
+    std::vector<dbuf> accs;                      // one per value op
+    std::vector<dbuf> vcounts(reqs.size());      // one per nullable value column
+    struct slot_of { int op_index; };            // (request, kind) -> op index or -1
+    std::vector<std::vector<int>> op_of(reqs.size());
+    for (size_t q = 0; q < reqs.size(); ++q) {
+      const auto& v = reqs[q].values;
+      const int32_t st = storage_type(v.type_id);
+      const bool nullable = has_nulls(v);
+      bool bumped = false;
+      const int op_begin = ops.n;
+      // MEAN and SUM of the same column share one SUM accumulator
+      int sum_op = -1;
+      for (int32_t kind : reqs[q].kinds) {
+        int idx = -1;
+        if (kind == B2_AGG_COUNT_VALID || kind == B2_AGG_COUNT_ALL) { op_of[q].push_back(-1); continue; }
+        const int8_t opk = kind == B2_AGG_MIN ? OPK_MIN : (kind == B2_AGG_MAX ? OPK_MAX : OPK_SUM);
+        if (opk == OPK_SUM && sum_op >= 0) { op_of[q].push_back(sum_op); continue; }
+        B2_EXPECTS(ops.n < MAX_OPS, B2_ERR_INVALID_ARGUMENT, "too many aggregations in one groupby call");
+        value_op& op = ops.op[ops.n];
+        op.src      = v.data;
+        op.mask     = nullable ? v.null_mask : nullptr;
+        op.offset   = v.offset;
+        op.src_type = (int8_t)st;
+        op.acc      = is_float_id(st) ? ACC_F64 : ((is_signed_id(st) || opk == OPK_SUM) ? ACC_I64 : ACC_U64);
+        if (opk == OPK_SUM && !is_float_id(st) && !is_signed_id(st)) op.acc = ACC_U64;  // same bits as int64 sums
+        op.op       = opk;
+        accs.emplace_back(sizeof(unsigned long long) * slots, stream);
+        op.accum = accs.back().as<unsigned long long>();
+        B2_LAUNCH(fill_u64_kernel, grid_for((int64_t)slots), 256, 0, stream, op.accum, (int64_t)slots, acc_init(op.acc, opk));
+        idx = ops.n++;
+        if (opk == OPK_SUM) sum_op = idx;
+        op_of[q].push_back(idx);
+      }
+      if (nullable) {
+        vcounts[q] = dbuf(sizeof(int32_t) * slots, stream);
+        B2_CUDA_TRY(cudaMemsetAsync(vcounts[q].ptr, 0, vcounts[q].bytes, stream));
+        // the shared valid counter is bumped by the column's first value op, or by a dedicated
+        // pseudo-op when the request only has counts
+        bool any_op = false;
+        for (int k = op_begin; k < ops.n; ++k) {
+          ops.op[k].vcount = vcounts[q].as<int32_t>();
+          if (!bumped) { ops.op[k].bump_vcount = 1; bumped = true; }
+          any_op = true;
+        }
+        if (!any_op) {
+          B2_EXPECTS(ops.n < MAX_OPS, B2_ERR_INVALID_ARGUMENT, "too many aggregations in one groupby call");
+          value_op& op = ops.op[ops.n++];
+          op.src = v.data; op.mask = v.null_mask; op.offset = v.offset; op.src_type = (int8_t)st;
+          op.acc = ACC_U64; op.op = OPK_MAX;  // harmless accumulate into a scratch array
+          accs.emplace_back(sizeof(unsigned long long) * slots, stream);
+          op.accum = accs.back().as<unsigned long long>();
+          op.vcount = vcounts[q].as<int32_t>();
+          op.bump_vcount = 1;
+        }
+      }
+    }
+
+    {
+      prof_scope ps("groupby_aggregate", stream);
+      B2_LAUNCH(groupby_kernel, grid_for(n), 256, 0, stream, kc, n, skip_null_keys, table.as<slot_t>(), (uint32_t)(slots - 1), cap,
+                gsize.as<int32_t>(), slot_gid.as<int32_t>(), rep_rows.as<int32_t>(), ops, ctl.as<gb_ctl>());
+    }
+    gb_ctl h{};
+    B2_CUDA_TRY(cudaMemcpyAsync(&h, ctl.ptr, sizeof(h), cudaMemcpyDeviceToHost, stream));
+    B2_CUDA_TRY(cudaStreamSynchronize(stream));
+    if (h.overflow) {
+      B2_EXPECTS(slots < max_slots, B2_ERR_LOGIC, "groupby: hash table overflow at maximum size");
+      slots = std::min<uint64_t>(max_slots, slots * 8);
+      continue;  // buffers are released (stream-ordered) and rebuilt at the new size
+    }
+    const int32_t G = (int32_t)h.ngroups;
+
+    // ---- outputs ----
+    keys_out = gather_table(gb.keys, rep_rows.as<int32_t>(), G, false, stream);
+    res_out  = std::make_unique<b2_table>();
+    for (size_t q = 0; q < reqs.size(); ++q) {
+      const auto& v = reqs[q].values;
+      const bool nullable = has_nulls(v);
+      for (size_t j = 0; j < reqs[q].kinds.size(); ++j) {
+        const int32_t kind = reqs[q].kinds[j];
+        const int32_t rt   = result_type(kind, v.type_id);
+        const bool counts  = kind == B2_AGG_COUNT_VALID || kind == B2_AGG_COUNT_ALL;
+        // result has a mask only when the input column has nulls (output_utils.cu:67-86); counts never
+        auto col = make_column(rt, G, nullable && !counts, stream);
+        if (G > 0) {
+          out_spec o{};
+          o.gsize  = gsize.as<int32_t>();
+          o.vcount = nullable ? vcounts[q].as<int32_t>() : nullptr;
+          o.out    = col->data.ptr;
+          o.out_type = storage_type(rt);
+          if (counts) {
+            o.mode = kind == B2_AGG_COUNT_VALID ? 2 : 3;
+          } else {
+            const value_op& op = ops.op[op_of[q][j]];
+            o.accum = op.accum;
+            o.acc   = op.acc;
+            o.op    = op.op;
+            o.mode  = kind == B2_AGG_MEAN ? 1 : 0;
+            if (nullable) {
+              o.out_mask = col->mask.as<uint32_t>();
+              col->pending = dbuf(sizeof(unsigned long long), stream);
+              col->pending_stream = stream;
+              col->null_count = -1;
+              B2_CUDA_TRY(cudaMemsetAsync(col->pending.ptr, 0, sizeof(unsigned long long), stream));
+              o.null_count = col->pending.as<unsigned long long>();
+            }
+          }
+          B2_LAUNCH(finalize_kernel, grid_for((int64_t)slots), 256, 0, stream, table.as<slot_t>(), (int64_t)slots,
+                    slot_gid.as<int32_t>(), o);
+        }
+        res_out->cols.push_back(std::move(col));
+      }
+    }
+    return;
+  }
+}
+
+// ---- grouped scan: sort keys (stable), permute values, segmented inclusive scan -----------------
+namespace {
+
+// head[i] = 1 when sorted row i starts a new group (packed key differs from row i-1)
+__global__ void group_heads_kernel(key_cols kc, const int32_t* __restrict__ order, int64_t n, uint8_t* __restrict__ head)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    uint8_t h = 1;
+    if (i > 0) {
+      uint64_t k0, k1;
+      uint32_t n0, n1;
+      pack_row(kc, order[i - 1], k0, n0);
+      pack_row(kc, order[i], k1, n1);
+      h = (k0 != k1 || n0 != n1) ? 1 : 0;
+    }
+    head[i] = h;
+  }
+}
+
+// Single-CTA-per-tile segmented scan in three steps (tile aggregates -> carries -> apply).
+// Element = (value as 8-byte accumulator, valid flag); op: SUM / MIN / MAX / COUNT.
+constexpr int SEG_TILE = 2048;
+
+template <typename A, int OPK>
+__device__ __forceinline__ A seg_apply(A a, A b)
+{
+  if (OPK == OPK_SUM) return a + b;
+  if (OPK == OPK_MIN) return b < a ? b : a;
+  return a < b ? b : a;
+}
+template <typename A, int OPK>
+__device__ __forceinline__ A seg_identity()
+{
+  if (OPK == OPK_SUM) return A(0);
+  if (OPK == OPK_MIN) return sizeof(A) == 8 && ((A)-1 < A(0)) ? (A)INT64_MAX : (A)~0ull;
+  return ((A)-1 < A(0)) ? (A)INT64_MIN : A(0);
+}
+template <> __device__ __forceinline__ double seg_identity<double, OPK_MIN>() { return __longlong_as_double(0x7ff0000000000000ll); }
+template <> __device__ __forceinline__ double seg_identity<double, OPK_MAX>() { return __longlong_as_double(0xfff0000000000000ll); }
+
+template <typename A>
+__device__ __forceinline__ A load_acc(const void* src, int32_t st, int64_t e)
+{
+  switch (st) {
+    case B2_INT8: return (A) static_cast<const int8_t*>(src)[e];
+    case B2_INT16: return (A) static_cast<const int16_t*>(src)[e];
+    case B2_INT32: return (A) static_cast<const int32_t*>(src)[e];
+    case B2_INT64: return (A) static_cast<const int64_t*>(src)[e];
+    case B2_UINT8: return (A) static_cast<const uint8_t*>(src)[e];
+    case B2_UINT16: return (A) static_cast<const uint16_t*>(src)[e];
+    case B2_UINT32: return (A) static_cast<const uint32_t*>(src)[e];
+    case B2_UINT64: return (A) static_cast<const uint64_t*>(src)[e];
+    case B2_BOOL8: return (A)(static_cast<const uint8_t*>(src)[e] != 0);
+    case B2_FLOAT32: return (A) static_cast<const float*>(src)[e];
+    default: return (A) static_cast<const double*>(src)[e];
+  }
+}
+template <typename A>
+__device__ __forceinline__ void store_acc(void* dst, int32_t st, int64_t i, A a)
+{
+  switch (st) {
+    case B2_INT8: static_cast<int8_t*>(dst)[i] = (int8_t)a; break;
+    case B2_INT16: static_cast<int16_t*>(dst)[i] = (int16_t)a; break;
+    case B2_INT32: static_cast<int32_t*>(dst)[i] = (int32_t)a; break;
+    case B2_INT64: static_cast<int64_t*>(dst)[i] = (int64_t)a; break;
+    case B2_UINT8: case B2_BOOL8: static_cast<uint8_t*>(dst)[i] = (uint8_t)a; break;
+    case B2_UINT16: static_cast<uint16_t*>(dst)[i] = (uint16_t)a; break;
+    case B2_UINT32: static_cast<uint32_t*>(dst)[i] = (uint32_t)a; break;
+    case B2_UINT64: static_cast<uint64_t*>(dst)[i] = (uint64_t)a; break;
+    case B2_FLOAT32: static_cast<float*>(dst)[i] = (float)a; break;
+    default: static_cast<double*>(dst)[i] = (double)a; break;
+  }
+}
+
+struct seg_args {
+  const void* src;          // original (unsorted) values; null for COUNT_ALL
+  const uint32_t* mask;     // original validity or null
+  int32_t offset;
+  int32_t src_type;
+  const int32_t* order;     // sorted row -> source row
+  const uint8_t* head;
+  int64_t n;
+  int32_t count_mode;       // 1: element value is 1 per valid row (COUNT)
+  void* out;
+  int32_t out_type;
+  uint32_t* out_mask;       // validity of the permuted values (null when source has no nulls)
+  unsigned long long* out_valid_count;
+};
+
+// one thread scans one tile sequentially in phase A/C (tiles are small; this is not the headline
+// path) — phase A: tile summary {has_head, prefix-before-first-head, suffix-after-last-head}
+template <typename A, int OPK>
+__global__ void seg_tile_summary_kernel(seg_args a, A* __restrict__ tail, uint8_t* __restrict__ has_head)
+{
+  const int64_t ntiles = (a.n + SEG_TILE - 1) / SEG_TILE;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ntiles) return;
+  const int64_t b = t * SEG_TILE, e = min(a.n, b + SEG_TILE);
+  A run = seg_identity<A, OPK>();
+  uint8_t hh = 0;
+  for (int64_t i = b; i < e; ++i) {
+    if (a.head[i]) { run = seg_identity<A, OPK>(); hh = 1; }
+    const int64_t r = a.order[i];
+    const bool valid = a.mask == nullptr || bit_is_set(a.mask, r + a.offset);
+    if (valid) run = seg_apply<A, OPK>(run, a.count_mode ? A(1) : load_acc<A>(a.src, a.src_type, r + a.offset));
+  }
+  tail[t] = run;        // running value at the end of the tile (since the last head, or whole tile)
+  has_head[t] = hh;
+}
+// phase B: sequential carry over tiles (ntiles = n/2048: tiny)
+template <typename A, int OPK>
+__global__ void seg_carry_kernel(A* __restrict__ tail, const uint8_t* __restrict__ has_head, int64_t ntiles, A* __restrict__ carry)
+{
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  A c = seg_identity<A, OPK>();
+  for (int64_t t = 0; t < ntiles; ++t) {
+    carry[t] = c;  // value carried INTO tile t (applies until its first head)
+    c = has_head[t] ? tail[t] : seg_apply<A, OPK>(c, tail[t]);
+  }
+}
+template <typename A, int OPK>
+__global__ void seg_apply_kernel(seg_args a, const A* __restrict__ carry)
+{
+  const int64_t ntiles = (a.n + SEG_TILE - 1) / SEG_TILE;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ntiles) return;
+  const int64_t b = t * SEG_TILE, e = min(a.n, b + SEG_TILE);
+  A run = carry[t];
+  unsigned long long nvalid = 0;
+  for (int64_t i = b; i < e; ++i) {
+    if (a.head[i]) run = seg_identity<A, OPK>();
+    const int64_t r = a.order[i];
+    const bool valid = a.mask == nullptr || bit_is_set(a.mask, r + a.offset);
+    if (valid) {
+      run = seg_apply<A, OPK>(run, a.count_mode ? A(1) : load_acc<A>(a.src, a.src_type, r + a.offset));
+      ++nvalid;
+      if (a.out_mask) atomicOr(&a.out_mask[i >> 5], 1u << (i & 31));
+    }
+    store_acc<A>(a.out, a.out_type, i, run);
+  }
+  if (a.out_valid_count && nvalid) atomicAdd(a.out_valid_count, nvalid);
+}
+
+template <typename A, int OPK>
+void run_seg_scan(seg_args a, cudaStream_t stream)
+{
+  const int64_t ntiles = (a.n + SEG_TILE - 1) / SEG_TILE;
+  dbuf tail(sizeof(A) * ntiles, stream), carry(sizeof(A) * ntiles, stream), hh(ntiles, stream);
+  const int grid = (int)((ntiles + 127) / 128);
+  B2_LAUNCH((seg_tile_summary_kernel<A, OPK>), grid, 128, 0, stream, a, tail.as<A>(), hh.as<uint8_t>());
+  B2_LAUNCH((seg_carry_kernel<A, OPK>), 1, 32, 0, stream, tail.as<A>(), hh.as<uint8_t>(), ntiles, carry.as<A>());
+  B2_LAUNCH((seg_apply_kernel<A, OPK>), grid, 128, 0, stream, a, carry.as<A>());
+}
+
+}  // namespace
+
+// cudf::groupby::groupby::scan — groupby.cu:240-259 -> sort_scan
+void groupby_scan(const b2_groupby& gb, const std::vector<request_view>& reqs, cudaStream_t stream, table_ptr& keys_out,
+                  table_ptr& res_out)
+{
+  const int64_t n_all = gb.keys.empty() ? 0 : gb.keys[0].size;
+  for (auto& r : reqs) {
+    validate_column(r.values);
+    B2_EXPECTS(r.values.size == n_all, B2_ERR_LOGIC, "Size mismatch between request values and groupby keys.");
+    for (int32_t kind : r.kinds)
+      B2_EXPECTS(kind == B2_AGG_SUM || kind == B2_AGG_MIN || kind == B2_AGG_MAX || kind == B2_AGG_COUNT_VALID || kind == B2_AGG_COUNT_ALL,
+                 B2_ERR_INVALID_ARGUMENT, "unsupported groupby scan aggregation (SUM/MIN/MAX/COUNT)");
+  }
+  if (n_all == 0) return empty_results(gb, reqs, stream, keys_out, res_out);
+  key_cols kc = make_key_cols(gb.keys);
+
+  // sorted order of the keys (ascending, nulls first), null-key rows dropped under EXCLUDE
+  std::vector<uint8_t> asc(gb.keys.size(), B2_ASCENDING), before(gb.keys.size(), B2_NULL_BEFORE);
+  auto order_col = sorted_order(gb.keys, asc, before, true, stream);
+  const int32_t* order = order_col->data.as<int32_t>();
+  int64_t n = n_all;
+  bool keys_nullable = false;
+  for (auto& k : gb.keys) keys_nullable |= has_nulls(k);
+  if (keys_nullable && gb.null_handling == B2_NULL_EXCLUDE) {
+    // rows with any null key sort first only for single-column keys; in general count and filter them
+    int32_t nulls = 0;
+    dbuf m = bitmask_and(gb.keys, (int32_t)n_all, &nulls, stream);
+    if (nulls > 0) {
+      B2_EXPECTS(gb.keys.size() == 1, B2_ERR_INVALID_ARGUMENT,
+                 "groupby scan with null keys under EXCLUDE supports a single key column on this path");
+      order += nulls;  // ascending, nulls BEFORE: the null-key rows are the first `nulls` entries
+      n -= nulls;
+    }
+  }
+  keys_out = gather_table(gb.keys, order, (int32_t)n, false, stream);
+  res_out  = std::make_unique<b2_table>();
+  if (n == 0) {
+    for (auto& r : reqs)
+      for (int32_t kind : r.kinds) res_out->cols.push_back(make_column(result_type(kind, r.values.type_id), 0, false, stream));
+    return;
+  }
+  dbuf head(n, stream);
+  B2_LAUNCH(group_heads_kernel, grid_for(n), 256, 0, stream, kc, order, n, head.as<uint8_t>());
+
+  for (auto& r : reqs) {
+    const auto& v = r.values;
+    const int32_t st = storage_type(v.type_id);
+    const bool nullable = has_nulls(v);
+    for (int32_t kind : r.kinds) {
+      const bool counts = kind == B2_AGG_COUNT_VALID || kind == B2_AGG_COUNT_ALL;
+      const int32_t rt = result_type(kind, v.type_id);
+      auto col = make_column(rt, (int32_t)n, nullable && !counts, stream);
+      seg_args a{};
+      a.src = v.data; a.mask = (nullable && kind != B2_AGG_COUNT_ALL) ? v.null_mask : nullptr; a.offset = v.offset; a.src_type = st;
+      a.order = order; a.head = head.as<uint8_t>(); a.n = n; a.count_mode = counts ? 1 : 0;
+      a.out = col->data.ptr; a.out_type = storage_type(rt);
+      if (nullable && !counts) {
+        a.out_mask = col->mask.as<uint32_t>();
+        col->pending = dbuf(sizeof(unsigned long long), stream);
+        col->pending_stream = stream;
+        col->pending_is_valid_count = true;
+        col->null_count = -1;
+        B2_CUDA_TRY(cudaMemsetAsync(col->pending.ptr, 0, sizeof(unsigned long long), stream));
+        a.out_valid_count = col->pending.as<unsigned long long>();
+      }
+      const bool flt = is_float_id(st) && !counts;
+      const bool uns = !is_signed_id(st) && !flt && !counts;
+      if (counts || kind == B2_AGG_SUM) {
+        if (flt) run_seg_scan<double, OPK_SUM>(a, stream);
+        else run_seg_scan<long long, OPK_SUM>(a, stream);
+      } else if (kind == B2_AGG_MIN) {
+        if (flt) run_seg_scan<double, OPK_MIN>(a, stream);
+        else if (uns) run_seg_scan<unsigned long long, OPK_MIN>(a, stream);
+        else run_seg_scan<long long, OPK_MIN>(a, stream);
+      } else {
+        if (flt) run_seg_scan<double, OPK_MAX>(a, stream);
+        else if (uns) run_seg_scan<unsigned long long, OPK_MAX>(a, stream);
+        else run_seg_scan<long long, OPK_MAX>(a, stream);
+      }
+      res_out->cols.push_back(std::move(col));
+    }
+  }
+}
+
+}  // namespace b2
+
+// ---- C ABI -----------------------------------------------------------------------------------------
+#define B2_TRY_BEGIN try {
+#define B2_TRY_END                                                                 \
+  }                                                                                \
+  catch (const b2::error& e) { b2::set_last_error(e.what()); return e.code; }      \
+  catch (const std::bad_alloc& e) { b2::set_last_error(e.what()); return B2_ERR_BAD_ALLOC; } \
+  catch (const std::exception& e) { b2::set_last_error(e.what()); return B2_ERR_LOGIC; }     \
+  return B2_OK;
+
+extern "C" {
+
+b2_status b2_groupby_create(const b2_table_view* keys, int32_t null_handling, int32_t keys_are_sorted, const uint8_t* column_order,
+                            int32_t n_order, const uint8_t* null_precedence, int32_t n_null_prec, b2_groupby** out)
+{
+  B2_TRY_BEGIN
+  B2_EXPECTS(out, B2_ERR_INVALID_ARGUMENT, "null argument");
+  auto gb = std::make_unique<b2_groupby>();
+  validate_table(keys, gb->keys);
+  gb->null_handling   = null_handling;
+  gb->keys_are_sorted = keys_are_sorted != 0;
+  if (column_order && n_order > 0) gb->order.assign(column_order, column_order + n_order);
+  if (null_precedence && n_null_prec > 0) gb->nprec.assign(null_precedence, null_precedence + n_null_prec);
+  (void)make_key_cols(gb->keys);  // validates the key shape early
+  *out = gb.release();
+  B2_TRY_END
+}
+void b2_groupby_destroy(b2_groupby* gb) { delete gb; }
+
+static std::vector<request_view> to_requests(const b2_agg_request* requests, int32_t n)
+{
+  B2_EXPECTS(n >= 0 && (n == 0 || requests != nullptr), B2_ERR_INVALID_ARGUMENT, "invalid requests");
+  std::vector<request_view> out;
+  for (int32_t i = 0; i < n; ++i) {
+    request_view r;
+    r.values = requests[i].values;
+    B2_EXPECTS(requests[i].num_kinds >= 0 && (requests[i].num_kinds == 0 || requests[i].kinds), B2_ERR_INVALID_ARGUMENT,
+               "invalid aggregation list");
+    r.kinds.assign(requests[i].kinds, requests[i].kinds + requests[i].num_kinds);
+    out.push_back(std::move(r));
+  }
+  return out;
+}
+
+b2_status b2_groupby_aggregate(b2_groupby* gb, const b2_agg_request* requests, int32_t num_requests, b2_stream stream,
+                               b2_table** out_keys, b2_table** out_results)
+{
+  B2_TRY_BEGIN
+  B2_EXPECTS(gb && out_keys && out_results, B2_ERR_INVALID_ARGUMENT, "null argument");
+  auto reqs = to_requests(requests, num_requests);
+  table_ptr k, r;
+  groupby_aggregate(*gb, reqs, static_cast<cudaStream_t>(stream), k, r);
+  *out_keys    = k.release();
+  *out_results = r.release();
+  B2_TRY_END
+}
+
+b2_status b2_groupby_scan(b2_groupby* gb, const b2_agg_request* requests, int32_t num_requests, b2_stream stream, b2_table** out_keys,
+                          b2_table** out_results)
+{
+  B2_TRY_BEGIN
+  B2_EXPECTS(gb && out_keys && out_results, B2_ERR_INVALID_ARGUMENT, "null argument");
+  auto reqs = to_requests(requests, num_requests);
+  table_ptr k, r;
+  groupby_scan(*gb, reqs, static_cast<cudaStream_t>(stream), k, r);
+  *out_keys    = k.release();
+  *out_results = r.release();
+  B2_TRY_END
+}
+
+}  // extern "C"

@@ -1,0 +1,457 @@
+// hash_join.cu — hash join (inner / left / full) over an open-addressing table in HBM (no cuco).
+//
+// Replaces cpp/src/join/join.cu:27-124 (free functions, build on the smaller side for inner),
+// cpp/src/join/hash_join/hash_join.cu:32-299 (cudf::hash_join: ctor validation, build, probe entry
+// points, *_join_size), size_impl.cuh:26-62 (count pass), retrieve_impl.cuh:28-196 (retrieve pass),
+// join_utils.cu (full-join complement) and the cuco::static_multiset they sit on.
+//
+// Table: S = pow2 >= rows / load_factor slots of 16 bytes {uint64 key, int32 row, uint32 nullbits};
+// row == -1 marks an empty slot (the table is initialised with 0xFF bytes). Keys of all join columns
+// are packed into 64 bits (sum of widths <= 8 bytes), floats normalised so that bit equality is the
+// reference's row equality (-0 == +0, NaN == NaN: primitive_row_operators.cuh:121-143,
+// common_utils.cuh:214-220); `nullbits` has bit c set when column c is null (value bits zeroed) so
+// null == null under null_equality::EQUAL, and rows with nulls are skipped under UNEQUAL
+// (hash_join.cu:77-84).  It is a multiset: every build row owns one slot (claimed with a 32-bit CAS
+// on the row field, then the key is written; nobody compares keys during the build).
+// Probe = count pass (per-row match counts + 64-bit total) -> exclusive scan -> retrieve pass that
+// only re-walks rows that have matches; output pairs come out ordered by left row (a legal choice:
+// the reference leaves the order unspecified, join.hpp:130-136).
+#include "common.cuh"
+#include "device_utils.cuh"
+#include "key_pack.cuh"
+
+#include <algorithm>
+#include <cmath>
+
+namespace b2 {
+namespace {
+
+__global__ void __launch_bounds__(256) build_kernel(key_cols kc, int64_t n, bool skip_nulls, slot_t* __restrict__ table,
+                                                    uint32_t mask)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
+    uint64_t key;
+    uint32_t nb;
+    pack_row(kc, r, key, nb);
+    if (skip_nulls && nb) continue;
+    uint32_t i = slot_hash(key, nb, mask);
+    while (true) {
+      int old = atomicCAS(&table[i].row, -1, (int)r);
+      if (old == -1) {
+        slot_t s{key, (int32_t)r, nb};
+        int4 v;
+        memcpy(&v, &s, 16);
+        *reinterpret_cast<int4*>(&table[i]) = v;
+        break;
+      }
+      i = (i + 1) & mask;
+    }
+  }
+}
+
+// counts[r] = number of build rows equal to probe row r; total += sum (LEFT: rows without match count 1)
+template <bool LEFT>
+__global__ void __launch_bounds__(256) count_kernel(key_cols kc, int64_t n, bool skip_nulls, const slot_t* __restrict__ table,
+                                                    uint32_t mask, int32_t* __restrict__ counts,
+                                                    unsigned long long* __restrict__ total)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  unsigned long long local = 0;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
+    uint64_t key;
+    uint32_t nb;
+    pack_row(kc, r, key, nb);
+    uint32_t c = 0;
+    if (!(skip_nulls && nb) && table != nullptr) {
+      uint32_t i = slot_hash(key, nb, mask);
+      while (true) {
+        const slot_t s = load_slot(&table[i]);
+        if (s.row == -1) break;
+        c += (s.key == key && s.nullbits == nb) ? 1u : 0u;
+        i = (i + 1) & mask;
+      }
+    }
+    // counts hold the TRUE match count (0 = no match) so that the retrieve pass can tell the
+    // unmatched rows of a left join; the output size counts those rows once.
+    if (counts) counts[r] = (int32_t)min(c, 0x7fffffffu);
+    local += (LEFT && c == 0) ? 1ull : (unsigned long long)c;
+  }
+  local = warp_sum(local);
+  if (lane_id() == 0 && local) atomicAdd(total, local);
+}
+
+// out offsets for LEFT joins: max(count,1) per row -> done by transforming counts in place
+__global__ void left_adjust_kernel(const int32_t* __restrict__ counts, int64_t n, int32_t* __restrict__ adj)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) adj[r] = max(counts[r], 1);
+}
+
+template <bool LEFT>
+__global__ void __launch_bounds__(256) retrieve_kernel(key_cols kc, int64_t n, const slot_t* __restrict__ table, uint32_t mask,
+                                                       const int32_t* __restrict__ counts, const int32_t* __restrict__ offsets,
+                                                       int32_t* __restrict__ out_left, int32_t* __restrict__ out_right)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
+    const int32_t c = counts[r];
+    if (c == 0) {
+      if (LEFT) {
+        const int32_t o = offsets[r];
+        out_left[o]  = (int32_t)r;
+        out_right[o] = B2_JOIN_NO_MATCH;
+      }
+      continue;
+    }
+    uint64_t key;
+    uint32_t nb;
+    pack_row(kc, r, key, nb);
+    int32_t o = offsets[r];
+    const int32_t end = o + c;
+    uint32_t i = slot_hash(key, nb, mask);
+    while (o < end) {
+      const slot_t s = load_slot(&table[i]);
+      if (s.row == -1) break;
+      if (s.key == key && s.nullbits == nb) {
+        out_left[o]  = (int32_t)r;
+        out_right[o] = s.row;
+        ++o;
+      }
+      i = (i + 1) & mask;
+    }
+  }
+}
+
+// ---- full join complement (join_utils.cu finalize_full_join): build rows that never matched ----
+__global__ void mark_kernel(const int32_t* __restrict__ right_idx, int64_t m, uint32_t* __restrict__ bitmap)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
+    const int32_t r = right_idx[i];
+    if (r >= 0) atomicOr(&bitmap[r >> 5], 1u << (r & 31));
+  }
+}
+__global__ void unmatched_count_kernel(const uint32_t* __restrict__ bitmap, int64_t nrows, int32_t* __restrict__ word_counts)
+{
+  const int64_t nwords = (nrows + 31) / 32;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += stride) {
+    uint32_t b = ~bitmap[w];
+    int64_t rem = nrows - w * 32;
+    if (rem < 32) b &= (1u << rem) - 1u;
+    word_counts[w] = __popc(b);
+  }
+}
+__global__ void unmatched_write_kernel(const uint32_t* __restrict__ bitmap, int64_t nrows, const int32_t* __restrict__ word_offsets,
+                                       int64_t base, int32_t* __restrict__ out_left, int32_t* __restrict__ out_right)
+{
+  const int64_t nwords = (nrows + 31) / 32;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += stride) {
+    uint32_t b = ~bitmap[w];
+    int64_t rem = nrows - w * 32;
+    if (rem < 32) b &= (1u << rem) - 1u;
+    int64_t o = base + word_offsets[w];
+    while (b) {
+      int bit = __ffs(b) - 1;
+      b &= b - 1;
+      out_left[o]  = B2_JOIN_NO_MATCH;
+      out_right[o] = (int32_t)(w * 32 + bit);
+      ++o;
+    }
+  }
+}
+
+int grid_for(int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, NUM_SMS_B200 * 16)); }
+
+}  // namespace
+}  // namespace b2
+
+using namespace b2;
+
+struct b2_hash_join {
+  std::vector<int32_t> build_types;
+  int32_t build_rows = 0;
+  bool has_nulls     = false;  // nullable_join
+  int32_t compare_nulls = B2_NULLS_EQUAL;
+  uint32_t mask      = 0;
+  dbuf table;                  // empty when the build table has no rows
+};
+
+namespace b2 {
+
+enum join_kind { JOIN_INNER = 0, JOIN_LEFT = 1, JOIN_FULL = 2 };
+
+static bool table_has_nulls(const std::vector<b2_column_view>& cols)
+{
+  for (auto& c : cols)
+    if (has_nulls(c)) return true;
+  return false;
+}
+
+// cudf::hash_join ctor — hash_join.cu:112-148,189-198
+b2_hash_join* hash_join_create(const std::vector<b2_column_view>& build, int has_nulls_arg, int compare_nulls,
+                               double load_factor, cudaStream_t stream)
+{
+  B2_EXPECTS(!build.empty(), B2_ERR_INVALID_ARGUMENT, "Hash join build table is empty");
+  B2_EXPECTS(load_factor > 0 && load_factor <= 1, B2_ERR_INVALID_ARGUMENT, "Invalid load factor: must be greater than 0 and at most 1.");
+  auto hj = std::make_unique<b2_hash_join>();
+  for (auto& c : build) hj->build_types.push_back(c.type_id);
+  hj->build_rows    = build[0].size;
+  hj->has_nulls     = has_nulls_arg < 0 ? true : has_nulls_arg != 0;  // ctor #1 = nullable_join::YES (hash_join.hpp)
+  hj->compare_nulls = compare_nulls;
+  key_cols kc = make_key_cols(build);
+  if (hj->build_rows == 0) return hj.release();
+  const double want = std::ceil((double)hj->build_rows / load_factor);
+  uint64_t slots = 16;
+  while ((double)slots < want) slots <<= 1;
+  B2_EXPECTS(slots <= (1ull << 31), B2_ERR_INVALID_ARGUMENT, "hash join: build table too large for this load factor");
+  hj->mask  = (uint32_t)(slots - 1);
+  hj->table = dbuf(slots * sizeof(slot_t), stream);
+  B2_CUDA_TRY(cudaMemsetAsync(hj->table.ptr, 0xff, hj->table.bytes, stream));
+  const bool skip_nulls = compare_nulls == B2_NULLS_UNEQUAL;
+  {
+    prof_scope ps("join_build", stream);
+    B2_LAUNCH(build_kernel, grid_for(hj->build_rows), 256, 0, stream, kc, (int64_t)hj->build_rows, skip_nulls,
+              hj->table.as<slot_t>(), hj->mask);
+  }
+  return hj.release();
+}
+
+// validate_hash_join_probe — hash_join.cu:47-59
+static void validate_probe(const b2_hash_join& hj, const std::vector<b2_column_view>& probe)
+{
+  B2_EXPECTS(!probe.empty(), B2_ERR_INVALID_ARGUMENT, "Hash join probe table is empty");
+  B2_EXPECTS(probe.size() == hj.build_types.size(), B2_ERR_INVALID_ARGUMENT, "Mismatch in number of columns to be joined on");
+  B2_EXPECTS(hj.has_nulls || !table_has_nulls(probe), B2_ERR_INVALID_ARGUMENT,
+             "Probe table has nulls while build table was not hashed with null check.");
+  for (size_t i = 0; i < probe.size(); ++i)
+    B2_EXPECTS(probe[i].type_id == hj.build_types[i], B2_ERR_DATA_TYPE, "Mismatch in joining column data types");
+}
+
+struct probe_counts {
+  dbuf counts;  // int32 per probe row (true match counts)
+  size_t total = 0;
+};
+
+static probe_counts run_count(const b2_hash_join& hj, const key_cols& kc, int64_t n, bool left, bool keep_counts,
+                              cudaStream_t stream)
+{
+  probe_counts pc;
+  if (n == 0) return pc;
+  if (keep_counts) pc.counts = dbuf(sizeof(int32_t) * n, stream);
+  dbuf tot(sizeof(unsigned long long), stream);
+  B2_CUDA_TRY(cudaMemsetAsync(tot.ptr, 0, sizeof(unsigned long long), stream));
+  const bool skip_nulls = hj.compare_nulls == B2_NULLS_UNEQUAL;
+  const slot_t* table = hj.table.as<slot_t>();
+  {
+    prof_scope ps("join_count", stream);
+    if (left)
+      B2_LAUNCH((count_kernel<true>), grid_for(n), 256, 0, stream, kc, n, skip_nulls, table, hj.mask, pc.counts.as<int32_t>(),
+                tot.as<unsigned long long>());
+    else
+      B2_LAUNCH((count_kernel<false>), grid_for(n), 256, 0, stream, kc, n, skip_nulls, table, hj.mask, pc.counts.as<int32_t>(),
+                tot.as<unsigned long long>());
+  }
+  unsigned long long h = 0;
+  B2_CUDA_TRY(cudaMemcpyAsync(&h, tot.ptr, sizeof(h), cudaMemcpyDeviceToHost, stream));
+  B2_CUDA_TRY(cudaStreamSynchronize(stream));  // the reference syncs here too (size_impl.cuh:52-61)
+  pc.total = (size_t)h;
+  return pc;
+}
+
+void hash_join_probe(const b2_hash_join* hj, const std::vector<b2_column_view>& probe, int kind, bool has_size, size_t size_hint,
+                     cudaStream_t stream, column_ptr& out_left, column_ptr& out_right);
+
+size_t hash_join_size(const b2_hash_join* hj, const std::vector<b2_column_view>& probe, int kind, cudaStream_t stream)
+{
+  validate_probe(*hj, probe);
+  const int64_t n = probe[0].size;
+  key_cols kc = make_key_cols(probe);
+  if (kind == JOIN_INNER) {
+    if (n == 0 || hj->build_rows == 0) return 0;
+    return run_count(*hj, kc, n, false, false, stream).total;
+  }
+  size_t left_total = n == 0 ? 0 : run_count(*hj, kc, n, true, kind == JOIN_FULL, stream).total;
+  if (kind == JOIN_LEFT) return left_total;
+  // FULL: + build rows that no probe row matched. Needs the actual right indices -> run the join.
+  column_ptr l, r;
+  hash_join_probe(hj, probe, JOIN_FULL, false, 0, stream, l, r);
+  return (size_t)l->size;
+}
+
+void hash_join_probe(const b2_hash_join* hj, const std::vector<b2_column_view>& probe, int kind, bool has_size, size_t size_hint,
+                     cudaStream_t stream, column_ptr& out_left, column_ptr& out_right)
+{
+  (void)has_size; (void)size_hint;  // the size is always recomputed: the count pass also yields the offsets
+  validate_probe(*hj, probe);
+  const int64_t n = probe[0].size;
+  key_cols kc = make_key_cols(probe);
+  const bool left = kind != JOIN_INNER;
+
+  size_t m = 0;
+  probe_counts pc;
+  if (n > 0 && (left || hj->build_rows > 0)) {
+    pc = run_count(*hj, kc, n, left, true, stream);
+    m  = pc.total;
+  }
+  B2_EXPECTS(m <= (size_t)INT32_MAX, B2_ERR_LOGIC /* std::overflow_error in libcudf */,
+             "join output exceeds size_type (use hash_join::*_join_size and partition the probe side)");
+
+  // unmatched build rows (FULL) are appended after the left-join part
+  dbuf bitmap, word_counts;
+  column_ptr word_offsets;
+  int64_t extra = 0;
+
+  auto L = make_column(B2_INT32, (int32_t)m, false, stream);
+  auto R = make_column(B2_INT32, (int32_t)m, false, stream);
+  if (m > 0) {
+    // offsets = exclusive scan of per-row output counts
+    dbuf adj;
+    const int32_t* cnt_for_scan = pc.counts.as<int32_t>();
+    if (left) {
+      adj = dbuf(sizeof(int32_t) * n, stream);
+      B2_LAUNCH(left_adjust_kernel, grid_for(n), 256, 0, stream, pc.counts.as<int32_t>(), n, adj.as<int32_t>());
+      cnt_for_scan = adj.as<int32_t>();
+    }
+    b2_column_view cv{B2_INT32, (int32_t)n, cnt_for_scan, nullptr, 0, 0};
+    auto offs = scan(cv, B2_AGG_SUM, B2_SCAN_EXCLUSIVE, B2_NULL_EXCLUDE, stream);
+    prof_scope ps("join_retrieve", stream);
+    if (left)
+      B2_LAUNCH((retrieve_kernel<true>), grid_for(n), 256, 0, stream, kc, n, hj->table.as<slot_t>(), hj->mask,
+                pc.counts.as<int32_t>(), offs->data.as<int32_t>(), L->data.as<int32_t>(), R->data.as<int32_t>());
+    else
+      B2_LAUNCH((retrieve_kernel<false>), grid_for(n), 256, 0, stream, kc, n, hj->table.as<slot_t>(), hj->mask,
+                pc.counts.as<int32_t>(), offs->data.as<int32_t>(), L->data.as<int32_t>(), R->data.as<int32_t>());
+  }
+  if (kind == JOIN_FULL && hj->build_rows > 0) {
+    const int64_t nb = hj->build_rows;
+    const int64_t nwords = (nb + 31) / 32;
+    bitmap = dbuf(sizeof(uint32_t) * nwords, stream);
+    B2_CUDA_TRY(cudaMemsetAsync(bitmap.ptr, 0, bitmap.bytes, stream));
+    if (m > 0) B2_LAUNCH(mark_kernel, grid_for((int64_t)m), 256, 0, stream, R->data.as<int32_t>(), (int64_t)m, bitmap.as<uint32_t>());
+    word_counts = dbuf(sizeof(int32_t) * nwords, stream);
+    B2_LAUNCH(unmatched_count_kernel, grid_for(nwords), 256, 0, stream, bitmap.as<uint32_t>(), nb, word_counts.as<int32_t>());
+    b2_column_view wc{B2_INT32, (int32_t)nwords, word_counts.ptr, nullptr, 0, 0};
+    word_offsets = scan(wc, B2_AGG_SUM, B2_SCAN_EXCLUSIVE, B2_NULL_EXCLUDE, stream);
+    int32_t last_off = 0, last_cnt = 0;
+    B2_CUDA_TRY(cudaMemcpyAsync(&last_off, word_offsets->data.as<int32_t>() + (nwords - 1), 4, cudaMemcpyDeviceToHost, stream));
+    B2_CUDA_TRY(cudaMemcpyAsync(&last_cnt, word_counts.as<int32_t>() + (nwords - 1), 4, cudaMemcpyDeviceToHost, stream));
+    B2_CUDA_TRY(cudaStreamSynchronize(stream));
+    extra = (int64_t)last_off + last_cnt;
+    if (extra > 0) {
+      B2_EXPECTS(m + (size_t)extra <= (size_t)INT32_MAX, B2_ERR_LOGIC, "join output exceeds size_type");
+      auto L2 = make_column(B2_INT32, (int32_t)(m + extra), false, stream);
+      auto R2 = make_column(B2_INT32, (int32_t)(m + extra), false, stream);
+      if (m > 0) {
+        B2_CUDA_TRY(cudaMemcpyAsync(L2->data.ptr, L->data.ptr, m * 4, cudaMemcpyDeviceToDevice, stream));
+        B2_CUDA_TRY(cudaMemcpyAsync(R2->data.ptr, R->data.ptr, m * 4, cudaMemcpyDeviceToDevice, stream));
+      }
+      B2_LAUNCH(unmatched_write_kernel, grid_for(nwords), 256, 0, stream, bitmap.as<uint32_t>(), nb, word_offsets->data.as<int32_t>(),
+                (int64_t)m, L2->data.as<int32_t>(), R2->data.as<int32_t>());
+      L = std::move(L2);
+      R = std::move(R2);
+    }
+  }
+  out_left  = std::move(L);
+  out_right = std::move(R);
+}
+
+}  // namespace b2
+
+// ---- C ABI -----------------------------------------------------------------------------------------
+#define B2_TRY_BEGIN try {
+#define B2_TRY_END                                                                 \
+  }                                                                                \
+  catch (const b2::error& e) { b2::set_last_error(e.what()); return e.code; }      \
+  catch (const std::bad_alloc& e) { b2::set_last_error(e.what()); return B2_ERR_BAD_ALLOC; } \
+  catch (const std::exception& e) { b2::set_last_error(e.what()); return B2_ERR_LOGIC; }     \
+  return B2_OK;
+
+static cudaStream_t S(b2_stream s) { return static_cast<cudaStream_t>(s); }
+
+// free functions: cpp/src/join/join.cu:27-110
+static b2_status free_join(const b2_table_view* left, const b2_table_view* right, int32_t compare_nulls, int kind,
+                           b2_stream stream, b2_column** out_left, b2_column** out_right)
+{
+  B2_TRY_BEGIN
+  B2_EXPECTS(out_left && out_right, B2_ERR_INVALID_ARGUMENT, "null argument");
+  std::vector<b2_column_view> l, r;
+  validate_table(left, l);
+  validate_table(right, r);
+  B2_EXPECTS(l.size() == r.size(), B2_ERR_INVALID_ARGUMENT, "Mismatch in number of columns to be joined on");
+  B2_EXPECTS(!l.empty(), B2_ERR_INVALID_ARGUMENT, "Join key tables are empty");
+  for (size_t i = 0; i < l.size(); ++i) B2_EXPECTS(l[i].type_id == r[i].type_id, B2_ERR_DATA_TYPE, "Mismatch in joining column data types");
+  const bool nulls = table_has_nulls(l) || table_has_nulls(r);
+  column_ptr lo, ro;
+  // inner join builds on the smaller table and swaps the outputs back (join.cu:52-59)
+  if (kind == JOIN_INNER && r[0].size > l[0].size) {
+    std::unique_ptr<b2_hash_join> hj(hash_join_create(l, nulls, compare_nulls, 0.5, S(stream)));
+    hash_join_probe(hj.get(), r, JOIN_INNER, false, 0, S(stream), ro, lo);
+  } else {
+    std::unique_ptr<b2_hash_join> hj(hash_join_create(r, nulls, compare_nulls, 0.5, S(stream)));
+    hash_join_probe(hj.get(), l, kind, false, 0, S(stream), lo, ro);
+  }
+  *out_left  = lo.release();
+  *out_right = ro.release();
+  B2_TRY_END
+}
+
+extern "C" {
+
+b2_status b2_inner_join(const b2_table_view* l, const b2_table_view* r, int32_t cn, b2_stream s, b2_column** ol, b2_column** orr)
+{
+  return free_join(l, r, cn, JOIN_INNER, s, ol, orr);
+}
+b2_status b2_left_join(const b2_table_view* l, const b2_table_view* r, int32_t cn, b2_stream s, b2_column** ol, b2_column** orr)
+{
+  return free_join(l, r, cn, JOIN_LEFT, s, ol, orr);
+}
+b2_status b2_full_join(const b2_table_view* l, const b2_table_view* r, int32_t cn, b2_stream s, b2_column** ol, b2_column** orr)
+{
+  return free_join(l, r, cn, JOIN_FULL, s, ol, orr);
+}
+
+b2_status b2_hash_join_create(const b2_table_view* build, int32_t has_nulls, int32_t compare_nulls, double load_factor,
+                              b2_stream stream, b2_hash_join** out)
+{
+  B2_TRY_BEGIN
+  B2_EXPECTS(out, B2_ERR_INVALID_ARGUMENT, "null argument");
+  std::vector<b2_column_view> cols;
+  validate_table(build, cols);
+  *out = hash_join_create(cols, has_nulls, compare_nulls, load_factor, S(stream));
+  B2_TRY_END
+}
+void b2_hash_join_destroy(b2_hash_join* hj) { delete hj; }
+
+static b2_status obj_join(const b2_hash_join* hj, const b2_table_view* probe, int kind, int32_t has_size, size_t size, b2_stream stream,
+                          b2_column** ol, b2_column** orr)
+{
+  B2_TRY_BEGIN
+  B2_EXPECTS(hj && ol && orr, B2_ERR_INVALID_ARGUMENT, "null argument");
+  std::vector<b2_column_view> cols;
+  validate_table(probe, cols);
+  column_ptr l, r;
+  hash_join_probe(hj, cols, kind, has_size != 0, size, S(stream), l, r);
+  *ol  = l.release();
+  *orr = r.release();
+  B2_TRY_END
+}
+static b2_status obj_size(const b2_hash_join* hj, const b2_table_view* probe, int kind, b2_stream stream, size_t* out)
+{
+  B2_TRY_BEGIN
+  B2_EXPECTS(hj && out, B2_ERR_INVALID_ARGUMENT, "null argument");
+  std::vector<b2_column_view> cols;
+  validate_table(probe, cols);
+  *out = hash_join_size(hj, cols, kind, S(stream));
+  B2_TRY_END
+}
+b2_status b2_hash_join_inner_join(const b2_hash_join* hj, const b2_table_view* p, int32_t hs, size_t sz, b2_stream s, b2_column** l, b2_column** r) { return obj_join(hj, p, JOIN_INNER, hs, sz, s, l, r); }
+b2_status b2_hash_join_left_join(const b2_hash_join* hj, const b2_table_view* p, int32_t hs, size_t sz, b2_stream s, b2_column** l, b2_column** r) { return obj_join(hj, p, JOIN_LEFT, hs, sz, s, l, r); }
+b2_status b2_hash_join_full_join(const b2_hash_join* hj, const b2_table_view* p, int32_t hs, size_t sz, b2_stream s, b2_column** l, b2_column** r) { return obj_join(hj, p, JOIN_FULL, hs, sz, s, l, r); }
+b2_status b2_hash_join_inner_join_size(const b2_hash_join* hj, const b2_table_view* p, b2_stream s, size_t* out) { return obj_size(hj, p, JOIN_INNER, s, out); }
+b2_status b2_hash_join_left_join_size(const b2_hash_join* hj, const b2_table_view* p, b2_stream s, size_t* out) { return obj_size(hj, p, JOIN_LEFT, s, out); }
+b2_status b2_hash_join_full_join_size(const b2_hash_join* hj, const b2_table_view* p, b2_stream s, size_t* out) { return obj_size(hj, p, JOIN_FULL, s, out); }
+
+}  // extern "C"

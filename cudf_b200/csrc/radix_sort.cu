@@ -265,12 +265,19 @@ __device__ __forceinline__ uint4 ld_volatile_v4(const uint32_t* p)
   return v;
 }
 
-// One CTA = THREADS ranking threads (NWARPS warps holding IPT keys per thread) + ONE look-back warp.
-// The look-back warp resolves the 256 per-digit decoupled look-backs (8 consecutive digits per lane,
-// 128-bit volatile loads, LBT predecessor tiles per round) while the ranking warps run the latency-heavy
-// MATCH ranking, so the tile's inclusive prefix is published early and nobody idles on it.
+// One CTA = THREADS ranking threads (NWARPS warps holding IPT keys per thread) + LBW look-back warps.
+// Throughput model of a decoupled look-back (measured): the inclusive-prefix frontier
+// advances `window` tiles per status round trip (~370 cycles from L2), so tiles/cycle <= window / 370.
+// The look-back warps therefore fetch LBT predecessor tiles per round for their digits (DPL consecutive
+// digits per lane) and run concurrently with the ranking warps, publishing the tile's inclusive prefix
+// as early as possible.
+constexpr int LBW = 4;                      // look-back warps per CTA
+constexpr int DPL = RADIX / (32 * LBW);     // digits per look-back lane (2)
+constexpr int LBT = 16;                     // predecessor tiles examined per round (the window)
+static_assert(DPL == 2, "look-back lanes load their digits as one 64-bit word pair");
+
 template <typename UK, int THREADS, int IPT, int MINB>
-__global__ void __launch_bounds__(THREADS + 32, MINB) onesweep_kernel(pass_args a)
+__global__ void __launch_bounds__(THREADS + 32 * LBW, MINB) onesweep_kernel(pass_args a)
 {
   constexpr int TILE   = THREADS * IPT;
   constexpr int NWARPS = THREADS / 32;
@@ -284,9 +291,10 @@ __global__ void __launch_bounds__(THREADS + 32, MINB) onesweep_kernel(pass_args 
   UK* s_keys          = reinterpret_cast<UK*>(smem_raw);
   uint32_t* s_vals    = reinterpret_cast<uint32_t*>(smem_raw);
   uint32_t* s_whist   = reinterpret_cast<uint32_t*>(smem_raw + (size_t)STAGE_W * TILE);  // [NWARPS][256]
-  uint32_t* s_off     = s_whist + NWARPS * RADIX;  // [256] global offset of digit - tile-local start
-  uint32_t* s_cnt     = s_off + RADIX;             // [256] tile count of digit (without padding)
-  uint32_t* s_misc    = s_cnt + RADIX;             // [16]
+  uint32_t* s_bm      = s_whist + NWARPS * RADIX;  // [NWARPS][256] per-warp digit -> lane bitmaps (ranking)
+  uint32_t* s_off     = s_bm + NWARPS * RADIX;     // [256] global offset of digit - tile-local start
+  uint32_t* s_cnt     = s_off + RADIX;             // [256] {tile count of digit, tile-local start} pairs
+  uint32_t* s_misc    = s_cnt + 2 * RADIX;         // [16]
 
   const int tid  = threadIdx.x;
   const int lane = tid & 31;
@@ -296,7 +304,10 @@ __global__ void __launch_bounds__(THREADS + 32, MINB) onesweep_kernel(pass_args 
   if (tid == 0) s_misc[0] = atomicAdd(a.tile_counter, 1u);
   if (ranker) {
 #pragma unroll
-    for (int j = 0; j < RADIX / 32; ++j) s_whist[warp * RADIX + j * 32 + lane] = 0;
+    for (int j = 0; j < RADIX / 32; ++j) {
+      s_whist[warp * RADIX + j * 32 + lane] = 0;
+      s_bm[warp * RADIX + j * 32 + lane]    = 0;
+    }
   }
   __syncthreads();
   const uint32_t tile = s_misc[0];
@@ -308,82 +319,53 @@ __global__ void __launch_bounds__(THREADS + 32, MINB) onesweep_kernel(pass_args 
   const UK desc = (UK)a.desc_mask;
 
   if (!ranker) {
-    // ================================ look-back warp =============================================
-    __syncthreads();  // (S2) tile counts are in s_cnt, aggregate already published by the rankers
-    const int d0 = lane * 8;
-    uint32_t cnt[8], excl[8];
-    {
-      const uint4 c0 = *reinterpret_cast<const uint4*>(s_cnt + d0);
-      const uint4 c1 = *reinterpret_cast<const uint4*>(s_cnt + d0 + 4);
-      cnt[0] = c0.x; cnt[1] = c0.y; cnt[2] = c0.z; cnt[3] = c0.w;
-      cnt[4] = c1.x; cnt[5] = c1.y; cnt[6] = c1.z; cnt[7] = c1.w;
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) excl[j] = 0;
+    // ================================ look-back warps ============================================
+    __syncthreads();  // (S2) s_cnt = {count, tile-local start} per digit; aggregate already published
+    const int d0 = ((warp - NWARPS) * 32 + lane) * DPL;
+    const uint4 cs = *reinterpret_cast<const uint4*>(s_cnt + 2 * d0);  // {cnt0, start0, cnt1, start1}
+    uint32_t excl0 = 0, excl1 = 0;
     if (tile > 0) {
-      constexpr int LBT = 4;
-      int64_t t = (int64_t)tile - 1;  // next predecessor tile to fold (common to the 8 digits:
-      uint32_t done = 0;              // a tile publishes all its digits, usually at the same time)
-      while (done != 0xffu) {
-        uint32_t v[LBT][8];
+      int64_t t = (int64_t)tile - 1;  // next predecessor tile to fold
+      uint32_t done = 0;              // bit j: digit j has met an inclusive word
+      while (done != 3u) {
+        uint2 v[LBT];
 #pragma unroll
         for (int r = 0; r < LBT; ++r) {
           const int64_t tt = t - r;
+          v[r] = make_uint2(FLAG_INCL, FLAG_INCL);
           if (tt >= 0) {
             const uint32_t* p = a.status + (size_t)tt * RADIX + d0;
-            const uint4 x = ld_volatile_v4(p), y = ld_volatile_v4(p + 4);
-            v[r][0] = x.x; v[r][1] = x.y; v[r][2] = x.z; v[r][3] = x.w;
-            v[r][4] = y.x; v[r][5] = y.y; v[r][6] = y.z; v[r][7] = y.w;
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[r][j] = FLAG_INCL;
+            asm volatile("ld.volatile.global.v2.u32 {%0,%1}, [%2];" : "=r"(v[r].x), "=r"(v[r].y) : "l"(p) : "memory");
           }
         }
-        // a round is folded only as far as EVERY still-open digit of this lane is ready
+        // fold the window as far as both still-open digits are ready
         int consumed = 0;
 #pragma unroll
         for (int r = 0; r < LBT; ++r) {
-          if (consumed == r && done != 0xffu) {
-            bool ready = true;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) ready = ready && (((done >> j) & 1u) || (v[r][j] >> 30) != 0);
-            if (ready) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                if (!((done >> j) & 1u)) {
-                  excl[j] += v[r][j] & VAL_MASK;
-                  if (v[r][j] & FLAG_INCL) done |= 1u << j;
-                }
-              }
+          if (consumed == r && done != 3u) {
+            const bool r0 = (done & 1u) || (v[r].x >> 30) != 0;
+            const bool r1 = (done & 2u) || (v[r].y >> 30) != 0;
+            if (r0 && r1) {
+              if (!(done & 1u)) { excl0 += v[r].x & VAL_MASK; if (v[r].x & FLAG_INCL) done |= 1u; }
+              if (!(done & 2u)) { excl1 += v[r].y & VAL_MASK; if (v[r].y & FLAG_INCL) done |= 2u; }
               ++consumed;
             }
           }
         }
         t -= consumed;
+        if (consumed == 0) __nanosleep(64);  // nothing ready yet: do not burn issue slots
       }
-      // publish the inclusive prefix
       uint32_t* st = a.status + (size_t)tile * RADIX + d0;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const uint32_t word = FLAG_INCL | (excl[j] + cnt[j]);
-        asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(st + j), "r"(word) : "memory");
-      }
+      const uint32_t w0 = FLAG_INCL | (excl0 + cs.x), w1 = FLAG_INCL | (excl1 + cs.z);
+      asm volatile("st.volatile.global.v2.u32 [%0], {%1,%2};" ::"l"(st), "r"(w0), "r"(w1) : "memory");
     }
-    // tile-local start of each digit (exclusive scan of the padded counts) and the scatter offsets
-    uint32_t run = 0, loc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      loc[j] = run;
-      run += cnt[j] + ((lane == 31 && j == 7) ? pad : 0u);
-    }
-    const uint32_t lane_excl = warp_inclusive_sum(run) - run;
     const uint32_t* gb = &a.ctl->base[a.portion_parity][a.pass][d0];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const uint32_t gbase = gb[j];
-      s_off[d0 + j] = gbase + excl[j] - (lane_excl + loc[j]);
-      if (a.has_next_portion && tile_base + tile_n == a.portion_n)
-        a.ctl->base[a.portion_parity ^ 1][a.pass][d0 + j] = gbase + excl[j] + cnt[j];
+    const uint32_t g0 = gb[0], g1 = gb[1];
+    s_off[d0]     = g0 + excl0 - cs.y;
+    s_off[d0 + 1] = g1 + excl1 - cs.w;
+    if (a.has_next_portion && tile_base + tile_n == a.portion_n) {
+      a.ctl->base[a.portion_parity ^ 1][a.pass][d0]     = g0 + excl0 + cs.x;
+      a.ctl->base[a.portion_parity ^ 1][a.pass][d0 + 1] = g1 + excl1 + cs.z;
     }
     __syncthreads();  // (S4) offsets ready
     return;
@@ -421,12 +403,17 @@ __global__ void __launch_bounds__(THREADS + 32, MINB) onesweep_kernel(pass_args 
   uint32_t* my_hist = s_whist + warp * RADIX;
 #pragma unroll
   for (int i = 0; i < IPT; ++i) atomicAdd(&my_hist[(unsigned)(key[i] >> shift) & 255u], 1u);
+  __syncwarp();
+  // number of distinct digits in this warp's 32*IPT keys: picks the ranking flavour below
+  int distinct = 0;
+#pragma unroll
+  for (int j = 0; j < RADIX / 32; ++j) distinct += my_hist[j * 32 + lane] != 0u;
+  distinct = __reduce_add_sync(0xffffffffu, distinct);
   ranker_barrier(THREADS);  // (S1)
 
   // ---- per digit: warp counts -> warp offsets; publish the aggregate ---------------------------
-  uint32_t tstart = 0;
+  uint32_t tstart = 0, count = 0;
   if (tid < RADIX) {
-    uint32_t count = 0;
 #pragma unroll
     for (int w = 0; w < NWARPS; ++w) {
       uint32_t c = s_whist[w * RADIX + tid];
@@ -437,55 +424,66 @@ __global__ void __launch_bounds__(THREADS + 32, MINB) onesweep_kernel(pass_args 
     if (tid == RADIX - 1) count -= pad;
     uint32_t word = (tile == 0 ? FLAG_INCL : FLAG_AGG) | count;
     asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(a.status + (size_t)tile * RADIX + tid), "r"(word) : "memory");
-    s_cnt[tid] = count;
     // exclusive scan of the padded counts over digits: 8 warps of 32 digits
     uint32_t inc = warp_inclusive_sum(padded);
     if (lane == 31) s_misc[1 + warp] = inc;
     tstart = inc - padded;
   }
-  __syncthreads();  // (S2) releases the look-back warp
+  ranker_barrier(THREADS);  // (S1b)
   if (tid < RADIX) {
     uint32_t woff = 0;
 #pragma unroll
     for (int w = 0; w < RADIX / 32; ++w) woff += (w < warp) ? s_misc[1 + w] : 0u;
     tstart += woff;
+    s_cnt[2 * tid]     = count;
+    s_cnt[2 * tid + 1] = tstart;
     // fold the tile-local digit start into the warp offsets: position = s_whist[w][d] + rank in warp
 #pragma unroll
     for (int w = 0; w < NWARPS; ++w) s_whist[w * RADIX + tid] += tstart;
   }
-  ranker_barrier(THREADS);  // (S3)
+  __syncthreads();  // (S2) releases the look-back warps; warp offsets final
 
   // ---- rank within warp (stable): MATCH.ANY peers + running per-warp digit offsets --------------
   // All MATCH ops are issued first (independent, pipelined); only the counter chain is serial.
-  // Peer masks come from 8 ballots per item rather than MATCH.ANY: on sm_100 MATCH.ANY measured at
-  // roughly one per 30-90 cycles per SM with ~30 distinct digits per warp (ncu: mio_throttle on the
-  // MATCH cluster, 33 % of the kernel), while VOTE + LOP3 stay on the ALU path.
+  // Peer masks (lanes of the warp holding the same digit), measured cost per warp-item per SM
+  // (scripts/ubench/rank_probe.cu): MATCH.ANY 60 cycles at ~30 distinct digits but 9 at <= 4;
+  // 8 ballots 24; shared-memory atomicOr bitmap 17 (36 when all lanes collide).  Hence: bitmap for
+  // the general case, MATCH.ANY when the warp holds only a handful of distinct digits.
   uint32_t pos[IPT];
+  uint32_t* my_bm = s_bm + warp * RADIX;
+  if (distinct > 4) {
 #pragma unroll
-  for (int i = 0; i < IPT; ++i) {
-    const unsigned d = (unsigned)(key[i] >> shift) & 255u;
-    unsigned peers = 0xffffffffu;
-#pragma unroll
-    for (int b = 0; b < RADIX_BITS; ++b) {
-      const unsigned bit = (d >> b) & 1u;
-      const unsigned v = __ballot_sync(0xffffffffu, bit);
-      peers &= v ^ (bit - 1u);  // bit ? v : ~v
+    for (int i = 0; i < IPT; ++i) {
+      const unsigned d = (unsigned)(key[i] >> shift) & 255u;
+      atomicOr(&my_bm[d], 1u << lane);
+      __syncwarp();
+      const unsigned peers = my_bm[d];
+      const unsigned lt = __popc(peers & lanemask_lt());
+      uint32_t prev = 0;
+      if (lt == 0) {
+        prev = my_hist[d];
+        my_hist[d] = prev + __popc(peers);
+        my_bm[d] = 0;
+      }
+      __syncwarp();
+      prev = __shfl_sync(0xffffffffu, prev, __ffs(peers) - 1);
+      pos[i] = prev + lt;
     }
-    pos[i] = peers;
-  }
+  } else {
 #pragma unroll
-  for (int i = 0; i < IPT; ++i) {
-    const unsigned d = (unsigned)(key[i] >> shift) & 255u;
-    const unsigned peers = pos[i];
-    const unsigned lt = __popc(peers & lanemask_lt());
-    uint32_t prev = 0;
-    if (lt == 0) {
-      prev = my_hist[d];
-      my_hist[d] = prev + __popc(peers);
+    for (int i = 0; i < IPT; ++i) {
+      const unsigned d = (unsigned)(key[i] >> shift) & 255u;
+      const unsigned peers = __match_any_sync(0xffffffffu, d);
+      const unsigned lt = __popc(peers & lanemask_lt());
+      uint32_t prev = 0;
+      if (lt == 0) {
+        prev = my_hist[d];
+        my_hist[d] = prev + __popc(peers);
+      }
+      __syncwarp();
+      prev = __shfl_sync(0xffffffffu, prev, __ffs(peers) - 1);
+      pos[i] = prev + lt;
     }
-    __syncwarp();
-    prev = __shfl_sync(0xffffffffu, prev, __ffs(peers) - 1);
-    pos[i] = prev + lt;
   }
   // tile-sorted staging of the keys
 #pragma unroll
@@ -686,7 +684,7 @@ struct tile_cfg { int threads; int ipt; };
 template <typename UK, int T, int I>
 size_t onesweep_smem()
 {
-  return (sizeof(UK) > 4 ? sizeof(UK) : 4) * (size_t)T * I + sizeof(uint32_t) * ((T / 32) * RADIX + 2 * RADIX + 16);
+  return (sizeof(UK) > 4 ? sizeof(UK) : 4) * (size_t)T * I + sizeof(uint32_t) * (2 * (T / 32) * RADIX + 3 * RADIX + 16);
 }
 
 int64_t portion_limit()
@@ -771,7 +769,7 @@ void run_radix_cfg(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int
       const int64_t ntiles = (pn + TILE - 1) / TILE;
       const size_t smem_bytes = onesweep_smem<UK, T, I>();
       prof_scope ps("onesweep", stream);
-      B2_LAUNCH((onesweep_kernel<UK, T, I, MINB>), (unsigned)ntiles, T + 32, smem_bytes, stream, a);
+      B2_LAUNCH((onesweep_kernel<UK, T, I, MINB>), (unsigned)ntiles, T + 32 * LBW, smem_bytes, stream, a);
     }
   }
   {
@@ -800,13 +798,15 @@ void run_radix(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int32_t
   run_radix_cfg<UK, T, I, MINB>(raw_keys, bufA, bufB, idx_out, idx_tmp, idx_tmp2, pre_idx_buf, n, kind, descending, pairs, stream)
   if constexpr (sizeof(UK) == 8) {
     switch (sort_cfg_env()) {  // tuning knob (B2_SORT_CFG); 0 is the shipped default
-      case 1: B2_RUN(256, 16, 3); break;
-      case 2: B2_RUN(512, 12, 2); break;
-      case 3: B2_RUN(256, 12, 4); break;
+      case 1: B2_RUN(256, 16, 2); break;
+      case 2: B2_RUN(256, 16, 3); break;
+      case 3: B2_RUN(384, 12, 2); break;
       case 4: B2_RUN(512, 16, 1); break;
-      case 5: B2_RUN(384, 12, 3); break;
-      case 6: B2_RUN(256, 16, 4); break;
-      case 7: B2_RUN(256, 20, 3); break;
+      case 5: B2_RUN(512, 12, 1); break;
+      case 6: B2_RUN(640, 12, 1); break;
+      case 7: B2_RUN(256, 20, 2); break;
+      case 8: B2_RUN(320, 16, 2); break;
+      case 9: B2_RUN(320, 12, 2); break;
       default: B2_RUN(384, 16, 2); break;
     }
   } else {

@@ -39,7 +39,7 @@ def result_dtype(kind, in_dtype):
     in_dtype = np.dtype(in_dtype)
     if kind == SUM or kind == PRODUCT:
         if in_dtype.kind in "iu" or in_dtype == np.bool_:
-            return np.dtype(np.int64) if in_dtype.kind != "u" else np.dtype(np.uint64)
+            return np.dtype(np.int64)  # aggregation.hpp:935-939: every integral source sums into int64
         return in_dtype
     if kind in (COUNT_VALID, COUNT_ALL):
         return np.dtype(np.int32)

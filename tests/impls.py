@@ -1,0 +1,128 @@
+"""Two implementations behind one tiny interface so that the same golden/parity cases run against the
+oracle (CPU) and against the CUDA path through the pylibcudf-named shim (GPU)."""
+from __future__ import annotations
+
+import numpy as np
+
+import oracle
+from oracle import groupby as ogb
+from oracle import join as ojoin
+from oracle import reduce as ored
+
+KINDS = {"sum": 0, "product": 2, "min": 3, "max": 4, "count": 5, "count_all": 6, "mean": 10}
+
+
+class OracleImpl:
+    name = "oracle"
+
+    def inner_join(self, l, r, ne=0):
+        return ojoin.inner_join(l, r, ne)
+
+    def left_join(self, l, r, ne=0):
+        return ojoin.left_join(l, r, ne)
+
+    def full_join(self, l, r, ne=0):
+        return ojoin.full_join(l, r, ne)
+
+    def inner_join_size(self, l, r, ne=0):
+        return ojoin.inner_join_size(l, r, ne)
+
+    def groupby(self, keys, requests, include_nulls=False):
+        k, res = ogb.aggregate(keys, [(c, [KINDS[x] for x in kinds]) for c, kinds in requests], 1 if include_nulls else 0)
+        return k, res
+
+    def groupby_scan(self, keys, requests, include_nulls=False):
+        return ogb.scan(keys, [(c, [KINDS[x] for x in kinds]) for c, kinds in requests], 1 if include_nulls else 0)
+
+    def reduce(self, col, kind, out_dtype, init=None):
+        return ored.reduce(col[0], col[1], KINDS[kind], out_dtype, init)
+
+    def scan(self, col, kind, inclusive=True, include=False):
+        return ored.scan(col[0], col[1], KINDS[kind], inclusive, 1 if include else 0)
+
+    def segmented_reduce(self, col, offsets, kind, out_dtype, include=False, init=None):
+        return ored.segmented_reduce(col[0], col[1], offsets, KINDS[kind], out_dtype, 1 if include else 0, init)
+
+
+class PlcImpl:
+    name = "cuda"
+
+    def __init__(self, plc):
+        self.plc = plc
+
+    def _tbl(self, cols):
+        return self.plc.Table([self.plc.Column.from_numpy(v, m) for v, m in cols])
+
+    def _pairs(self, res):
+        l, r = res
+        return ojoin.canonical(l.to_numpy()[0], r.to_numpy()[0])
+
+    def inner_join(self, l, r, ne=0):
+        return self._pairs(self.plc.join.inner_join(self._tbl(l), self._tbl(r), ne))
+
+    def left_join(self, l, r, ne=0):
+        return self._pairs(self.plc.join.left_join(self._tbl(l), self._tbl(r), ne))
+
+    def full_join(self, l, r, ne=0):
+        return self._pairs(self.plc.join.full_join(self._tbl(l), self._tbl(r), ne))
+
+    def inner_join_size(self, l, r, ne=0):
+        hj = self.plc.join.HashJoin(self._tbl(r), ne)
+        return hj.inner_join_size(self._tbl(l))
+
+    def _agg(self, name):
+        a = self.plc.aggregation
+        return {"sum": a.sum, "min": a.min, "max": a.max, "mean": a.mean, "product": a.product,
+                "count": lambda: a.count(self.plc.NullPolicy.EXCLUDE), "count_all": lambda: a.count(self.plc.NullPolicy.INCLUDE)}[name]()
+
+    def _gb(self, keys, requests, include_nulls, scan):
+        plc = self.plc
+        gb = plc.groupby.GroupBy(self._tbl(keys), plc.NullPolicy.INCLUDE if include_nulls else plc.NullPolicy.EXCLUDE)
+        reqs = [plc.groupby.GroupByRequest(plc.Column.from_numpy(c[0], c[1]), [self._agg(k) for k in kinds]) for c, kinds in requests]
+        k, res = (gb.scan if scan else gb.aggregate)(reqs)
+        kcols = [c.to_numpy() for c in k.columns()]
+        rcols = [[c.to_numpy() for c in t.columns()] for t in res]
+        return kcols, rcols
+
+    def groupby(self, keys, requests, include_nulls=False):
+        return self._gb(keys, requests, include_nulls, False)
+
+    def groupby_scan(self, keys, requests, include_nulls=False):
+        return self._gb(keys, requests, include_nulls, True)
+
+    def reduce(self, col, kind, out_dtype, init=None):
+        plc = self.plc
+        c = plc.Column.from_numpy(col[0], col[1])
+        s = None
+        if init is not None:
+            s = plc.Scalar.from_py(init[0], c.type(), valid=init[1])
+        out = plc.reduce.reduce(c, self._agg(kind), plc.DataType.from_numpy(out_dtype), s)
+        v, ok = out._get()
+        return (v if ok else None), ok
+
+    def scan(self, col, kind, inclusive=True, include=False):
+        plc = self.plc
+        c = plc.Column.from_numpy(col[0], col[1])
+        out = plc.reduce.scan(c, self._agg(kind), plc.reduce.ScanType.INCLUSIVE if inclusive else plc.reduce.ScanType.EXCLUSIVE,
+                              plc.NullPolicy.INCLUDE if include else plc.NullPolicy.EXCLUDE)
+        return out.to_numpy()
+
+    def segmented_reduce(self, col, offsets, kind, out_dtype, include=False, init=None):
+        plc = self.plc
+        c = plc.Column.from_numpy(col[0], col[1])
+        o = plc.Column.from_numpy(np.asarray(offsets, dtype=np.int32))
+        s = None
+        if init is not None:
+            s = plc.Scalar.from_py(init[0], c.type(), valid=init[1])
+        out = plc.reduce.segmented_reduce(c, o, self._agg(kind), plc.DataType.from_numpy(out_dtype),
+                                          plc.NullPolicy.INCLUDE if include else plc.NullPolicy.EXCLUDE, s)
+        return out.to_numpy()
+
+
+def sort_groups(keys, results):
+    """Canonical order for groupby output: sort groups by key (nulls first)."""
+    from oracle import sort as osort
+
+    order = osort.sorted_order(keys, [0] * len(keys), [1] * len(keys)) if keys and len(keys[0][0]) else np.empty(0, np.int32)
+    take = lambda c: (np.asarray(c[0])[order], None if c[1] is None else np.asarray(c[1])[order])
+    return [take(k) for k in keys], [[take(c) for c in per] for per in results]
