@@ -1,0 +1,239 @@
+// partition.cu — stable partition of table rows into P buckets (the bucket step either side of the
+// NCCL all-to-all of the sharded sort / join; role of cudf::hash_partition,
+// cpp/include/cudf/partitioning.hpp:103-145 / cpp/src/partitioning/partitioning.cu, and of the range
+// partition by sampled splitters in python/cudf_polars/cudf_polars/streaming/sort.py:169-235).
+//   mode 0 (range): bucket(row) = #splitters <= key  (P-1 ascending splitters of the key's type)
+//   mode 1 (hash):  bucket(row) = mix64(key bits) % P
+// Implementation: bucket ids (uint8) + per-bucket counts in one pass over the key column, a stable
+// one-pass radix sorted_order of the ids (radix_sort.cu) as gather map, then the fused gather.
+#include "common.cuh"
+#include "device_utils.cuh"
+
+#include <algorithm>
+
+namespace b2 {
+namespace {
+
+template <typename UK>
+__device__ __forceinline__ uint64_t order_bits(UK raw, int kind)
+{
+  if (kind == (int)key_kind::SIGNED) return (uint64_t)twiddle_in<UK, key_kind::SIGNED>(raw);
+  if (kind == (int)key_kind::FLOAT) {
+    if constexpr (sizeof(UK) >= 4) return (uint64_t)twiddle_in<UK, key_kind::FLOAT>(raw);
+  }
+  return (uint64_t)raw;
+}
+
+constexpr int PT_TILE = 4096;  // rows per CTA tile (256 threads x 16 steps)
+
+// pass 1: bucket id per row (uint8) + per-tile bucket counts
+template <typename UK>
+__global__ void __launch_bounds__(256) bucket_kernel(const UK* __restrict__ keys, int64_t n, int mode, int kind,
+                                                     const UK* __restrict__ splitters, int P, uint8_t* __restrict__ ids,
+                                                     uint32_t* __restrict__ tile_counts)
+{
+  __shared__ uint64_t s_split[256];
+  __shared__ unsigned int s_cnt[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+    s_cnt[i] = 0;
+    s_split[i] = (mode == 0 && i < P - 1) ? order_bits<UK>(splitters[i], kind) : ~0ull;
+  }
+  __syncthreads();
+  const int64_t tile = blockIdx.x;
+  const int64_t end = min(n, (tile + 1) * (int64_t)PT_TILE);
+  for (int64_t i = tile * PT_TILE + threadIdx.x; i < end; i += blockDim.x) {
+    const UK raw = keys[i];
+    int b;
+    if (mode == 0) {
+      const uint64_t k = order_bits<UK>(raw, kind);
+      int lo = 0, hi = P - 1;  // number of splitters <= k
+      while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (s_split[mid] <= k) lo = mid + 1; else hi = mid;
+      }
+      b = lo;
+    } else {
+      b = (int)(mix64((uint64_t)raw) % (uint64_t)P);
+    }
+    ids[i] = (uint8_t)b;
+    atomicAdd(&s_cnt[b], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < P; i += blockDim.x) tile_counts[tile * P + i] = s_cnt[i];
+}
+
+// pass 2 (one CTA): tile_counts[t][b] -> global start of bucket b's rows of tile t; totals[b]
+__global__ void __launch_bounds__(1024) tile_scan_kernel(uint32_t* __restrict__ tile_counts, int64_t ntiles, int P,
+                                                         unsigned long long* __restrict__ totals)
+{
+  __shared__ uint32_t wsum[32];
+  __shared__ uint32_t carry;
+  __shared__ uint32_t bucket_start;
+  if (threadIdx.x == 0) bucket_start = 0;
+  __syncthreads();
+  for (int b = 0; b < P; ++b) {
+    if (threadIdx.x == 0) carry = bucket_start;
+    __syncthreads();
+    for (int64_t t0 = 0; t0 < ntiles; t0 += 1024) {
+      const int64_t t = t0 + threadIdx.x;
+      const uint32_t v = t < ntiles ? tile_counts[t * P + b] : 0u;
+      uint32_t inc = warp_inclusive_sum(v);
+      if (lane_id() == 31) wsum[threadIdx.x >> 5] = inc;
+      __syncthreads();
+      uint32_t woff = 0;
+      for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) woff += wsum[w];
+      const uint32_t c = carry;
+      if (t < ntiles) tile_counts[t * P + b] = c + woff + inc - v;
+      __syncthreads();
+      if (threadIdx.x == 1023) carry = c + woff + inc;
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      totals[b] = (unsigned long long)(carry - bucket_start);
+      bucket_start = carry;
+    }
+    __syncthreads();
+  }
+}
+
+// pass 3: stable destination of every row: dest[row] = start(tile, bucket) + rank of the row among the
+// tile's rows of the same bucket (warp counts by smem atomics, MATCH.ANY ranking: few distinct ids)
+__global__ void __launch_bounds__(256) dest_kernel(const uint8_t* __restrict__ ids, int64_t n, int P,
+                                                   const uint32_t* __restrict__ tile_starts, int32_t* __restrict__ dest)
+{
+  __shared__ uint32_t woff[8][256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = lane; i < P; i += 32) woff[warp][i] = 0;
+  __syncwarp();
+  const int64_t tile = blockIdx.x;
+  const int64_t wbase = tile * PT_TILE + (int64_t)warp * (PT_TILE / 8);
+  uint8_t id[PT_TILE / 8 / 32];
+#pragma unroll
+  for (int s = 0; s < PT_TILE / 8 / 32; ++s) {
+    const int64_t r = wbase + s * 32 + lane;
+    id[s] = r < n ? ids[r] : (uint8_t)255;
+    if (r < n) atomicAdd(&woff[warp][id[s]], 1u);
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < P; b += blockDim.x) {
+    uint32_t run = tile_starts[tile * P + b];
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const uint32_t c = woff[w][b];
+      woff[w][b] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int s = 0; s < PT_TILE / 8 / 32; ++s) {
+    const int64_t r = wbase + s * 32 + lane;
+    const bool in = r < n;
+    const unsigned peers = __match_any_sync(0xffffffffu, in ? (unsigned)id[s] : 0x100u);
+    const unsigned lt = __popc(peers & lanemask_lt());
+    uint32_t prev = 0;
+    if (in && lt == 0) {
+      prev = woff[warp][id[s]];
+      woff[warp][id[s]] = prev + __popc(peers);
+    }
+    __syncwarp();
+    prev = __shfl_sync(0xffffffffu, prev, __ffs(peers) - 1);
+    if (in) dest[r] = (int32_t)(prev + lt);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) scatter_kernel(const T* __restrict__ in, const int32_t* __restrict__ dest, int64_t n,
+                                                      T* __restrict__ out)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[dest[i]] = ld_stream(in + i);
+}
+
+}  // namespace
+
+table_ptr partition_table(const std::vector<b2_column_view>& input, const b2_column_view& keys, int mode, const void* splitters,
+                          int P, int32_t* out_offsets, cudaStream_t stream)
+{
+  B2_EXPECTS(P >= 1 && P <= 256, B2_ERR_INVALID_ARGUMENT, "num_partitions must be in [1, 256]");
+  B2_EXPECTS(!has_nulls(keys), B2_ERR_INVALID_ARGUMENT, "partition key column must not contain nulls");
+  B2_EXPECTS(mode == 1 || P == 1 || splitters != nullptr, B2_ERR_INVALID_ARGUMENT, "range partition needs splitters");
+  const int64_t n = keys.size;
+  for (auto& c : input) B2_EXPECTS(c.size == n, B2_ERR_LOGIC, "Column size mismatch.");
+  const int64_t ntiles = (n + PT_TILE - 1) / PT_TILE;
+  dbuf ids(std::max<int64_t>(n, 1), stream), totals(sizeof(unsigned long long) * 256, stream);
+  dbuf tile_counts(sizeof(uint32_t) * std::max<int64_t>(ntiles, 1) * P, stream);
+  B2_CUDA_TRY(cudaMemsetAsync(totals.ptr, 0, totals.bytes, stream));
+  const int sid  = storage_type(keys.type_id);
+  const int kind = is_float_id(sid) ? (int)key_kind::FLOAT : (is_signed_id(sid) ? (int)key_kind::SIGNED : (int)key_kind::UNSIGNED);
+  auto out = std::make_unique<b2_table>();
+  if (n > 0) {
+    {
+      prof_scope ps("partition_bucket", stream);
+      const unsigned grid = (unsigned)ntiles;
+      switch (type_width(keys.type_id)) {
+        case 1: B2_LAUNCH((bucket_kernel<uint8_t>), grid, 256, 0, stream, static_cast<const uint8_t*>(keys.data) + keys.offset, n, mode, kind, static_cast<const uint8_t*>(splitters), P, ids.as<uint8_t>(), tile_counts.as<uint32_t>()); break;
+        case 2: B2_LAUNCH((bucket_kernel<uint16_t>), grid, 256, 0, stream, static_cast<const uint16_t*>(keys.data) + keys.offset, n, mode, kind, static_cast<const uint16_t*>(splitters), P, ids.as<uint8_t>(), tile_counts.as<uint32_t>()); break;
+        case 4: B2_LAUNCH((bucket_kernel<uint32_t>), grid, 256, 0, stream, static_cast<const uint32_t*>(keys.data) + keys.offset, n, mode, kind, static_cast<const uint32_t*>(splitters), P, ids.as<uint8_t>(), tile_counts.as<uint32_t>()); break;
+        case 8: B2_LAUNCH((bucket_kernel<uint64_t>), grid, 256, 0, stream, static_cast<const uint64_t*>(keys.data) + keys.offset, n, mode, kind, static_cast<const uint64_t*>(splitters), P, ids.as<uint8_t>(), tile_counts.as<uint32_t>()); break;
+        default: B2_FAIL(B2_ERR_DATA_TYPE, "partition: unsupported key type");
+      }
+    }
+    B2_LAUNCH(tile_scan_kernel, 1, 1024, 0, stream, tile_counts.as<uint32_t>(), ntiles, P, totals.as<unsigned long long>());
+    bool any_nullable = false;
+    for (auto& c : input) any_nullable |= has_nulls(c);
+    dbuf dest(sizeof(int32_t) * n, stream);
+    {
+      prof_scope ps("partition_dest", stream);
+      B2_LAUNCH(dest_kernel, (unsigned)ntiles, 256, 0, stream, ids.as<uint8_t>(), n, P, tile_counts.as<uint32_t>(), dest.as<int32_t>());
+    }
+    if (!any_nullable) {
+      prof_scope ps("partition_scatter", stream);
+      const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, NUM_SMS_B200 * 16));
+      for (auto& c : input) {
+        auto oc = make_column(c.type_id, (int32_t)n, false, stream);
+        switch (type_width(c.type_id)) {
+          case 1: B2_LAUNCH((scatter_kernel<uint8_t>), grid, 256, 0, stream, static_cast<const uint8_t*>(c.data) + c.offset, dest.as<int32_t>(), n, oc->data.as<uint8_t>()); break;
+          case 2: B2_LAUNCH((scatter_kernel<uint16_t>), grid, 256, 0, stream, static_cast<const uint16_t*>(c.data) + c.offset, dest.as<int32_t>(), n, oc->data.as<uint16_t>()); break;
+          case 4: B2_LAUNCH((scatter_kernel<uint32_t>), grid, 256, 0, stream, static_cast<const uint32_t*>(c.data) + c.offset, dest.as<int32_t>(), n, oc->data.as<uint32_t>()); break;
+          default: B2_LAUNCH((scatter_kernel<uint64_t>), grid, 256, 0, stream, static_cast<const uint64_t*>(c.data) + c.offset, dest.as<int32_t>(), n, oc->data.as<uint64_t>()); break;
+        }
+        out->cols.push_back(std::move(oc));
+      }
+    } else {
+      // nullable payloads: invert through a stable one-pass radix order of the ids and the fused gather
+      b2_column_view idv{B2_UINT8, (int32_t)n, ids.ptr, nullptr, 0, 0};
+      auto order = sorted_order({idv}, {}, {}, true, stream);
+      out = gather_table(input, order->data.as<int32_t>(), (int32_t)n, false, stream);
+    }
+  } else {
+    for (auto& c : input) out->cols.push_back(make_column(c.type_id, 0, false, stream));
+  }
+  unsigned long long h[256];
+  B2_CUDA_TRY(cudaMemcpyAsync(h, totals.ptr, sizeof(unsigned long long) * 256, cudaMemcpyDeviceToHost, stream));
+  B2_CUDA_TRY(cudaStreamSynchronize(stream));
+  out_offsets[0] = 0;
+  for (int b = 0; b < P; ++b) out_offsets[b + 1] = out_offsets[b] + (int32_t)h[b];
+  return out;
+}
+
+}  // namespace b2
+
+extern "C" b2_status b2_partition(const b2_table_view* input, const b2_column_view* keys, int32_t mode, const void* splitters,
+                                  int32_t num_partitions, b2_stream stream, b2_table** out, int32_t* out_offsets)
+{
+  try {
+    B2_EXPECTS(input && keys && out && out_offsets, B2_ERR_INVALID_ARGUMENT, "null argument");
+    std::vector<b2_column_view> cols;
+    b2::validate_table(input, cols);
+    b2::validate_column(*keys);
+    *out = b2::partition_table(cols, *keys, mode, splitters, num_partitions, out_offsets, static_cast<cudaStream_t>(stream)).release();
+  } catch (const b2::error& e) {
+    b2::set_last_error(e.what());
+    return e.code;
+  } catch (const std::exception& e) {
+    b2::set_last_error(e.what());
+    return B2_ERR_LOGIC;
+  }
+  return B2_OK;
+}

@@ -1,0 +1,164 @@
+"""Sharded (multi-GPU) sort_by_key and inner_join: one process per GPU, torch.distributed for the plumbing.
+
+No libcudf equivalent (libcudf is single-GPU); this replaces the role of the rapidsmpf/dask shuffle above it
+(python/cudf_polars/cudf_polars/streaming/sort.py:169-235 sample -> allgather -> splitters -> range partition
+-> shuffle -> local sort; hash_partition -> shuffle -> local join for joins, cpp/include/cudf/partitioning.hpp).
+
+  sort:  regular sample of each shard -> all_gather -> P-1 splitters -> b2_partition(range) ->
+         all_to_all_single of the buckets (NCCL over NVLink) -> local LSD radix sort.
+         Rank r ends up with the r-th key range; concatenating the shards in rank order is the global order.
+  join:  b2_partition(hash) of (key, global row id) on both sides -> two all_to_all -> local hash join ->
+         global row-id pairs (the output stays sharded).
+
+The device work goes through an `ops` object (CudaOps = the CUDA library); tests inject a numpy twin to cover the
+host logic with the gloo backend on CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import time
+
+import torch
+import torch.distributed as dist
+
+_TIMING = os.environ.get("B2_SHARD_TIMING", "0") == "1"
+
+
+class _Phase:
+    """Optional wall-clock phase timing (B2_SHARD_TIMING=1): synchronises the device around each phase."""
+
+    def __init__(self):
+        self.t = {}
+        self._last = None
+
+    def mark(self, name):
+        if not _TIMING:
+            return
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        now = time.perf_counter()
+        if self._last is not None:
+            self.t[self._last[0]] = self.t.get(self._last[0], 0.0) + (now - self._last[1]) * 1e3
+        self._last = (name, now)
+
+    def done(self, tag):
+        self.mark("_end")
+        if _TIMING and dist.get_rank() == 0:
+            print(f"[{tag}] " + " ".join(f"{k}={v:.1f}ms" for k, v in self.t.items() if k != "_end"), flush=True)
+
+
+class CudaOps:
+    """Device primitives backed by libcudf_b200 (through the pylibcudf-named shim)."""
+
+    def __init__(self):
+        from . import _lib
+        from . import pylibcudf as plc
+
+        self.plc, self._lib = plc, _lib
+
+    def sort_keys(self, t: torch.Tensor) -> torch.Tensor:
+        plc = self.plc
+        out = plc.sorting.sort(plc.Table([plc.Column.from_torch(t)]), [plc.Order.ASCENDING], [])
+        return out.columns()[0].to_torch()
+
+    def partition(self, columns, key, mode: int, splitters, nparts: int):
+        """-> (list of partitioned tensors, offsets list[nparts+1]); stable within a bucket."""
+        plc, lib = self.plc, self._lib
+        tbl = plc.Table([plc.Column.from_torch(c) for c in columns])
+        kcol = plc.Column.from_torch(key)
+        tv, kv = tbl._view(), kcol._view()
+        out = C.c_void_p()
+        offs = (C.c_int32 * (nparts + 1))()
+        sp = C.c_void_p(splitters.data_ptr()) if splitters is not None and splitters.numel() else None
+        lib.check(lib.lib.b2_partition(C.byref(tv), C.byref(kv), mode, sp, nparts, lib.stream_arg(None), C.byref(out), offs))
+        res = plc.Table._from_handle(out.value)
+        return [c.to_torch() for c in res.columns()], list(offs)
+
+    def sort_by_key(self, values: torch.Tensor, keys: torch.Tensor) -> torch.Tensor:
+        plc = self.plc
+        out = plc.sorting.sort_by_key(plc.Table([plc.Column.from_torch(values)]), plc.Table([plc.Column.from_torch(keys)]),
+                                      [plc.Order.ASCENDING], [])
+        return out.columns()[0].to_torch()
+
+    def inner_join(self, left: torch.Tensor, right: torch.Tensor):
+        plc = self.plc
+        l, r = plc.join.inner_join(plc.Table([plc.Column.from_torch(left)]), plc.Table([plc.Column.from_torch(right)]),
+                                   plc.NullEquality.EQUAL)
+        return l.to_torch(), r.to_torch()
+
+
+def _exchange(buckets: torch.Tensor, offsets, group=None) -> torch.Tensor:
+    """all-to-all-v of contiguous buckets; returns the concatenation of what every rank sent to us."""
+    world = dist.get_world_size(group)
+    send = torch.tensor([offsets[i + 1] - offsets[i] for i in range(world)], dtype=torch.int64, device=buckets.device)
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send, group=group)
+    send_l, recv_l = send.tolist(), recv.tolist()
+    out = torch.empty(sum(recv_l), dtype=buckets.dtype, device=buckets.device)
+    dist.all_to_all_single(out, buckets, output_split_sizes=recv_l, input_split_sizes=send_l, group=group)
+    return out
+
+
+def choose_splitters(samples_sorted: torch.Tensor, world: int) -> torch.Tensor:
+    """P-1 splitters at the i/P quantiles of the gathered, sorted sample."""
+    m = samples_sorted.numel()
+    idx = torch.tensor([(i * m) // world for i in range(1, world)], dtype=torch.int64, device=samples_sorted.device)
+    return samples_sorted[idx.clamp_(0, max(m - 1, 0))] if m else samples_sorted[:0]
+
+
+def sort_by_key_sharded(values: torch.Tensor, keys: torch.Tensor, ops=None, group=None, samples_per_rank: int = 1 << 16) -> torch.Tensor:
+    """Global sort of the row-sharded (values, keys); returns this rank's slice of the result (values ordered by key)."""
+    ops = ops or CudaOps()
+    world = dist.get_world_size(group)
+    if world == 1:
+        return ops.sort_by_key(values, keys)
+    ph = _Phase()
+    ph.mark("sample")
+    n = keys.numel()
+    stride = max(1, n // samples_per_rank)
+    sample = keys[::stride][:samples_per_rank].contiguous()
+    # every rank contributes exactly samples_per_rank entries (pad by repeating the last sample)
+    if sample.numel() < samples_per_rank:
+        pad = sample[-1:].expand(samples_per_rank - sample.numel()) if sample.numel() else keys.new_zeros(samples_per_rank)
+        sample = torch.cat([sample, pad])
+    gathered = torch.empty(world * samples_per_rank, dtype=keys.dtype, device=keys.device)
+    dist.all_gather_into_tensor(gathered, sample, group=group) if keys.is_cuda else dist.all_gather(
+        list(gathered.view(world, -1).unbind(0)), sample, group=group)
+    splitters = choose_splitters(ops.sort_keys(gathered), world)
+    same = values.data_ptr() == keys.data_ptr() and values.numel() == keys.numel()
+    ph.mark("partition")
+    cols, offsets = ops.partition([keys] if same else [keys, values], keys, 0, splitters, world)
+    ph.mark("exchange")
+    rk = _exchange(cols[0], offsets, group)
+    rv = rk if same else _exchange(cols[1], offsets, group)
+    del cols
+    ph.mark("local_sort")
+    out = ops.sort_by_key(rv, rk)
+    ph.done("sort_by_key_sharded")
+    return out
+
+
+def inner_join_sharded(left_keys: torch.Tensor, right_keys: torch.Tensor, ops=None, group=None):
+    """Inner join of two row-sharded int64 key columns -> (left_global_row, right_global_row) pairs found on this rank."""
+    ops = ops or CudaOps()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+
+    def global_ids(t):
+        counts = torch.tensor([t.numel()], dtype=torch.int64, device=t.device)
+        allc = [torch.empty_like(counts) for _ in range(world)]
+        dist.all_gather(allc, counts, group=group)
+        base = int(sum(int(c.item()) for c in allc[:rank]))
+        return torch.arange(base, base + t.numel(), dtype=torch.int64, device=t.device)
+
+    def shuffle(keys):
+        gid = global_ids(keys)
+        if world == 1:
+            return keys, gid
+        cols, offsets = ops.partition([keys, gid], keys, 1, None, world)
+        return _exchange(cols[0], offsets, group), _exchange(cols[1], offsets, group)
+
+    lk, lg = shuffle(left_keys)
+    rk, rg = shuffle(right_keys)
+    li, ri = ops.inner_join(lk, rk)
+    return lg[li.long()], rg[ri.long()]
