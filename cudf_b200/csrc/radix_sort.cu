@@ -241,7 +241,8 @@ struct pass_args {
   const void* key_bufs[3];  // [0] raw input column data (already offset), [1], [2]
   int32_t* idx_bufs[3];
   sort_ctl* ctl;
-  uint32_t* status;         // [num_tiles][256] for this (pass, portion)
+  uint32_t* status;         // agg[tiles][256], incl[tiles][256], state[tiles] for this (pass, portion)
+  uint32_t status_tiles;    // tiles per portion (row count of the arrays above)
   uint32_t* tile_counter;   // for this (pass, portion)
   int64_t portion_start;    // element offset of this portion
   uint32_t portion_n;       // elements in this portion
@@ -254,6 +255,16 @@ struct pass_args {
   int32_t pre_n_is_dynamic; // unused
 };
 
+__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v)
+{
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p)
+{
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void ranker_barrier(int nthreads)
 {
   asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
@@ -266,15 +277,18 @@ __device__ __forceinline__ uint4 ld_volatile_v4(const uint32_t* p)
 }
 
 // One CTA = THREADS ranking threads (NWARPS warps holding IPT keys per thread) + LBW look-back warps.
-// Throughput model of a decoupled look-back (measured): the inclusive-prefix frontier
-// advances `window` tiles per status round trip (~370 cycles from L2), so tiles/cycle <= window / 370.
-// The look-back warps therefore fetch LBT predecessor tiles per round for their digits (DPL consecutive
-// digits per lane) and run concurrently with the ranking warps, publishing the tile's inclusive prefix
-// as early as possible.
-constexpr int LBW = 4;                      // look-back warps per CTA
-constexpr int DPL = RADIX / (32 * LBW);     // digits per look-back lane (2)
-constexpr int LBT = 16;                     // predecessor tiles examined per round (the window)
-static_assert(DPL == 2, "look-back lanes load their digits as one 64-bit word pair");
+// Decoupled look-back without fences: a tile's digit counts (later: inclusive prefixes) are published
+// as rows of 256 words written in 16-byte groups, ONE lane per group, with a 2-bit state in the top
+// bits of the group's first word (0 nothing, 1 aggregate, 2 inclusive; the other three words carry
+// plain 32-bit values).  A 16-byte aligned store is observed all-or-nothing by a 16-byte load, so a
+// reader lane checks one flag per group and needs no memory fence (measured: the release/acquire
+// variant with a separate state word was 1.6x slower; polling 256 individually flagged words spent
+// 35 % of all issued instructions in the polling loops).  Each look-back lane owns one group
+// (DPL = 4 digits), fetches LBT predecessor rows per round with independent 128-bit loads and folds
+// them with warp-uniform decisions (REDUX and/or over the ready / inclusive bits).
+constexpr int LBW = 2;   // look-back warps per CTA
+constexpr int DPL = 4;   // digits per look-back lane (one 128-bit load per predecessor tile)
+constexpr int LBT = 8;   // predecessor tiles fetched per round
 
 template <typename UK, int THREADS, int IPT, int MINB>
 __global__ void __launch_bounds__(THREADS + 32 * LBW, MINB) onesweep_kernel(pass_args a)
@@ -319,53 +333,64 @@ __global__ void __launch_bounds__(THREADS + 32 * LBW, MINB) onesweep_kernel(pass
   const UK desc = (UK)a.desc_mask;
 
   if (!ranker) {
-    // ================================ look-back warps ============================================
-    __syncthreads();  // (S2) s_cnt = {count, tile-local start} per digit; aggregate already published
+    // ================================ look-back warp ==============================================
+    __syncthreads();  // (S2) agg[tile][*] written by the rankers; s_cnt = {count, tile-local start}
     const int d0 = ((warp - NWARPS) * 32 + lane) * DPL;
-    const uint4 cs = *reinterpret_cast<const uint4*>(s_cnt + 2 * d0);  // {cnt0, start0, cnt1, start1}
-    uint32_t excl0 = 0, excl1 = 0;
-    if (tile > 0) {
-      int64_t t = (int64_t)tile - 1;  // next predecessor tile to fold
-      uint32_t done = 0;              // bit j: digit j has met an inclusive word
-      while (done != 3u) {
-        uint2 v[LBT];
+    uint32_t cnt[DPL], loc[DPL], excl[DPL];
+#pragma unroll
+    for (int j = 0; j < DPL; j += 2) {
+      const uint4 cs = *reinterpret_cast<const uint4*>(s_cnt + 2 * (d0 + j));  // {cnt, start, cnt, start}
+      cnt[j] = cs.x; loc[j] = cs.y; cnt[j + 1] = cs.z; loc[j + 1] = cs.w;
+      excl[j] = 0; excl[j + 1] = 0;
+    }
+    uint32_t* const my_row = a.status + (size_t)tile * RADIX + d0;
+    auto publish = [&](uint32_t flag, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+      asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(my_row), "r"(flag | w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+    };
+    if (tile == 0) {
+      publish(FLAG_INCL, cnt[0], cnt[1], cnt[2], cnt[3]);  // first tile of the portion: counts are inclusive
+    } else {
+      publish(FLAG_AGG, cnt[0], cnt[1], cnt[2], cnt[3]);
+      int64_t t = (int64_t)tile - 1;  // nearest predecessor not folded yet
+      bool done = false;
+      while (!done) {
+        uint4 v[LBT];
 #pragma unroll
         for (int r = 0; r < LBT; ++r) {
           const int64_t tt = t - r;
-          v[r] = make_uint2(FLAG_INCL, FLAG_INCL);
-          if (tt >= 0) {
-            const uint32_t* p = a.status + (size_t)tt * RADIX + d0;
-            asm volatile("ld.volatile.global.v2.u32 {%0,%1}, [%2];" : "=r"(v[r].x), "=r"(v[r].y) : "l"(p) : "memory");
-          }
+          v[r] = make_uint4(FLAG_INCL, 0, 0, 0);  // tiles before the first one: inclusive zero
+          if (tt >= 0) v[r] = ld_volatile_v4(a.status + (size_t)tt * RADIX + d0);
         }
-        // fold the window as far as both still-open digits are ready
-        int consumed = 0;
+        uint32_t rdy = 0, inc = 0;
 #pragma unroll
         for (int r = 0; r < LBT; ++r) {
-          if (consumed == r && done != 3u) {
-            const bool r0 = (done & 1u) || (v[r].x >> 30) != 0;
-            const bool r1 = (done & 2u) || (v[r].y >> 30) != 0;
-            if (r0 && r1) {
-              if (!(done & 1u)) { excl0 += v[r].x & VAL_MASK; if (v[r].x & FLAG_INCL) done |= 1u; }
-              if (!(done & 2u)) { excl1 += v[r].y & VAL_MASK; if (v[r].y & FLAG_INCL) done |= 2u; }
-              ++consumed;
-            }
-          }
+          rdy |= ((v[r].x >> 30) != 0u ? 1u : 0u) << r;
+          inc |= (v[r].x >> 31) << r;
         }
-        t -= consumed;
-        if (consumed == 0) __nanosleep(64);  // nothing ready yet: do not burn issue slots
+        const uint32_t rdy_all = __reduce_and_sync(0xffffffffu, rdy);
+        const uint32_t inc_all = __reduce_and_sync(0xffffffffu, inc);
+        const uint32_t inc_any = __reduce_or_sync(0xffffffffu, inc);
+        const uint32_t usable  = rdy_all & ~(inc_any & ~inc_all);      // rows every lane sees in the same state
+        const int n_ready   = __ffs(~usable) - 1;                       // leading usable rows (LBT if all)
+        const int first_inc = (inc_all & usable) ? (__ffs(inc_all & usable) - 1) : LBT;
+        const int take = min(n_ready, first_inc + 1);
+        if (take == 0) { __nanosleep(40); continue; }
+#pragma unroll
+        for (int r = 0; r < LBT; ++r) {
+          if (r < take) { excl[0] += v[r].x & VAL_MASK; excl[1] += v[r].y; excl[2] += v[r].z; excl[3] += v[r].w; }
+        }
+        done = first_inc < n_ready;
+        t -= take;
       }
-      uint32_t* st = a.status + (size_t)tile * RADIX + d0;
-      const uint32_t w0 = FLAG_INCL | (excl0 + cs.x), w1 = FLAG_INCL | (excl1 + cs.z);
-      asm volatile("st.volatile.global.v2.u32 [%0], {%1,%2};" ::"l"(st), "r"(w0), "r"(w1) : "memory");
+      publish(FLAG_INCL, excl[0] + cnt[0], excl[1] + cnt[1], excl[2] + cnt[2], excl[3] + cnt[3]);
     }
     const uint32_t* gb = &a.ctl->base[a.portion_parity][a.pass][d0];
-    const uint32_t g0 = gb[0], g1 = gb[1];
-    s_off[d0]     = g0 + excl0 - cs.y;
-    s_off[d0 + 1] = g1 + excl1 - cs.w;
-    if (a.has_next_portion && tile_base + tile_n == a.portion_n) {
-      a.ctl->base[a.portion_parity ^ 1][a.pass][d0]     = g0 + excl0 + cs.x;
-      a.ctl->base[a.portion_parity ^ 1][a.pass][d0 + 1] = g1 + excl1 + cs.z;
+    const bool last_of_portion = a.has_next_portion && tile_base + tile_n == a.portion_n;
+#pragma unroll
+    for (int j = 0; j < DPL; ++j) {
+      const uint32_t g = gb[j];
+      s_off[d0 + j] = g + excl[j] - loc[j];
+      if (last_of_portion) a.ctl->base[a.portion_parity ^ 1][a.pass][d0 + j] = g + excl[j] + cnt[j];
     }
     __syncthreads();  // (S4) offsets ready
     return;
@@ -422,8 +447,6 @@ __global__ void __launch_bounds__(THREADS + 32 * LBW, MINB) onesweep_kernel(pass
     }
     const uint32_t padded = count;
     if (tid == RADIX - 1) count -= pad;
-    uint32_t word = (tile == 0 ? FLAG_INCL : FLAG_AGG) | count;
-    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(a.status + (size_t)tile * RADIX + tid), "r"(word) : "memory");
     // exclusive scan of the padded counts over digits: 8 warps of 32 digits
     uint32_t inc = warp_inclusive_sum(padded);
     if (lane == 31) s_misc[1 + warp] = inc;
@@ -764,7 +787,8 @@ void run_radix_cfg(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int
       a.portion_n = (uint32_t)pn;
       a.portion_parity = (int)(q & 1);
       a.has_next_portion = q + 1 < nportions;
-      a.status = status + (size_t)(p * nportions + q) * RADIX * (size_t)tiles_per_portion;
+      a.status = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(status) + (size_t)(p * nportions + q) * status_per);
+      a.status_tiles = (uint32_t)tiles_per_portion;
       a.tile_counter = counters + p * nportions + q;
       const int64_t ntiles = (pn + TILE - 1) / TILE;
       const size_t smem_bytes = onesweep_smem<UK, T, I>();
