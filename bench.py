@@ -297,7 +297,7 @@ def run_ours(args):
 
     extra = None
     if args.extra and world == 1:
-        from cudf_b200 import bench_extra
+        import bench_extra
 
         del keys
         extra = bench_extra.run(plc, _lib, n, peak)

@@ -96,18 +96,19 @@ __device__ __forceinline__ double ordered_to_f64(long long o)
 
 __device__ __forceinline__ void load_value(const value_op& op, int64_t e, long long& iv, unsigned long long& uv, double& fv)
 {
+  // values are streamed once: evict-first loads keep the group table and accumulators L2-resident
   switch (op.src_type) {
-    case B2_INT8: iv = static_cast<const int8_t*>(op.src)[e]; break;
-    case B2_INT16: iv = static_cast<const int16_t*>(op.src)[e]; break;
-    case B2_INT32: iv = static_cast<const int32_t*>(op.src)[e]; break;
-    case B2_INT64: iv = static_cast<const int64_t*>(op.src)[e]; break;
-    case B2_UINT8: uv = static_cast<const uint8_t*>(op.src)[e]; iv = (long long)uv; break;
-    case B2_UINT16: uv = static_cast<const uint16_t*>(op.src)[e]; iv = (long long)uv; break;
-    case B2_UINT32: uv = static_cast<const uint32_t*>(op.src)[e]; iv = (long long)uv; break;
-    case B2_UINT64: uv = static_cast<const uint64_t*>(op.src)[e]; iv = (long long)uv; break;
-    case B2_BOOL8: uv = static_cast<const uint8_t*>(op.src)[e] != 0; iv = (long long)uv; break;
-    case B2_FLOAT32: fv = static_cast<const float*>(op.src)[e]; break;
-    default: fv = static_cast<const double*>(op.src)[e]; break;
+    case B2_INT8: iv = __ldcs(static_cast<const signed char*>(op.src) + e); break;
+    case B2_INT16: iv = __ldcs(static_cast<const short*>(op.src) + e); break;
+    case B2_INT32: iv = __ldcs(static_cast<const int*>(op.src) + e); break;
+    case B2_INT64: iv = __ldcs(static_cast<const long long*>(op.src) + e); break;
+    case B2_UINT8: uv = __ldcs(static_cast<const unsigned char*>(op.src) + e); iv = (long long)uv; break;
+    case B2_UINT16: uv = __ldcs(static_cast<const unsigned short*>(op.src) + e); iv = (long long)uv; break;
+    case B2_UINT32: uv = __ldcs(static_cast<const unsigned int*>(op.src) + e); iv = (long long)uv; break;
+    case B2_UINT64: uv = __ldcs(static_cast<const unsigned long long*>(op.src) + e); iv = (long long)uv; break;
+    case B2_BOOL8: uv = __ldcs(static_cast<const unsigned char*>(op.src) + e) != 0; iv = (long long)uv; break;
+    case B2_FLOAT32: fv = __ldcs(static_cast<const float*>(op.src) + e); break;
+    default: fv = __ldcs(static_cast<const double*>(op.src) + e); break;
   }
 }
 
@@ -119,14 +120,20 @@ __global__ void __launch_bounds__(256) groupby_kernel(key_cols kc, int64_t n, bo
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   slot_t empty;
   memset(&empty, 0xff, sizeof(empty));
-  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
-    if (*reinterpret_cast<volatile unsigned int*>(&ctl->overflow)) return;  // table too small: host will grow it
+  int iter = 0;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride, ++iter) {
+    // table too small -> the host grows it and reruns. Polled rarely: a per-row volatile read of one
+    // word turned a single L2 slice into the bottleneck (49 ms -> see profiles/r1_notes.md).
+    if ((iter & 63) == 0 && *reinterpret_cast<volatile unsigned int*>(&ctl->overflow)) return;
     uint64_t key;
     uint32_t nb;
     pack_row(kc, r, key, nb);
     if (skip_null_keys && nb) continue;
     uint32_t i = slot_hash(key, nb, mask);
+    int probes = 0;
     while (true) {
+      // a full table (overflow in progress) must not trap the probe loop
+      if (((++probes) & 127) == 0 && *reinterpret_cast<volatile unsigned int*>(&ctl->overflow)) return;
       // cheap read first: most rows find their group already present
       slot_t cur = load_slot_volatile(&table[i]);
       if (cur.row == -1) {

@@ -38,10 +38,10 @@ __device__ __forceinline__ void pack_row(const key_cols& kc, int64_t r, uint64_t
     const bool valid = kc.mask[c] == nullptr || bit_is_set(kc.mask[c], e);
     if (valid) {
       switch (w) {
-        case 1: bits = static_cast<const uint8_t*>(kc.data[c])[e]; break;
-        case 2: bits = static_cast<const uint16_t*>(kc.data[c])[e]; break;
+        case 1: bits = __ldcs(static_cast<const uint8_t*>(kc.data[c]) + e); break;  // streamed once: evict-first
+        case 2: bits = __ldcs(static_cast<const uint16_t*>(kc.data[c]) + e); break;
         case 4: {
-          uint32_t b = static_cast<const uint32_t*>(kc.data[c])[e];
+          uint32_t b = __ldcs(static_cast<const uint32_t*>(kc.data[c]) + e);
           if (kc.is_float[c]) {
             if ((b << 1) == 0) b = 0;                                // -0 -> +0
             else if ((b & 0x7fffffffu) > 0x7f800000u) b = 0x7fc00000u;  // canonical NaN
@@ -50,7 +50,7 @@ __device__ __forceinline__ void pack_row(const key_cols& kc, int64_t r, uint64_t
           break;
         }
         default: {
-          uint64_t b = static_cast<const uint64_t*>(kc.data[c])[e];
+          uint64_t b = __ldcs(reinterpret_cast<const unsigned long long*>(kc.data[c]) + e);
           if (kc.is_float[c]) {
             if ((b << 1) == 0) b = 0;
             else if ((b & 0x7fffffffffffffffull) > 0x7ff0000000000000ull) b = 0x7ff8000000000000ull;

@@ -337,7 +337,7 @@ std::unique_ptr<b2_scalar> reduce(const b2_column_view& col, int32_t kind, int32
 // ------------------------------------------------------------------------------------------------
 namespace {
 
-constexpr int SC_THREADS = 256;
+constexpr int SC_THREADS = 512;
 constexpr int SC_K       = 4;  // 16-byte vectors per lane per tile
 
 __device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v)
@@ -351,12 +351,30 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p)
   return v;
 }
 
+// One 16-byte record per tile: {flag (0 nothing, 1 aggregate, 2 inclusive), pad, 8-byte value}. A 16-byte
+// aligned store is observed all-or-nothing by a 16-byte load, so the look-back needs no fences.
 struct scan_state {
-  uint32_t* flags;      // 0 not ready, 1 aggregate, 2 inclusive
-  void* agg;            // T[num_tiles]
-  void* incl;           // T[num_tiles]
+  uint4* rec;
   uint32_t* ticket;
 };
+template <typename T>
+__device__ __forceinline__ void publish_rec(uint4* p, uint32_t flag, T v)
+{
+  unsigned long long bits = 0;
+  memcpy(&bits, &v, sizeof(T));
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(flag), "r"(0u), "r"((uint32_t)bits),
+               "r"((uint32_t)(bits >> 32))
+               : "memory");
+}
+template <typename T>
+__device__ __forceinline__ uint32_t read_rec(const uint4* p, T& v)
+{
+  uint4 r;
+  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  unsigned long long bits = (unsigned long long)r.z | ((unsigned long long)r.w << 32);
+  memcpy(&v, &bits, sizeof(T));
+  return r.x;
+}
 
 // valid bits of rows [r, r+cnt) (cnt <= 16) at absolute bit position
 __device__ __forceinline__ uint32_t valid_bits_at(const uint32_t* mask, int64_t bit, int64_t last_word)
@@ -435,37 +453,27 @@ __global__ void __launch_bounds__(SC_THREADS) scan_kernel(const T* __restrict__ 
     T block_tot = s_wtot[0];
 #pragma unroll
     for (int w = 1; w < NW; ++w) block_tot = B::apply(block_tot, s_wtot[w]);
-    T* agg  = static_cast<T*>(st.agg);
-    T* incl = static_cast<T*>(st.incl);
     if (tile == 0) {
       if (lane == 0) {
-        incl[0] = block_tot;
-        st_release_u32(st.flags, 2u);
+        publish_rec<T>(st.rec, 2u, block_tot);
         s_prefix = B::identity();
       }
     } else {
-      if (lane == 0) {
-        agg[tile] = block_tot;
-        st_release_u32(st.flags + tile, 1u);
-      }
+      if (lane == 0) publish_rec<T>(st.rec + tile, 1u, block_tot);
       T excl = B::identity();
       int64_t base = tile - 1;
       while (true) {
         const int64_t idx = base - lane;
         uint32_t f = 2u;  // tiles before the first one act as an inclusive identity
-        if (idx >= 0) f = ld_acquire_u32(st.flags + idx);
+        T c = B::identity();
+        if (idx >= 0) f = read_rec<T>(st.rec + idx, c);
         // all lanes must be ready before we can fold the window
         while (__any_sync(0xffffffffu, f == 0u)) {
-          if (f == 0u) f = ld_acquire_u32(st.flags + idx);
+          if (f == 0u) f = read_rec<T>(st.rec + idx, c);
         }
         const unsigned incl_mask = __ballot_sync(0xffffffffu, f == 2u);
         const int first = incl_mask ? (__ffs(incl_mask) - 1) : 32;
-        T c = B::identity();
-        if (idx >= 0) {
-          if (lane < first) c = static_cast<volatile T*>(agg)[idx];
-          else if (lane == first) c = static_cast<volatile T*>(incl)[idx];
-        }
-        // fold in predecessor order: farther tiles first (matters only for float rounding)
+        if (lane > first) c = B::identity();
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) c = B::apply(__shfl_xor_sync(0xffffffffu, c, o), c);
         excl = B::apply(c, excl);
@@ -473,8 +481,7 @@ __global__ void __launch_bounds__(SC_THREADS) scan_kernel(const T* __restrict__ 
         base -= 32;
       }
       if (lane == 0) {
-        incl[tile] = B::apply(excl, block_tot);
-        st_release_u32(st.flags + tile, 2u);
+        publish_rec<T>(st.rec + tile, 2u, B::apply(excl, block_tot));
         s_prefix = excl;
       }
     }
@@ -520,15 +527,11 @@ void launch_scan(const T* in, const uint32_t* mask, int64_t bit_offset, int64_t 
   constexpr int V = 16 / sizeof(T);
   constexpr int64_t TILE = (int64_t)32 * V * SC_K * (SC_THREADS / 32);
   const int64_t ntiles = (n + TILE - 1) / TILE;
-  const size_t flag_bytes = (sizeof(uint32_t) * (ntiles + 1) + 255) / 256 * 256;
-  const size_t val_bytes  = (sizeof(T) * ntiles + 255) / 256 * 256;
-  dbuf work(flag_bytes + 2 * val_bytes, stream);
-  B2_CUDA_TRY(cudaMemsetAsync(work.ptr, 0, flag_bytes, stream));
+  dbuf work(sizeof(uint4) * (ntiles + 1), stream);
+  B2_CUDA_TRY(cudaMemsetAsync(work.ptr, 0, work.bytes, stream));
   scan_state st;
-  st.flags  = work.as<uint32_t>();
-  st.ticket = work.as<uint32_t>() + ntiles;
-  st.agg    = static_cast<char*>(work.ptr) + flag_bytes;
-  st.incl   = static_cast<char*>(work.ptr) + flag_bytes + val_bytes;
+  st.rec    = work.as<uint4>();
+  st.ticket = reinterpret_cast<uint32_t*>(work.as<uint4>() + ntiles);
   const bool aligned = in == nullptr || (reinterpret_cast<uintptr_t>(in) & 15) == 0;
   B2_LAUNCH((scan_kernel<T, OP, COUNT>), (unsigned)ntiles, SC_THREADS, 0, stream, in, mask, bit_offset, n, exclusive, aligned,
             out, st);

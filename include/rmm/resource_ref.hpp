@@ -1,0 +1,3 @@
+// rmm/resource_ref.hpp stand-in — see cudf/detail/b2_bridge.hpp
+#pragma once
+#include "../cudf/detail/b2_bridge.hpp"
