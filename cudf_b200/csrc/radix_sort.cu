@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(512) histogram_kernel(const UK* __restrict__ k
 // (implicit indices), 0 keys already twiddled in buffer A with explicit indices in idx buffer
 // `pre_idx_buf`.
 __global__ void plan_kernel(const uint32_t* __restrict__ ghist, int npass, uint32_t n, int raw, int pre_idx_buf,
-                            sort_ctl* ctl)
+                            sort_ctl* ctl, int first_pass, int last_pass)
 {
   __shared__ uint32_t warp_tot[8];
   __shared__ int triv[8];
@@ -192,7 +192,7 @@ __global__ void plan_kernel(const uint32_t* __restrict__ ghist, int npass, uint3
     uint32_t c = ghist[p * RADIX + d];
     if (d == 0) triv[p] = 0;
     __syncthreads();
-    if (c == n) triv[p] = 1;
+    if (c == n || p < first_pass || p > last_pass) triv[p] = 1;  // passes outside [first,last] are skipped
     uint32_t inc = warp_inclusive_sum(c);
     if ((d & 31) == 31) warp_tot[d >> 5] = inc;
     __syncthreads();
@@ -252,7 +252,7 @@ struct pass_args {
   int32_t kind;             // key_kind for raw loads / keys-only untwiddle
   int32_t pairs;            // 1: (key, idx) ; 0: keys only
   uint64_t desc_mask;
-  int32_t pre_n_is_dynamic; // unused
+  int32_t keep_keys;        // pairs mode: also write the keys in the last executed pass (partial sorts)
 };
 
 __device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v)
@@ -534,7 +534,7 @@ __global__ void __launch_bounds__(THREADS + 32 * LBW, MINB) onesweep_kernel(pass
   }
   __syncthreads();  // (S4) keys staged, scatter offsets ready
 
-  const bool write_keys = !(a.pairs && pl.last);
+  const bool write_keys = !(a.pairs && pl.last) || a.keep_keys;
   UK* kdst = static_cast<UK*>(const_cast<void*>(pl.key_dst == 1 ? a.key_bufs[1] : a.key_bufs[2]));
   uint32_t dst[IPT];
 #pragma unroll
@@ -572,6 +572,7 @@ __global__ void finalize_kernel(pass_args a, int64_t n, int raw, int pre_idx_buf
     if (a.pairs) {
       if (raw) a.idx_bufs[0][i] = (int32_t)i;
       else if (pre_idx_buf != 0) a.idx_bufs[0][i] = a.idx_bufs[1][i];
+      if (a.keep_keys && raw) static_cast<UK*>(const_cast<void*>(a.key_bufs[1]))[i] = static_cast<const UK*>(a.key_bufs[0])[i];
     } else {
       // keys-only (always raw): copy input to output
       static_cast<UK*>(const_cast<void*>(a.key_bufs[1]))[i] = static_cast<const UK*>(a.key_bufs[0])[i];
@@ -727,7 +728,8 @@ int64_t portion_limit()
 //  pairs: idx_out receives the permutation ; keys-only: bufA is the OUTPUT, bufB the temp.
 template <typename UK, int T, int I, int MINB>
 void run_radix_cfg(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int32_t* idx_tmp, int32_t* idx_tmp2, int pre_idx_buf, int64_t n,
-                   int kind, bool descending, bool pairs, cudaStream_t stream)
+                   int kind, bool descending, bool pairs, cudaStream_t stream, int first_pass = 0, int last_pass = 7,
+                   bool keep_keys = false)
 {
   constexpr int NP = sizeof(UK);
   constexpr int TILE = T * I;
@@ -758,7 +760,7 @@ void run_radix_cfg(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int
     B2_LAUNCH((histogram_kernel<UK>), grid, 512, 0, stream, raw ? raw_keys : bufA, n, raw ? 1 : 0, kind, desc_mask, ghist,
               (raw && kind == (int)key_kind::FLOAT) ? &ctl->nan_count : nullptr);
   }
-  B2_LAUNCH(plan_kernel, 1, RADIX, 0, stream, ghist, NP, (uint32_t)n, raw ? 1 : 0, pre_idx_buf, ctl);
+  B2_LAUNCH(plan_kernel, 1, RADIX, 0, stream, ghist, NP, (uint32_t)n, raw ? 1 : 0, pre_idx_buf, ctl, first_pass, last_pass);
 
   static bool attr_set = [] {
     cudaFuncSetAttribute(onesweep_kernel<UK, T, I, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -777,8 +779,9 @@ void run_radix_cfg(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int
   a.ctl = ctl;
   a.kind = kind;
   a.pairs = pairs ? 1 : 0;
+  a.keep_keys = keep_keys ? 1 : 0;
   a.desc_mask = (uint64_t)desc_mask;
-  for (int p = 0; p < NP; ++p) {
+  for (int p = std::max(0, first_pass); p < NP && p <= last_pass; ++p) {
     for (int64_t q = 0; q < nportions; ++q) {
       const int64_t start = q * plim;
       const int64_t pn = std::min(plim, n - start);
@@ -838,6 +841,20 @@ void run_radix(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int32_t
   }
 #undef B2_RUN
 }
+
+}  // namespace
+
+// Stable partial sort of n 64-bit keys by their two most significant bytes (passes 6 and 7 only):
+// keys_out / idx_out receive the keys and their original positions grouped by the 16-bit prefix.
+// Used by the hash join to make build and probe walk the table region by region (L2 locality).
+void radix_partition_top16(const uint64_t* keys_in, int64_t n, uint64_t* keys_out, int32_t* idx_out, cudaStream_t stream)
+{
+  dbuf b(sizeof(uint64_t) * n, stream), it(sizeof(int32_t) * n, stream);
+  run_radix_cfg<uint64_t, 384, 16, 2>(keys_in, keys_out, b.as<uint64_t>(), idx_out, it.as<int32_t>(), nullptr, 0, n,
+                                      (int)key_kind::UNSIGNED, false, true, stream, 6, 7, true);
+}
+
+namespace {
 
 int kind_of(int32_t storage_id)
 {
