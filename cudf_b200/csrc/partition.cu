@@ -142,6 +142,21 @@ __global__ void __launch_bounds__(256) dest_kernel(const uint8_t* __restrict__ i
   }
 }
 
+struct dest_table {
+  void* ptr[128];            // destination base address per bucket
+  uint32_t bucket_start[128];  // global start of the bucket in the plan's dest numbering
+};
+template <typename T>
+__global__ void __launch_bounds__(256) scatter_to_kernel(const T* __restrict__ in, const uint8_t* __restrict__ ids,
+                                                         const int32_t* __restrict__ dest, int64_t n, dest_table dt)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int b = ids[i];
+    static_cast<T*>(dt.ptr[b])[(uint32_t)dest[i] - dt.bucket_start[b]] = ld_stream(in + i);
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) scatter_kernel(const T* __restrict__ in, const int32_t* __restrict__ dest, int64_t n,
                                                       T* __restrict__ out)
@@ -237,3 +252,140 @@ extern "C" b2_status b2_partition(const b2_table_view* input, const b2_column_vi
   }
   return B2_OK;
 }
+
+// ---- two-phase partition (plan + scatter to arbitrary destinations) and CUDA-IPC buffers --------------------
+struct b2_partition_plan {
+  int64_t n = 0;
+  int32_t P = 0;
+  b2::dbuf ids, dest;
+  uint32_t bucket_start[257] = {0};
+};
+
+namespace b2 {
+static std::unique_ptr<b2_partition_plan> make_plan(const b2_column_view& keys, int mode, const void* splitters, int P,
+                                                    int64_t* out_counts, cudaStream_t stream)
+{
+  B2_EXPECTS(P >= 1 && P <= 128, B2_ERR_INVALID_ARGUMENT, "num_partitions must be in [1, 128]");
+  B2_EXPECTS(!has_nulls(keys), B2_ERR_INVALID_ARGUMENT, "partition key column must not contain nulls");
+  B2_EXPECTS(mode == 1 || P == 1 || splitters != nullptr, B2_ERR_INVALID_ARGUMENT, "range partition needs splitters");
+  auto plan = std::make_unique<b2_partition_plan>();
+  const int64_t n = keys.size;
+  plan->n = n;
+  plan->P = P;
+  for (int b = 0; b <= P; ++b) plan->bucket_start[b] = 0;
+  if (n == 0) {
+    for (int b = 0; b < P; ++b) out_counts[b] = 0;
+    return plan;
+  }
+  const int64_t ntiles = (n + PT_TILE - 1) / PT_TILE;
+  plan->ids  = dbuf(n, stream);
+  plan->dest = dbuf(sizeof(int32_t) * n, stream);
+  dbuf totals(sizeof(unsigned long long) * 256, stream), tile_counts(sizeof(uint32_t) * ntiles * P, stream);
+  B2_CUDA_TRY(cudaMemsetAsync(totals.ptr, 0, totals.bytes, stream));
+  const int sid  = storage_type(keys.type_id);
+  const int kind = is_float_id(sid) ? (int)key_kind::FLOAT : (is_signed_id(sid) ? (int)key_kind::SIGNED : (int)key_kind::UNSIGNED);
+  {
+    prof_scope ps("partition_bucket", stream);
+    const unsigned grid = (unsigned)ntiles;
+    switch (type_width(keys.type_id)) {
+      case 1: B2_LAUNCH((bucket_kernel<uint8_t>), grid, 256, 0, stream, static_cast<const uint8_t*>(keys.data) + keys.offset, n, mode, kind, static_cast<const uint8_t*>(splitters), P, plan->ids.as<uint8_t>(), tile_counts.as<uint32_t>()); break;
+      case 2: B2_LAUNCH((bucket_kernel<uint16_t>), grid, 256, 0, stream, static_cast<const uint16_t*>(keys.data) + keys.offset, n, mode, kind, static_cast<const uint16_t*>(splitters), P, plan->ids.as<uint8_t>(), tile_counts.as<uint32_t>()); break;
+      case 4: B2_LAUNCH((bucket_kernel<uint32_t>), grid, 256, 0, stream, static_cast<const uint32_t*>(keys.data) + keys.offset, n, mode, kind, static_cast<const uint32_t*>(splitters), P, plan->ids.as<uint8_t>(), tile_counts.as<uint32_t>()); break;
+      case 8: B2_LAUNCH((bucket_kernel<uint64_t>), grid, 256, 0, stream, static_cast<const uint64_t*>(keys.data) + keys.offset, n, mode, kind, static_cast<const uint64_t*>(splitters), P, plan->ids.as<uint8_t>(), tile_counts.as<uint32_t>()); break;
+      default: B2_FAIL(B2_ERR_DATA_TYPE, "partition: unsupported key type");
+    }
+  }
+  B2_LAUNCH(tile_scan_kernel, 1, 1024, 0, stream, tile_counts.as<uint32_t>(), ntiles, P, totals.as<unsigned long long>());
+  {
+    prof_scope ps("partition_dest", stream);
+    B2_LAUNCH(dest_kernel, (unsigned)ntiles, 256, 0, stream, plan->ids.as<uint8_t>(), n, P, tile_counts.as<uint32_t>(), plan->dest.as<int32_t>());
+  }
+  unsigned long long h[256];
+  B2_CUDA_TRY(cudaMemcpyAsync(h, totals.ptr, sizeof(unsigned long long) * 256, cudaMemcpyDeviceToHost, stream));
+  B2_CUDA_TRY(cudaStreamSynchronize(stream));
+  for (int b = 0; b < P; ++b) {
+    out_counts[b] = (int64_t)h[b];
+    plan->bucket_start[b + 1] = plan->bucket_start[b] + (uint32_t)h[b];
+  }
+  return plan;
+}
+}  // namespace b2
+
+extern "C" {
+
+b2_status b2_partition_plan_create(const b2_column_view* keys, int32_t mode, const void* splitters, int32_t num_partitions,
+                                   b2_stream stream, b2_partition_plan** out, int64_t* out_counts)
+{
+  try {
+    B2_EXPECTS(keys && out && out_counts, B2_ERR_INVALID_ARGUMENT, "null argument");
+    b2::validate_column(*keys);
+    *out = b2::make_plan(*keys, mode, splitters, num_partitions, out_counts, static_cast<cudaStream_t>(stream)).release();
+  } catch (const b2::error& e) { b2::set_last_error(e.what()); return e.code;
+  } catch (const std::exception& e) { b2::set_last_error(e.what()); return B2_ERR_LOGIC; }
+  return B2_OK;
+}
+
+b2_status b2_partition_scatter(const b2_partition_plan* plan, const b2_column_view* column, void* const* dest_ptrs, b2_stream stream)
+{
+  try {
+    B2_EXPECTS(plan && column && dest_ptrs, B2_ERR_INVALID_ARGUMENT, "null argument");
+    b2::validate_column(*column);
+    B2_EXPECTS(column->size == plan->n, B2_ERR_LOGIC, "Column size mismatch.");
+    B2_EXPECTS(!b2::has_nulls(*column), B2_ERR_INVALID_ARGUMENT, "b2_partition_scatter: nullable columns are not supported");
+    if (plan->n == 0) return B2_OK;
+    b2::dest_table dt{};
+    for (int b = 0; b < plan->P; ++b) { dt.ptr[b] = dest_ptrs[b]; dt.bucket_start[b] = plan->bucket_start[b]; }
+    const int64_t n = plan->n;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, b2::NUM_SMS_B200 * 16));
+    auto s = static_cast<cudaStream_t>(stream);
+    b2::prof_scope ps("partition_scatter_p2p", s);
+    switch (b2::type_width(column->type_id)) {
+      case 1: B2_LAUNCH((b2::scatter_to_kernel<uint8_t>), grid, 256, 0, s, static_cast<const uint8_t*>(column->data) + column->offset, plan->ids.as<uint8_t>(), plan->dest.as<int32_t>(), n, dt); break;
+      case 2: B2_LAUNCH((b2::scatter_to_kernel<uint16_t>), grid, 256, 0, s, static_cast<const uint16_t*>(column->data) + column->offset, plan->ids.as<uint8_t>(), plan->dest.as<int32_t>(), n, dt); break;
+      case 4: B2_LAUNCH((b2::scatter_to_kernel<uint32_t>), grid, 256, 0, s, static_cast<const uint32_t*>(column->data) + column->offset, plan->ids.as<uint8_t>(), plan->dest.as<int32_t>(), n, dt); break;
+      default: B2_LAUNCH((b2::scatter_to_kernel<uint64_t>), grid, 256, 0, s, static_cast<const uint64_t*>(column->data) + column->offset, plan->ids.as<uint8_t>(), plan->dest.as<int32_t>(), n, dt); break;
+    }
+  } catch (const b2::error& e) { b2::set_last_error(e.what()); return e.code;
+  } catch (const std::exception& e) { b2::set_last_error(e.what()); return B2_ERR_LOGIC; }
+  return B2_OK;
+}
+
+void b2_partition_plan_free(b2_partition_plan* plan) { delete plan; }
+
+b2_status b2_ipc_alloc(size_t bytes, void** out_ptr, uint8_t* out_handle64)
+{
+  try {
+    B2_EXPECTS(out_ptr && out_handle64, B2_ERR_INVALID_ARGUMENT, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    void* p = nullptr;
+    B2_CUDA_TRY(cudaMalloc(&p, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); B2_CUDA_TRY(e); }
+    memcpy(out_handle64, &h, 64);
+    *out_ptr = p;
+  } catch (const b2::error& e) { b2::set_last_error(e.what()); return e.code; }
+  return B2_OK;
+}
+b2_status b2_ipc_open(const uint8_t* handle64, void** out_ptr)
+{
+  try {
+    B2_EXPECTS(out_ptr && handle64, B2_ERR_INVALID_ARGUMENT, "null argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    B2_CUDA_TRY(cudaIpcOpenMemHandle(out_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  } catch (const b2::error& e) { b2::set_last_error(e.what()); return e.code; }
+  return B2_OK;
+}
+b2_status b2_ipc_close(void* ptr)
+{
+  try { if (ptr) B2_CUDA_TRY(cudaIpcCloseMemHandle(ptr)); } catch (const b2::error& e) { b2::set_last_error(e.what()); return e.code; }
+  return B2_OK;
+}
+b2_status b2_ipc_free(void* ptr)
+{
+  try { if (ptr) B2_CUDA_TRY(cudaFree(ptr)); } catch (const b2::error& e) { b2::set_last_error(e.what()); return e.code; }
+  return B2_OK;
+}
+
+}  // extern "C"

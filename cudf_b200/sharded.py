@@ -75,6 +75,37 @@ class CudaOps:
         res = plc.Table._from_handle(out.value)
         return [c.to_torch() for c in res.columns()], list(offs)
 
+    def partition_exchange(self, column: torch.Tensor, key: torch.Tensor, mode: int, splitters, group=None):
+        """Fused partition + all-to-all of ONE column over peer memory. Returns this rank's received rows (a view of
+        the exchange buffer, valid until the next call) or None when P2P is unavailable."""
+        plc, lib = self.plc, self._lib
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        kcol = plc.Column.from_torch(key)
+        kv = kcol._view()
+        plan = C.c_void_p()
+        counts = (C.c_int64 * world)()
+        sp = C.c_void_p(splitters.data_ptr()) if splitters is not None and splitters.numel() else None
+        lib.check(lib.lib.b2_partition_plan_create(C.byref(kv), mode, sp, world, lib.stream_arg(None), C.byref(plan), counts))
+        try:
+            mine = torch.tensor(list(counts), dtype=torch.int64, device=key.device)
+            allc = torch.empty(world * world, dtype=torch.int64, device=key.device)
+            dist.all_gather_into_tensor(allc, mine, group=group)
+            cm = allc.view(world, world).cpu()                      # cm[r][d] = rows rank r sends to rank d
+            recv_total = int(cm[:, rank].sum())
+            max_recv = int(cm.sum(dim=0).max())
+            esz = column.element_size()
+            ex = PeerExchange.get(lib, int(max(max_recv, key.numel()) * esz * 1.05) + (1 << 20), group)
+            my_off = cm[:rank, :].sum(dim=0)                          # rows written before mine in each destination
+            dest = (C.c_void_p * world)(*[ex.peer_ptrs[d] + int(my_off[d]) * esz for d in range(world)])
+            dist.barrier(group=group)                                 # peers are done reading the previous contents
+            ccol = plc.Column.from_torch(column)
+            cv = ccol._view()
+            lib.check(lib.lib.b2_partition_scatter(plan, C.byref(cv), dest, lib.stream_arg(None)))
+            dist.barrier(group=group)                                 # stream-ordered after the scatter: all buckets landed
+            return ex.view(recv_total, column.dtype)
+        finally:
+            lib.lib.b2_partition_plan_free(plan)
+
     def sort_by_key(self, values: torch.Tensor, keys: torch.Tensor) -> torch.Tensor:
         plc = self.plc
         out = plc.sorting.sort_by_key(plc.Table([plc.Column.from_torch(values)]), plc.Table([plc.Column.from_torch(keys)]),
@@ -86,6 +117,53 @@ class CudaOps:
         l, r = plc.join.inner_join(plc.Table([plc.Column.from_torch(left)]), plc.Table([plc.Column.from_torch(right)]),
                                    plc.NullEquality.EQUAL)
         return l.to_torch(), r.to_torch()
+
+
+class PeerExchange:
+    """Receive buffers mapped into every peer with CUDA IPC (b2_ipc_*): the partition scatter kernel writes each
+    bucket directly into its destination GPU's buffer over NVLink, so partition + all-to-all is ONE kernel
+    (plus a barrier) instead of scatter -> NCCL send/recv -> copy.  One instance per (group, capacity); reused
+    across calls."""
+
+    _cache: dict = {}
+
+    def __init__(self, lib, capacity_bytes: int, group=None):
+        self._lib, self.capacity, self.group = lib, int(capacity_bytes), group
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        ptr = C.c_void_p()
+        handle = (C.c_uint8 * 64)()
+        lib.check(lib.lib.b2_ipc_alloc(self.capacity, C.byref(ptr), handle))
+        self.local_ptr = ptr.value
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device="cuda")
+        allh = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allh, mine, group=group)
+        self.peer_ptrs = []
+        for r in range(world):
+            if r == rank:
+                self.peer_ptrs.append(self.local_ptr)
+                continue
+            hb = (C.c_uint8 * 64)(*allh[r].cpu().tolist())
+            p = C.c_void_p()
+            lib.check(lib.lib.b2_ipc_open(hb, C.byref(p)))
+            self.peer_ptrs.append(p.value)
+        dist.barrier(group=group)
+
+    @classmethod
+    def get(cls, lib, capacity_bytes: int, group=None) -> "PeerExchange":
+        key = (id(group), dist.get_world_size(group))
+        cur = cls._cache.get(key)
+        if cur is None or cur.capacity < capacity_bytes:
+            cur = cls(lib, capacity_bytes, group)  # a larger buffer replaces the cached one (the old mapping stays alive)
+            cls._cache[key] = cur
+        return cur
+
+    def view(self, nelems: int, dtype: torch.dtype) -> torch.Tensor:
+        import numpy as np
+
+        from .pylibcudf.column import DeviceSpan
+
+        npdt = np.dtype(str(dtype).replace("torch.", ""))
+        return torch.as_tensor(DeviceSpan(self.local_ptr, nelems, npdt, self), device="cuda")
 
 
 def _exchange(buckets: torch.Tensor, offsets, group=None) -> torch.Tensor:
@@ -127,12 +205,18 @@ def sort_by_key_sharded(values: torch.Tensor, keys: torch.Tensor, ops=None, grou
         list(gathered.view(world, -1).unbind(0)), sample, group=group)
     splitters = choose_splitters(ops.sort_keys(gathered), world)
     same = values.data_ptr() == keys.data_ptr() and values.numel() == keys.numel()
-    ph.mark("partition")
-    cols, offsets = ops.partition([keys] if same else [keys, values], keys, 0, splitters, world)
-    ph.mark("exchange")
-    rk = _exchange(cols[0], offsets, group)
-    rv = rk if same else _exchange(cols[1], offsets, group)
-    del cols
+    use_p2p = same and keys.is_cuda and hasattr(ops, "partition_exchange") and os.environ.get("B2_SHARD_P2P", "1") == "1"
+    if use_p2p:
+        ph.mark("partition+exchange(p2p)")
+        rk = ops.partition_exchange(keys, keys, 0, splitters, group)
+        rv = rk
+    else:
+        ph.mark("partition")
+        cols, offsets = ops.partition([keys] if same else [keys, values], keys, 0, splitters, world)
+        ph.mark("exchange")
+        rk = _exchange(cols[0], offsets, group)
+        rv = rk if same else _exchange(cols[1], offsets, group)
+        del cols
     ph.mark("local_sort")
     out = ops.sort_by_key(rv, rk)
     ph.done("sort_by_key_sharded")

@@ -242,6 +242,24 @@ B2_API b2_status b2_partition(const b2_table_view* input, const b2_column_view* 
                               const void* splitters, int32_t num_partitions, b2_stream stream,
                               b2_table** out, int32_t* out_offsets);
 
+/* Two-phase form of b2_partition for the fused partition + exchange: the plan holds the bucket id and the
+ * stable in-bucket rank of every row; out_counts[b] = rows of bucket b.  b2_partition_scatter then writes one
+ * fixed-width column straight to P destination base addresses — local buffers or PEER device memory mapped with
+ * b2_ipc_open — so that the all-to-all exchange happens inside the scatter kernel over NVLink
+ * (dest_ptrs[b] = address of bucket b's first row; host array of P device pointers). */
+typedef struct b2_partition_plan b2_partition_plan;
+B2_API b2_status b2_partition_plan_create(const b2_column_view* keys, int32_t mode, const void* splitters,
+                                          int32_t num_partitions, b2_stream stream, b2_partition_plan** out,
+                                          int64_t* out_counts);
+B2_API b2_status b2_partition_scatter(const b2_partition_plan* plan, const b2_column_view* column,
+                                      void* const* dest_ptrs, b2_stream stream);
+B2_API void      b2_partition_plan_free(b2_partition_plan* plan);
+/* CUDA-IPC exchange buffers (cudaMalloc + cudaIpcGetMemHandle / cudaIpcOpenMemHandle); handle = 64 bytes */
+B2_API b2_status b2_ipc_alloc(size_t bytes, void** out_ptr, uint8_t* out_handle64);
+B2_API b2_status b2_ipc_open(const uint8_t* handle64, void** out_ptr);
+B2_API b2_status b2_ipc_close(void* ptr);
+B2_API b2_status b2_ipc_free(void* ptr);
+
 /* ---- synthetic data (SURVEY §8d generator): x_i = splitmix64(seed + first + i) -------------- */
 /* kind 0: raw uint64 -> int64 ; 1: float64 uniform [0,1) ; 2: x mod modulus as int64 ;
  * 3: int32 low bits ; 4: validity bitmask words with P(valid)=0.5 (n = number of bits) */
