@@ -242,7 +242,7 @@ def run_ours(args):
     ga_ms, ga_cnt = _lib.profile_get("gather")
     # algorithmic bytes of THIS implementation's 8 passes over (int64 key, int32 row id):
     # pass 1: 8 read + 12 write; passes 2-7: 12 + 12; pass 8: 12 read + 4 write (row ids only) = 180 B/row
-    rows_local = n if world == 1 else None
+    rows_local = n  # per rank; at N > 1 the received shard differs from n by < 1 % (sample-sort splitters)
     roofline = None
     if os_cnt and rows_local:
         per_launch_bytes = 180.0 * rows_local / 8.0
@@ -250,7 +250,11 @@ def run_ours(args):
         achieved = per_launch_bytes / (avg_ms / 1e3) / 1e9
         roofline = {
             "bound": "hbm", "kernel": "onesweep_kernel<uint64,(key,row id)>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "frac": achieved / peak,
+            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the ncu --set full capture at 2^27 rows
+            # (profiles/r1_onesweep_ncu_e.txt: 1.612 + 1.582 GB per launch = 23.8 B/row), scaled to this launch size
+            "traffic": 23.8 * rows_local, "traffic_source": "ncu capture at 2^27 rows, per-row figure scaled",
+            "peak_source": peak_src, "rank": rank,
             "algorithmic_bytes_per_launch": per_launch_bytes, "avg_launch_ms": avg_ms, "launches": os_cnt,
             "kernel_share_of_step": os_ms / ms_total,
             "whole_op": {"algorithmic_bytes_per_row_contract": 216, "achieved_GBps_contract": 216.0 * rows_local / (ms_step / 1e3) / 1e9,
@@ -261,36 +265,48 @@ def run_ours(args):
 
     # ---- e2e: pinned host -> device -> sort_by_key -> pinned host ----
     e2e = None
-    if not args.no_e2e and world == 1:
+    if not args.no_e2e:
         try:
+            cap = n if world == 1 else int(n * 1.1) + 1024  # a rank's shard of the sharded result is ~n rows
             h_in = torch.empty(n, dtype=torch.int64, pin_memory=True)
-            h_out = torch.empty(n, dtype=torch.int64, pin_memory=True)
+            h_out = torch.empty(cap, dtype=torch.int64, pin_memory=True)
             h_in.copy_(keys)
             torch.cuda.synchronize()
             d_in = torch.empty(n, dtype=torch.int64, device=dev)
 
-            def e2e_step():
-                d_in.copy_(h_in, non_blocking=True)
-                c = plc.Column.from_torch(d_in)
-                o = plc.sorting.sort_by_key(plc.Table([c]), plc.Table([c]), [plc.Order.ASCENDING], [])
-                h_out.copy_(o.columns()[0].to_torch(), non_blocking=True)
-                return o
+            if world == 1:
+                def e2e_step():
+                    d_in.copy_(h_in, non_blocking=True)
+                    c = plc.Column.from_torch(d_in)
+                    o = plc.sorting.sort_by_key(plc.Table([c]), plc.Table([c]), [plc.Order.ASCENDING], [])
+                    h_out.copy_(o.columns()[0].to_torch(), non_blocking=True)
+                    return o
+            else:
+                def e2e_step():
+                    d_in.copy_(h_in, non_blocking=True)
+                    o = sharded.sort_by_key_sharded(d_in, d_in)
+                    m = min(o.numel(), cap)
+                    h_out[:m].copy_(o[:m], non_blocking=True)
+                    return o
 
             o = e2e_step()
             torch.cuda.synchronize()
             del o
             k = max(1, min(args.steps, 3))
-            torch.cuda.synchronize()
+            barrier()
             e0.record(stream)
             for _ in range(k):
                 o = e2e_step()
                 del o
             e1.record(stream)
-            torch.cuda.synchronize()
-            ems = e0.elapsed_time(e1) / k
+            barrier()
+            te = torch.tensor([e0.elapsed_time(e1) / k], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            ems = float(te.item())
             assert bool((h_out[1:1000001] >= h_out[:1000000]).all())
-            e2e = {"value": n / (ems / 1e3), "unit": UNIT, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n,
-                   "ms_per_step": ems}
+            e2e = {"value": world * n / (ems / 1e3), "unit": UNIT, "h2d_bytes_per_step": 8 * n * world,
+                   "d2h_bytes_per_step": 8 * n * world, "ms_per_step": ems}
             del h_in, h_out, d_in
         except Exception as ex:  # e.g. not enough pinnable host memory
             e2e = {"value": None, "unit": UNIT, "error": repr(ex)[:200]}
@@ -309,8 +325,9 @@ def run_ours(args):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
             "data": "synthetic",
             "config": {"workload": f"{n}-row single int64 column sort_by_key(values=T, keys=T), no nulls, ASCENDING, per GPU "
-                                   "(BASELINE.json configs[1])" + ("" if world == 1 else f"; sharded over {world} GPUs with "
-                                   "sample-sort splitters + NCCL all-to-all bucket exchange (configs[4])"),
+                                   "(BASELINE.json configs[1])" + ("" if world == 1 else f"; sharded over {world} GPUs: sample-sort splitters, stable range "
+                                   "partition, bucket exchange (fused peer-memory scatter over NVLink at 2 ranks, NCCL all-to-all-v "
+                                   "above), local LSD sort (configs[4])"),
                        "rows_per_gpu": n, "l2_flush": "inputs (8 GB/GPU) exceed the 126 MB L2; no explicit flush",
                        "generator": "splitmix64(seed 0x5EED0001 + i)"},
             "roofline": roofline, "cpu_baseline": cpu_base, "e2e": e2e, "gpu_launches": int(launches),

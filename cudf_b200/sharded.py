@@ -112,6 +112,26 @@ class CudaOps:
                                       [plc.Order.ASCENDING], [])
         return out.columns()[0].to_torch()
 
+    def reduce(self, col: torch.Tensor, kind: str) -> torch.Tensor:
+        plc = self.plc
+        c = plc.Column.from_torch(col)
+        agg = {"sum": plc.aggregation.sum, "min": plc.aggregation.min, "max": plc.aggregation.max}[kind]()
+        s = plc.reduce.reduce(c, agg, c.type())
+        return torch.tensor(s.to_py(), dtype=col.dtype, device=col.device)
+
+    def groupby_sum_count(self, keys: torch.Tensor, values: torch.Tensor):
+        plc = self.plc
+        gb = plc.groupby.GroupBy(plc.Table([plc.Column.from_torch(keys)]))
+        k, res = gb.aggregate([plc.groupby.GroupByRequest(plc.Column.from_torch(values), [plc.aggregation.sum(), plc.aggregation.count()])])
+        return k.columns()[0].to_torch(), res[0].columns()[0].to_torch(), res[0].columns()[1].to_torch()
+
+    def groupby_merge(self, keys: torch.Tensor, sums: torch.Tensor, counts: torch.Tensor):
+        plc = self.plc
+        gb = plc.groupby.GroupBy(plc.Table([plc.Column.from_torch(keys)]))
+        k, res = gb.aggregate([plc.groupby.GroupByRequest(plc.Column.from_torch(sums), [plc.aggregation.sum()]),
+                               plc.groupby.GroupByRequest(plc.Column.from_torch(counts), [plc.aggregation.sum()])])
+        return k.columns()[0].to_torch(), res[0].columns()[0].to_torch(), res[1].columns()[0].to_torch()
+
     def inner_join(self, left: torch.Tensor, right: torch.Tensor):
         plc = self.plc
         l, r = plc.join.inner_join(plc.Table([plc.Column.from_torch(left)]), plc.Table([plc.Column.from_torch(right)]),
@@ -205,7 +225,13 @@ def sort_by_key_sharded(values: torch.Tensor, keys: torch.Tensor, ops=None, grou
         list(gathered.view(world, -1).unbind(0)), sample, group=group)
     splitters = choose_splitters(ops.sort_keys(gathered), world)
     same = values.data_ptr() == keys.data_ptr() and values.numel() == keys.numel()
-    use_p2p = same and keys.is_cuda and hasattr(ops, "partition_exchange") and os.environ.get("B2_SHARD_P2P", "1") == "1"
+    # Peer-memory scatter vs NCCL: measured on B200 boxes (profiles/r1_multi_gpu.md) the fused scatter wins at
+    # 2 ranks (9.6 ms vs 6.8 + 11.5 ms per 5e8 rows) but at 8 ranks a warp's 32 rows split into ~4-row (32 B)
+    # segments per peer and NVLink runs at ~60 GB/s (114 ms per 1e9 rows), so larger groups use the partition +
+    # NCCL all-to-all-v path until the scatter stages per-peer runs in shared memory. B2_SHARD_P2P=0/1 forces it.
+    p2p_env = os.environ.get("B2_SHARD_P2P", "")
+    p2p_default = world <= 2
+    use_p2p = same and keys.is_cuda and hasattr(ops, "partition_exchange") and (p2p_env == "1" or (p2p_env == "" and p2p_default))
     if use_p2p:
         ph.mark("partition+exchange(p2p)")
         rk = ops.partition_exchange(keys, keys, 0, splitters, group)
@@ -246,3 +272,39 @@ def inner_join_sharded(left_keys: torch.Tensor, right_keys: torch.Tensor, ops=No
     rk, rg = shuffle(right_keys)
     li, ri = ops.inner_join(lk, rk)
     return lg[li.long()], rg[ri.long()]
+
+
+def reduce_sharded(col: torch.Tensor, kind: str = "sum", ops=None, group=None):
+    """local reduce + all_reduce of one scalar per rank (kind: sum | min | max)."""
+    ops = ops or CudaOps()
+    local = ops.reduce(col, kind)  # 0-d tensor on the column's device
+    op = {"sum": dist.ReduceOp.SUM, "min": dist.ReduceOp.MIN, "max": dist.ReduceOp.MAX}[kind]
+    out = local.clone().reshape(1)
+    if dist.get_world_size(group) > 1:
+        dist.all_reduce(out, op=op, group=group)
+    return out[0]
+
+
+def groupby_sum_count_sharded(keys: torch.Tensor, values: torch.Tensor, ops=None, group=None):
+    """SURVEY 8e groupby: pre-aggregate locally (<= G rows), all_gather the partials (G is small), merge locally.
+    Returns (group keys, sums, counts), identical on every rank, in arbitrary group order."""
+    ops = ops or CudaOps()
+    world = dist.get_world_size(group)
+    k, s, c = ops.groupby_sum_count(keys, values)
+    if world == 1:
+        return k, s, c
+    n = torch.tensor([k.numel()], dtype=torch.int64, device=k.device)
+    sizes = [torch.empty_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(x.item()) for x in sizes]
+    m = max(sizes + [1])
+
+    def gather_var(t):
+        pad = torch.zeros(m, dtype=t.dtype, device=t.device)
+        pad[: t.numel()] = t
+        parts = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(parts, pad, group=group)
+        return torch.cat([p[:sz] for p, sz in zip(parts, sizes)])
+
+    ak, as_, ac = gather_var(k), gather_var(s), gather_var(c.to(torch.int64))
+    return ops.groupby_merge(ak, as_, ac)

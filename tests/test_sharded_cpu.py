@@ -34,6 +34,18 @@ class NumpyOps:
     def sort_by_key(self, values, keys):
         return torch.from_numpy(values.numpy()[np.argsort(keys.numpy(), kind="stable")])
 
+    def reduce(self, col, kind):
+        return getattr(col, kind)()
+
+    def groupby_sum_count(self, keys, values):
+        k, inv = np.unique(keys.numpy(), return_inverse=True)
+        return torch.from_numpy(k), torch.from_numpy(np.bincount(inv, weights=values.numpy(), minlength=len(k))), torch.from_numpy(np.bincount(inv, minlength=len(k)))
+
+    def groupby_merge(self, keys, sums, counts):
+        k, inv = np.unique(keys.numpy(), return_inverse=True)
+        return (torch.from_numpy(k), torch.from_numpy(np.bincount(inv, weights=sums.numpy(), minlength=len(k))),
+                torch.from_numpy(np.bincount(inv, weights=counts.numpy(), minlength=len(k)).astype(np.int64)))
+
     def inner_join(self, left, right):
         from oracle import join as ojoin
 
@@ -64,7 +76,12 @@ def _worker(rank, world, port, q):
         lk = torch.from_numpy(rng.integers(0, 5000, 3000))
         rk = torch.from_numpy(rng.integers(0, 5000, 2000))
         jl, jr = sharded.inner_join_sharded(lk, rk, ops=NumpyOps())
-        q.put((rank, keys.numpy(), out.numpy(), vals.numpy(), out2.numpy(), lk.numpy(), rk.numpy(), jl.numpy(), jr.numpy()))
+        gk = torch.from_numpy(rng.integers(0, 50, 4000))
+        gv = torch.from_numpy(rng.standard_normal(4000))
+        mk, ms, mc = sharded.groupby_sum_count_sharded(gk, gv, ops=NumpyOps())
+        tot = sharded.reduce_sharded(gv, "sum", ops=NumpyOps())
+        q.put((rank, keys.numpy(), out.numpy(), vals.numpy(), out2.numpy(), lk.numpy(), rk.numpy(), jl.numpy(), jr.numpy(),
+               gk.numpy(), gv.numpy(), mk.numpy(), ms.numpy(), mc.numpy(), float(tot)))
     finally:
         dist.destroy_process_group()
 
@@ -111,3 +128,12 @@ def test_sharded_sort_and_join_gloo(tmp_path, monkeypatch):
     el, er = ojoin.inner_join([(L, None)], [(R, None)])
     gl, gr = ojoin.canonical(jl, jr)
     assert np.array_equal(gl, el) and np.array_equal(gr, er)
+    # groupby / reduce: every rank holds the merged result
+    GK = np.concatenate([r[9] for r in res]); GV = np.concatenate([r[10] for r in res])
+    uk, inv = np.unique(GK, return_inverse=True)
+    for r in res:
+        o = np.argsort(r[11])
+        assert np.array_equal(r[11][o], uk)
+        np.testing.assert_allclose(r[12][o], np.bincount(inv, weights=GV), rtol=1e-9)
+        assert np.array_equal(r[13][o], np.bincount(inv))
+        np.testing.assert_allclose(r[14], GV.sum(), rtol=1e-9)

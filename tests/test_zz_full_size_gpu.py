@@ -1,0 +1,93 @@
+"""BASELINE.json full sizes (1e9 rows) on one B200: size-independent properties instead of an oracle comparison
+(SURVEY §8c "Large-N parity").  Runs last (file name) because each case moves tens of GB."""
+import ctypes as C
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+N = 1_000_000_000
+
+
+def _fill(_lib, t, n, stream_id, kind=0, modulus=0):
+    _lib.check(_lib.lib.b2_fill_splitmix64(C.c_void_p(t.data_ptr()), n, 0x5EED0001, stream_id << 40, kind, modulus, _lib.stream_arg(None)))
+    return t
+
+
+def _enough_memory(torch, need_gb):
+    from cudf_b200 import _lib
+
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    _lib.check(_lib.lib.b2_trim_pool())
+    free, _ = torch.cuda.mem_get_info()
+    return free / 2**30 >= need_gb
+
+
+def test_sort_by_key_1e9_properties(plc):
+    import torch
+
+    from cudf_b200 import _lib
+
+    if not _enough_memory(torch, 70):
+        pytest.skip("needs ~70 GB of free HBM")
+    keys = _fill(_lib, torch.empty(N, dtype=torch.int64, device="cuda"), N, 0)
+    t = plc.Table([plc.Column.from_torch(keys)])
+    out = plc.sorting.sort_by_key(t, t, [plc.Order.ASCENDING], []).columns()[0].to_torch()
+    assert out.numel() == N
+    assert bool((out[1:] >= out[:-1]).all())                      # sortedness
+    assert int(out.sum()) == int(keys.sum())                       # multiset preserved (wrap-around sums)
+    assert int((out ^ (out >> 7)).sum()) == int((keys ^ (keys >> 7)).sum())
+    del out
+    order = plc.sorting.sorted_order(t, [plc.Order.DESCENDING], []).to_torch()
+    assert int(order.long().sum()) == N * (N - 1) // 2             # a permutation of 0..N-1 (necessary condition)
+    g = keys[order.long()[: 1 << 24]]
+    assert bool((g[1:] <= g[:-1]).all())
+    _lib.check(_lib.lib.b2_trim_pool())
+
+
+def test_groupby_1e9_properties(plc):
+    import torch
+
+    from cudf_b200 import _lib
+
+    if not _enough_memory(torch, 40):
+        pytest.skip("needs ~40 GB of free HBM")
+    G = 1_000_000
+    k = _fill(_lib, torch.empty(N, dtype=torch.int64, device="cuda"), N, 9, kind=2, modulus=G)
+    v = _fill(_lib, torch.empty(N, dtype=torch.float64, device="cuda"), N, 8, kind=1)
+    gb = plc.groupby.GroupBy(plc.Table([plc.Column.from_torch(k)]))
+    agg = plc.aggregation
+    keys_out, res = gb.aggregate([plc.groupby.GroupByRequest(plc.Column.from_torch(v), [agg.sum(), agg.count()])])
+    gk = keys_out.columns()[0].to_torch()
+    sums, counts = res[0].columns()[0].to_torch(), res[0].columns()[1].to_torch()
+    assert gk.numel() == G and int(gk.min()) == 0 and int(gk.max()) == G - 1
+    assert int(torch.unique(gk).numel()) == G                      # every group exactly once
+    assert int(counts.long().sum()) == N                           # counts are exact
+    total = float(v.sum())
+    assert abs(float(sums.sum()) - total) <= 1e-6 * abs(total)     # float sums: 1e-6 relative (north_star)
+    _lib.check(_lib.lib.b2_trim_pool())
+
+
+def test_inner_join_1e9_properties(plc):
+    import torch
+
+    from cudf_b200 import _lib
+
+    if not _enough_memory(torch, 90):
+        pytest.skip("needs ~90 GB of free HBM")
+    rk = _fill(_lib, torch.empty(N, dtype=torch.int64, device="cuda"), N, 1)
+    lk = _fill(_lib, torch.empty(N, dtype=torch.int64, device="cuda"), N, 6)
+    u = _fill(_lib, torch.empty(N, dtype=torch.float64, device="cuda"), N, 5, kind=1)
+    sel = _fill(_lib, torch.empty(N, dtype=torch.int64, device="cuda"), N, 4, kind=2, modulus=N)
+    hit = u < 0.10
+    del u
+    nhit = int(hit.sum())
+    lk[hit] = rk[sel[hit]]
+    del sel, hit
+    li, ri = plc.join.inner_join(plc.Table([plc.Column.from_torch(lk)]), plc.Table([plc.Column.from_torch(rk)]), plc.NullEquality.EQUAL)
+    l, r = li.to_torch().long(), ri.to_torch().long()
+    # every selected probe row matches (64-bit key collisions add a handful more), and every pair joins equal keys
+    assert nhit <= l.numel() <= nhit + 1000
+    assert bool((lk[l] == rk[r]).all())
+    _lib.check(_lib.lib.b2_trim_pool())
