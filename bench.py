@@ -74,6 +74,15 @@ def cpu_sort_sample(cpu_rows: int, steps: int, warmup: int):
     }, sum(times) / len(times)
 
 
+def workload_config(n: int, world: int) -> dict:
+    return {"workload": f"{n}-row single int64 column sort_by_key(values=T, keys=T), no nulls, ASCENDING, per GPU "
+                        "(BASELINE.json configs[1])" + ("" if world == 1 else f"; sharded over {world} GPUs: sample-sort splitters, stable range "
+                        "partition, bucket exchange (fused peer-memory scatter over NVLink at 2 ranks, NCCL all-to-all-v "
+                        "above), local LSD sort (configs[4])"),
+            "rows_per_gpu": n, "l2_flush": "inputs (8 GB/GPU) exceed the 126 MB L2; no explicit flush",
+            "generator": "splitmix64(seed 0x5EED0001 + i)"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -85,8 +94,9 @@ def run_reference(args):
         "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
         "ms_per_step": mean_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int64", "data": "synthetic",
-        "config": {"workload": f"pandas CPU sort_values on a {args.cpu_rows}-row int64 sample (configs[0]) of the "
-                               "1e9-row sort_by_key workload", "rows_per_step": args.cpu_rows},
+        "config": dict(workload_config(args.rows, max(1, args.gpus)),
+                       sample=f"each step = pandas DataFrame.sort_values(kind='stable') on a {args.cpu_rows}-row sample of the key "
+                              "stream (BASELINE.json configs[0]: the reference's CPU-runnable case)", rows_per_step=args.cpu_rows),
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -324,12 +334,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
             "data": "synthetic",
-            "config": {"workload": f"{n}-row single int64 column sort_by_key(values=T, keys=T), no nulls, ASCENDING, per GPU "
-                                   "(BASELINE.json configs[1])" + ("" if world == 1 else f"; sharded over {world} GPUs: sample-sort splitters, stable range "
-                                   "partition, bucket exchange (fused peer-memory scatter over NVLink at 2 ranks, NCCL all-to-all-v "
-                                   "above), local LSD sort (configs[4])"),
-                       "rows_per_gpu": n, "l2_flush": "inputs (8 GB/GPU) exceed the 126 MB L2; no explicit flush",
-                       "generator": "splitmix64(seed 0x5EED0001 + i)"},
+            "config": workload_config(n, world),
             "roofline": roofline, "cpu_baseline": cpu_base, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks.summary(),
         }

@@ -241,8 +241,7 @@ struct pass_args {
   const void* key_bufs[3];  // [0] raw input column data (already offset), [1], [2]
   int32_t* idx_bufs[3];
   sort_ctl* ctl;
-  uint32_t* status;         // agg[tiles][256], incl[tiles][256], state[tiles] for this (pass, portion)
-  uint32_t status_tiles;    // tiles per portion (row count of the arrays above)
+  uint32_t* status;         // [tiles][256] flagged count / prefix rows for this (pass, portion)
   uint32_t* tile_counter;   // for this (pass, portion)
   int64_t portion_start;    // element offset of this portion
   uint32_t portion_n;       // elements in this portion
@@ -255,16 +254,6 @@ struct pass_args {
   int32_t keep_keys;        // pairs mode: also write the keys in the last executed pass (partial sorts)
 };
 
-__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v)
-{
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p)
-{
-  uint32_t v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 __device__ __forceinline__ void ranker_barrier(int nthreads)
 {
   asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
@@ -791,7 +780,6 @@ void run_radix_cfg(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int
       a.portion_parity = (int)(q & 1);
       a.has_next_portion = q + 1 < nportions;
       a.status = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(status) + (size_t)(p * nportions + q) * status_per);
-      a.status_tiles = (uint32_t)tiles_per_portion;
       a.tile_counter = counters + p * nportions + q;
       const int64_t ntiles = (pn + TILE - 1) / TILE;
       const size_t smem_bytes = onesweep_smem<UK, T, I>();
