@@ -114,3 +114,70 @@ def test_reduce_min_max_product(impl, dtype):
     assert impl.reduce(coln, "sum", dtype) == (np.dtype(dtype).type(31), True)
     p, ok = impl.reduce(make_col([1, 2, 3, N, 2], dtype), "product", dtype)
     assert ok and p == np.dtype(dtype).type(12)
+
+
+# cpp/tests/groupby/{min,max,mean,count}_tests.cpp: basic and null_keys_and_values (min :33-40,100-118; max :33-40,104-122;
+# mean :100-125; count :104-123).  Groups compared after sorting by key, like test_single_agg.
+GKEYS = [1, 2, 3, 1, 2, 2, 1, 3, 3, 2]
+GVALS = [0, 1, 2, 3, 4, 5, 6, 7, 8, 9]
+NKEYS = [1, 2, 3, 1, 2, 2, 1, N, 3, 2, 4]
+NVALS = [N, 1, 2, 3, 4, N, 6, 7, 8, 9, N]
+GB_MORE = [
+    ("min", GKEYS, GVALS, [1, 2, 3], [0, 1, 2]),
+    ("max", GKEYS, GVALS, [1, 2, 3], [6, 9, 8]),
+    ("min", NKEYS, NVALS, [1, 2, 3, 4], [3, 1, 2, N]),
+    ("max", NKEYS, NVALS, [1, 2, 3, 4], [6, 9, 8, N]),
+    ("mean", NKEYS, NVALS, [1, 2, 3, 4], [4.5, 14.0 / 3, 5.0, N]),
+    ("count", NKEYS, NVALS, [1, 2, 3, 4], [2, 3, 2, 0]),
+]
+
+
+@pytest.mark.parametrize("case", GB_MORE, ids=lambda c: f"{c[0]}-{len(c[1])}")
+@pytest.mark.parametrize("vdtype", [np.int8, np.int16, np.int32, np.int64, np.float32, np.float64])
+def test_groupby_min_max_mean_count_golden(impl, case, vdtype):
+    from tests.impls import sort_groups
+
+    kind, keys, vals, ekeys, evals = case
+    k, res = sort_groups(*impl.groupby([make_col(keys, np.int32)], [(make_col(vals, vdtype), [kind])]))
+    assert np.asarray(k[0][0]).tolist() == ekeys
+    got = res[0][0]
+    ev = np.array([v is not None for v in evals])
+    gm = np.ones(len(evals), bool) if got[1] is None else np.asarray(got[1])
+    assert gm.tolist() == ev.tolist()
+    exp = np.array([0 if v is None else v for v in evals], dtype=np.float64)
+    np.testing.assert_allclose(np.asarray(got[0], dtype=np.float64)[ev], exp[ev], rtol=1e-6)
+    want = {"min": np.dtype(vdtype), "max": np.dtype(vdtype), "mean": np.dtype(np.float64), "count": np.dtype(np.int32)}[kind]
+    assert np.asarray(got[0]).dtype == want
+
+
+# cpp/tests/copying/gather_tests.cpp:44-250 (IdentityTest, ReverseIdentityTest, EveryOtherNullOdds/Evens, AllNull,
+# MultiColReverseIdentityTest, MultiColNulls) — run against the library only (the oracle's gather is trivial numpy)
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", TYPES)
+def test_gather_golden(plc, dtype):
+    n = 1000
+    data = np.arange(n) % (100 if np.dtype(dtype).itemsize == 1 else n)
+    src = plc.Column.from_numpy(data.astype(dtype))
+    ident = plc.Column.from_numpy(np.arange(n, dtype=np.int32))
+    rev = plc.Column.from_numpy(np.arange(n - 1, -1, -1, dtype=np.int32))
+    out = plc.copying.gather(plc.Table([src]), ident, plc.OutOfBoundsPolicy.DONT_CHECK).columns()[0]
+    assert np.array_equal(out.to_numpy()[0], data.astype(dtype)) and out.null_count() == 0 and out.null_mask() is None
+    out = plc.copying.gather(plc.Table([src, src]), rev, plc.OutOfBoundsPolicy.DONT_CHECK)
+    for c in out.columns():
+        assert np.array_equal(c.to_numpy()[0], data.astype(dtype)[::-1])
+    # every other element null: gathering the null rows gives all nulls, the others none
+    valid = (np.arange(n) % 2) != 0
+    srcn = plc.Column.from_numpy(data.astype(dtype), valid)
+    evens = plc.Column.from_numpy((np.arange(n // 2) * 2).astype(np.int32))
+    odds = plc.Column.from_numpy((np.arange(n // 2) * 2 + 1).astype(np.int32))
+    o = plc.copying.gather(plc.Table([srcn]), evens, plc.OutOfBoundsPolicy.DONT_CHECK).columns()[0]
+    assert o.null_count() == n // 2 and not o.to_numpy()[1].any()
+    o = plc.copying.gather(plc.Table([srcn]), odds, plc.OutOfBoundsPolicy.DONT_CHECK).columns()[0]
+    v, m = o.to_numpy()
+    assert o.null_count() == 0 and m.all() and np.array_equal(v, data.astype(dtype)[1::2])
+    alln = plc.Column.from_numpy(data.astype(dtype), np.zeros(n, bool))
+    o = plc.copying.gather(plc.Table([alln]), rev, plc.OutOfBoundsPolicy.DONT_CHECK).columns()[0]
+    assert o.null_count() == n
+    # zero-column table keeps the row count semantics trivially; empty gather map -> empty table
+    e = plc.copying.gather(plc.Table([src]), plc.Column.from_numpy(np.empty(0, np.int32)), plc.OutOfBoundsPolicy.DONT_CHECK)
+    assert e.num_rows() == 0 and e.columns()[0].type().id() == src.type().id()
