@@ -100,7 +100,8 @@ class CudaOps:
             dist.barrier(group=group)                                 # peers are done reading the previous contents
             ccol = plc.Column.from_torch(column)
             cv = ccol._view()
-            lib.check(lib.lib.b2_partition_scatter(plan, C.byref(cv), dest, lib.stream_arg(None)))
+            scatter = lib.lib.b2_partition_scatter_staged if os.environ.get("B2_SHARD_P2P", "") == "staged" else lib.lib.b2_partition_scatter
+            lib.check(scatter(plan, C.byref(cv), dest, lib.stream_arg(None)))
             dist.barrier(group=group)                                 # stream-ordered after the scatter: all buckets landed
             return ex.view(recv_total, column.dtype)
         finally:
@@ -231,7 +232,7 @@ def sort_by_key_sharded(values: torch.Tensor, keys: torch.Tensor, ops=None, grou
     # NCCL all-to-all-v path until the scatter stages per-peer runs in shared memory. B2_SHARD_P2P=0/1 forces it.
     p2p_env = os.environ.get("B2_SHARD_P2P", "")
     p2p_default = world <= 2
-    use_p2p = same and keys.is_cuda and hasattr(ops, "partition_exchange") and (p2p_env == "1" or (p2p_env == "" and p2p_default))
+    use_p2p = same and keys.is_cuda and hasattr(ops, "partition_exchange") and (p2p_env in ("1", "staged") or (p2p_env == "" and p2p_default))
     if use_p2p:
         ph.mark("partition+exchange(p2p)")
         rk = ops.partition_exchange(keys, keys, 0, splitters, group)

@@ -253,6 +253,10 @@ B2_API b2_status b2_partition_plan_create(const b2_column_view* keys, int32_t mo
                                           int64_t* out_counts);
 B2_API b2_status b2_partition_scatter(const b2_partition_plan* plan, const b2_column_view* column,
                                       void* const* dest_ptrs, b2_stream stream);
+/* EXPERIMENTAL variant of b2_partition_scatter: stages per-destination runs of a 4096-row tile in shared memory
+ * before the (remote) stores; compiled in round 1 but not yet validated on hardware and not used by default. */
+B2_API b2_status b2_partition_scatter_staged(const b2_partition_plan* plan, const b2_column_view* column,
+                                             void* const* dest_ptrs, b2_stream stream);
 B2_API void      b2_partition_plan_free(b2_partition_plan* plan);
 /* CUDA-IPC exchange buffers (cudaMalloc + cudaIpcGetMemHandle / cudaIpcOpenMemHandle); handle = 64 bytes */
 B2_API b2_status b2_ipc_alloc(size_t bytes, void** out_ptr, uint8_t* out_handle64);
