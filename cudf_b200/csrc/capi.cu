@@ -346,6 +346,14 @@ static table_ptr sort_by_key_impl(const std::vector<b2_column_view>& values, con
   const int32_t vrows = values.empty() ? 0 : values[0].size;
   const int32_t krows = keys.empty() ? 0 : keys[0].size;
   B2_EXPECTS(vrows == krows, B2_ERR_LOGIC, "Mismatch in number of rows for values and keys");
+  if (keys.size() == 1 && values.size() == 1 && order.size() <= 1 && nprec.size() <= 1) {
+    const bool asc = order.empty() ? true : order[0] == B2_ASCENDING;
+    if (sort_carry_applicable(keys[0], values[0], asc)) {  // opt-in experimental path, off by default
+      auto t = std::make_unique<b2_table>();
+      t->cols.push_back(sort_by_key_carry(keys[0], values[0], asc, stream));
+      return t;
+    }
+  }
   auto order_col = sorted_order(keys, order, nprec, stable, stream);
   return gather_table(values, order_col->data.as<int32_t>(), order_col->size, false, stream);
 }

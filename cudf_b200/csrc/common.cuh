@@ -201,6 +201,8 @@ column_ptr sorted_order(const std::vector<b2_column_view>& keys, const std::vect
                         const std::vector<uint8_t>& null_prec, bool stable, cudaStream_t stream);
 column_ptr sort_single_column(const b2_column_view& col, bool ascending, cudaStream_t stream);
 bool is_radix_sortable(const b2_column_view& c);
+bool sort_carry_applicable(const b2_column_view& keys, const b2_column_view& values, bool ascending);
+column_ptr sort_by_key_carry(const b2_column_view& keys, const b2_column_view& values, bool ascending, cudaStream_t stream);
 void radix_partition_top16(const uint64_t* keys_in, int64_t n, uint64_t* keys_out, int32_t* idx_out, cudaStream_t stream);
 
 // scan_reduce.cu

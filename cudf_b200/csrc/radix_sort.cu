@@ -252,6 +252,7 @@ struct pass_args {
   int32_t pairs;            // 1: (key, idx) ; 0: keys only
   uint64_t desc_mask;
   int32_t keep_keys;        // pairs mode: also write the keys in the last executed pass (partial sorts)
+  const void* val_in;       // CARRY kernels: the caller's payload column (first pass source); last member on purpose
 };
 
 __device__ __forceinline__ void ranker_barrier(int nthreads)
@@ -279,7 +280,11 @@ constexpr int LBW = 2;   // look-back warps per CTA
 constexpr int DPL = 4;   // digits per look-back lane (one 128-bit load per predecessor tile)
 constexpr int LBT = 8;   // predecessor tiles fetched per round
 
-template <typename UK, int THREADS, int IPT, int MINB>
+// VT = uint32_t: payload = 32-bit row ids (generated in the first pass) — the shipped path.
+// VT = uint64_t / CARRY: payload = the caller's 8-byte (or 4-byte with VT = uint32_t) values column, loaded coalesced in
+// the first pass and carried through every pass, so that sort_by_key needs neither row ids nor a gather
+// (EXPERIMENTAL in round 1: opt-in with B2_SORT_CARRY=1, not yet run on hardware).
+template <typename UK, int THREADS, int IPT, int MINB, typename VT = uint32_t, bool CARRY = false>
 __global__ void __launch_bounds__(THREADS + 32 * LBW, MINB) onesweep_kernel(pass_args a)
 {
   constexpr int TILE   = THREADS * IPT;
@@ -290,9 +295,9 @@ __global__ void __launch_bounds__(THREADS + 32 * LBW, MINB) onesweep_kernel(pass
   if (pl.trivial) return;
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int STAGE_W = sizeof(UK) > 4 ? sizeof(UK) : 4;  // staging holds keys, then 32-bit row ids
+  constexpr int STAGE_W = sizeof(UK) > sizeof(VT) ? sizeof(UK) : sizeof(VT);  // staging holds keys, then the payload
   UK* s_keys          = reinterpret_cast<UK*>(smem_raw);
-  uint32_t* s_vals    = reinterpret_cast<uint32_t*>(smem_raw);
+  VT* s_vals          = reinterpret_cast<VT*>(smem_raw);
   uint32_t* s_whist   = reinterpret_cast<uint32_t*>(smem_raw + (size_t)STAGE_W * TILE);  // [NWARPS][256]
   uint32_t* s_bm      = s_whist + NWARPS * RADIX;  // [NWARPS][256] per-warp digit -> lane bitmaps (ranking)
   uint32_t* s_off     = s_bm + NWARPS * RADIX;     // [256] global offset of digit - tile-local start
@@ -502,13 +507,23 @@ __global__ void __launch_bounds__(THREADS + 32 * LBW, MINB) onesweep_kernel(pass
   for (int i = 0; i < IPT; ++i) s_keys[pos[i]] = key[i];
   // row ids are fetched only now (their registers replace the dead key registers); the loads
   // overlap with the key write-out below
-  uint32_t idx[IPT];
+  VT idx[IPT];
   if (a.pairs) {
     if (pl.idx_src < 0) {
+      if constexpr (CARRY) {
+        // first pass: the payload column is read at the rows' input positions (coalesced)
+        const VT* vsrc = static_cast<const VT*>(a.val_in) + a.portion_start;
 #pragma unroll
-      for (int i = 0; i < IPT; ++i) idx[i] = (uint32_t)(a.portion_start + wbase + i * 32);
+        for (int i = 0; i < IPT; ++i) {
+          const uint32_t e = wbase + i * 32;
+          idx[i] = e < a.portion_n ? ld_stream(vsrc + e) : VT(0);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) idx[i] = (uint32_t)(a.portion_start + wbase + i * 32);
+      }
     } else {
-      const uint32_t* isrc = reinterpret_cast<const uint32_t*>(pl.idx_src == 0 ? a.idx_bufs[0] : (pl.idx_src == 1 ? a.idx_bufs[1] : a.idx_bufs[2])) + a.portion_start;
+      const VT* isrc = reinterpret_cast<const VT*>(pl.idx_src == 0 ? a.idx_bufs[0] : (pl.idx_src == 1 ? a.idx_bufs[1] : a.idx_bufs[2])) + a.portion_start;
       if (full) {
 #pragma unroll
         for (int i = 0; i < IPT; ++i) idx[i] = ld_stream(isrc + wbase + i * 32);
@@ -516,7 +531,7 @@ __global__ void __launch_bounds__(THREADS + 32 * LBW, MINB) onesweep_kernel(pass
 #pragma unroll
         for (int i = 0; i < IPT; ++i) {
           uint32_t e = wbase + i * 32;
-          idx[i] = e < a.portion_n ? ld_stream(isrc + e) : 0u;
+          idx[i] = e < a.portion_n ? ld_stream(isrc + e) : VT(0);
         }
       }
     }
@@ -542,7 +557,7 @@ __global__ void __launch_bounds__(THREADS + 32 * LBW, MINB) onesweep_kernel(pass
 #pragma unroll
     for (int i = 0; i < IPT; ++i) s_vals[pos[i]] = idx[i];
     ranker_barrier(THREADS);
-    uint32_t* idst = reinterpret_cast<uint32_t*>(pl.idx_dst == 0 ? a.idx_bufs[0] : (pl.idx_dst == 1 ? a.idx_bufs[1] : a.idx_bufs[2]));
+    VT* idst = reinterpret_cast<VT*>(pl.idx_dst == 0 ? a.idx_bufs[0] : (pl.idx_dst == 1 ? a.idx_bufs[1] : a.idx_bufs[2]));
 #pragma unroll
     for (int j = 0; j < IPT; ++j) {
       const uint32_t q = j * THREADS + tid;
@@ -553,9 +568,17 @@ __global__ void __launch_bounds__(THREADS + 32 * LBW, MINB) onesweep_kernel(pass
 
 // all passes trivial: the sorted order is the input order
 template <typename UK>
-__global__ void finalize_kernel(pass_args a, int64_t n, int raw, int pre_idx_buf)
+__global__ void finalize_kernel(pass_args a, int64_t n, int raw, int pre_idx_buf, int carry_bytes)
 {
   if (a.ctl->any_pass != 0) return;
+  if (carry_bytes) {  // carried payload and no executed pass: the output is the payload column itself
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+      if (carry_bytes == 8) reinterpret_cast<uint64_t*>(a.idx_bufs[0])[i] = static_cast<const uint64_t*>(a.val_in)[i];
+      else reinterpret_cast<uint32_t*>(a.idx_bufs[0])[i] = static_cast<const uint32_t*>(a.val_in)[i];
+    }
+    return;
+  }
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     if (a.pairs) {
@@ -694,10 +717,10 @@ __global__ void __launch_bounds__(CP_THREADS) compact_kernel(const UK* __restric
 struct tile_cfg { int threads; int ipt; };
 
 
-template <typename UK, int T, int I>
+template <typename UK, int T, int I, typename VT = uint32_t>
 size_t onesweep_smem()
 {
-  return (sizeof(UK) > 4 ? sizeof(UK) : 4) * (size_t)T * I + sizeof(uint32_t) * (2 * (T / 32) * RADIX + 3 * RADIX + 16);
+  return (sizeof(UK) > sizeof(VT) ? sizeof(UK) : sizeof(VT)) * (size_t)T * I + sizeof(uint32_t) * (2 * (T / 32) * RADIX + 3 * RADIX + 16);
 }
 
 int64_t portion_limit()
@@ -715,10 +738,10 @@ int64_t portion_limit()
 //  raw_keys != nullptr : keys are the user's raw column (twiddled on load, implicit row ids)
 //  raw_keys == nullptr : keys are pre-twiddled in bufA with explicit row ids in idx buffer pre_idx_buf
 //  pairs: idx_out receives the permutation ; keys-only: bufA is the OUTPUT, bufB the temp.
-template <typename UK, int T, int I, int MINB>
+template <typename UK, int T, int I, int MINB, typename VT = uint32_t, bool CARRY = false>
 void run_radix_cfg(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int32_t* idx_tmp, int32_t* idx_tmp2, int pre_idx_buf, int64_t n,
                    int kind, bool descending, bool pairs, cudaStream_t stream, int first_pass = 0, int last_pass = 7,
-                   bool keep_keys = false)
+                   bool keep_keys = false, const void* val_in = nullptr)
 {
   constexpr int NP = sizeof(UK);
   constexpr int TILE = T * I;
@@ -752,8 +775,8 @@ void run_radix_cfg(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int
   B2_LAUNCH(plan_kernel, 1, RADIX, 0, stream, ghist, NP, (uint32_t)n, raw ? 1 : 0, pre_idx_buf, ctl, first_pass, last_pass);
 
   static bool attr_set = [] {
-    cudaFuncSetAttribute(onesweep_kernel<UK, T, I, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)onesweep_smem<UK, T, I>());
+    cudaFuncSetAttribute(onesweep_kernel<UK, T, I, MINB, VT, CARRY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)onesweep_smem<UK, T, I, VT>());
     return true;
   }();
   (void)attr_set;
@@ -769,6 +792,7 @@ void run_radix_cfg(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int
   a.kind = kind;
   a.pairs = pairs ? 1 : 0;
   a.keep_keys = keep_keys ? 1 : 0;
+  a.val_in = val_in;
   a.desc_mask = (uint64_t)desc_mask;
   for (int p = std::max(0, first_pass); p < NP && p <= last_pass; ++p) {
     for (int64_t q = 0; q < nportions; ++q) {
@@ -782,14 +806,14 @@ void run_radix_cfg(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int
       a.status = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(status) + (size_t)(p * nportions + q) * status_per);
       a.tile_counter = counters + p * nportions + q;
       const int64_t ntiles = (pn + TILE - 1) / TILE;
-      const size_t smem_bytes = onesweep_smem<UK, T, I>();
+      const size_t smem_bytes = onesweep_smem<UK, T, I, VT>();
       prof_scope ps("onesweep", stream);
-      B2_LAUNCH((onesweep_kernel<UK, T, I, MINB>), (unsigned)ntiles, T + 32 * LBW, smem_bytes, stream, a);
+      B2_LAUNCH((onesweep_kernel<UK, T, I, MINB, VT, CARRY>), (unsigned)ntiles, T + 32 * LBW, smem_bytes, stream, a);
     }
   }
   {
     int grid = (int)std::min<int64_t>((n + 255) / 256, NUM_SMS_B200 * 8);
-    B2_LAUNCH((finalize_kernel<UK>), std::max(grid, 1), 256, 0, stream, a, n, raw ? 1 : 0, pre_idx_buf);
+    B2_LAUNCH((finalize_kernel<UK>), std::max(grid, 1), 256, 0, stream, a, n, raw ? 1 : 0, pre_idx_buf, CARRY ? (int)sizeof(VT) : 0);
   }
   if (pairs && raw && kind == (int)key_kind::FLOAT && descending) {
     B2_LAUNCH(reverse_nan_prefix_kernel, NUM_SMS_B200 * 4, 256, 0, stream, idx_out, &ctl->nan_count);
@@ -1048,6 +1072,56 @@ column_ptr sorted_order(const std::vector<b2_column_view>& keys, const std::vect
     B2_CUDA_TRY(cudaMemcpyAsync(out->data.ptr, perm, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, stream));
     // `alt` now aliases the live result until the copy has run; it is freed stream-ordered after it.
   }
+  return out;
+}
+
+// EXPERIMENTAL (B2_SORT_CARRY=1): sort_by_key of ONE non-null 4- or 8-byte values column by ONE non-null
+// fixed-width key column, carrying the payload through the passes instead of row ids (no gather).
+bool sort_carry_enabled()
+{
+  static bool v = [] {
+    const char* e = std::getenv("B2_SORT_CARRY");
+    return e && std::atoi(e) != 0;
+  }();
+  return v;
+}
+bool sort_carry_applicable(const b2_column_view& keys, const b2_column_view& values, bool ascending)
+{
+  const int vw = type_width(values.type_id);
+  const bool float_desc = is_float_id(storage_type(keys.type_id)) && !ascending;  // NaN-prefix reversal works on row ids only
+  return sort_carry_enabled() && is_radix_sortable(keys) && !has_nulls(values) && (vw == 4 || vw == 8) && !float_desc &&
+         keys.size == values.size && keys.size > 0;
+}
+column_ptr sort_by_key_carry(const b2_column_view& keys, const b2_column_view& values, bool ascending, cudaStream_t stream)
+{
+  const int64_t n = keys.size;
+  const int kind = kind_of(storage_type(keys.type_id));
+  auto out = make_column(values.type_id, (int32_t)n, false, stream);
+  const int vw = type_width(values.type_id);
+  dbuf vtmp((size_t)vw * n, stream);
+  const void* vin = static_cast<const char*>(values.data) + (size_t)values.offset * vw;
+  auto go = [&](auto ktag, auto vtag) {
+    using UK = decltype(ktag);
+    using VT = decltype(vtag);
+    dbuf a(sizeof(UK) * n, stream), b(sizeof(UK) > 1 ? sizeof(UK) * n : 0, stream);
+    if constexpr (sizeof(UK) == 8)
+      run_radix_cfg<UK, 384, 16, 2, VT, true>(static_cast<const UK*>(keys.data) + keys.offset, a.as<UK>(), b.as<UK>(),
+                                              out->data.as<int32_t>(), vtmp.as<int32_t>(), nullptr, 0, n, kind, !ascending, true,
+                                              stream, 0, 7, false, vin);
+    else
+      run_radix_cfg<UK, 512, 16, 1, VT, true>(static_cast<const UK*>(keys.data) + keys.offset, a.as<UK>(), b.as<UK>(),
+                                              out->data.as<int32_t>(), vtmp.as<int32_t>(), nullptr, 0, n, kind, !ascending, true,
+                                              stream, 0, 7, false, vin);
+  };
+  auto by_key = [&](auto vtag) {
+    switch (type_width(keys.type_id)) {
+      case 1: go(uint8_t{}, vtag); break;
+      case 2: go(uint16_t{}, vtag); break;
+      case 4: go(uint32_t{}, vtag); break;
+      default: go(uint64_t{}, vtag); break;
+    }
+  };
+  if (vw == 8) by_key(uint64_t{}); else by_key(uint32_t{});
   return out;
 }
 
