@@ -29,6 +29,19 @@ def _digest(paths) -> str:
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
+    # several ranks of a torchrun job may call build() at once: serialise them on a lock file
+    import fcntl
+
+    OBJ.mkdir(exist_ok=True)
+    with open(OBJ / ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force: bool, verbose: bool) -> Path:
     sources = sorted(CSRC.glob("*.cu"))
     headers = sorted(CSRC.glob("*.cuh")) + [HERE.parent / "include" / "cudf_b200.h"]
     OBJ.mkdir(exist_ok=True)
