@@ -63,6 +63,22 @@ def cpu_sort_sample(cpu_rows: int, steps: int, warmup: int):
             times.append(t1 - t0)
     assert bool(np.all(np.diff(out["k"].to_numpy()) >= 0))
     best = min(times)
+    # other host implementations of the same sort on the same sample (one run each; reported, not the baseline value)
+    alt = {}
+    try:
+        t0 = time.perf_counter()
+        np.sort(keys, kind="stable")
+        alt["numpy_stable_sort_rows_per_s"] = cpu_rows / (time.perf_counter() - t0)
+        import pyarrow as pa
+        import pyarrow.compute as pc
+
+        arr = pa.array(keys)
+        t0 = time.perf_counter()
+        pc.take(arr, pc.sort_indices(arr))
+        alt["pyarrow_sort_indices_take_rows_per_s"] = cpu_rows / (time.perf_counter() - t0)
+        alt["pyarrow_threads"] = pa.cpu_count()
+    except Exception as ex:  # optional extras only
+        alt["error"] = repr(ex)[:120]
     return {
         "value": cpu_rows / best,
         "unit": UNIT,
@@ -71,6 +87,7 @@ def cpu_sort_sample(cpu_rows: int, steps: int, warmup: int):
         "sample": f"pandas {pd.__version__} DataFrame.sort_values(kind='stable') on {cpu_rows} int64 rows "
                   f"(same splitmix64 key stream), best of {steps}; host has {os.cpu_count()} logical cores",
         "ms": best * 1e3,
+        "alternatives": alt,
     }, sum(times) / len(times)
 
 
