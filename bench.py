@@ -295,11 +295,20 @@ def run_ours(args):
     if not args.no_e2e:
         try:
             cap = n if world == 1 else int(n * 1.1) + 1024  # a rank's shard of the sharded result is ~n rows
-            h_in = torch.empty(n, dtype=torch.int64, pin_memory=True)
-            h_out = torch.empty(cap, dtype=torch.int64, pin_memory=True)
+            alloc_err = None
+            try:
+                h_in = torch.empty(n, dtype=torch.int64, pin_memory=True)
+                h_out = torch.empty(cap, dtype=torch.int64, pin_memory=True)
+                d_in = torch.empty(n, dtype=torch.int64, device=dev)
+            except Exception as ex:  # e.g. not enough pinnable host memory on this rank
+                alloc_err = ex
+            ok = torch.tensor([0 if alloc_err else 1], dtype=torch.int32, device=dev)
+            if world > 1:  # every rank must take the same branch, or the collectives below would hang
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                raise RuntimeError(f"e2e buffers could not be allocated on every rank: {alloc_err!r}")
             h_in.copy_(keys)
             torch.cuda.synchronize()
-            d_in = torch.empty(n, dtype=torch.int64, device=dev)
 
             if world == 1:
                 def e2e_step():
