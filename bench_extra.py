@@ -45,6 +45,22 @@ def run(plc, _lib, n, peak_gbs):
     res["scan_sum_float64"] = entry(_time(torch, lambda: plc.reduce.scan(cf, agg.sum(), plc.reduce.ScanType.INCLUSIVE)), n, 16 * n)
     res["reduce_sum_int64"] = entry(_time(torch, lambda: plc.reduce.reduce(ci, agg.sum(), plc.DataType(plc.TypeId.INT64))), n, 8 * n)
     res["reduce_sum_float64"] = entry(_time(torch, lambda: plc.reduce.reduce(cf, agg.sum(), plc.DataType(plc.TypeId.FLOAT64))), n, 8 * n)
+    # keys-only radix: cudf::sort of one int64 column, and (opt-in B2_SORT_ALIAS=1) sort_by_key(T, T) routed to it
+    ti = plc.Table([ci])
+    res["sort_single_int64_keys_only"] = entry(_time(torch, lambda: plc.sorting.sort(ti, [plc.Order.ASCENDING], [])), n, 136 * n,
+                                               note="histogram 8 B/row + 8 passes x 16 B/row")
+    import os
+
+    prev = os.environ.get("B2_SORT_ALIAS")
+    os.environ["B2_SORT_ALIAS"] = "1"
+    try:
+        res["sort_by_key_aliased_opt_in"] = entry(_time(torch, lambda: plc.sorting.sort_by_key(ti, ti, [plc.Order.ASCENDING], [])), n, 136 * n)
+    finally:
+        if prev is None:
+            del os.environ["B2_SORT_ALIAS"]
+        else:
+            os.environ["B2_SORT_ALIAS"] = prev
+    del ti
     S = 1_000_000
     offs = torch.linspace(0, n, S + 1, device=dev).to(torch.int32)
     co = plc.Column.from_torch(offs)

@@ -354,6 +354,18 @@ static table_ptr sort_by_key_impl(const std::vector<b2_column_view>& values, con
       return t;
     }
   }
+  // Opt-in (B2_SORT_ALIAS=1): sort_by_key(values = T, keys = T) of one null-free integer-like column is
+  // sort(T); the keys-only radix (the validated b2_sort fast path, sort.cu:58-65) needs neither row ids nor the gather.
+  if (keys.size() == 1 && values.size() == 1 && order.size() <= 1 && nprec.size() <= 1 && krows > 0 &&
+      values[0].data == keys[0].data && values[0].offset == keys[0].offset && values[0].type_id == keys[0].type_id &&
+      is_radix_sortable(keys[0]) && !is_float_id(storage_type(keys[0].type_id))) {
+    const char* e = std::getenv("B2_SORT_ALIAS");
+    if (e && std::atoi(e) != 0) {
+      auto t = std::make_unique<b2_table>();
+      t->cols.push_back(sort_single_column(keys[0], order.empty() ? true : order[0] == B2_ASCENDING, stream));
+      return t;
+    }
+  }
   auto order_col = sorted_order(keys, order, nprec, stable, stream);
   return gather_table(values, order_col->data.as<int32_t>(), order_col->size, false, stream);
 }
