@@ -100,6 +100,28 @@ def run(plc, _lib, n, peak_gbs):
         res["inner_join_10pct"] = entry(ms, n, alg, matches=M, table_slots=slots,
                                         phases_ms={k_: _lib.profile_get(k_)[0] / max(_lib.profile_get(k_)[1], 1) for k_ in ("join_build", "join_count", "join_retrieve")})
         _lib.lib.b2_profile_enable(0)
+        # opt-in partitioned shared-memory join (radix_join.cu) on the same inputs
+        import os
+
+        prev = os.environ.get("B2_JOIN_RADIX_ROWS")
+        os.environ["B2_JOIN_RADIX_ROWS"] = "1000000"
+        try:
+            _lib.check(_lib.lib.b2_trim_pool())
+            _lib.lib.b2_profile_reset()
+            _lib.lib.b2_profile_enable(1)
+            rms = _time(torch, lambda: plc.join.inner_join(L, R, plc.NullEquality.EQUAL), steps=2, warmup=1)
+            li2, _ri2 = plc.join.inner_join(L, R, plc.NullEquality.EQUAL)
+            res["inner_join_10pct_radix_opt_in"] = entry(rms, n, alg, matches=li2.size(), same_match_count=bool(li2.size() == M),
+                                                         phases_ms={k_: _lib.profile_get(k_)[0] / max(_lib.profile_get(k_)[1], 1) for k_ in ("rjoin_partition", "rjoin_count", "rjoin_retrieve")})
+            del li2, _ri2
+        except Exception as ex:
+            res["inner_join_10pct_radix_opt_in"] = {"error": repr(ex)[:200]}
+        finally:
+            _lib.lib.b2_profile_enable(0)
+            if prev is None:
+                del os.environ["B2_JOIN_RADIX_ROWS"]
+            else:
+                os.environ["B2_JOIN_RADIX_ROWS"] = prev
         # materialisation: gather both payload columns (float64, 50 % nulls) through the index columns
         pay = f
         nwords = (n + 31) // 32

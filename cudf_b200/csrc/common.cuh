@@ -205,6 +205,11 @@ bool sort_carry_applicable(const b2_column_view& keys, const b2_column_view& val
 column_ptr sort_by_key_carry(const b2_column_view& keys, const b2_column_view& values, bool ascending, cudaStream_t stream);
 void radix_partition_top16(const uint64_t* keys_in, int64_t n, uint64_t* keys_out, int32_t* idx_out, cudaStream_t stream);
 
+// radix_join.cu (experimental, opt-in: B2_JOIN_RADIX_ROWS)
+bool radix_join_applicable(const std::vector<b2_column_view>& a, const std::vector<b2_column_view>& b);
+void radix_inner_join(const std::vector<b2_column_view>& build, const std::vector<b2_column_view>& probe, cudaStream_t stream,
+                      column_ptr& out_probe, column_ptr& out_build);
+
 // scan_reduce.cu
 std::unique_ptr<b2_scalar> reduce(const b2_column_view& col, int32_t kind, int32_t out_type,
                                   const b2_scalar* init, cudaStream_t stream);

@@ -494,7 +494,11 @@ static b2_status free_join(const b2_table_view* left, const b2_table_view* right
   const bool nulls = table_has_nulls(l) || table_has_nulls(r);
   column_ptr lo, ro;
   // inner join builds on the smaller table and swaps the outputs back (join.cu:52-59)
-  if (kind == JOIN_INNER && r[0].size > l[0].size) {
+  if (kind == JOIN_INNER && radix_join_applicable(l, r)) {  // opt-in partitioned path (radix_join.cu), off by default
+    make_key_cols(l);  // same argument checks as the hash path
+    if (r[0].size > l[0].size) radix_inner_join(l, r, S(stream), ro, lo);
+    else radix_inner_join(r, l, S(stream), lo, ro);
+  } else if (kind == JOIN_INNER && r[0].size > l[0].size) {
     std::unique_ptr<b2_hash_join> hj(hash_join_create(l, nulls, compare_nulls, 0.5, S(stream)));
     hash_join_probe(hj.get(), r, JOIN_INNER, false, 0, S(stream), ro, lo);
   } else {

@@ -1,0 +1,223 @@
+// radix_join.cu — partitioned ("radix") inner join for large null-free key tables.
+//
+// EXPERIMENTAL in round 1: written after the round's GPU budget was spent, compiled for sm_100a but not yet run on
+// hardware; OFF by default (B2_JOIN_RADIX_ROWS=<rows> routes cudf::inner_join calls whose two sides both have at
+// least that many rows through it).  DESIGN.md §7.4.
+//
+// Same contract as the hash path it stands in for (cpp/src/join/join.cu:27-110 inner_join over
+// cpp/src/join/hash_join/hash_join.cu:32-299): all (probe row, build row) pairs with equal keys, in unspecified
+// order (join.hpp:130-136).  Why: the open-addressing table in HBM costs one 128-byte DRAM fetch per build row
+// (CAS claim) and per probe row; at 1e9 x 1e9 rows build + count take 97 + 51 ms although the algorithmic traffic
+// is ~80 GB (12 ms).  Here every byte moves in streams:
+//   1. both sides: h = mix64(packed key) (a bijection: h equality is key equality), then two one-sweep radix
+//      passes on the top 16 bits of h (radix_partition_top16) -> h and the original row ids grouped into 65536
+//      partitions; partition bounds by binary search.
+//   2. one CTA per partition: the build rows' h go to shared memory (16384 x 8 B) with an open-addressing table of
+//      16-bit local row numbers (32768 slots, load factor <= 0.5, slot = bits 33..47 of h); the partition's probe
+//      rows stream through it.  Larger partitions (skew, duplicates, > ~1e9 rows) are handled in chunks of 16384
+//      build rows, re-streaming the probe rows per chunk.
+//   3. count pass (matches per partition) -> exclusive scan -> retrieve pass (same kernel, writes the pairs at the
+//      partition's offset; positions inside a partition come from a shared-memory cursor).
+#include "common.cuh"
+#include "device_utils.cuh"
+#include "key_pack.cuh"
+
+#include <algorithm>
+#include <climits>
+#include <cstdlib>
+
+namespace b2 {
+namespace {
+
+constexpr int RJ_PARTS   = 1 << 16;
+constexpr int RJ_THREADS = 1024;
+constexpr int RJ_CAP     = 16384;  // build rows per shared-memory table (local row numbers fit 16 bits, 0xFFFF = empty)
+constexpr int RJ_SLOTS   = 32768;
+constexpr size_t RJ_SMEM = (size_t)RJ_CAP * sizeof(uint64_t) + (size_t)RJ_SLOTS * sizeof(uint16_t);
+
+__global__ void __launch_bounds__(256) rj_mix_pack_kernel(key_cols kc, int64_t n, uint64_t* __restrict__ h)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
+    uint64_t key;
+    uint32_t nb;
+    pack_row(kc, r, key, nb);
+    h[r] = mix64(key);
+  }
+}
+
+// off[p] = first row whose 16-bit prefix is >= p (p in [0, 65536]); rows are grouped by prefix in ascending order
+__global__ void __launch_bounds__(256) rj_bounds_kernel(const uint64_t* __restrict__ h, int64_t n, int32_t* __restrict__ off)
+{
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p > RJ_PARTS) return;
+  int64_t lo = 0, hi = n;
+  while (lo < hi) {
+    const int64_t mid = lo + (hi - lo) / 2;
+    if ((h[mid] >> 48) < (uint64_t)p) lo = mid + 1;
+    else hi = mid;
+  }
+  off[p] = (int32_t)lo;
+}
+
+__device__ __forceinline__ uint32_t rj_slot(uint64_t h) { return (uint32_t)(h >> 33) & (uint32_t)(RJ_SLOTS - 1); }
+
+// One CTA joins partition blockIdx.x.  RETRIEVE = false: part_counts[p] = number of pairs, *total += it.
+// RETRIEVE = true: pairs are written to out_probe / out_build starting at part_offsets[p].
+template <bool RETRIEVE>
+__global__ void __launch_bounds__(RJ_THREADS, 1)
+rj_join_kernel(const uint64_t* __restrict__ bh, const int32_t* __restrict__ bid, const int32_t* __restrict__ boff,
+               const uint64_t* __restrict__ ph, const int32_t* __restrict__ pid, const int32_t* __restrict__ poff,
+               int32_t* __restrict__ part_counts, const int32_t* __restrict__ part_offsets, unsigned long long* __restrict__ total,
+               int32_t* __restrict__ out_probe, int32_t* __restrict__ out_build)
+{
+  extern __shared__ __align__(16) unsigned char rj_smem[];
+  uint64_t* bk  = reinterpret_cast<uint64_t*>(rj_smem);
+  uint32_t* tab = reinterpret_cast<uint32_t*>(rj_smem + (size_t)RJ_CAP * sizeof(uint64_t));  // RJ_SLOTS / 2 words
+  const uint16_t* tab16 = reinterpret_cast<const uint16_t*>(tab);
+  __shared__ unsigned int s_cursor;
+  __shared__ unsigned long long s_total;
+
+  const int part = blockIdx.x;
+  const int tid  = threadIdx.x;
+  const int b0 = boff[part], b1 = boff[part + 1];
+  const int p0 = poff[part], p1 = poff[part + 1];
+  if (b0 == b1 || p0 == p1) {  // uniform over the CTA
+    if (!RETRIEVE && tid == 0) part_counts[part] = 0;
+    return;
+  }
+  if (tid == 0) {
+    s_total = 0;
+    if (RETRIEVE) s_cursor = (unsigned int)part_offsets[part];
+  }
+  unsigned long long local = 0;
+  for (int c0 = b0; c0 < b1; c0 += RJ_CAP) {
+    const int cn = min(RJ_CAP, b1 - c0);
+    __syncthreads();  // the previous chunk's probes are done before the table is reset
+    for (int i = tid; i < RJ_SLOTS / 2; i += RJ_THREADS) tab[i] = 0xFFFFFFFFu;
+    for (int j = tid; j < cn; j += RJ_THREADS) bk[j] = ld_stream(bh + c0 + j);
+    __syncthreads();
+    // insert: claim a 16-bit slot with a 32-bit CAS on the word that holds it
+    for (int j = tid; j < cn; j += RJ_THREADS) {
+      uint32_t s = rj_slot(bk[j]);
+      while (true) {
+        uint32_t* w = &tab[s >> 1];
+        const int sh = (int)(s & 1u) * 16;
+        const uint32_t old = *reinterpret_cast<volatile uint32_t*>(w);
+        if (((old >> sh) & 0xFFFFu) == 0xFFFFu) {
+          const uint32_t neu = (old & ~(0xFFFFu << sh)) | ((uint32_t)j << sh);
+          if (atomicCAS(w, old, neu) == old) break;
+          // the word changed under us (either half): look at the same slot again
+        } else {
+          s = (s + 1) & (uint32_t)(RJ_SLOTS - 1);
+        }
+      }
+    }
+    __syncthreads();
+    for (int i = p0 + tid; i < p1; i += RJ_THREADS) {
+      const uint64_t h = ld_stream(ph + i);
+      uint32_t s = rj_slot(h);
+      while (true) {
+        const uint32_t e = tab16[s];
+        if (e == 0xFFFFu) break;
+        if (bk[e] == h) {
+          if (RETRIEVE) {
+            const unsigned int pos = atomicAdd(&s_cursor, 1u);
+            out_probe[pos] = pid[i];
+            out_build[pos] = bid[c0 + (int)e];
+          } else {
+            ++local;
+          }
+        }
+        s = (s + 1) & (uint32_t)(RJ_SLOTS - 1);
+      }
+    }
+  }
+  if (!RETRIEVE) {
+    local = warp_sum(local);
+    if (lane_id() == 0 && local) atomicAdd(&s_total, local);
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned long long t = s_total;
+      part_counts[part] = (int32_t)min(t, (unsigned long long)INT32_MAX);  // the 64-bit total catches overflow
+      if (t) atomicAdd(total, t);
+    }
+  }
+}
+
+bool any_nulls(const std::vector<b2_column_view>& cols)
+{
+  for (auto& c : cols)
+    if (has_nulls(c)) return true;
+  return false;
+}
+
+struct rj_side {
+  dbuf h, ids, off;
+};
+
+void rj_partition(const std::vector<b2_column_view>& cols, cudaStream_t stream, rj_side& s)
+{
+  const int64_t n = cols[0].size;
+  const key_cols kc = make_key_cols(cols);
+  dbuf raw(sizeof(uint64_t) * n, stream);
+  s.h   = dbuf(sizeof(uint64_t) * n, stream);
+  s.ids = dbuf(sizeof(int32_t) * n, stream);
+  s.off = dbuf(sizeof(int32_t) * (RJ_PARTS + 1), stream);
+  prof_scope ps("rjoin_partition", stream);
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, NUM_SMS_B200 * 16));
+  B2_LAUNCH(rj_mix_pack_kernel, grid, 256, 0, stream, kc, n, raw.as<uint64_t>());
+  radix_partition_top16(raw.as<uint64_t>(), n, s.h.as<uint64_t>(), s.ids.as<int32_t>(), stream);
+  B2_LAUNCH(rj_bounds_kernel, (RJ_PARTS + 1 + 255) / 256, 256, 0, stream, s.h.as<uint64_t>(), n, s.off.as<int32_t>());
+}
+
+}  // namespace
+
+// rows threshold of the experimental path (both sides); unset = off
+bool radix_join_applicable(const std::vector<b2_column_view>& a, const std::vector<b2_column_view>& b)
+{
+  const char* e = std::getenv("B2_JOIN_RADIX_ROWS");
+  if (!e || a.empty() || b.empty()) return false;
+  const int64_t thr = std::max<int64_t>(1, std::atoll(e));
+  return a[0].size >= thr && b[0].size >= thr && !any_nulls(a) && !any_nulls(b);
+}
+
+// pairs (probe row, build row) with equal keys; both tables null-free and non-empty
+void radix_inner_join(const std::vector<b2_column_view>& build, const std::vector<b2_column_view>& probe, cudaStream_t stream,
+                      column_ptr& out_probe, column_ptr& out_build)
+{
+  static bool attr_set = [] {
+    cudaFuncSetAttribute(rj_join_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RJ_SMEM);
+    cudaFuncSetAttribute(rj_join_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RJ_SMEM);
+    return true;
+  }();
+  (void)attr_set;
+  rj_side bs, ps;
+  rj_partition(build, stream, bs);
+  rj_partition(probe, stream, ps);
+
+  dbuf counts(sizeof(int32_t) * RJ_PARTS, stream), tot(sizeof(unsigned long long), stream);
+  B2_CUDA_TRY(cudaMemsetAsync(tot.ptr, 0, sizeof(unsigned long long), stream));
+  {
+    prof_scope sc("rjoin_count", stream);
+    B2_LAUNCH((rj_join_kernel<false>), RJ_PARTS, RJ_THREADS, RJ_SMEM, stream, bs.h.as<uint64_t>(), bs.ids.as<int32_t>(),
+              bs.off.as<int32_t>(), ps.h.as<uint64_t>(), ps.ids.as<int32_t>(), ps.off.as<int32_t>(), counts.as<int32_t>(),
+              (const int32_t*)nullptr, tot.as<unsigned long long>(), (int32_t*)nullptr, (int32_t*)nullptr);
+  }
+  unsigned long long m = 0;
+  B2_CUDA_TRY(cudaMemcpyAsync(&m, tot.ptr, sizeof(m), cudaMemcpyDeviceToHost, stream));
+  B2_CUDA_TRY(cudaStreamSynchronize(stream));  // the reference syncs for the output size too (size_impl.cuh:52-61)
+  B2_EXPECTS(m <= (unsigned long long)INT32_MAX, B2_ERR_LOGIC /* std::overflow_error in libcudf */,
+             "join output exceeds size_type (use hash_join::*_join_size and partition the probe side)");
+  out_probe = make_column(B2_INT32, (int32_t)m, false, stream);
+  out_build = make_column(B2_INT32, (int32_t)m, false, stream);
+  if (m == 0) return;
+  b2_column_view cv{B2_INT32, (int32_t)RJ_PARTS, counts.ptr, nullptr, 0, 0};
+  auto offs = scan(cv, B2_AGG_SUM, B2_SCAN_EXCLUSIVE, B2_NULL_EXCLUDE, stream);
+  prof_scope sr("rjoin_retrieve", stream);
+  B2_LAUNCH((rj_join_kernel<true>), RJ_PARTS, RJ_THREADS, RJ_SMEM, stream, bs.h.as<uint64_t>(), bs.ids.as<int32_t>(),
+            bs.off.as<int32_t>(), ps.h.as<uint64_t>(), ps.ids.as<int32_t>(), ps.off.as<int32_t>(), (int32_t*)nullptr,
+            offs->data.as<int32_t>(), (unsigned long long*)nullptr, out_probe->data.as<int32_t>(), out_build->data.as<int32_t>());
+}
+
+}  // namespace b2
