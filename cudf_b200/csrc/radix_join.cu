@@ -91,8 +91,8 @@ rj_join_kernel(const uint64_t* __restrict__ bh, const int32_t* __restrict__ bid,
     if (RETRIEVE) s_cursor = (unsigned int)part_offsets[part];
   }
   unsigned long long local = 0;
-  for (int c0 = b0; c0 < b1; c0 += RJ_CAP) {
-    const int cn = min(RJ_CAP, b1 - c0);
+  for (int64_t c0 = b0; c0 < b1; c0 += RJ_CAP) {  // 64-bit: row numbers go up to 2^31 - 1
+    const int cn = (int)min((int64_t)RJ_CAP, (int64_t)b1 - c0);
     __syncthreads();  // the previous chunk's probes are done before the table is reset
     for (int i = tid; i < RJ_SLOTS / 2; i += RJ_THREADS) tab[i] = 0xFFFFFFFFu;
     for (int j = tid; j < cn; j += RJ_THREADS) bk[j] = ld_stream(bh + c0 + j);
@@ -114,7 +114,7 @@ rj_join_kernel(const uint64_t* __restrict__ bh, const int32_t* __restrict__ bid,
       }
     }
     __syncthreads();
-    for (int i = p0 + tid; i < p1; i += RJ_THREADS) {
+    for (int64_t i = (int64_t)p0 + tid; i < p1; i += RJ_THREADS) {
       const uint64_t h = ld_stream(ph + i);
       uint32_t s = rj_slot(h);
       while (true) {
@@ -124,7 +124,7 @@ rj_join_kernel(const uint64_t* __restrict__ bh, const int32_t* __restrict__ bid,
           if (RETRIEVE) {
             const unsigned int pos = atomicAdd(&s_cursor, 1u);
             out_probe[pos] = pid[i];
-            out_build[pos] = bid[c0 + (int)e];
+            out_build[pos] = bid[c0 + e];
           } else {
             ++local;
           }
