@@ -204,6 +204,7 @@ bool is_radix_sortable(const b2_column_view& c);
 bool sort_carry_applicable(const b2_column_view& keys, const b2_column_view& values, bool ascending);
 column_ptr sort_by_key_carry(const b2_column_view& keys, const b2_column_view& values, bool ascending, cudaStream_t stream);
 void radix_partition_top16(const uint64_t* keys_in, int64_t n, uint64_t* keys_out, int32_t* idx_out, cudaStream_t stream);
+void radix_partition_top16_mix(const uint64_t* packed_keys, int64_t n, uint64_t* keys_out, int32_t* idx_out, cudaStream_t stream);
 
 // radix_join.cu (experimental, opt-in: B2_JOIN_RADIX_ROWS)
 bool radix_join_applicable(const std::vector<b2_column_view>& a, const std::vector<b2_column_view>& b);

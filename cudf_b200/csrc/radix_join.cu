@@ -9,9 +9,9 @@
 // order (join.hpp:130-136).  Why: the open-addressing table in HBM costs one 128-byte DRAM fetch per build row
 // (CAS claim) and per probe row; at 1e9 x 1e9 rows build + count take 97 + 51 ms although the algorithmic traffic
 // is ~80 GB (12 ms).  Here every byte moves in streams:
-//   1. both sides: h = mix64(packed key) (a bijection: h equality is key equality), then two one-sweep radix
-//      passes on the top 16 bits of h (radix_partition_top16) -> h and the original row ids grouped into 65536
-//      partitions; partition bounds by binary search.
+//   1. both sides: h = mix64(packed key) (a bijection: h equality is key equality), computed on load inside two
+//      one-sweep radix passes on the top 16 bits of h (radix_partition_top16_mix; a single 8-byte integer key column
+//      is read in place) -> h and the original row ids grouped into 65536 partitions; bounds by binary search.
 //   2. one CTA per partition: the build rows' h go to shared memory (16384 x 8 B) with an open-addressing table of
 //      16-bit local row numbers (32768 slots, load factor <= 0.5, slot = bits 33..47 of h); the partition's probe
 //      rows stream through it.  Larger partitions (skew, duplicates, > ~1e9 rows) are handled in chunks of 16384
@@ -35,14 +35,15 @@ constexpr int RJ_CAP     = 16384;  // build rows per shared-memory table (local 
 constexpr int RJ_SLOTS   = 32768;
 constexpr size_t RJ_SMEM = (size_t)RJ_CAP * sizeof(uint64_t) + (size_t)RJ_SLOTS * sizeof(uint16_t);
 
-__global__ void __launch_bounds__(256) rj_mix_pack_kernel(key_cols kc, int64_t n, uint64_t* __restrict__ h)
+// packed (normalised) key per row; the mixing happens inside the partition passes (radix_partition_top16_mix)
+__global__ void __launch_bounds__(256) rj_pack_kernel(key_cols kc, int64_t n, uint64_t* __restrict__ packed)
 {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
     uint64_t key;
     uint32_t nb;
     pack_row(kc, r, key, nb);
-    h[r] = mix64(key);
+    packed[r] = key;
   }
 }
 
@@ -160,14 +161,21 @@ void rj_partition(const std::vector<b2_column_view>& cols, cudaStream_t stream, 
 {
   const int64_t n = cols[0].size;
   const key_cols kc = make_key_cols(cols);
-  dbuf raw(sizeof(uint64_t) * n, stream);
   s.h   = dbuf(sizeof(uint64_t) * n, stream);
   s.ids = dbuf(sizeof(int32_t) * n, stream);
   s.off = dbuf(sizeof(int32_t) * (RJ_PARTS + 1), stream);
   prof_scope ps("rjoin_partition", stream);
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, NUM_SMS_B200 * 16));
-  B2_LAUNCH(rj_mix_pack_kernel, grid, 256, 0, stream, kc, n, raw.as<uint64_t>());
-  radix_partition_top16(raw.as<uint64_t>(), n, s.h.as<uint64_t>(), s.ids.as<int32_t>(), stream);
+  // one 8-byte integer-like key column IS its packed form: the partition passes read it in place
+  const bool in_place = cols.size() == 1 && type_width(cols[0].type_id) == 8 && !is_float_id(cols[0].type_id);
+  dbuf packed;
+  const uint64_t* src = static_cast<const uint64_t*>(cols[0].data) + cols[0].offset;
+  if (!in_place) {
+    packed = dbuf(sizeof(uint64_t) * n, stream);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, NUM_SMS_B200 * 16));
+    B2_LAUNCH(rj_pack_kernel, grid, 256, 0, stream, kc, n, packed.as<uint64_t>());
+    src = packed.as<uint64_t>();
+  }
+  radix_partition_top16_mix(src, n, s.h.as<uint64_t>(), s.ids.as<int32_t>(), stream);
   B2_LAUNCH(rj_bounds_kernel, (RJ_PARTS + 1 + 255) / 256, 256, 0, stream, s.h.as<uint64_t>(), n, s.off.as<int32_t>());
 }
 

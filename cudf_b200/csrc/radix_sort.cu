@@ -75,7 +75,8 @@ __device__ __forceinline__ UK untwiddle_rt(UK k, int kind, UK desc_mask)
 // ------------------------------------------------------------------------------------------------
 // 1. histogram
 // ------------------------------------------------------------------------------------------------
-template <typename UK>
+// MIX (64-bit keys, join partitioning): keys are mix64(raw) and only the digits of passes 6 and 7 are counted.
+template <typename UK, bool MIX = false>
 __global__ void __launch_bounds__(512) histogram_kernel(const UK* __restrict__ keys, int64_t n, int raw, int kind,
                                                        UK desc_mask, uint32_t* __restrict__ ghist,
                                                        uint32_t* __restrict__ nan_count)
@@ -95,10 +96,13 @@ __global__ void __launch_bounds__(512) histogram_kernel(const UK* __restrict__ k
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
 
   auto account = [&](UK rawbits, bool active) {
-    UK k = raw ? twiddle_rt<UK>(rawbits, kind, desc_mask) : rawbits;
+    UK k;
+    if constexpr (MIX) k = (UK)mix64((uint64_t)rawbits);
+    else k = raw ? twiddle_rt<UK>(rawbits, kind, desc_mask) : rawbits;
     if (active && raw && kind == (int)key_kind::FLOAT && (UK)(k ^ desc_mask) == (UK)~UK(0)) nans++;
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
+      if (MIX && p < 6) continue;
       unsigned d = (unsigned)(k >> (p * 8)) & 255u;
       unsigned amask = __ballot_sync(0xffffffffu, active);
       if (amask == 0) continue;
@@ -117,7 +121,9 @@ __global__ void __launch_bounds__(512) histogram_kernel(const UK* __restrict__ k
   // common case for the high bytes of real data) are detected with two REDUX ops on key ^ key(lane 0)
   // and counted by one lane, so that skewed inputs do not serialise on same-address atomics.
   auto account_fast = [&](UK rawbits) {
-    UK k = raw ? twiddle_rt<UK>(rawbits, kind, desc_mask) : rawbits;
+    UK k;
+    if constexpr (MIX) k = (UK)mix64((uint64_t)rawbits);
+    else k = raw ? twiddle_rt<UK>(rawbits, kind, desc_mask) : rawbits;
     if (raw && kind == (int)key_kind::FLOAT && (UK)(k ^ desc_mask) == (UK)~UK(0)) nans++;
     const uint64_t k64 = (uint64_t)k;
     const uint64_t d64 = k64 ^ __shfl_sync(0xffffffffu, k64, 0);
@@ -126,6 +132,7 @@ __global__ void __launch_bounds__(512) histogram_kernel(const UK* __restrict__ k
     const uint64_t vary = ((uint64_t)vary_hi << 32) | vary_lo;
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
+      if (MIX && p < 6) continue;
       const unsigned d = (unsigned)(k >> (p * 8)) & 255u;
       if (((vary >> (p * 8)) & 255u) == 0) {
         if (lane_id() == 0) atomicAdd(&sh[p][d], 32u);
@@ -284,7 +291,9 @@ constexpr int LBT = 8;   // predecessor tiles fetched per round
 // VT = uint64_t / CARRY: payload = the caller's 8-byte (or 4-byte with VT = uint32_t) values column, loaded coalesced in
 // the first pass and carried through every pass, so that sort_by_key needs neither row ids nor a gather
 // (EXPERIMENTAL in round 1: opt-in with B2_SORT_CARRY=1, not yet run on hardware).
-template <typename UK, int THREADS, int IPT, int MINB, typename VT = uint32_t, bool CARRY = false>
+// MIX: raw 64-bit keys are replaced by mix64(key) on load (hash-join partitioning: the first executed pass reads the
+// packed key column itself, so the mixed keys are never materialised unsorted).
+template <typename UK, int THREADS, int IPT, int MINB, typename VT = uint32_t, bool CARRY = false, bool MIX = false>
 __global__ void __launch_bounds__(THREADS + 32 * LBW, MINB) onesweep_kernel(pass_args a)
 {
   constexpr int TILE   = THREADS * IPT;
@@ -408,7 +417,10 @@ __global__ void __launch_bounds__(THREADS + 32 * LBW, MINB) onesweep_kernel(pass
     }
     if (pl.key_src == 0) {
 #pragma unroll
-      for (int i = 0; i < IPT; ++i) key[i] = twiddle_rt<UK>(key[i], a.kind, desc);
+      for (int i = 0; i < IPT; ++i) {
+        if constexpr (MIX) key[i] = (UK)mix64((uint64_t)key[i]);
+        else key[i] = twiddle_rt<UK>(key[i], a.kind, desc);
+      }
     }
     if (!full) {
       // padding items take the maximum key so that they rank last in the tile
@@ -567,7 +579,7 @@ __global__ void __launch_bounds__(THREADS + 32 * LBW, MINB) onesweep_kernel(pass
 }
 
 // all passes trivial: the sorted order is the input order
-template <typename UK>
+template <typename UK, bool MIX = false>
 __global__ void finalize_kernel(pass_args a, int64_t n, int raw, int pre_idx_buf, int carry_bytes)
 {
   if (a.ctl->any_pass != 0) return;
@@ -584,7 +596,11 @@ __global__ void finalize_kernel(pass_args a, int64_t n, int raw, int pre_idx_buf
     if (a.pairs) {
       if (raw) a.idx_bufs[0][i] = (int32_t)i;
       else if (pre_idx_buf != 0) a.idx_bufs[0][i] = a.idx_bufs[1][i];
-      if (a.keep_keys && raw) static_cast<UK*>(const_cast<void*>(a.key_bufs[1]))[i] = static_cast<const UK*>(a.key_bufs[0])[i];
+      if (a.keep_keys && raw) {
+        UK k = static_cast<const UK*>(a.key_bufs[0])[i];
+        if constexpr (MIX) k = (UK)mix64((uint64_t)k);
+        static_cast<UK*>(const_cast<void*>(a.key_bufs[1]))[i] = k;
+      }
     } else {
       // keys-only (always raw): copy input to output
       static_cast<UK*>(const_cast<void*>(a.key_bufs[1]))[i] = static_cast<const UK*>(a.key_bufs[0])[i];
@@ -738,7 +754,7 @@ int64_t portion_limit()
 //  raw_keys != nullptr : keys are the user's raw column (twiddled on load, implicit row ids)
 //  raw_keys == nullptr : keys are pre-twiddled in bufA with explicit row ids in idx buffer pre_idx_buf
 //  pairs: idx_out receives the permutation ; keys-only: bufA is the OUTPUT, bufB the temp.
-template <typename UK, int T, int I, int MINB, typename VT = uint32_t, bool CARRY = false>
+template <typename UK, int T, int I, int MINB, typename VT = uint32_t, bool CARRY = false, bool MIX = false>
 void run_radix_cfg(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int32_t* idx_tmp, int32_t* idx_tmp2, int pre_idx_buf, int64_t n,
                    int kind, bool descending, bool pairs, cudaStream_t stream, int first_pass = 0, int last_pass = 7,
                    bool keep_keys = false, const void* val_in = nullptr)
@@ -769,13 +785,13 @@ void run_radix_cfg(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int
     int grid = (int)std::min<int64_t>((n + 512 * 16 - 1) / (512 * 16), NUM_SMS_B200 * 4);
     grid = std::max(grid, 1);
     prof_scope ps("histogram", stream);
-    B2_LAUNCH((histogram_kernel<UK>), grid, 512, 0, stream, raw ? raw_keys : bufA, n, raw ? 1 : 0, kind, desc_mask, ghist,
+    B2_LAUNCH((histogram_kernel<UK, MIX>), grid, 512, 0, stream, raw ? raw_keys : bufA, n, raw ? 1 : 0, kind, desc_mask, ghist,
               (raw && kind == (int)key_kind::FLOAT) ? &ctl->nan_count : nullptr);
   }
   B2_LAUNCH(plan_kernel, 1, RADIX, 0, stream, ghist, NP, (uint32_t)n, raw ? 1 : 0, pre_idx_buf, ctl, first_pass, last_pass);
 
   static bool attr_set = [] {
-    cudaFuncSetAttribute(onesweep_kernel<UK, T, I, MINB, VT, CARRY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncSetAttribute(onesweep_kernel<UK, T, I, MINB, VT, CARRY, MIX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)onesweep_smem<UK, T, I, VT>());
     return true;
   }();
@@ -808,12 +824,12 @@ void run_radix_cfg(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int
       const int64_t ntiles = (pn + TILE - 1) / TILE;
       const size_t smem_bytes = onesweep_smem<UK, T, I, VT>();
       prof_scope ps("onesweep", stream);
-      B2_LAUNCH((onesweep_kernel<UK, T, I, MINB, VT, CARRY>), (unsigned)ntiles, T + 32 * LBW, smem_bytes, stream, a);
+      B2_LAUNCH((onesweep_kernel<UK, T, I, MINB, VT, CARRY, MIX>), (unsigned)ntiles, T + 32 * LBW, smem_bytes, stream, a);
     }
   }
   {
     int grid = (int)std::min<int64_t>((n + 255) / 256, NUM_SMS_B200 * 8);
-    B2_LAUNCH((finalize_kernel<UK>), std::max(grid, 1), 256, 0, stream, a, n, raw ? 1 : 0, pre_idx_buf, CARRY ? (int)sizeof(VT) : 0);
+    B2_LAUNCH((finalize_kernel<UK, MIX>), std::max(grid, 1), 256, 0, stream, a, n, raw ? 1 : 0, pre_idx_buf, CARRY ? (int)sizeof(VT) : 0);
   }
   if (pairs && raw && kind == (int)key_kind::FLOAT && descending) {
     B2_LAUNCH(reverse_nan_prefix_kernel, NUM_SMS_B200 * 4, 256, 0, stream, idx_out, &ctl->nan_count);
@@ -864,6 +880,15 @@ void radix_partition_top16(const uint64_t* keys_in, int64_t n, uint64_t* keys_ou
   dbuf b(sizeof(uint64_t) * n, stream), it(sizeof(int32_t) * n, stream);
   run_radix_cfg<uint64_t, 384, 16, 2>(keys_in, keys_out, b.as<uint64_t>(), idx_out, it.as<int32_t>(), nullptr, 0, n,
                                       (int)key_kind::UNSIGNED, false, true, stream, 6, 7, true);
+}
+
+// Same, but `packed_keys` are the raw packed join keys: the kernels apply mix64 on load (histogram of the two
+// needed digits only), so keys_out receives mix64(key) grouped by its top 16 bits. EXPERIMENTAL (radix_join.cu).
+void radix_partition_top16_mix(const uint64_t* packed_keys, int64_t n, uint64_t* keys_out, int32_t* idx_out, cudaStream_t stream)
+{
+  dbuf b(sizeof(uint64_t) * n, stream), it(sizeof(int32_t) * n, stream);
+  run_radix_cfg<uint64_t, 384, 16, 2, uint32_t, false, true>(packed_keys, keys_out, b.as<uint64_t>(), idx_out, it.as<int32_t>(), nullptr, 0,
+                                                             n, (int)key_kind::UNSIGNED, false, true, stream, 6, 7, true);
 }
 
 namespace {
