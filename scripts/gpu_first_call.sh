@@ -20,7 +20,7 @@ step tests_validated 1500 python -m pytest tests -q -m gpu -x --ignore tests/tes
   --ignore tests/test_zz_full_size_gpu.py --ignore tests/test_zzz_cpp_api.py --ignore tests/test_zy_more_golden.py
 step tests_more_golden 300 python -m pytest tests/test_zy_more_golden.py -q -m gpu
 step tests_cpp_api 300 python -m pytest tests/test_zzz_cpp_api.py -q -m gpu
-step tests_experimental 900 python -m pytest tests/test_zz_experimental_gpu.py -q -m gpu -rxX
+B2_RUN_EXPERIMENTAL=1 step tests_experimental 1000 python -m pytest tests/test_zz_experimental_gpu.py -q -m gpu -rxX
 step tests_full_size 900 python -m pytest tests/test_zz_full_size_gpu.py -q -m gpu
 
 # 2. headline bench, the reference arm, and the secondary ops (keys-only / aliased sort, join, groupby, scan, reduce)

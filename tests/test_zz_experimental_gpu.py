@@ -7,8 +7,11 @@ import sys
 
 import pytest
 
-pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# Never-run code can hang a kernel; the default GPU suite must not depend on it. scripts/gpu_first_call.sh sets the switch.
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("B2_RUN_EXPERIMENTAL", "0") != "1",
+                                 reason="opt-in paths not yet validated on hardware: set B2_RUN_EXPERIMENTAL=1")]
 
 
 @pytest.mark.xfail(strict=False, reason="payload-carrying sort_by_key (B2_SORT_CARRY=1) not yet validated on hardware")
@@ -31,7 +34,7 @@ for n in (1, 33, 6144, 6145, 200_003):
 print('CARRY_OK')
 """
     env = dict(os.environ, B2_SORT_CARRY="1")
-    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=ROOT, timeout=600)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=ROOT, timeout=300)
     assert "CARRY_OK" in r.stdout, r.stdout[-1500:] + r.stderr[-2500:]
 
 
@@ -55,7 +58,7 @@ for n in (1, 33, 6145, 200_003, 3_000_001):
 print('ALIAS_OK')
 """
     env = dict(os.environ, B2_SORT_ALIAS="1")
-    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=ROOT, timeout=600)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=ROOT, timeout=300)
     assert "ALIAS_OK" in r.stdout, r.stdout[-1500:] + r.stderr[-2500:]
 
 
@@ -95,5 +98,5 @@ check([(f, None)], [(g, None)], 'float specials')
 print('RADIX_JOIN_OK')
 """
     env = dict(os.environ, B2_JOIN_RADIX_ROWS="1")
-    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=ROOT, timeout=900)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=ROOT, timeout=300)
     assert "RADIX_JOIN_OK" in r.stdout, r.stdout[-1500:] + r.stderr[-2500:]
