@@ -112,6 +112,9 @@ __device__ __forceinline__ void load_value(const value_op& op, int64_t e, long l
   }
 }
 
+// WIDE (keys wider than 8 bytes): the slot holds a 64-bit hash of the row; a hash hit is confirmed by comparing the
+// key columns of this row with the slot's representative row (key_pack.cuh).
+template <bool WIDE = false>
 __global__ void __launch_bounds__(256) groupby_kernel(key_cols kc, int64_t n, bool skip_null_keys, slot_t* __restrict__ table,
                                                       uint32_t mask, uint32_t cap, int32_t* __restrict__ gsize,
                                                       int32_t* __restrict__ slot_gid, int32_t* __restrict__ rep_rows, value_ops ops,
@@ -127,7 +130,8 @@ __global__ void __launch_bounds__(256) groupby_kernel(key_cols kc, int64_t n, bo
     if ((iter & 63) == 0 && *reinterpret_cast<volatile unsigned int*>(&ctl->overflow)) return;
     uint64_t key;
     uint32_t nb;
-    pack_row(kc, r, key, nb);
+    if constexpr (WIDE) hash_row_wide(kc, r, key, nb);
+    else pack_row(kc, r, key, nb);
     if (skip_null_keys && nb) continue;
     uint32_t i = slot_hash(key, nb, mask);
     int probes = 0;
@@ -147,7 +151,11 @@ __global__ void __launch_bounds__(256) groupby_kernel(key_cols kc, int64_t n, bo
           break;
         }
       }
-      if (cur.key == key && cur.nullbits == nb) break;
+      if constexpr (WIDE) {
+        if (cur.key == key && cur.nullbits == nb && rows_equal_wide(kc, r, kc, cur.row)) break;
+      } else {
+        if (cur.key == key && cur.nullbits == nb) break;
+      }
       i = (i + 1) & mask;
     }
     atomicAdd(&gsize[i], 1);
@@ -313,7 +321,8 @@ void groupby_aggregate(const b2_groupby& gb, const std::vector<request_view>& re
   }
   if (n == 0) return empty_results(gb, reqs, stream, keys_out, res_out);
 
-  key_cols kc = make_key_cols(gb.keys);
+  const bool wide = keys_are_wide(gb.keys);
+  key_cols kc = make_key_cols(gb.keys, true);
   bool keys_nullable = false;
   for (auto& k : gb.keys) keys_nullable |= has_nulls(k);
   const bool skip_null_keys = keys_nullable && gb.null_handling == B2_NULL_EXCLUDE;
@@ -394,8 +403,12 @@ void groupby_aggregate(const b2_groupby& gb, const std::vector<request_view>& re
 
     {
       prof_scope ps("groupby_aggregate", stream);
-      B2_LAUNCH(groupby_kernel, grid_for(n), 256, 0, stream, kc, n, skip_null_keys, table.as<slot_t>(), (uint32_t)(slots - 1), cap,
-                gsize.as<int32_t>(), slot_gid.as<int32_t>(), rep_rows.as<int32_t>(), ops, ctl.as<gb_ctl>());
+      if (wide)
+        B2_LAUNCH((groupby_kernel<true>), grid_for(n), 256, 0, stream, kc, n, skip_null_keys, table.as<slot_t>(), (uint32_t)(slots - 1),
+                  cap, gsize.as<int32_t>(), slot_gid.as<int32_t>(), rep_rows.as<int32_t>(), ops, ctl.as<gb_ctl>());
+      else
+        B2_LAUNCH((groupby_kernel<false>), grid_for(n), 256, 0, stream, kc, n, skip_null_keys, table.as<slot_t>(), (uint32_t)(slots - 1),
+                  cap, gsize.as<int32_t>(), slot_gid.as<int32_t>(), rep_rows.as<int32_t>(), ops, ctl.as<gb_ctl>());
     }
     gb_ctl h{};
     B2_CUDA_TRY(cudaMemcpyAsync(&h, ctl.ptr, sizeof(h), cudaMemcpyDeviceToHost, stream));
@@ -456,17 +469,22 @@ void groupby_aggregate(const b2_groupby& gb, const std::vector<request_view>& re
 namespace {
 
 // head[i] = 1 when sorted row i starts a new group (packed key differs from row i-1)
+template <bool WIDE = false>
 __global__ void group_heads_kernel(key_cols kc, const int32_t* __restrict__ order, int64_t n, uint8_t* __restrict__ head)
 {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     uint8_t h = 1;
     if (i > 0) {
-      uint64_t k0, k1;
-      uint32_t n0, n1;
-      pack_row(kc, order[i - 1], k0, n0);
-      pack_row(kc, order[i], k1, n1);
-      h = (k0 != k1 || n0 != n1) ? 1 : 0;
+      if constexpr (WIDE) {
+        h = rows_equal_wide(kc, order[i - 1], kc, order[i]) ? 0 : 1;
+      } else {
+        uint64_t k0, k1;
+        uint32_t n0, n1;
+        pack_row(kc, order[i - 1], k0, n0);
+        pack_row(kc, order[i], k1, n1);
+        h = (k0 != k1 || n0 != n1) ? 1 : 0;
+      }
     }
     head[i] = h;
   }
@@ -622,7 +640,7 @@ void groupby_scan(const b2_groupby& gb, const std::vector<request_view>& reqs, c
                  B2_ERR_INVALID_ARGUMENT, "unsupported groupby scan aggregation (SUM/MIN/MAX/COUNT)");
   }
   if (n_all == 0) return empty_results(gb, reqs, stream, keys_out, res_out);
-  key_cols kc = make_key_cols(gb.keys);
+  key_cols kc = make_key_cols(gb.keys, true);
 
   // sorted order of the keys (ascending, nulls first), null-key rows dropped under EXCLUDE
   std::vector<uint8_t> asc(gb.keys.size(), B2_ASCENDING), before(gb.keys.size(), B2_NULL_BEFORE);
@@ -650,7 +668,8 @@ void groupby_scan(const b2_groupby& gb, const std::vector<request_view>& reqs, c
     return;
   }
   dbuf head(n, stream);
-  B2_LAUNCH(group_heads_kernel, grid_for(n), 256, 0, stream, kc, order, n, head.as<uint8_t>());
+  if (keys_are_wide(gb.keys)) B2_LAUNCH((group_heads_kernel<true>), grid_for(n), 256, 0, stream, kc, order, n, head.as<uint8_t>());
+  else B2_LAUNCH((group_heads_kernel<false>), grid_for(n), 256, 0, stream, kc, order, n, head.as<uint8_t>());
 
   for (auto& r : reqs) {
     const auto& v = r.values;
@@ -716,7 +735,7 @@ b2_status b2_groupby_create(const b2_table_view* keys, int32_t null_handling, in
   gb->keys_are_sorted = keys_are_sorted != 0;
   if (column_order && n_order > 0) gb->order.assign(column_order, column_order + n_order);
   if (null_precedence && n_null_prec > 0) gb->nprec.assign(null_precedence, null_precedence + n_null_prec);
-  (void)make_key_cols(gb->keys);  // validates the key shape early
+  (void)make_key_cols(gb->keys, true);  // validates the key shape early
   *out = gb.release();
   B2_TRY_END
 }

@@ -166,6 +166,95 @@ __global__ void __launch_bounds__(256) retrieve_kernel(key_src ks, int64_t n, co
   }
 }
 
+// ---- wide keys (sum of key widths > 8 bytes) ----------------------------------------------------------
+// Same table and the same three passes, but the slot holds a 64-bit hash of the row (hash_row_wide) and a hash hit
+// is confirmed by comparing the key columns of the probe row with those of the slot's build row (rows_equal_wide).
+__global__ void __launch_bounds__(256) build_wide_kernel(key_cols kc, int64_t n, bool skip_nulls, slot_t* __restrict__ table,
+                                                         uint32_t mask)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
+    uint64_t h;
+    uint32_t nb;
+    hash_row_wide(kc, r, h, nb);
+    if (skip_nulls && nb) continue;
+    uint32_t i = slot_hash(h, nb, mask);
+    while (true) {
+      int old = atomicCAS(&table[i].row, -1, (int32_t)r);
+      if (old == -1) {
+        slot_t s{h, (int32_t)r, nb};
+        int4 v;
+        memcpy(&v, &s, 16);
+        *reinterpret_cast<int4*>(&table[i]) = v;
+        break;
+      }
+      i = (i + 1) & mask;
+    }
+  }
+}
+
+template <bool LEFT>
+__global__ void __launch_bounds__(256) count_wide_kernel(key_cols pk, key_cols bk, int64_t n, bool skip_nulls, bool table_has_null_rows,
+                                                         const slot_t* __restrict__ table, uint32_t mask, int32_t* __restrict__ counts,
+                                                         unsigned long long* __restrict__ total)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  unsigned long long local = 0;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
+    uint64_t h;
+    uint32_t nb;
+    hash_row_wide(pk, r, h, nb);
+    uint32_t c = 0;
+    if (!(nb && (skip_nulls || !table_has_null_rows)) && table != nullptr) {
+      uint32_t i = slot_hash(h, nb, mask);
+      while (true) {
+        const slot_t s = load_slot(&table[i]);
+        if (s.row == -1) break;
+        if (s.key == h && s.nullbits == nb && rows_equal_wide(pk, r, bk, s.row)) ++c;
+        i = (i + 1) & mask;
+      }
+    }
+    if (counts) counts[r] = (int32_t)min(c, 0x7fffffffu);
+    local += (LEFT && c == 0) ? 1ull : (unsigned long long)c;
+  }
+  local = warp_sum(local);
+  if (lane_id() == 0 && local) atomicAdd(total, local);
+}
+
+template <bool LEFT>
+__global__ void __launch_bounds__(256) retrieve_wide_kernel(key_cols pk, key_cols bk, int64_t n, const slot_t* __restrict__ table,
+                                                            uint32_t mask, const int32_t* __restrict__ counts,
+                                                            const int32_t* __restrict__ offsets, int32_t* __restrict__ out_left,
+                                                            int32_t* __restrict__ out_right)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
+    const int32_t c = counts[r];
+    if (c == 0 && !LEFT) continue;
+    int32_t o = offsets[r];
+    if (c == 0) {
+      out_left[o]  = (int32_t)r;
+      out_right[o] = B2_JOIN_NO_MATCH;
+      continue;
+    }
+    uint64_t h;
+    uint32_t nb;
+    hash_row_wide(pk, r, h, nb);
+    const int32_t end = o + c;
+    uint32_t i = slot_hash(h, nb, mask);
+    while (o < end) {
+      const slot_t s = load_slot(&table[i]);
+      if (s.row == -1) break;
+      if (s.key == h && s.nullbits == nb && rows_equal_wide(pk, r, bk, s.row)) {
+        out_left[o]  = (int32_t)r;
+        out_right[o] = s.row;
+        ++o;
+      }
+      i = (i + 1) & mask;
+    }
+  }
+}
+
 // ---- full join complement (join_utils.cu finalize_full_join): build rows that never matched ----
 __global__ void mark_kernel(const int32_t* __restrict__ right_idx, int64_t m, uint32_t* __restrict__ bitmap)
 {
@@ -221,6 +310,9 @@ struct b2_hash_join {
   uint32_t mask      = 0;
   int32_t mixed_shift = 0;     // > 0: "mixed" table (keys = mix64(packed key), slot = top bits)
   bool table_has_null_rows = false;
+  bool wide = false;           // keys wider than 8 bytes: hash in the slot + column comparison (build_cols must stay alive,
+                               // like the reference's build table: hash_join.hpp "must outlive this object")
+  std::vector<b2_column_view> build_cols;
   dbuf table;                  // empty when the build table has no rows
 };
 
@@ -260,7 +352,9 @@ b2_hash_join* hash_join_create(const std::vector<b2_column_view>& build, int has
   hj->build_rows    = build[0].size;
   hj->has_nulls     = has_nulls_arg < 0 ? true : has_nulls_arg != 0;  // ctor #1 = nullable_join::YES (hash_join.hpp)
   hj->compare_nulls = compare_nulls;
-  key_cols kc = make_key_cols(build);
+  hj->wide       = keys_are_wide(build);
+  hj->build_cols = build;
+  key_cols kc = make_key_cols(build, true);
   if (hj->build_rows == 0) return hj.release();
   const double want = std::ceil((double)hj->build_rows / load_factor);
   uint64_t slots = 16;
@@ -275,7 +369,7 @@ b2_hash_join* hash_join_create(const std::vector<b2_column_view>& build, int has
   int log2s = 0;
   while ((1ull << log2s) < slots) ++log2s;
   // large builds without null keys: mixed table + rows pre-partitioned by the top 16 bits of the mixed key
-  const bool mixed = !table_has_nulls(build) && n >= join_partition_threshold();
+  const bool mixed = !hj->wide && !table_has_nulls(build) && n >= join_partition_threshold();
   key_src ks{};
   ks.kc = kc;
   dbuf hk, hk_sorted, ids;
@@ -296,7 +390,8 @@ b2_hash_join* hash_join_create(const std::vector<b2_column_view>& build, int has
   }
   {
     prof_scope ps("join_build", stream);
-    B2_LAUNCH(build_kernel, grid_for(n), 256, 0, stream, ks, n, skip_nulls, hj->table.as<slot_t>(), hj->mask);
+    if (hj->wide) B2_LAUNCH(build_wide_kernel, grid_for(n), 256, 0, stream, kc, n, skip_nulls, hj->table.as<slot_t>(), hj->mask);
+    else B2_LAUNCH(build_kernel, grid_for(n), 256, 0, stream, ks, n, skip_nulls, hj->table.as<slot_t>(), hj->mask);
   }
   return hj.release();
 }
@@ -329,7 +424,15 @@ static probe_counts run_count(const b2_hash_join& hj, const key_src& ks, int64_t
   const slot_t* table = hj.table.as<slot_t>();
   {
     prof_scope ps("join_count", stream);
-    if (left)
+    if (hj.wide) {
+      const key_cols bk = make_key_cols(hj.build_cols, true);
+      if (left)
+        B2_LAUNCH((count_wide_kernel<true>), grid_for(n), 256, 0, stream, ks.kc, bk, n, skip_nulls, hj.table_has_null_rows, table,
+                  hj.mask, pc.counts.as<int32_t>(), tot.as<unsigned long long>());
+      else
+        B2_LAUNCH((count_wide_kernel<false>), grid_for(n), 256, 0, stream, ks.kc, bk, n, skip_nulls, hj.table_has_null_rows, table,
+                  hj.mask, pc.counts.as<int32_t>(), tot.as<unsigned long long>());
+    } else if (left)
       B2_LAUNCH((count_kernel<true>), grid_for(n), 256, 0, stream, ks, n, skip_nulls, hj.table_has_null_rows, table, hj.mask,
                 pc.counts.as<int32_t>(), tot.as<unsigned long long>());
     else
@@ -354,7 +457,7 @@ struct probe_keys {
 static void make_probe_keys(const b2_hash_join& hj, const std::vector<b2_column_view>& probe, cudaStream_t stream, probe_keys& pk)
 {
   const int64_t n = probe[0].size;
-  pk.ks.kc = make_key_cols(probe);
+  pk.ks.kc = make_key_cols(probe, hj.wide);
   pk.ks.mixed_shift = hj.mixed_shift;
   if (hj.mixed_shift && !table_has_nulls(probe) && n >= join_partition_threshold()) {
     dbuf hk(sizeof(uint64_t) * n, stream);
@@ -426,7 +529,15 @@ void hash_join_probe(const b2_hash_join* hj, const std::vector<b2_column_view>& 
     b2_column_view cv{B2_INT32, (int32_t)n, cnt_for_scan, nullptr, 0, 0};
     auto offs = scan(cv, B2_AGG_SUM, B2_SCAN_EXCLUSIVE, B2_NULL_EXCLUDE, stream);
     prof_scope ps("join_retrieve", stream);
-    if (left)
+    if (hj->wide) {
+      const key_cols bk = make_key_cols(hj->build_cols, true);
+      if (left)
+        B2_LAUNCH((retrieve_wide_kernel<true>), grid_for(n), 256, 0, stream, kc.kc, bk, n, hj->table.as<slot_t>(), hj->mask,
+                  pc.counts.as<int32_t>(), offs->data.as<int32_t>(), L->data.as<int32_t>(), R->data.as<int32_t>());
+      else
+        B2_LAUNCH((retrieve_wide_kernel<false>), grid_for(n), 256, 0, stream, kc.kc, bk, n, hj->table.as<slot_t>(), hj->mask,
+                  pc.counts.as<int32_t>(), offs->data.as<int32_t>(), L->data.as<int32_t>(), R->data.as<int32_t>());
+    } else if (left)
       B2_LAUNCH((retrieve_kernel<true>), grid_for(n), 256, 0, stream, kc, n, hj->table.as<slot_t>(), hj->mask,
                 pc.counts.as<int32_t>(), offs->data.as<int32_t>(), L->data.as<int32_t>(), R->data.as<int32_t>());
     else
@@ -495,7 +606,7 @@ static b2_status free_join(const b2_table_view* left, const b2_table_view* right
   column_ptr lo, ro;
   // inner join builds on the smaller table and swaps the outputs back (join.cu:52-59)
   if (kind == JOIN_INNER && radix_join_applicable(l, r)) {  // opt-in partitioned path (radix_join.cu), off by default
-    make_key_cols(l);  // same argument checks as the hash path
+    make_key_cols(l, true);  // same argument checks as the hash path
     if (r[0].size > l[0].size) radix_inner_join(l, r, S(stream), ro, lo);
     else radix_inner_join(r, l, S(stream), lo, ro);
   } else if (kind == JOIN_INNER && r[0].size > l[0].size) {

@@ -187,7 +187,7 @@ bool radix_join_applicable(const std::vector<b2_column_view>& a, const std::vect
   const char* e = std::getenv("B2_JOIN_RADIX_ROWS");
   if (!e || a.empty() || b.empty()) return false;
   const int64_t thr = std::max<int64_t>(1, std::atoll(e));
-  return a[0].size >= thr && b[0].size >= thr && !any_nulls(a) && !any_nulls(b);
+  return a[0].size >= thr && b[0].size >= thr && !any_nulls(a) && !any_nulls(b) && !keys_are_wide(a);
 }
 
 // pairs (probe row, build row) with equal keys; both tables null-free and non-empty
