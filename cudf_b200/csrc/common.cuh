@@ -51,12 +51,22 @@ void set_last_error(const char* msg);
 
 // every kernel launch goes through this so bench.py can report gpu_launches
 extern std::atomic<uint64_t> g_launch_count;
+#ifdef B2_EMU  // tests/emu: the kernels run on the CPU emulator (test infrastructure, never part of the product build)
+#define B2_LAUNCH(kernel, grid, block, smem, stream, ...)                                               \
+  do {                                                                                                  \
+    ::emu::launch(#kernel, dim3(grid), dim3(block), (size_t)(smem), [&]() { kernel(__VA_ARGS__); });    \
+    ::b2::g_launch_count.fetch_add(1, std::memory_order_relaxed);                                       \
+  } while (0)
+#define B2_DYNAMIC_SMEM(name) unsigned char* name = ::emu::dynamic_smem()
+#else
 #define B2_LAUNCH(kernel, grid, block, smem, stream, ...)                \
   do {                                                                   \
     kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);          \
     ::b2::g_launch_count.fetch_add(1, std::memory_order_relaxed);        \
     B2_CUDA_TRY(cudaGetLastError());                                     \
   } while (0)
+#define B2_DYNAMIC_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
 
 // optional event timing of a kernel family (see b2_profile_* in the C ABI)
 extern std::atomic<int> g_profile_on;

@@ -12,9 +12,13 @@ constexpr int NUM_SMS_B200 = 148;
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ unsigned lanemask_lt()
 {
+#ifdef B2_EMU  // tests/emu: CPU emulation of the kernels (test infrastructure)
+  return (1u << lane_id()) - 1u;
+#else
   unsigned m;
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
   return m;
+#endif
 }
 
 // ---- bit.hpp semantics: bit i of word i/32, LSB first -----------------------------------------
@@ -44,17 +48,25 @@ template <typename T> __device__ __forceinline__ void st_stream(T* p, T v) { __s
 
 __device__ __forceinline__ int4 ld_nc_v4(const void* p)
 {
+#ifdef B2_EMU
+  return *static_cast<const int4*>(p);
+#else
   int4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                : "l"(p));
   return r;
+#endif
 }
 __device__ __forceinline__ void st_na_v4(void* p, const int4& v)
 {
+#ifdef B2_EMU
+  *static_cast<int4*>(p) = v;
+#else
   asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
                "r"(v.w)
                : "memory");
+#endif
 }
 
 // ---- warp scans / reductions ----------------------------------------------------------------------

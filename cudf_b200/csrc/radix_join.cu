@@ -72,7 +72,7 @@ rj_join_kernel(const uint64_t* __restrict__ bh, const int32_t* __restrict__ bid,
                int32_t* __restrict__ part_counts, const int32_t* __restrict__ part_offsets, unsigned long long* __restrict__ total,
                int32_t* __restrict__ out_probe, int32_t* __restrict__ out_build)
 {
-  extern __shared__ __align__(16) unsigned char rj_smem[];
+  B2_DYNAMIC_SMEM(rj_smem);
   uint64_t* bk  = reinterpret_cast<uint64_t*>(rj_smem);
   uint32_t* tab = reinterpret_cast<uint32_t*>(rj_smem + (size_t)RJ_CAP * sizeof(uint64_t));  // RJ_SLOTS / 2 words
   const uint16_t* tab16 = reinterpret_cast<const uint16_t*>(tab);

@@ -264,13 +264,23 @@ struct pass_args {
 
 __device__ __forceinline__ void ranker_barrier(int nthreads)
 {
+#ifdef B2_EMU
+  ::emu::named_barrier(1, nthreads);
+#else
   asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+#endif
 }
 __device__ __forceinline__ uint4 ld_volatile_v4(const uint32_t* p)
 {
+#ifdef B2_EMU
+  uint4 v;
+  memcpy(&v, p, sizeof(v));
+  return v;
+#else
   uint4 v;
   asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
   return v;
+#endif
 }
 
 // One CTA = THREADS ranking threads (NWARPS warps holding IPT keys per thread) + LBW look-back warps.
@@ -303,7 +313,7 @@ __global__ void __launch_bounds__(THREADS + 32 * LBW, MINB) onesweep_kernel(pass
   const pass_plan pl = a.ctl->plan[a.pass];
   if (pl.trivial) return;
 
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  B2_DYNAMIC_SMEM(smem_raw);
   constexpr int STAGE_W = sizeof(UK) > sizeof(VT) ? sizeof(UK) : sizeof(VT);  // staging holds keys, then the payload
   UK* s_keys          = reinterpret_cast<UK*>(smem_raw);
   VT* s_vals          = reinterpret_cast<VT*>(smem_raw);
@@ -348,7 +358,11 @@ __global__ void __launch_bounds__(THREADS + 32 * LBW, MINB) onesweep_kernel(pass
     }
     uint32_t* const my_row = a.status + (size_t)tile * RADIX + d0;
     auto publish = [&](uint32_t flag, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+#ifdef B2_EMU
+      my_row[0] = flag | w0; my_row[1] = w1; my_row[2] = w2; my_row[3] = w3;
+#else
       asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(my_row), "r"(flag | w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+#endif
     };
     if (tile == 0) {
       publish(FLAG_INCL, cnt[0], cnt[1], cnt[2], cnt[3]);  // first tile of the portion: counts are inclusive
@@ -489,6 +503,12 @@ __global__ void __launch_bounds__(THREADS + 32 * LBW, MINB) onesweep_kernel(pass
       const unsigned peers = my_bm[d];
       const unsigned lt = __popc(peers & lanemask_lt());
       uint32_t prev = 0;
+#ifdef B2_EMU
+      // The emulator runs the lanes of a warp one after the other between rendezvous points, so the leader's clear
+      // below would be seen by the followers' read above. On the GPU the warp executes this straight-line stretch
+      // converged (validated on hardware); DESIGN.md §7 lists the formally race-free variant (a third __syncwarp).
+      __syncwarp();
+#endif
       if (lt == 0) {
         prev = my_hist[d];
         my_hist[d] = prev + __popc(peers);

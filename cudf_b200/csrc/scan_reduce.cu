@@ -342,13 +342,21 @@ constexpr int SC_K       = 4;  // 16-byte vectors per lane per tile
 
 __device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v)
 {
+#ifdef B2_EMU
+  *reinterpret_cast<volatile uint32_t*>(p) = v;
+#else
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#endif
 }
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p)
 {
+#ifdef B2_EMU
+  return *reinterpret_cast<const volatile uint32_t*>(p);
+#else
   uint32_t v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
+#endif
 }
 
 // One 16-byte record per tile: {flag (0 nothing, 1 aggregate, 2 inclusive), pad, 8-byte value}. A 16-byte
@@ -362,15 +370,23 @@ __device__ __forceinline__ void publish_rec(uint4* p, uint32_t flag, T v)
 {
   unsigned long long bits = 0;
   memcpy(&bits, &v, sizeof(T));
+#ifdef B2_EMU
+  *p = make_uint4(flag, 0u, (uint32_t)bits, (uint32_t)(bits >> 32));
+#else
   asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(flag), "r"(0u), "r"((uint32_t)bits),
                "r"((uint32_t)(bits >> 32))
                : "memory");
+#endif
 }
 template <typename T>
 __device__ __forceinline__ uint32_t read_rec(const uint4* p, T& v)
 {
+#ifdef B2_EMU
+  const uint4 r = *p;
+#else
   uint4 r;
   asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+#endif
   unsigned long long bits = (unsigned long long)r.z | ((unsigned long long)r.w << 32);
   memcpy(&v, &bits, sizeof(T));
   return r.x;

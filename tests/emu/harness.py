@@ -1,0 +1,73 @@
+"""Run the pylibcudf-named shim against the CPU emulation of the kernels (tests/emu) — TEST INFRASTRUCTURE ONLY.
+
+`install()` must be called in a dedicated (sub)process: it rebinds every ctypes entry point of `cudf_b200._lib.lib` to
+tests/emu/_build/libcudf_b200_emu.so and replaces Column.from_numpy / Column.to_numpy by host-memory versions ("device"
+pointers of the emulator are host pointers). The package itself has no switch that does this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent.parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+
+def install():
+    from tests.emu.build_emu import build
+
+    emu = C.CDLL(str(build()))
+    import cudf_b200._lib as L
+    from cudf_b200.pylibcudf import column as colmod
+    from cudf_b200.pylibcudf.types import DataType
+
+    for name in L.DECLARED_SYMBOLS:
+        real = getattr(L.lib, name)
+        fn = getattr(emu, name)
+        fn.argtypes, fn.restype = real.argtypes, real.restype
+        setattr(L.lib, name, fn)
+    L.current_stream = lambda: 0
+
+    Column = colmod.Column
+
+    def from_numpy(cls, values, valid=None, dtype=None, device="cpu"):
+        values = np.ascontiguousarray(values)
+        if dtype is None:
+            dtype = DataType.from_numpy(values.dtype)
+        raw = (values.view(np.uint8) if values.dtype != np.bool_ else values.astype(np.uint8)).copy()
+        raw = np.concatenate([raw.reshape(-1), np.zeros(64, np.uint8)])  # the library may read whole 16-byte vectors
+        mask_arr, nulls = None, 0
+        if valid is not None:
+            valid = np.asarray(valid, dtype=bool)
+            nulls = int((~valid).sum())
+            bits = np.packbits(valid, bitorder="little")
+            mask_arr = np.zeros(L.lib.b2_bitmask_allocation_size_bytes(len(valid)) or 64, dtype=np.uint8)
+            mask_arr[: len(bits)] = bits
+        return cls(dtype, len(values), raw.ctypes.data, mask_arr.ctypes.data if mask_arr is not None else 0, nulls, 0, [raw, mask_arr])
+
+    def _host_bytes(ptr: int, nbytes: int) -> np.ndarray:
+        return np.frombuffer(C.string_at(ptr, nbytes), dtype=np.uint8).copy()
+
+    def to_numpy(self):
+        dt = self._type.numpy_dtype()
+        if self._size == 0:
+            vals = np.empty(0, dtype=dt)
+        else:
+            raw = _host_bytes(self._data + self._offset * dt.itemsize, self._size * dt.itemsize)
+            vals = raw.view(np.uint8 if dt == np.bool_ else dt)
+            if dt == np.bool_:
+                vals = vals != 0
+        valid = None
+        if self._mask:
+            nwords = (self._offset + self._size + 31) // 32
+            bits = np.unpackbits(_host_bytes(self._mask, nwords * 4), bitorder="little")
+            valid = bits[self._offset: self._offset + self._size].astype(bool)
+        return vals, valid
+
+    Column.from_numpy = classmethod(from_numpy)
+    Column.to_numpy = to_numpy
+    return emu
