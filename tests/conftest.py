@@ -22,8 +22,14 @@ def _has_gpu() -> bool:
         return False
 
 
+# B2_EMU_RUN=1: run the gpu-marked parity tests against the CPU emulation of the kernels (tests/emu) instead of
+# skipping them — a development aid for kernels that have not been on hardware yet; never a substitute for `-m gpu`
+# on a B200 (the emulator knows nothing about memory ordering or speed). Tests that touch torch.cuda directly fail.
+EMU_RUN = os.environ.get("B2_EMU_RUN", "0") == "1"
+
+
 def pytest_collection_modifyitems(config, items):
-    if _has_gpu():
+    if _has_gpu() or EMU_RUN:
         return
     skip = pytest.mark.skip(reason="no CUDA device in this container")
     for item in items:
@@ -37,6 +43,10 @@ def plc():
     import __graft_entry__ as g
 
     g.build()
+    if EMU_RUN and not _has_gpu():
+        from tests.emu.harness import install
+
+        install()
     import cudf_b200.pylibcudf as plc
 
     return plc

@@ -2,6 +2,8 @@
 // TEST INFRASTRUCTURE ONLY.
 #include <cuda_runtime.h>
 
+#include <sys/mman.h>
+
 #include <chrono>
 #include <cstdio>
 #include <map>
@@ -285,8 +287,40 @@ void launch(const char* name, dim3 grid, dim3 block, size_t smem, const std::fun
 // ---- host API --------------------------------------------------------------------------------------------------
 using emu::g_allocs;
 
+// B2_EMU_GUARDPAGE=1: every allocation ends (up to 16-byte alignment) at an inaccessible page, so that reads or writes
+// past the end fault immediately instead of going unnoticed.
+static bool guard_pages()
+{
+  static const bool on = std::getenv("B2_EMU_GUARDPAGE") != nullptr;
+  return on;
+}
+static std::map<void*, std::pair<void*, size_t>> g_maps;  // user pointer -> (mapping base, mapping bytes)
+
+static cudaError_t guarded_alloc(void** p, size_t bytes)
+{
+  const size_t page = 4096;
+  const size_t rounded = (bytes + 15) / 16 * 16;
+  const size_t body = (rounded + page - 1) / page * page;
+  unsigned char* base = static_cast<unsigned char*>(mmap(nullptr, body + page, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0));
+  if (base == MAP_FAILED) return cudaErrorMemoryAllocation;
+  mprotect(base + body, page, PROT_NONE);
+  unsigned char* user = base + body - rounded;
+  std::memset(base, 0xCD, body);
+  *p = user;
+  g_maps[user] = {base, body + page};
+  return cudaSuccess;
+}
+
+extern "C" void* emu_alloc(size_t bytes)
+{
+  void* p = nullptr;
+  return cudaMalloc(&p, bytes) == cudaSuccess ? p : nullptr;
+}
+extern "C" void emu_free(void* p) { cudaFree(p); }
+
 cudaError_t cudaMalloc(void** p, size_t bytes)
 {
+  if (guard_pages()) return guarded_alloc(p, bytes ? bytes : 1);
   unsigned char* raw = static_cast<unsigned char*>(std::malloc(bytes + 2 * emu::GUARD + 64));
   if (!raw) return cudaErrorMemoryAllocation;
   std::memset(raw, emu::GUARD_BYTE, emu::GUARD);
@@ -299,6 +333,16 @@ cudaError_t cudaMalloc(void** p, size_t bytes)
 cudaError_t cudaFree(void* p)
 {
   if (!p) return cudaSuccess;
+  if (guard_pages()) {
+    auto it = g_maps.find(p);
+    if (it == g_maps.end()) {
+      std::fprintf(stderr, "emu: cudaFree of an unknown pointer\n");
+      std::abort();
+    }
+    munmap(it->second.first, it->second.second);
+    g_maps.erase(it);
+    return cudaSuccess;
+  }
   auto it = g_allocs.find(p);
   if (it == g_allocs.end()) {
     std::fprintf(stderr, "emu: cudaFree of an unknown pointer\n");

@@ -33,21 +33,36 @@ def install():
     L.current_stream = lambda: 0
 
     Column = colmod.Column
+    emu.emu_alloc.restype, emu.emu_alloc.argtypes = C.c_void_p, [C.c_size_t]
+    emu.emu_free.restype, emu.emu_free.argtypes = None, [C.c_void_p]
+
+    class _DevCopy:
+        """A host array copied into emulator-owned memory of EXACTLY its size (guard bytes / guard page right behind it)."""
+
+        def __init__(self, arr: np.ndarray):
+            self.nbytes = int(arr.nbytes)
+            self.ptr = emu.emu_alloc(max(self.nbytes, 1))
+            C.memmove(self.ptr, arr.ctypes.data, self.nbytes)
+
+        def __del__(self):
+            if self.ptr:
+                emu.emu_free(self.ptr)
+                self.ptr = None
 
     def from_numpy(cls, values, valid=None, dtype=None, device="cpu"):
         values = np.ascontiguousarray(values)
         if dtype is None:
             dtype = DataType.from_numpy(values.dtype)
-        raw = (values.view(np.uint8) if values.dtype != np.bool_ else values.astype(np.uint8)).copy()
-        raw = np.concatenate([raw.reshape(-1), np.zeros(64, np.uint8)])  # the library may read whole 16-byte vectors
+        raw = _DevCopy(np.ascontiguousarray(values.view(np.uint8) if values.dtype != np.bool_ else values.astype(np.uint8)))
         mask_arr, nulls = None, 0
         if valid is not None:
             valid = np.asarray(valid, dtype=bool)
             nulls = int((~valid).sum())
             bits = np.packbits(valid, bitorder="little")
-            mask_arr = np.zeros(L.lib.b2_bitmask_allocation_size_bytes(len(valid)) or 64, dtype=np.uint8)
-            mask_arr[: len(bits)] = bits
-        return cls(dtype, len(values), raw.ctypes.data, mask_arr.ctypes.data if mask_arr is not None else 0, nulls, 0, [raw, mask_arr])
+            padded = np.zeros(L.lib.b2_bitmask_allocation_size_bytes(len(valid)) or 64, dtype=np.uint8)
+            padded[: len(bits)] = bits
+            mask_arr = _DevCopy(padded)
+        return cls(dtype, len(values), raw.ptr, mask_arr.ptr if mask_arr is not None else 0, nulls, 0, [raw, mask_arr])
 
     def _host_bytes(ptr: int, nbytes: int) -> np.ndarray:
         return np.frombuffer(C.string_at(ptr, nbytes), dtype=np.uint8).copy()

@@ -197,3 +197,14 @@ for n, P, dt in [(1, 1, np.int64), (17, 2, np.int64), (4096, 8, np.int64), (4097
             assert (outs[b][int(counts[b]):] == 113).all(), (name, n, P, b, 'wrote past the bucket')
 print('STAGED_OK')
 """, "STAGED_OK")
+
+
+def test_emu_cpp_api(emu_lib, tmp_path):
+    """tests/cpp/api_smoke.cpp (the cudf:: header surface over the C ABI) linked against the emulator library."""
+    exe = tmp_path / "api_smoke_emu"
+    cmd = ["g++", "-std=c++17", f"-I{ROOT}/include", f"-I{ROOT}/tests/emu/include", f"{ROOT}/tests/cpp/api_smoke.cpp", "-o", str(exe),
+           f"-L{os.path.dirname(str(emu_lib))}", "-lcudf_b200_emu", f"-Wl,-rpath,{os.path.dirname(str(emu_lib))}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert "CPP_API_OK" in r.stdout, r.stdout + r.stderr
