@@ -303,7 +303,14 @@ constexpr int LBT = 8;   // predecessor tiles fetched per round
 // (EXPERIMENTAL in round 1: opt-in with B2_SORT_CARRY=1, not yet run on hardware).
 // MIX: raw 64-bit keys are replaced by mix64(key) on load (hash-join partitioning: the first executed pass reads the
 // packed key column itself, so the mixed keys are never materialised unsorted).
-template <typename UK, int THREADS, int IPT, int MINB, typename VT = uint32_t, bool CARRY = false, bool MIX = false>
+// SAFE: one more __syncwarp in the bitmap ranking loop (formally race-free under independent thread scheduling; the
+// shipped form relies on the warp staying converged, which hardware validation confirms) — B2_SORT_CFG=10 measures it.
+#ifdef B2_EMU
+constexpr bool EMU_BUILD = true;
+#else
+constexpr bool EMU_BUILD = false;
+#endif
+template <typename UK, int THREADS, int IPT, int MINB, typename VT = uint32_t, bool CARRY = false, bool MIX = false, bool SAFE = false>
 __global__ void __launch_bounds__(THREADS + 32 * LBW, MINB) onesweep_kernel(pass_args a)
 {
   constexpr int TILE   = THREADS * IPT;
@@ -503,12 +510,10 @@ __global__ void __launch_bounds__(THREADS + 32 * LBW, MINB) onesweep_kernel(pass
       const unsigned peers = my_bm[d];
       const unsigned lt = __popc(peers & lanemask_lt());
       uint32_t prev = 0;
-#ifdef B2_EMU
-      // The emulator runs the lanes of a warp one after the other between rendezvous points, so the leader's clear
-      // below would be seen by the followers' read above. On the GPU the warp executes this straight-line stretch
-      // converged (validated on hardware); DESIGN.md §7 lists the formally race-free variant (a third __syncwarp).
-      __syncwarp();
-#endif
+      // The emulator (tests/emu) runs the lanes of a warp one after the other between rendezvous points, so the
+      // leader's clear below would be seen by the followers' read above. On the GPU the warp executes this
+      // straight-line stretch converged (validated on hardware); SAFE is the formally race-free variant.
+      if constexpr (SAFE || EMU_BUILD) __syncwarp();
       if (lt == 0) {
         prev = my_hist[d];
         my_hist[d] = prev + __popc(peers);
@@ -774,7 +779,7 @@ int64_t portion_limit()
 //  raw_keys != nullptr : keys are the user's raw column (twiddled on load, implicit row ids)
 //  raw_keys == nullptr : keys are pre-twiddled in bufA with explicit row ids in idx buffer pre_idx_buf
 //  pairs: idx_out receives the permutation ; keys-only: bufA is the OUTPUT, bufB the temp.
-template <typename UK, int T, int I, int MINB, typename VT = uint32_t, bool CARRY = false, bool MIX = false>
+template <typename UK, int T, int I, int MINB, typename VT = uint32_t, bool CARRY = false, bool MIX = false, bool SAFE = false>
 void run_radix_cfg(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int32_t* idx_tmp, int32_t* idx_tmp2, int pre_idx_buf, int64_t n,
                    int kind, bool descending, bool pairs, cudaStream_t stream, int first_pass = 0, int last_pass = 7,
                    bool keep_keys = false, const void* val_in = nullptr)
@@ -811,7 +816,7 @@ void run_radix_cfg(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int
   B2_LAUNCH(plan_kernel, 1, RADIX, 0, stream, ghist, NP, (uint32_t)n, raw ? 1 : 0, pre_idx_buf, ctl, first_pass, last_pass);
 
   static bool attr_set = [] {
-    cudaFuncSetAttribute(onesweep_kernel<UK, T, I, MINB, VT, CARRY, MIX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncSetAttribute(onesweep_kernel<UK, T, I, MINB, VT, CARRY, MIX, SAFE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)onesweep_smem<UK, T, I, VT>());
     return true;
   }();
@@ -844,7 +849,7 @@ void run_radix_cfg(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int
       const int64_t ntiles = (pn + TILE - 1) / TILE;
       const size_t smem_bytes = onesweep_smem<UK, T, I, VT>();
       prof_scope ps("onesweep", stream);
-      B2_LAUNCH((onesweep_kernel<UK, T, I, MINB, VT, CARRY, MIX>), (unsigned)ntiles, T + 32 * LBW, smem_bytes, stream, a);
+      B2_LAUNCH((onesweep_kernel<UK, T, I, MINB, VT, CARRY, MIX, SAFE>), (unsigned)ntiles, T + 32 * LBW, smem_bytes, stream, a);
     }
   }
   {
@@ -882,6 +887,10 @@ void run_radix(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int32_t
       case 7: B2_RUN(256, 20, 2); break;
       case 8: B2_RUN(320, 16, 2); break;
       case 9: B2_RUN(320, 12, 2); break;
+      case 10:  // default shape, formally race-free bitmap ranking
+        run_radix_cfg<UK, 384, 16, 2, uint32_t, false, false, true>(raw_keys, bufA, bufB, idx_out, idx_tmp, idx_tmp2, pre_idx_buf, n, kind,
+                                                                    descending, pairs, stream);
+        break;
       default: B2_RUN(384, 16, 2); break;
     }
   } else {
