@@ -310,7 +310,10 @@ constexpr bool EMU_BUILD = true;
 #else
 constexpr bool EMU_BUILD = false;
 #endif
-template <typename UK, int THREADS, int IPT, int MINB, typename VT = uint32_t, bool CARRY = false, bool MIX = false, bool SAFE = false>
+// RMW: the leader advances the warp's running digit offset with one ATOMS.ADD (returning the old value) instead of
+// LDS + STS — one shared-memory operation less per key in a kernel bound by shared-memory wavefronts (B2_SORT_CFG=11).
+template <typename UK, int THREADS, int IPT, int MINB, typename VT = uint32_t, bool CARRY = false, bool MIX = false, bool SAFE = false,
+          bool RMW = false>
 __global__ void __launch_bounds__(THREADS + 32 * LBW, MINB) onesweep_kernel(pass_args a)
 {
   constexpr int TILE   = THREADS * IPT;
@@ -515,8 +518,12 @@ __global__ void __launch_bounds__(THREADS + 32 * LBW, MINB) onesweep_kernel(pass
       // straight-line stretch converged (validated on hardware); SAFE is the formally race-free variant.
       if constexpr (SAFE || EMU_BUILD) __syncwarp();
       if (lt == 0) {
-        prev = my_hist[d];
-        my_hist[d] = prev + __popc(peers);
+        if constexpr (RMW) {
+          prev = atomicAdd(&my_hist[d], (uint32_t)__popc(peers));
+        } else {
+          prev = my_hist[d];
+          my_hist[d] = prev + __popc(peers);
+        }
         my_bm[d] = 0;
       }
       __syncwarp();
@@ -779,7 +786,8 @@ int64_t portion_limit()
 //  raw_keys != nullptr : keys are the user's raw column (twiddled on load, implicit row ids)
 //  raw_keys == nullptr : keys are pre-twiddled in bufA with explicit row ids in idx buffer pre_idx_buf
 //  pairs: idx_out receives the permutation ; keys-only: bufA is the OUTPUT, bufB the temp.
-template <typename UK, int T, int I, int MINB, typename VT = uint32_t, bool CARRY = false, bool MIX = false, bool SAFE = false>
+template <typename UK, int T, int I, int MINB, typename VT = uint32_t, bool CARRY = false, bool MIX = false, bool SAFE = false,
+          bool RMW = false>
 void run_radix_cfg(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int32_t* idx_tmp, int32_t* idx_tmp2, int pre_idx_buf, int64_t n,
                    int kind, bool descending, bool pairs, cudaStream_t stream, int first_pass = 0, int last_pass = 7,
                    bool keep_keys = false, const void* val_in = nullptr)
@@ -816,7 +824,7 @@ void run_radix_cfg(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int
   B2_LAUNCH(plan_kernel, 1, RADIX, 0, stream, ghist, NP, (uint32_t)n, raw ? 1 : 0, pre_idx_buf, ctl, first_pass, last_pass);
 
   static bool attr_set = [] {
-    cudaFuncSetAttribute(onesweep_kernel<UK, T, I, MINB, VT, CARRY, MIX, SAFE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncSetAttribute(onesweep_kernel<UK, T, I, MINB, VT, CARRY, MIX, SAFE, RMW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)onesweep_smem<UK, T, I, VT>());
     return true;
   }();
@@ -849,7 +857,7 @@ void run_radix_cfg(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int
       const int64_t ntiles = (pn + TILE - 1) / TILE;
       const size_t smem_bytes = onesweep_smem<UK, T, I, VT>();
       prof_scope ps("onesweep", stream);
-      B2_LAUNCH((onesweep_kernel<UK, T, I, MINB, VT, CARRY, MIX, SAFE>), (unsigned)ntiles, T + 32 * LBW, smem_bytes, stream, a);
+      B2_LAUNCH((onesweep_kernel<UK, T, I, MINB, VT, CARRY, MIX, SAFE, RMW>), (unsigned)ntiles, T + 32 * LBW, smem_bytes, stream, a);
     }
   }
   {
@@ -890,6 +898,10 @@ void run_radix(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int32_t
       case 10:  // default shape, formally race-free bitmap ranking
         run_radix_cfg<UK, 384, 16, 2, uint32_t, false, false, true>(raw_keys, bufA, bufB, idx_out, idx_tmp, idx_tmp2, pre_idx_buf, n, kind,
                                                                     descending, pairs, stream);
+        break;
+      case 11:  // default shape, running digit offsets advanced by one ATOMS.ADD
+        run_radix_cfg<UK, 384, 16, 2, uint32_t, false, false, false, true>(raw_keys, bufA, bufB, idx_out, idx_tmp, idx_tmp2, pre_idx_buf, n,
+                                                                           kind, descending, pairs, stream);
         break;
       default: B2_RUN(384, 16, 2); break;
     }

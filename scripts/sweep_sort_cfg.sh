@@ -1,12 +1,12 @@
 #!/usr/bin/env bash
-# One-sweep tile-shape sweep (B2_SORT_CFG 0..10, see radix_sort.cu::run_radix) on the headline workload.
+# One-sweep tile-shape sweep (B2_SORT_CFG 0..11, see radix_sort.cu::run_radix) on the headline workload.
 #   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash scripts/sweep_sort_cfg.sh'
 # Prints one line per configuration: ms per sort_by_key, average one-sweep launch, fraction of the HBM peak.
 set -u
 cd "$(dirname "$0")/.."
 O=gpurun_out/sweep
 mkdir -p "$O"
-for cfg in 0 1 2 3 4 5 6 7 8 9 10; do
+for cfg in 0 1 2 3 4 5 6 7 8 9 10 11; do
   B2_SORT_CFG=$cfg timeout 300 python bench.py --steps 3 --warmup 3 --no-e2e --cpu-rows 100000 > "$O/cfg$cfg.json" 2> "$O/cfg$cfg.err"
   python - "$O/cfg$cfg.json" "$cfg" <<'PY'
 import json, sys

@@ -97,6 +97,12 @@ print('VALIDATED_OK')
 """, "VALIDATED_OK", env={"B2_SORT_PORTION": "12288"})
 
 
+@pytest.mark.parametrize("cfg", ["3", "10", "11"])
+def test_emu_sort_tile_variants(emu_lib, cfg):
+    """B2_SORT_CFG variants of the 64-bit one-sweep kernel (another tile shape, the race-free and the ATOMS.ADD ranking)."""
+    run(SORT_PAYLOAD, "SORT_PAYLOAD_OK", env={"B2_SORT_CFG": cfg})
+
+
 def test_emu_sort_carry_payload(emu_lib):
     run(SORT_PAYLOAD, "SORT_PAYLOAD_OK", env={"B2_SORT_CARRY": "1"})
 
