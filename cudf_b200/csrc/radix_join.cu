@@ -16,8 +16,9 @@
 //      16-bit local row numbers (32768 slots, load factor <= 0.5, slot = bits 33..47 of h); the partition's probe
 //      rows stream through it.  Larger partitions (skew, duplicates, > ~1e9 rows) are handled in chunks of 16384
 //      build rows, re-streaming the probe rows per chunk.
-//   3. count pass (matches per partition) -> exclusive scan -> retrieve pass (same kernel, writes the pairs at the
-//      partition's offset; positions inside a partition come from a shared-memory cursor).
+//   3. count pass (matches per work item) -> exclusive scan -> retrieve pass (same kernel, writes the pairs at the
+//      item's offset; positions inside an item come from a shared-memory cursor).  A work item is (partition, piece of
+//      at most 65536 probe rows), so that a probe-side hot key is spread over many CTAs (each re-builds the table).
 #include "common.cuh"
 #include "device_utils.cuh"
 #include "key_pack.cuh"
@@ -34,6 +35,7 @@ constexpr int RJ_THREADS = 1024;
 constexpr int RJ_CAP     = 16384;  // build rows per shared-memory table (local row numbers fit 16 bits, 0xFFFF = empty)
 constexpr int RJ_SLOTS   = 32768;
 constexpr size_t RJ_SMEM = (size_t)RJ_CAP * sizeof(uint64_t) + (size_t)RJ_SLOTS * sizeof(uint16_t);
+constexpr int RJ_PIECE   = 65536;  // probe rows per work item
 
 // packed (normalised) key per row; the mixing happens inside the partition passes (radix_partition_top16_mix)
 __global__ void __launch_bounds__(256) rj_pack_kernel(key_cols kc, int64_t n, uint64_t* __restrict__ packed)
@@ -61,16 +63,32 @@ __global__ void __launch_bounds__(256) rj_bounds_kernel(const uint64_t* __restri
   off[p] = (int32_t)lo;
 }
 
+// pieces[p] = number of work items of partition p (0 when either side is empty there); pieces[RJ_PARTS] = 0
+__global__ void __launch_bounds__(256) rj_pieces_kernel(const int32_t* __restrict__ boff, const int32_t* __restrict__ poff,
+                                                        int32_t* __restrict__ pieces)
+{
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p > RJ_PARTS) return;
+  int32_t v = 0;
+  if (p < RJ_PARTS) {
+    const int64_t nb = (int64_t)boff[p + 1] - boff[p], np = (int64_t)poff[p + 1] - poff[p];
+    if (nb > 0 && np > 0) v = (int32_t)((np + RJ_PIECE - 1) / RJ_PIECE);
+  }
+  pieces[p] = v;
+}
+
 __device__ __forceinline__ uint32_t rj_slot(uint64_t h) { return (uint32_t)(h >> 33) & (uint32_t)(RJ_SLOTS - 1); }
 
-// One CTA joins partition blockIdx.x.  RETRIEVE = false: part_counts[p] = number of pairs, *total += it.
-// RETRIEVE = true: pairs are written to out_probe / out_build starting at part_offsets[p].
+// One CTA joins work item blockIdx.x = (partition, probe piece); item_first[p] is the first item of partition p
+// (exclusive scan of rj_pieces_kernel's output, item_first[RJ_PARTS] = number of items).
+// RETRIEVE = false: item_counts[item] = number of pairs, *total += it.
+// RETRIEVE = true: pairs are written to out_probe / out_build starting at item_offsets[item].
 template <bool RETRIEVE>
 __global__ void __launch_bounds__(RJ_THREADS, 1)
 rj_join_kernel(const uint64_t* __restrict__ bh, const int32_t* __restrict__ bid, const int32_t* __restrict__ boff,
                const uint64_t* __restrict__ ph, const int32_t* __restrict__ pid, const int32_t* __restrict__ poff,
-               int32_t* __restrict__ part_counts, const int32_t* __restrict__ part_offsets, unsigned long long* __restrict__ total,
-               int32_t* __restrict__ out_probe, int32_t* __restrict__ out_build)
+               const int32_t* __restrict__ item_first, int32_t* __restrict__ item_counts, const int32_t* __restrict__ item_offsets,
+               unsigned long long* __restrict__ total, int32_t* __restrict__ out_probe, int32_t* __restrict__ out_build)
 {
   B2_DYNAMIC_SMEM(rj_smem);
   uint64_t* bk  = reinterpret_cast<uint64_t*>(rj_smem);
@@ -78,19 +96,31 @@ rj_join_kernel(const uint64_t* __restrict__ bh, const int32_t* __restrict__ bid,
   const uint16_t* tab16 = reinterpret_cast<const uint16_t*>(tab);
   __shared__ unsigned int s_cursor;
   __shared__ unsigned long long s_total;
+  __shared__ int s_part;
 
-  const int part = blockIdx.x;
+  const int item = blockIdx.x;
   const int tid  = threadIdx.x;
-  const int b0 = boff[part], b1 = boff[part + 1];
-  const int p0 = poff[part], p1 = poff[part + 1];
-  if (b0 == b1 || p0 == p1) {  // uniform over the CTA
-    if (!RETRIEVE && tid == 0) part_counts[part] = 0;
+  if (item >= item_first[RJ_PARTS]) {  // the grid is sized for the worst case; uniform over the CTA
+    if (!RETRIEVE && tid == 0) item_counts[item] = 0;
     return;
   }
   if (tid == 0) {
+    // partition of this item: the last p with item_first[p] <= item (partitions without items repeat their successor's value)
+    int lo = 0, hi = RJ_PARTS;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (item_first[mid] <= item) lo = mid;
+      else hi = mid;
+    }
+    s_part  = lo;
     s_total = 0;
-    if (RETRIEVE) s_cursor = (unsigned int)part_offsets[part];
+    if (RETRIEVE) s_cursor = (unsigned int)item_offsets[item];
   }
+  __syncthreads();
+  const int part = s_part;
+  const int b0 = boff[part], b1 = boff[part + 1];
+  const int64_t p0 = (int64_t)poff[part] + (int64_t)(item - item_first[part]) * RJ_PIECE;
+  const int64_t p1 = min(p0 + RJ_PIECE, (int64_t)poff[part + 1]);
   unsigned long long local = 0;
   for (int64_t c0 = b0; c0 < b1; c0 += RJ_CAP) {  // 64-bit: row numbers go up to 2^31 - 1
     const int cn = (int)min((int64_t)RJ_CAP, (int64_t)b1 - c0);
@@ -115,7 +145,7 @@ rj_join_kernel(const uint64_t* __restrict__ bh, const int32_t* __restrict__ bid,
       }
     }
     __syncthreads();
-    for (int64_t i = (int64_t)p0 + tid; i < p1; i += RJ_THREADS) {
+    for (int64_t i = p0 + tid; i < p1; i += RJ_THREADS) {
       const uint64_t h = ld_stream(ph + i);
       uint32_t s = rj_slot(h);
       while (true) {
@@ -140,7 +170,7 @@ rj_join_kernel(const uint64_t* __restrict__ bh, const int32_t* __restrict__ bid,
     __syncthreads();
     if (tid == 0) {
       const unsigned long long t = s_total;
-      part_counts[part] = (int32_t)min(t, (unsigned long long)INT32_MAX);  // the 64-bit total catches overflow
+      item_counts[item] = (int32_t)min(t, (unsigned long long)INT32_MAX);  // the 64-bit total catches overflow
       if (t) atomicAdd(total, t);
     }
   }
@@ -204,13 +234,21 @@ void radix_inner_join(const std::vector<b2_column_view>& build, const std::vecto
   rj_partition(build, stream, bs);
   rj_partition(probe, stream, ps);
 
-  dbuf counts(sizeof(int32_t) * RJ_PARTS, stream), tot(sizeof(unsigned long long), stream);
+  // work items: (partition, piece of <= RJ_PIECE probe rows); at most RJ_PARTS + n_probe / RJ_PIECE of them
+  const int64_t n_probe = probe[0].size;
+  const int32_t max_items = (int32_t)(RJ_PARTS + n_probe / RJ_PIECE + 1);
+  dbuf pieces(sizeof(int32_t) * (RJ_PARTS + 1), stream);
+  B2_LAUNCH(rj_pieces_kernel, (RJ_PARTS + 1 + 255) / 256, 256, 0, stream, bs.off.as<int32_t>(), ps.off.as<int32_t>(), pieces.as<int32_t>());
+  b2_column_view pv{B2_INT32, (int32_t)(RJ_PARTS + 1), pieces.ptr, nullptr, 0, 0};
+  auto item_first = scan(pv, B2_AGG_SUM, B2_SCAN_EXCLUSIVE, B2_NULL_EXCLUDE, stream);
+
+  dbuf counts(sizeof(int32_t) * max_items, stream), tot(sizeof(unsigned long long), stream);
   B2_CUDA_TRY(cudaMemsetAsync(tot.ptr, 0, sizeof(unsigned long long), stream));
   {
     prof_scope sc("rjoin_count", stream);
-    B2_LAUNCH((rj_join_kernel<false>), RJ_PARTS, RJ_THREADS, RJ_SMEM, stream, bs.h.as<uint64_t>(), bs.ids.as<int32_t>(),
-              bs.off.as<int32_t>(), ps.h.as<uint64_t>(), ps.ids.as<int32_t>(), ps.off.as<int32_t>(), counts.as<int32_t>(),
-              (const int32_t*)nullptr, tot.as<unsigned long long>(), (int32_t*)nullptr, (int32_t*)nullptr);
+    B2_LAUNCH((rj_join_kernel<false>), max_items, RJ_THREADS, RJ_SMEM, stream, bs.h.as<uint64_t>(), bs.ids.as<int32_t>(),
+              bs.off.as<int32_t>(), ps.h.as<uint64_t>(), ps.ids.as<int32_t>(), ps.off.as<int32_t>(), item_first->data.as<int32_t>(),
+              counts.as<int32_t>(), (const int32_t*)nullptr, tot.as<unsigned long long>(), (int32_t*)nullptr, (int32_t*)nullptr);
   }
   unsigned long long m = 0;
   B2_CUDA_TRY(cudaMemcpyAsync(&m, tot.ptr, sizeof(m), cudaMemcpyDeviceToHost, stream));
@@ -220,12 +258,13 @@ void radix_inner_join(const std::vector<b2_column_view>& build, const std::vecto
   out_probe = make_column(B2_INT32, (int32_t)m, false, stream);
   out_build = make_column(B2_INT32, (int32_t)m, false, stream);
   if (m == 0) return;
-  b2_column_view cv{B2_INT32, (int32_t)RJ_PARTS, counts.ptr, nullptr, 0, 0};
+  b2_column_view cv{B2_INT32, max_items, counts.ptr, nullptr, 0, 0};
   auto offs = scan(cv, B2_AGG_SUM, B2_SCAN_EXCLUSIVE, B2_NULL_EXCLUDE, stream);
   prof_scope sr("rjoin_retrieve", stream);
-  B2_LAUNCH((rj_join_kernel<true>), RJ_PARTS, RJ_THREADS, RJ_SMEM, stream, bs.h.as<uint64_t>(), bs.ids.as<int32_t>(),
-            bs.off.as<int32_t>(), ps.h.as<uint64_t>(), ps.ids.as<int32_t>(), ps.off.as<int32_t>(), (int32_t*)nullptr,
-            offs->data.as<int32_t>(), (unsigned long long*)nullptr, out_probe->data.as<int32_t>(), out_build->data.as<int32_t>());
+  B2_LAUNCH((rj_join_kernel<true>), max_items, RJ_THREADS, RJ_SMEM, stream, bs.h.as<uint64_t>(), bs.ids.as<int32_t>(),
+            bs.off.as<int32_t>(), ps.h.as<uint64_t>(), ps.ids.as<int32_t>(), ps.off.as<int32_t>(), item_first->data.as<int32_t>(),
+            (int32_t*)nullptr, offs->data.as<int32_t>(), (unsigned long long*)nullptr, out_probe->data.as<int32_t>(),
+            out_build->data.as<int32_t>());
 }
 
 }  // namespace b2

@@ -137,6 +137,10 @@ l = [(rng.integers(0, 50, 20000).astype(np.int32), None), (rng.integers(0, 9, 20
 r = [(rng.integers(0, 50, 9000).astype(np.int32), None), (rng.integers(0, 9, 9000).astype(np.int16), None)]
 check(l, r, 'two columns')
 check([(np.array([0.0, -0.0, np.nan, 1.5, np.nan]), None)], [(np.array([-0.0, np.nan, 2.5, 0.0]), None)], 'float specials')
+# probe-side hot key: 150000 probe rows of one key -> its partition is split into three work items
+p = rng.integers(0, 100_000, 200_000); p[:150_000] = 777
+b = rng.integers(0, 100_000, 30_000); b[:5] = 777
+check([(p, None)], [(b, None)], 'probe pieces')
 print('RADIX_JOIN_OK')
 """, "RADIX_JOIN_OK", env={"B2_JOIN_RADIX_ROWS": "1"})
 

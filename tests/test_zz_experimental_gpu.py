@@ -88,6 +88,10 @@ check([(l, None)], [(r, None)], 'wide')
 b = rng.integers(0, 1000, 60_000); b[:40_000] = 424242
 p = rng.integers(0, 1000, 80_000); p[:30] = 424242
 check([(p, None)], [(b, None)], 'chunks'); check([(b, None)], [(p, None)], 'chunks-swapped')
+# probe-side hot key: its partition is split into several (partition, probe piece) work items
+p = rng.integers(0, 100_000, 400_000); p[:300_000] = 777
+b = rng.integers(0, 100_000, 30_000); b[:5] = 777
+check([(p, None)], [(b, None)], 'probe pieces')
 # two-column packed key
 l = [(rng.integers(0, 50, 20000).astype(np.int32), None), (rng.integers(0, 9, 20000).astype(np.int16), None)]
 r = [(rng.integers(0, 50, 9000).astype(np.int32), None), (rng.integers(0, 9, 9000).astype(np.int16), None)]
