@@ -125,6 +125,9 @@ for _j in ("inner", "left", "full"):
     _sig(f"b2_{_j}_join", [P(TableView), P(TableView), i32, b2_stream, P(vp), P(vp)])
     _sig(f"b2_hash_join_{_j}_join", [vp, P(TableView), i32, C.c_size_t, b2_stream, P(vp), P(vp)])
     _sig(f"b2_hash_join_{_j}_join_size", [vp, P(TableView), b2_stream, P(C.c_size_t)])
+_sig("b2_hash_join_match_counts", [vp, P(TableView), i32, b2_stream, P(vp)])
+_sig("b2_hash_join_partitioned_join", [vp, P(TableView), P(ColumnView), i32, i32, i32, b2_stream, P(vp), P(vp)])
+_sig("b2_hash_join_finalize_full_join", [P(ColumnView), P(ColumnView), i32, i32, i32, b2_stream, P(vp), P(vp)])
 _sig("b2_hash_join_create", [P(TableView), i32, i32, C.c_double, b2_stream, P(vp)])
 _sig("b2_hash_join_destroy", [vp], None)
 _sig("b2_groupby_create", [P(TableView), i32, i32, u8p, i32, u8p, i32, P(vp)])
@@ -156,7 +159,8 @@ DECLARED_SYMBOLS = [
     "b2_bitmask_and", "b2_gather", "b2_sorted_order", "b2_sort", "b2_sort_by_key", "b2_inner_join", "b2_left_join",
     "b2_full_join", "b2_hash_join_create", "b2_hash_join_destroy", "b2_hash_join_inner_join",
     "b2_hash_join_left_join", "b2_hash_join_full_join", "b2_hash_join_inner_join_size",
-    "b2_hash_join_left_join_size", "b2_hash_join_full_join_size", "b2_groupby_create", "b2_groupby_destroy",
+    "b2_hash_join_left_join_size", "b2_hash_join_full_join_size", "b2_hash_join_match_counts",
+    "b2_hash_join_partitioned_join", "b2_hash_join_finalize_full_join", "b2_groupby_create", "b2_groupby_destroy",
     "b2_groupby_aggregate", "b2_groupby_scan", "b2_reduce", "b2_segmented_reduce", "b2_scan", "b2_partition",
     "b2_partition_plan_create", "b2_partition_scatter", "b2_partition_scatter_staged", "b2_partition_plan_free", "b2_ipc_alloc", "b2_ipc_open", "b2_ipc_close",
     "b2_ipc_free",

@@ -255,6 +255,57 @@ __global__ void __launch_bounds__(256) retrieve_wide_kernel(key_cols pk, key_col
   }
 }
 
+// ---- partitioned probe (hash_join.hpp:331-411): retrieve rows [row_begin, row_begin + n) of the probe table from the
+// match counts of a join_match_context. For LEFT the counts are >= 1 (an unmatched row owns one output slot), so an
+// unmatched row is recognised by walking its chain without a hit. Offsets are local to the partition.
+template <bool LEFT, bool WIDE>
+__global__ void __launch_bounds__(256) retrieve_part_kernel(key_src ks, key_cols bk, int64_t row_begin, int64_t n,
+                                                            const slot_t* __restrict__ table, uint32_t mask,
+                                                            const int32_t* __restrict__ counts, const int32_t* __restrict__ offsets,
+                                                            int32_t* __restrict__ out_left, int32_t* __restrict__ out_right)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int64_t r = row_begin + i;
+    const int32_t c = counts[r];
+    if (c == 0) continue;  // inner context: no match
+    uint64_t key;
+    uint32_t nb;
+    int32_t orig = (int32_t)r;
+    if constexpr (WIDE) hash_row_wide(ks.kc, r, key, nb);
+    else fetch_key(ks, r, key, nb, orig);
+    int32_t o = offsets[i];
+    const int32_t end = o + c;
+    bool any = false;
+    if (table != nullptr) {
+      uint32_t s0 = WIDE ? slot_hash(key, nb, mask) : first_slot(ks, key, nb, mask);
+      while (o < end) {
+        const slot_t s = load_slot(&table[s0]);
+        if (s.row == -1) break;
+        bool hit = s.key == key && s.nullbits == nb;
+        if constexpr (WIDE) hit = hit && rows_equal_wide(ks.kc, r, bk, s.row);
+        if (hit) {
+          out_left[o]  = orig;
+          out_right[o] = s.row;
+          ++o;
+          any = true;
+        }
+        s0 = (s0 + 1) & mask;
+      }
+    }
+    if (LEFT && !any) {
+      out_left[o]  = orig;
+      out_right[o] = B2_JOIN_NO_MATCH;
+    }
+  }
+}
+
+__global__ void fill_i32_kernel(int32_t* p, int64_t n, int32_t v)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = v;
+}
+
 // ---- full join complement (join_utils.cu finalize_full_join): build rows that never matched ----
 __global__ void mark_kernel(const int32_t* __restrict__ right_idx, int64_t m, uint32_t* __restrict__ bitmap)
 {
@@ -577,6 +628,136 @@ void hash_join_probe(const b2_hash_join* hj, const std::vector<b2_column_view>& 
   out_right = std::move(R);
 }
 
+// cudf::hash_join::{inner,left,full}_join_match_context — hash_join.hpp:254-330, match_context.cu
+column_ptr hash_join_match_counts(const b2_hash_join* hj, const std::vector<b2_column_view>& probe, int kind, cudaStream_t stream)
+{
+  validate_probe(*hj, probe);
+  const int64_t n = probe[0].size;
+  const bool left = kind != JOIN_INNER;
+  auto out = make_column(B2_INT32, (int32_t)n, false, stream);
+  if (n == 0) return out;
+  // counts must come out in probe row order: pack the keys on the fly (no pre-partitioned key source)
+  key_src ks{};
+  ks.kc = make_key_cols(probe, hj->wide);
+  ks.mixed_shift = hj->mixed_shift;
+  int32_t* counts = out->data.as<int32_t>();
+  if (hj->build_rows == 0 || hj->table.ptr == nullptr) {
+    B2_LAUNCH(fill_i32_kernel, grid_for(n), 256, 0, stream, counts, n, left ? 1 : 0);
+    return out;
+  }
+  dbuf tot(sizeof(unsigned long long), stream);
+  B2_CUDA_TRY(cudaMemsetAsync(tot.ptr, 0, sizeof(unsigned long long), stream));
+  const bool skip_nulls = hj->compare_nulls == B2_NULLS_UNEQUAL;
+  const slot_t* table = hj->table.as<slot_t>();
+  {
+    prof_scope ps("join_count", stream);
+    if (hj->wide) {
+      const key_cols bk = make_key_cols(hj->build_cols, true);
+      B2_LAUNCH((count_wide_kernel<false>), grid_for(n), 256, 0, stream, ks.kc, bk, n, skip_nulls, hj->table_has_null_rows, table, hj->mask,
+                counts, tot.as<unsigned long long>());
+    } else {
+      B2_LAUNCH((count_kernel<false>), grid_for(n), 256, 0, stream, ks, n, skip_nulls, hj->table_has_null_rows, table, hj->mask, counts,
+                tot.as<unsigned long long>());
+    }
+  }
+  if (left) B2_LAUNCH(left_adjust_kernel, grid_for(n), 256, 0, stream, counts, n, counts);  // in place: max(count, 1)
+  return out;
+}
+
+// cudf::hash_join::partitioned_{inner,left,full}_join — hash_join.hpp:331-411, partitioned_*_join.cu
+void hash_join_partitioned(const b2_hash_join* hj, const std::vector<b2_column_view>& probe, const b2_column_view& match_counts,
+                           int32_t left_start, int32_t left_end, int kind, cudaStream_t stream, column_ptr& out_left,
+                           column_ptr& out_right)
+{
+  validate_probe(*hj, probe);
+  const int64_t n = probe[0].size;
+  B2_EXPECTS(match_counts.data != nullptr || n == 0, B2_ERR_INVALID_ARGUMENT, "join_partition_context without match counts");
+  B2_EXPECTS(match_counts.type_id == B2_INT32 && match_counts.size == n, B2_ERR_INVALID_ARGUMENT,
+             "match counts must be an INT32 column with one entry per probe row");
+  B2_EXPECTS(left_start >= 0 && left_start <= left_end && left_end <= n, B2_ERR_INVALID_ARGUMENT,
+             "partition bounds are outside the left table");
+  const bool left = kind != JOIN_INNER;
+  const int64_t m = (int64_t)left_end - left_start;
+  const int32_t* counts = static_cast<const int32_t*>(match_counts.data) + match_counts.offset;
+  size_t total = 0;
+  column_ptr offs;
+  if (m > 0) {
+    b2_column_view part{B2_INT32, (int32_t)m, counts, nullptr, 0, left_start};
+    auto sum = reduce(part, B2_AGG_SUM, B2_INT64, nullptr, stream);
+    long long h = 0;
+    B2_CUDA_TRY(cudaMemcpyAsync(&h, sum->data.ptr, sizeof(h), cudaMemcpyDeviceToHost, stream));
+    B2_CUDA_TRY(cudaStreamSynchronize(stream));
+    total = (size_t)h;
+    B2_EXPECTS(total <= (size_t)INT32_MAX, B2_ERR_LOGIC, "join output of this partition exceeds size_type");
+    offs = scan(part, B2_AGG_SUM, B2_SCAN_EXCLUSIVE, B2_NULL_EXCLUDE, stream);
+  }
+  out_left  = make_column(B2_INT32, (int32_t)total, false, stream);
+  out_right = make_column(B2_INT32, (int32_t)total, false, stream);
+  if (total == 0) return;
+  key_src ks{};
+  ks.kc = make_key_cols(probe, hj->wide);
+  ks.mixed_shift = hj->mixed_shift;
+  const key_cols bk = hj->wide ? make_key_cols(hj->build_cols, true) : key_cols{};
+  const slot_t* table = hj->build_rows > 0 ? hj->table.as<slot_t>() : nullptr;
+  prof_scope ps("join_retrieve", stream);
+#define B2_RP(L, W)                                                                                                              \
+  B2_LAUNCH((retrieve_part_kernel<L, W>), grid_for(m), 256, 0, stream, ks, bk, (int64_t)left_start, m, table, hj->mask, counts, \
+            offs->data.as<int32_t>(), out_left->data.as<int32_t>(), out_right->data.as<int32_t>())
+  if (left) { if (hj->wide) B2_RP(true, true); else B2_RP(true, false); }
+  else      { if (hj->wide) B2_RP(false, true); else B2_RP(false, false); }
+#undef B2_RP
+}
+
+// cudf::hash_join::finalize_partitioned_full_join — hash_join.hpp:413-440, finalize_partitioned_full_join.cpp
+void hash_join_finalize_full(const std::vector<b2_column_view>& lparts, const std::vector<b2_column_view>& rparts, int32_t left_rows,
+                             int32_t right_rows, cudaStream_t stream, column_ptr& out_left, column_ptr& out_right)
+{
+  (void)left_rows;
+  B2_EXPECTS(lparts.size() == rparts.size(), B2_ERR_INVALID_ARGUMENT, "left and right partials differ in number");
+  B2_EXPECTS(right_rows >= 0, B2_ERR_INVALID_ARGUMENT, "negative table size");
+  int64_t m = 0;
+  for (size_t i = 0; i < lparts.size(); ++i) {
+    B2_EXPECTS(lparts[i].size == rparts[i].size, B2_ERR_INVALID_ARGUMENT, "left and right partial of one partition differ in size");
+    B2_EXPECTS(lparts[i].type_id == B2_INT32 && rparts[i].type_id == B2_INT32, B2_ERR_DATA_TYPE, "join indices are INT32");
+    m += lparts[i].size;
+  }
+  const int64_t nwords = ((int64_t)right_rows + 31) / 32;
+  dbuf bitmap(sizeof(uint32_t) * std::max<int64_t>(nwords, 1), stream), word_counts(sizeof(int32_t) * std::max<int64_t>(nwords, 1), stream);
+  B2_CUDA_TRY(cudaMemsetAsync(bitmap.ptr, 0, bitmap.bytes, stream));
+  for (auto& r : rparts)
+    if (r.size > 0)
+      B2_LAUNCH(mark_kernel, grid_for(r.size), 256, 0, stream, static_cast<const int32_t*>(r.data) + r.offset, (int64_t)r.size,
+                bitmap.as<uint32_t>());
+  int64_t extra = 0;
+  column_ptr word_offsets;
+  if (right_rows > 0) {
+    B2_LAUNCH(unmatched_count_kernel, grid_for(nwords), 256, 0, stream, bitmap.as<uint32_t>(), (int64_t)right_rows, word_counts.as<int32_t>());
+    b2_column_view wc{B2_INT32, (int32_t)nwords, word_counts.ptr, nullptr, 0, 0};
+    word_offsets = scan(wc, B2_AGG_SUM, B2_SCAN_EXCLUSIVE, B2_NULL_EXCLUDE, stream);
+    int32_t last_off = 0, last_cnt = 0;
+    B2_CUDA_TRY(cudaMemcpyAsync(&last_off, word_offsets->data.as<int32_t>() + (nwords - 1), 4, cudaMemcpyDeviceToHost, stream));
+    B2_CUDA_TRY(cudaMemcpyAsync(&last_cnt, word_counts.as<int32_t>() + (nwords - 1), 4, cudaMemcpyDeviceToHost, stream));
+    B2_CUDA_TRY(cudaStreamSynchronize(stream));
+    extra = (int64_t)last_off + last_cnt;
+  }
+  B2_EXPECTS(m + extra <= (int64_t)INT32_MAX, B2_ERR_LOGIC, "join output exceeds size_type");
+  out_left  = make_column(B2_INT32, (int32_t)(m + extra), false, stream);
+  out_right = make_column(B2_INT32, (int32_t)(m + extra), false, stream);
+  int64_t at = 0;
+  for (size_t i = 0; i < lparts.size(); ++i) {
+    const int64_t k = lparts[i].size;
+    if (k == 0) continue;
+    B2_CUDA_TRY(cudaMemcpyAsync(out_left->data.as<int32_t>() + at, static_cast<const int32_t*>(lparts[i].data) + lparts[i].offset, k * 4,
+                                cudaMemcpyDeviceToDevice, stream));
+    B2_CUDA_TRY(cudaMemcpyAsync(out_right->data.as<int32_t>() + at, static_cast<const int32_t*>(rparts[i].data) + rparts[i].offset, k * 4,
+                                cudaMemcpyDeviceToDevice, stream));
+    at += k;
+  }
+  if (extra > 0)
+    B2_LAUNCH(unmatched_write_kernel, grid_for(nwords), 256, 0, stream, bitmap.as<uint32_t>(), (int64_t)right_rows,
+              word_offsets->data.as<int32_t>(), m, out_left->data.as<int32_t>(), out_right->data.as<int32_t>());
+}
+
 }  // namespace b2
 
 // ---- C ABI -----------------------------------------------------------------------------------------
@@ -673,6 +854,50 @@ static b2_status obj_size(const b2_hash_join* hj, const b2_table_view* probe, in
 b2_status b2_hash_join_inner_join(const b2_hash_join* hj, const b2_table_view* p, int32_t hs, size_t sz, b2_stream s, b2_column** l, b2_column** r) { return obj_join(hj, p, JOIN_INNER, hs, sz, s, l, r); }
 b2_status b2_hash_join_left_join(const b2_hash_join* hj, const b2_table_view* p, int32_t hs, size_t sz, b2_stream s, b2_column** l, b2_column** r) { return obj_join(hj, p, JOIN_LEFT, hs, sz, s, l, r); }
 b2_status b2_hash_join_full_join(const b2_hash_join* hj, const b2_table_view* p, int32_t hs, size_t sz, b2_stream s, b2_column** l, b2_column** r) { return obj_join(hj, p, JOIN_FULL, hs, sz, s, l, r); }
+b2_status b2_hash_join_match_counts(const b2_hash_join* hj, const b2_table_view* probe, int32_t join_kind, b2_stream stream,
+                                    b2_column** out_counts)
+{
+  B2_TRY_BEGIN
+  B2_EXPECTS(hj && out_counts, B2_ERR_INVALID_ARGUMENT, "null argument");
+  B2_EXPECTS(join_kind >= JOIN_INNER && join_kind <= JOIN_FULL, B2_ERR_INVALID_ARGUMENT, "unknown join kind");
+  std::vector<b2_column_view> p;
+  validate_table(probe, p);
+  *out_counts = hash_join_match_counts(hj, p, join_kind, S(stream)).release();
+  B2_TRY_END
+}
+
+b2_status b2_hash_join_partitioned_join(const b2_hash_join* hj, const b2_table_view* probe, const b2_column_view* match_counts,
+                                        int32_t left_start, int32_t left_end, int32_t join_kind, b2_stream stream, b2_column** out_left,
+                                        b2_column** out_right)
+{
+  B2_TRY_BEGIN
+  B2_EXPECTS(hj && out_left && out_right, B2_ERR_INVALID_ARGUMENT, "null argument");
+  B2_EXPECTS(match_counts != nullptr, B2_ERR_INVALID_ARGUMENT, "join_partition_context without a match context");
+  B2_EXPECTS(join_kind >= JOIN_INNER && join_kind <= JOIN_FULL, B2_ERR_INVALID_ARGUMENT, "unknown join kind");
+  std::vector<b2_column_view> p;
+  validate_table(probe, p);
+  column_ptr l, r;
+  hash_join_partitioned(hj, p, *match_counts, left_start, left_end, join_kind, S(stream), l, r);
+  *out_left  = l.release();
+  *out_right = r.release();
+  B2_TRY_END
+}
+
+b2_status b2_hash_join_finalize_full_join(const b2_column_view* left_partials, const b2_column_view* right_partials, int32_t num_partials,
+                                          int32_t left_table_num_rows, int32_t right_table_num_rows, b2_stream stream,
+                                          b2_column** out_left, b2_column** out_right)
+{
+  B2_TRY_BEGIN
+  B2_EXPECTS(out_left && out_right && num_partials >= 0 && (num_partials == 0 || (left_partials && right_partials)),
+             B2_ERR_INVALID_ARGUMENT, "null argument");
+  std::vector<b2_column_view> lp(left_partials, left_partials + num_partials), rp(right_partials, right_partials + num_partials);
+  column_ptr l, r;
+  hash_join_finalize_full(lp, rp, left_table_num_rows, right_table_num_rows, S(stream), l, r);
+  *out_left  = l.release();
+  *out_right = r.release();
+  B2_TRY_END
+}
+
 b2_status b2_hash_join_inner_join_size(const b2_hash_join* hj, const b2_table_view* p, b2_stream s, size_t* out) { return obj_size(hj, p, JOIN_INNER, s, out); }
 b2_status b2_hash_join_left_join_size(const b2_hash_join* hj, const b2_table_view* p, b2_stream s, size_t* out) { return obj_size(hj, p, JOIN_LEFT, s, out); }
 b2_status b2_hash_join_full_join_size(const b2_hash_join* hj, const b2_table_view* p, b2_stream s, size_t* out) { return obj_size(hj, p, JOIN_FULL, s, out); }

@@ -71,7 +71,71 @@ class HashJoin:
     def full_join_size(self, probe: Table, stream=None) -> int:
         return self._size("b2_hash_join_full_join_size", probe, stream)
 
+    # ---- match context / partitioned probes (hash_join.hpp:254-440) ---------------------------------
+    def _match_context(self, kind: int, probe: Table, stream) -> "JoinMatchContext":
+        out = C.c_void_p()
+        pv = probe._view()
+        check(lib.b2_hash_join_match_counts(C.c_void_p(self._handle), C.byref(pv), kind, _lib.stream_arg(stream), C.byref(out)))
+        return JoinMatchContext(probe, Column._from_handle(out.value), kind)
+
+    def inner_join_match_context(self, probe: Table, stream=None) -> "JoinMatchContext":
+        return self._match_context(0, probe, stream)
+
+    def left_join_match_context(self, probe: Table, stream=None) -> "JoinMatchContext":
+        return self._match_context(1, probe, stream)
+
+    def full_join_match_context(self, probe: Table, stream=None) -> "JoinMatchContext":
+        return self._match_context(2, probe, stream)
+
+    def _partitioned(self, kind: int, context: "JoinPartitionContext", stream):
+        ctx = context.left_table_context
+        if ctx is None or ctx._match_counts is None:
+            raise ValueError("join_partition_context without a match context")
+        lo, ro = C.c_void_p(), C.c_void_p()
+        pv, cv = ctx._left_table._view(), ctx._match_counts._view()
+        check(lib.b2_hash_join_partitioned_join(C.c_void_p(self._handle), C.byref(pv), C.byref(cv), int(context.left_start_idx),
+                                                int(context.left_end_idx), kind, _lib.stream_arg(stream), C.byref(lo), C.byref(ro)))
+        return Column._from_handle(lo.value), Column._from_handle(ro.value)
+
+    def partitioned_inner_join(self, context: "JoinPartitionContext", stream=None):
+        return self._partitioned(0, context, stream)
+
+    def partitioned_left_join(self, context: "JoinPartitionContext", stream=None):
+        return self._partitioned(1, context, stream)
+
+    def partitioned_full_join(self, context: "JoinPartitionContext", stream=None):
+        """Probe side only; finalize_partitioned_full_join appends the unmatched build rows."""
+        return self._partitioned(2, context, stream)
+
+    @staticmethod
+    def finalize_partitioned_full_join(left_partials, right_partials, left_table_num_rows: int, right_table_num_rows: int, stream=None):
+        n = len(left_partials)
+        lv = (_lib.ColumnView * max(n, 1))(*[c._view() for c in left_partials])
+        rv = (_lib.ColumnView * max(n, 1))(*[c._view() for c in right_partials])
+        lo, ro = C.c_void_p(), C.c_void_p()
+        check(lib.b2_hash_join_finalize_full_join(lv, rv, n, int(left_table_num_rows), int(right_table_num_rows), _lib.stream_arg(stream),
+                                                  C.byref(lo), C.byref(ro)))
+        return Column._from_handle(lo.value), Column._from_handle(ro.value)
+
     def __del__(self):
         if getattr(self, "_handle", 0):
             lib.b2_hash_join_destroy(C.c_void_p(self._handle))
             self._handle = 0
+
+
+class JoinMatchContext:
+    """cudf::join_match_context (join.hpp:81-107): the left table and its per-row match counts (INT32 column)."""
+
+    def __init__(self, left_table: Table, match_counts: Column, kind: int = 0):
+        self._left_table = left_table
+        self._match_counts = match_counts
+        self._kind = kind
+
+
+class JoinPartitionContext:
+    """cudf::join_partition_context (join.hpp:120-125)."""
+
+    def __init__(self, left_table_context: JoinMatchContext, left_start_idx: int, left_end_idx: int):
+        self.left_table_context = left_table_context
+        self.left_start_idx = left_start_idx
+        self.left_end_idx = left_end_idx

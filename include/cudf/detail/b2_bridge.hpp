@@ -399,6 +399,37 @@ CUDF_B2_FREE_JOIN(left_join)
 CUDF_B2_FREE_JOIN(full_join)
 #undef CUDF_B2_FREE_JOIN
 
+// join.hpp:81-125
+struct join_match_context {
+  table_view _left_table;
+  std::unique_ptr<rmm::device_uvector<size_type>> _match_counts;
+  join_match_context(table_view const& left_table, std::unique_ptr<rmm::device_uvector<size_type>> match_counts)
+    : _left_table{left_table}, _match_counts{std::move(match_counts)}
+  {
+  }
+  join_match_context(join_match_context const&)            = delete;
+  join_match_context& operator=(join_match_context const&) = delete;
+  join_match_context(join_match_context&&)                 = default;
+  join_match_context& operator=(join_match_context&&)      = default;
+  virtual ~join_match_context()                            = default;
+};
+struct join_partition_context {
+  std::unique_ptr<join_match_context> left_table_context;
+  size_type left_start_idx;
+  size_type left_end_idx;
+};
+template <typename T>
+struct device_span {  // cudf::device_span<T const> over device memory owned elsewhere
+  T* ptr{nullptr};
+  std::size_t n{0};
+  device_span() = default;
+  device_span(T* p, std::size_t size) : ptr(p), n(size) {}
+  template <typename U>
+  device_span(rmm::device_uvector<U> const& v) : ptr(v.data()), n(v.size()) {}  // NOLINT
+  [[nodiscard]] T* data() const noexcept { return ptr; }
+  [[nodiscard]] std::size_t size() const noexcept { return n; }
+};
+
 class hash_join {
  public:
   hash_join() = delete;
@@ -437,6 +468,53 @@ class hash_join {
   CUDF_B2_OBJ_JOIN(left_join)
   CUDF_B2_OBJ_JOIN(full_join)
 #undef CUDF_B2_OBJ_JOIN
+  // match context + partitioned probes (hash_join.hpp:254-440)
+#define CUDF_B2_MATCH_CTX(NAME, KIND)                                                                                \
+  [[nodiscard]] cudf::join_match_context NAME##_match_context(table_view const& left,                                \
+                                                              rmm::cuda_stream_view stream = cudf::get_default_stream(), \
+                                                              rmm::device_async_resource_ref = cudf::get_current_device_resource_ref()) const \
+  {                                                                                                                  \
+    auto p = left.native();                                                                                          \
+    b2_column* c = nullptr;                                                                                          \
+    detail::check(b2_hash_join_match_counts(h_, &p, KIND, stream.value(), &c));                                      \
+    return cudf::join_match_context{left, detail::to_uvector(c)};                                                    \
+  }                                                                                                                  \
+  [[nodiscard]] join_result partitioned_##NAME(cudf::join_partition_context const& context,                          \
+                                               rmm::cuda_stream_view stream = cudf::get_default_stream(),            \
+                                               rmm::device_async_resource_ref = cudf::get_current_device_resource_ref()) const \
+  {                                                                                                                  \
+    if (!context.left_table_context || !context.left_table_context->_match_counts)                                   \
+      throw std::invalid_argument("join_partition_context without a match context");                                 \
+    auto const& ctx = *context.left_table_context;                                                                   \
+    auto p = ctx._left_table.native();                                                                               \
+    b2_column_view counts{B2_INT32, (int32_t)ctx._match_counts->size(), ctx._match_counts->data(), nullptr, 0, 0};   \
+    b2_column *lo = nullptr, *ro = nullptr;                                                                          \
+    detail::check(b2_hash_join_partitioned_join(h_, &p, &counts, context.left_start_idx, context.left_end_idx, KIND, \
+                                                stream.value(), &lo, &ro));                                          \
+    return {detail::to_uvector(lo), detail::to_uvector(ro)};                                                         \
+  }
+  CUDF_B2_MATCH_CTX(inner_join, 0)
+  CUDF_B2_MATCH_CTX(left_join, 1)
+  CUDF_B2_MATCH_CTX(full_join, 2)
+#undef CUDF_B2_MATCH_CTX
+  [[nodiscard]] static join_result finalize_partitioned_full_join(std::vector<device_span<size_type const>> const& left_partials,
+                                                                  std::vector<device_span<size_type const>> const& right_partials,
+                                                                  size_type left_table_num_rows, size_type right_table_num_rows,
+                                                                  rmm::cuda_stream_view stream = cudf::get_default_stream(),
+                                                                  rmm::device_async_resource_ref = cudf::get_current_device_resource_ref())
+  {
+    if (left_partials.size() != right_partials.size()) throw std::invalid_argument("left and right partials differ in number");
+    std::vector<b2_column_view> l, r;
+    for (std::size_t i = 0; i < left_partials.size(); ++i) {
+      l.push_back(b2_column_view{B2_INT32, (int32_t)left_partials[i].size(), left_partials[i].data(), nullptr, 0, 0});
+      r.push_back(b2_column_view{B2_INT32, (int32_t)right_partials[i].size(), right_partials[i].data(), nullptr, 0, 0});
+    }
+    b2_column *lo = nullptr, *ro = nullptr;
+    detail::check(b2_hash_join_finalize_full_join(l.data(), r.data(), (int32_t)l.size(), left_table_num_rows, right_table_num_rows,
+                                                  stream.value(), &lo, &ro));
+    return {detail::to_uvector(lo), detail::to_uvector(ro)};
+  }
+
  private:
   b2_hash_join* h_{nullptr};
 };

@@ -209,6 +209,26 @@ B2_API b2_status b2_hash_join_left_join_size(const b2_hash_join* hj, const b2_ta
 B2_API b2_status b2_hash_join_full_join_size(const b2_hash_join* hj, const b2_table_view* probe,
                                              b2_stream stream, size_t* out);
 
+/* hash_join::{inner,left,full}_join_match_context (hash_join.hpp:254-330, join.hpp:81-125): per probe row, the
+ * number of matching build rows as an INT32 column of probe.num_rows (join_kind: 0 inner, 1 left, 2 full; for
+ * left / full a row without a match counts 1 — its null-placeholder output row). Golden: join_tests.cpp:2339-2527. */
+B2_API b2_status b2_hash_join_match_counts(const b2_hash_join* hj, const b2_table_view* probe, int32_t join_kind,
+                                           b2_stream stream, b2_column** out_counts);
+/* hash_join::partitioned_{inner,left,full}_join (hash_join.hpp:331-411): join rows [left_start, left_end) of the
+ * probe table given the match counts of the WHOLE probe table (from b2_hash_join_match_counts with the same
+ * join_kind). Left indices are relative to the whole probe table. join_kind 2 does not append the unmatched build
+ * rows: b2_hash_join_finalize_full_join does. Bounds outside [0, num_rows] -> INVALID_ARGUMENT. */
+B2_API b2_status b2_hash_join_partitioned_join(const b2_hash_join* hj, const b2_table_view* probe,
+                                               const b2_column_view* match_counts, int32_t left_start,
+                                               int32_t left_end, int32_t join_kind, b2_stream stream,
+                                               b2_column** out_left, b2_column** out_right);
+/* hash_join::finalize_partitioned_full_join (hash_join.hpp:413-440): concatenates the per-partition index pairs and
+ * appends (JoinNoMatch, r) for every build row r that no partition matched. */
+B2_API b2_status b2_hash_join_finalize_full_join(const b2_column_view* left_partials,
+                                                 const b2_column_view* right_partials, int32_t num_partials,
+                                                 int32_t left_table_num_rows, int32_t right_table_num_rows,
+                                                 b2_stream stream, b2_column** out_left, b2_column** out_right);
+
 /* ---- groupby: cpp/include/cudf/groupby.hpp:121-125,181-184, cpp/src/groupby/groupby.cu ----- */
 B2_API b2_status b2_groupby_create(const b2_table_view* keys, int32_t null_handling, int32_t keys_are_sorted,
                                    const uint8_t* column_order, int32_t n_order,

@@ -97,6 +97,17 @@ def inner_join_size(left_cols, right_cols, nulls_equal=EQUAL) -> int:
     return int(_matches_count(lid, rid))
 
 
+def match_counts(left_cols, right_cols, nulls_equal=EQUAL, kind="inner") -> np.ndarray:
+    """hash_join::{inner,left,full}_join_match_context (cpp/include/cudf/join/hash_join.hpp:254-330): matching build
+    rows per left row as int32; for left / full a row without a match counts 1 (join_tests.cpp:2403-2492)."""
+    lid, rid = _row_ids(left_cols, right_cols, nulls_equal)
+    rs = np.sort(rid)
+    c = np.where(lid >= 0, np.searchsorted(rs, lid, side="right") - np.searchsorted(rs, lid, side="left"), 0)
+    if kind != "inner":
+        c = np.maximum(c, 1)
+    return c.astype(np.int32)
+
+
 def _matches_count(lid, rid):
     rs = np.sort(rid)
     lo = np.searchsorted(rs, lid, side="left")

@@ -49,6 +49,24 @@ int main()
   std::sort(pairs.begin(), pairs.end());
   EXPECT((pairs == std::vector<std::pair<int, int>>{{0, 4}, {2, 0}, {2, 1}, {3, 2}, {4, 0}, {4, 1}}));
   try { cudf::hash_join bad(table_view{{rc}}, nullable_join::NO, null_equality::EQUAL, 1.5); EXPECT(false); } catch (std::invalid_argument const&) {}
+  // match context + partitioned probes (join_tests.cpp:2363-2377: counts {1, 0, 2, 1, 2})
+  {
+    auto ctx = hj.inner_join_match_context(table_view{{lc}});
+    EXPECT((to_host(ctx._match_counts->data(), 5) == std::vector<int32_t>{1, 0, 2, 1, 2}));
+    cudf::join_partition_context part{std::make_unique<cudf::join_match_context>(std::move(ctx)), 0, 3};
+    auto [pl, pr] = hj.partitioned_inner_join(part);
+    EXPECT(pl->size() == 3);  // rows 0..2 of the probe: (0,4), (2,0), (2,1)
+    part.left_start_idx = 3; part.left_end_idx = 5;
+    auto [ql, qr] = hj.partitioned_inner_join(part);
+    EXPECT(ql->size() == 3);  // (3,2), (4,0), (4,1)
+    part.left_start_idx = 4; part.left_end_idx = 9;
+    try { (void)hj.partitioned_inner_join(part); EXPECT(false); } catch (std::invalid_argument const&) {}
+    auto fctx = hj.full_join_match_context(table_view{{lc}});
+    cudf::join_partition_context fpart{std::make_unique<cudf::join_match_context>(std::move(fctx)), 0, 5};
+    auto [fl, fr] = hj.partitioned_full_join(fpart);
+    auto [gl, gr] = cudf::hash_join::finalize_partitioned_full_join({{fl->data(), fl->size()}}, {{fr->data(), fr->size()}}, 5, 5);
+    EXPECT(gl->size() == hj.full_join_size(table_view{{lc}}));
+  }
   // groupby sum (sum_tests.cpp:68-80)
   dev_vec<int32_t> gk({1, 2, 3, 1, 2, 2, 1, 3, 3, 2});
   dev_vec<double> gv({0, 1, 2, 3, 4, 5, 6, 7, 8, 9});

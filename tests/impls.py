@@ -27,6 +27,13 @@ class OracleImpl:
     def inner_join_size(self, l, r, ne=0):
         return ojoin.inner_join_size(l, r, ne)
 
+    def match_counts(self, l, r, ne=0, kind="inner"):
+        return ojoin.match_counts(l, r, ne, kind)
+
+    def partitioned_join(self, l, r, ne=0, kind="inner", bounds=(0,)):
+        """The whole join, however it is partitioned (the partitioned API must reproduce it)."""
+        return getattr(ojoin, f"{kind}_join")(l, r, ne)
+
     def groupby(self, keys, requests, include_nulls=False):
         k, res = ogb.aggregate(keys, [(c, [KINDS[x] for x in kinds]) for c, kinds in requests], 1 if include_nulls else 0)
         return k, res
@@ -69,6 +76,27 @@ class PlcImpl:
     def inner_join_size(self, l, r, ne=0):
         hj = self.plc.join.HashJoin(self._tbl(r), ne)
         return hj.inner_join_size(self._tbl(l))
+
+    def match_counts(self, l, r, ne=0, kind="inner"):
+        hj = self.plc.join.HashJoin(self._tbl(r), ne)
+        ctx = getattr(hj, f"{kind}_join_match_context")(self._tbl(l))
+        return ctx._match_counts.to_numpy()[0]
+
+    def partitioned_join(self, l, r, ne=0, kind="inner", bounds=(0,)):
+        """match context -> one partitioned probe per [bounds[i], bounds[i+1]) -> concatenation (full: finalize)."""
+        plc = self.plc
+        hj = plc.join.HashJoin(self._tbl(r), ne)
+        lt = self._tbl(l)
+        ctx = getattr(hj, f"{kind}_join_match_context")(lt)
+        n = lt.num_rows()
+        cuts = sorted(set([0, n] + [b for b in bounds if 0 <= b <= n]))
+        parts = [getattr(hj, f"partitioned_{kind}_join")(plc.join.JoinPartitionContext(ctx, a, b)) for a, b in zip(cuts[:-1], cuts[1:])]
+        if kind == "full":
+            lo, ro = plc.join.HashJoin.finalize_partitioned_full_join([p[0] for p in parts], [p[1] for p in parts], n, len(r[0][0]))
+            return ojoin.canonical(lo.to_numpy()[0], ro.to_numpy()[0])
+        ls = [p[0].to_numpy()[0] for p in parts] or [np.empty(0, np.int32)]
+        rs = [p[1].to_numpy()[0] for p in parts] or [np.empty(0, np.int32)]
+        return ojoin.canonical(np.concatenate(ls), np.concatenate(rs))
 
     def _agg(self, name):
         a = self.plc.aggregation

@@ -218,3 +218,11 @@ def test_emu_cpp_api(emu_lib, tmp_path):
     assert r.returncode == 0, r.stderr[-3000:]
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
     assert "CPP_API_OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_emu_match_context_suite(emu_lib):
+    """The gpu-marked cases of tests/test_zzzz_match_context.py (match context, partitioned probes, finalize) on the emulator."""
+    e = dict(os.environ, B2_EMU_RUN="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_zzzz_match_context.py", "-q", "-m", "gpu", "-p", "no:cacheprovider"],
+                       capture_output=True, text=True, env=e, cwd=ROOT, timeout=900)
+    assert r.returncode == 0 and " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
