@@ -30,7 +30,7 @@ namespace {
 constexpr int MAX_OPS = 24;
 
 enum acc_kind : int8_t { ACC_I64 = 0, ACC_U64 = 1, ACC_F64 = 2 };
-enum op_kind : int8_t { OPK_SUM = 0, OPK_MIN = 1, OPK_MAX = 2 };
+enum op_kind : int8_t { OPK_SUM = 0, OPK_MIN = 1, OPK_MAX = 2, OPK_SUMSQ = 3 };
 
 struct value_op {
   const void* src;
@@ -127,7 +127,9 @@ __device__ __forceinline__ void load_value(const value_op& op, int64_t e, long l
 
 // WIDE (keys wider than 8 bytes): the slot holds a 64-bit hash of the row; a hash hit is confirmed by comparing the
 // key columns of this row with the slot's representative row (key_pack.cuh).
-template <bool WIDE = false>
+// SQ: the request contains SUM_OF_SQUARES accumulators (M2 / VARIANCE / STD are derived from SUM, SUM_OF_SQUARES and
+// COUNT in the finalize step: cpp/src/groupby/common/m2_var_std.cu:35-62).
+template <bool WIDE = false, bool SQ = false>
 __global__ void __launch_bounds__(256) groupby_kernel(key_cols kc, int64_t n, bool skip_null_keys, slot_t* __restrict__ table,
                                                       uint32_t mask, uint32_t cap, int32_t* __restrict__ gsize,
                                                       int32_t* __restrict__ slot_gid, int32_t* __restrict__ rep_rows, value_ops ops,
@@ -184,6 +186,14 @@ __global__ void __launch_bounds__(256) groupby_kernel(key_cols kc, int64_t n, bo
       double fv = 0;
       load_value(op, e, iv, uv, fv);
       unsigned long long* a = op.accum + i;
+      if constexpr (SQ) {
+        if (op.op == OPK_SUMSQ) {  // device_aggregators.cuh:309-321: value * value in the target type
+          if (op.acc == ACC_F64) atomicAdd(reinterpret_cast<double*>(a), fv * fv);
+          else if (op.acc == ACC_I64) atomicAdd(a, (unsigned long long)iv * (unsigned long long)iv);
+          else atomicAdd(a, uv * uv);
+          continue;
+        }
+      }
       if (op.acc == ACC_F64) {
         if (op.op == OPK_SUM) atomicAdd(reinterpret_cast<double*>(a), fv);
         else if (op.op == OPK_MIN) atomicMin(reinterpret_cast<long long*>(a), f64_to_ordered(fv));
@@ -214,14 +224,18 @@ struct out_spec {
   const int32_t* gsize;
   int8_t acc;       // acc_kind of accum
   int8_t op;        // op_kind
-  int8_t mode;      // 0 value (SUM/MIN/MAX), 1 MEAN, 2 COUNT_VALID, 3 COUNT_ALL
+  int8_t mode;      // 0 value (SUM/MIN/MAX/SUM_OF_SQUARES), 1 MEAN, 2 COUNT_VALID, 3 COUNT_ALL, 5 M2, 6 VARIANCE, 7 STD
   int8_t pad;
   int32_t out_type; // storage type id of the output column
   void* out;
   uint32_t* out_mask;  // null: no mask
   unsigned long long* null_count;
+  // appended last so that the layout seen by the validated kernels does not move
+  const unsigned long long* accum2;  // modes 5-7: SUM_OF_SQUARES accumulator (accum = SUM accumulator)
+  int32_t ddof;
 };
 
+template <bool EXT = false>
 __global__ void __launch_bounds__(256) finalize_kernel(const slot_t* __restrict__ table, int64_t slots,
                                                        const int32_t* __restrict__ slot_gid, out_spec o)
 {
@@ -234,6 +248,27 @@ __global__ void __launch_bounds__(256) finalize_kernel(const slot_t* __restrict_
     if (o.mode == 2) { static_cast<int32_t*>(o.out)[g] = nvalid; continue; }
     if (o.mode == 3) { static_cast<int32_t*>(o.out)[g] = o.gsize[s]; continue; }
     const unsigned long long raw = o.accum[s];
+    if constexpr (EXT) {
+      if (o.mode >= 5) {  // M2 / VARIANCE / STD (m2_var_std.cu:35-62,150-196), always FLOAT64
+        const unsigned long long raw2 = o.accum2[s];
+        const double sum   = o.acc == ACC_F64 ? __longlong_as_double((long long)raw) : (double)(long long)raw;
+        const double sumsq = o.acc == ACC_F64 ? __longlong_as_double((long long)raw2) : (double)(long long)raw2;
+        const double m2 = nvalid == 0 ? 0.0 : sumsq - sum * sum / nvalid;
+        double out = m2;
+        bool valid = true;
+        if (o.mode != 5) {
+          const int df = nvalid - o.ddof;
+          valid = nvalid != 0 && df > 0;
+          out = valid ? (o.mode == 6 ? m2 / df : sqrt(m2 / df)) : 0.0;
+        }
+        static_cast<double*>(o.out)[g] = out;
+        if (o.out_mask) {
+          if (valid) atomicOr(&o.out_mask[g >> 5], 1u << (g & 31));
+          else ++nulls;
+        }
+        continue;
+      }
+    }
     if (o.mode == 1) {
       double sum = o.acc == ACC_F64 ? __longlong_as_double((long long)raw)
                                     : (o.acc == ACC_I64 ? (double)(long long)raw : (double)raw);
@@ -272,17 +307,23 @@ int grid_for(int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>((n 
 int32_t result_type(int32_t kind, int32_t src)
 {
   switch (kind) {
-    case B2_AGG_SUM: return is_float_id(src) ? src : B2_INT64;
+    case B2_AGG_SUM: case B2_AGG_SUM_OF_SQUARES: return is_float_id(src) ? src : B2_INT64;
+    case B2_AGG_M2: case B2_AGG_VARIANCE: case B2_AGG_STD: return B2_FLOAT64;
     case B2_AGG_MIN: case B2_AGG_MAX: return src;
     case B2_AGG_COUNT_VALID: case B2_AGG_COUNT_ALL: return B2_INT32;
     case B2_AGG_MEAN: return B2_FLOAT64;
-    default: B2_FAIL(B2_ERR_INVALID_ARGUMENT, "unsupported groupby aggregation on the hash path (SUM/MIN/MAX/COUNT/MEAN)");
+    default: B2_FAIL(B2_ERR_INVALID_ARGUMENT, "unsupported groupby aggregation on the hash path (SUM/MIN/MAX/COUNT/MEAN/SUM_OF_SQUARES/M2/VARIANCE/STD)");
   }
 }
 
+// B2_AGG_WITH_DDOF: bit 30 says "ddof given", bits 8..23 hold it; the plain kind means ddof = 1 (aggregation.hpp:231-260)
+inline int32_t base_kind(int32_t k) { return (k & (1 << 30)) ? (k & 0xFF) : k; }
+inline int32_t kind_ddof(int32_t k) { return (k & (1 << 30)) ? ((k >> 8) & 0xFFFF) : 1; }
+inline bool needs_sumsq(int32_t kind) { return kind == B2_AGG_SUM_OF_SQUARES || kind == B2_AGG_M2 || kind == B2_AGG_VARIANCE || kind == B2_AGG_STD; }
+
 unsigned long long acc_init(int8_t acc, int8_t op)
 {
-  if (op == OPK_SUM) return 0ull;
+  if (op == OPK_SUM || op == OPK_SUMSQ) return 0ull;
   if (acc == ACC_U64) return op == OPK_MIN ? ~0ull : 0ull;
   // I64, and F64 in ordered-int64 space
   return op == OPK_MIN ? (unsigned long long)INT64_MAX : (unsigned long long)INT64_MIN;
@@ -314,7 +355,7 @@ static void empty_results(const b2_groupby& gb, const std::vector<request_view>&
   for (auto& k : gb.keys) keys_out->cols.push_back(make_column(k.type_id, 0, false, stream));
   res_out = std::make_unique<b2_table>();
   for (auto& r : reqs)
-    for (int32_t kind : r.kinds) res_out->cols.push_back(make_column(result_type(kind, r.values.type_id), 0, false, stream));
+    for (int32_t kind : r.kinds) res_out->cols.push_back(make_column(result_type(base_kind(kind), r.values.type_id), 0, false, stream));
 }
 
 // cudf::groupby::groupby::aggregate — groupby.cu:220-237 -> hash path
@@ -326,10 +367,11 @@ void groupby_aggregate(const b2_groupby& gb, const std::vector<request_view>& re
     validate_column(r.values);
     B2_EXPECTS(r.values.size == n, B2_ERR_LOGIC, "Size mismatch between request values and groupby keys.");
     B2_EXPECTS(!r.kinds.empty(), B2_ERR_LOGIC, "Empty aggregation request");  // verify_valid_requests
-    for (int32_t kind : r.kinds) {
+    for (int32_t raw_kind : r.kinds) {
+      const int32_t kind = base_kind(raw_kind);
       (void)result_type(kind, r.values.type_id);
-      if (kind == B2_AGG_SUM || kind == B2_AGG_MEAN)
-        B2_EXPECTS(is_numeric(r.values.type_id), B2_ERR_LOGIC, "SUM/MEAN need a numeric values column");
+      if (kind == B2_AGG_SUM || kind == B2_AGG_MEAN || needs_sumsq(kind))
+        B2_EXPECTS(is_numeric(r.values.type_id), B2_ERR_LOGIC, "SUM/MEAN/SUM_OF_SQUARES/M2/VARIANCE/STD need a numeric values column");
     }
   }
   if (n == 0) return empty_results(gb, reqs, stream, keys_out, res_out);
@@ -360,35 +402,46 @@ void groupby_aggregate(const b2_groupby& gb, const std::vector<request_view>& re
     std::vector<dbuf> accs;                      // one per value op
     std::vector<dbuf> vcounts(reqs.size());      // one per nullable value column
     struct slot_of { int op_index; };            // (request, kind) -> op index or -1
-    std::vector<std::vector<int>> op_of(reqs.size());
+    std::vector<std::vector<int>> op_of(reqs.size()), op2_of(reqs.size());  // op2: SUM_OF_SQUARES partner of M2/VAR/STD
+    bool any_sumsq = false;
     for (size_t q = 0; q < reqs.size(); ++q) {
       const auto& v = reqs[q].values;
       const int32_t st = storage_type(v.type_id);
       const bool nullable = has_nulls(v);
       bool bumped = false;
       const int op_begin = ops.n;
-      // MEAN and SUM of the same column share one SUM accumulator
-      int sum_op = -1;
-      for (int32_t kind : reqs[q].kinds) {
-        int idx = -1;
-        if (kind == B2_AGG_COUNT_VALID || kind == B2_AGG_COUNT_ALL) { op_of[q].push_back(-1); continue; }
-        const int8_t opk = kind == B2_AGG_MIN ? OPK_MIN : (kind == B2_AGG_MAX ? OPK_MAX : OPK_SUM);
-        if (opk == OPK_SUM && sum_op >= 0) { op_of[q].push_back(sum_op); continue; }
+      // MEAN / SUM / M2 / VARIANCE / STD of the same column share one SUM accumulator; SUM_OF_SQUARES / M2 / VARIANCE /
+      // STD share one SUM_OF_SQUARES accumulator
+      int sum_op = -1, sumsq_op = -1;
+      auto new_op = [&](int8_t opk) {
         B2_EXPECTS(ops.n < MAX_OPS, B2_ERR_INVALID_ARGUMENT, "too many aggregations in one groupby call");
         value_op& op = ops.op[ops.n];
         op.src      = v.data;
         op.mask     = nullable ? v.null_mask : nullptr;
         op.offset   = v.offset;
         op.src_type = (int8_t)st;
-        op.acc      = is_float_id(st) ? ACC_F64 : ((is_signed_id(st) || opk == OPK_SUM) ? ACC_I64 : ACC_U64);
-        if (opk == OPK_SUM && !is_float_id(st) && !is_signed_id(st)) op.acc = ACC_U64;  // same bits as int64 sums
+        const bool sumlike = opk == OPK_SUM || opk == OPK_SUMSQ;
+        op.acc      = is_float_id(st) ? ACC_F64 : ((is_signed_id(st) || sumlike) ? ACC_I64 : ACC_U64);
+        if (sumlike && !is_float_id(st) && !is_signed_id(st)) op.acc = ACC_U64;  // same bits as int64 sums
         op.op       = opk;
         accs.emplace_back(sizeof(unsigned long long) * slots, stream);
         op.accum = accs.back().as<unsigned long long>();
         B2_LAUNCH(fill_u64_kernel, grid_for((int64_t)slots), 256, 0, stream, op.accum, (int64_t)slots, acc_init(op.acc, opk));
-        idx = ops.n++;
-        if (opk == OPK_SUM) sum_op = idx;
-        op_of[q].push_back(idx);
+        return ops.n++;
+      };
+      for (int32_t raw_kind : reqs[q].kinds) {
+        const int32_t kind = base_kind(raw_kind);
+        if (kind == B2_AGG_COUNT_VALID || kind == B2_AGG_COUNT_ALL) { op_of[q].push_back(-1); op2_of[q].push_back(-1); continue; }
+        if (kind == B2_AGG_MIN || kind == B2_AGG_MAX) {
+          op_of[q].push_back(new_op(kind == B2_AGG_MIN ? OPK_MIN : OPK_MAX));
+          op2_of[q].push_back(-1);
+          continue;
+        }
+        const bool want_sum = kind != B2_AGG_SUM_OF_SQUARES;  // SUM, MEAN, M2, VARIANCE, STD
+        if (want_sum && sum_op < 0) sum_op = new_op(OPK_SUM);
+        if (needs_sumsq(kind) && sumsq_op < 0) { sumsq_op = new_op(OPK_SUMSQ); any_sumsq = true; }
+        op_of[q].push_back(kind == B2_AGG_SUM_OF_SQUARES ? sumsq_op : sum_op);
+        op2_of[q].push_back(kind == B2_AGG_SUM_OF_SQUARES ? -1 : (needs_sumsq(kind) ? sumsq_op : -1));
       }
       if (nullable) {
         vcounts[q] = dbuf(sizeof(int32_t) * slots, stream);
@@ -416,12 +469,12 @@ void groupby_aggregate(const b2_groupby& gb, const std::vector<request_view>& re
 
     {
       prof_scope ps("groupby_aggregate", stream);
-      if (wide)
-        B2_LAUNCH((groupby_kernel<true>), grid_for(n), 256, 0, stream, kc, n, skip_null_keys, table.as<slot_t>(), (uint32_t)(slots - 1),
-                  cap, gsize.as<int32_t>(), slot_gid.as<int32_t>(), rep_rows.as<int32_t>(), ops, ctl.as<gb_ctl>());
-      else
-        B2_LAUNCH((groupby_kernel<false>), grid_for(n), 256, 0, stream, kc, n, skip_null_keys, table.as<slot_t>(), (uint32_t)(slots - 1),
-                  cap, gsize.as<int32_t>(), slot_gid.as<int32_t>(), rep_rows.as<int32_t>(), ops, ctl.as<gb_ctl>());
+#define B2_GB(W, Q)                                                                                                                    \
+  B2_LAUNCH((groupby_kernel<W, Q>), grid_for(n), 256, 0, stream, kc, n, skip_null_keys, table.as<slot_t>(), (uint32_t)(slots - 1), cap, \
+            gsize.as<int32_t>(), slot_gid.as<int32_t>(), rep_rows.as<int32_t>(), ops, ctl.as<gb_ctl>())
+      if (wide) { if (any_sumsq) B2_GB(true, true); else B2_GB(true, false); }
+      else      { if (any_sumsq) B2_GB(false, true); else B2_GB(false, false); }
+#undef B2_GB
     }
     gb_ctl h{};
     B2_CUDA_TRY(cudaMemcpyAsync(&h, ctl.ptr, sizeof(h), cudaMemcpyDeviceToHost, stream));
@@ -440,11 +493,14 @@ void groupby_aggregate(const b2_groupby& gb, const std::vector<request_view>& re
       const auto& v = reqs[q].values;
       const bool nullable = has_nulls(v);
       for (size_t j = 0; j < reqs[q].kinds.size(); ++j) {
-        const int32_t kind = reqs[q].kinds[j];
+        const int32_t kind = base_kind(reqs[q].kinds[j]);
         const int32_t rt   = result_type(kind, v.type_id);
         const bool counts  = kind == B2_AGG_COUNT_VALID || kind == B2_AGG_COUNT_ALL;
-        // result has a mask only when the input column has nulls (output_utils.cu:67-86); counts never
-        auto col = make_column(rt, G, nullable && !counts, stream);
+        const bool var_std = kind == B2_AGG_VARIANCE || kind == B2_AGG_STD;  // null where count - ddof <= 0 (m2_var_std.cu:150-196)
+        const bool ext     = var_std || kind == B2_AGG_M2;
+        // result has a mask only when the input column has nulls (output_utils.cu:67-86); counts and M2 never;
+        // VARIANCE / STD build theirs from the group counts
+        auto col = make_column(rt, G, var_std || (nullable && !counts && kind != B2_AGG_M2), stream);
         if (G > 0) {
           out_spec o{};
           o.gsize  = gsize.as<int32_t>();
@@ -457,9 +513,13 @@ void groupby_aggregate(const b2_groupby& gb, const std::vector<request_view>& re
             const value_op& op = ops.op[op_of[q][j]];
             o.accum = op.accum;
             o.acc   = op.acc;
-            o.op    = op.op;
-            o.mode  = kind == B2_AGG_MEAN ? 1 : 0;
-            if (nullable) {
+            o.op    = op.op == OPK_SUMSQ ? (int8_t)OPK_SUM : op.op;  // finalize: "plain accumulator bits", like SUM
+            o.mode  = kind == B2_AGG_MEAN ? 1 : (kind == B2_AGG_M2 ? 5 : (kind == B2_AGG_VARIANCE ? 6 : (kind == B2_AGG_STD ? 7 : 0)));
+            if (ext) {
+              o.accum2 = ops.op[op2_of[q][j]].accum;
+              o.ddof   = kind_ddof(reqs[q].kinds[j]);
+            }
+            if (var_std || (nullable && kind != B2_AGG_M2)) {
               o.out_mask = col->mask.as<uint32_t>();
               col->pending = dbuf(sizeof(unsigned long long), stream);
               col->pending_stream = stream;
@@ -468,8 +528,12 @@ void groupby_aggregate(const b2_groupby& gb, const std::vector<request_view>& re
               o.null_count = col->pending.as<unsigned long long>();
             }
           }
-          B2_LAUNCH(finalize_kernel, grid_for((int64_t)slots), 256, 0, stream, table.as<slot_t>(), (int64_t)slots,
-                    slot_gid.as<int32_t>(), o);
+          if (ext)
+            B2_LAUNCH((finalize_kernel<true>), grid_for((int64_t)slots), 256, 0, stream, table.as<slot_t>(), (int64_t)slots,
+                      slot_gid.as<int32_t>(), o);
+          else
+            B2_LAUNCH((finalize_kernel<false>), grid_for((int64_t)slots), 256, 0, stream, table.as<slot_t>(), (int64_t)slots,
+                      slot_gid.as<int32_t>(), o);
         }
         res_out->cols.push_back(std::move(col));
       }

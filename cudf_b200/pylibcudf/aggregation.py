@@ -14,17 +14,28 @@ class Kind(enum.IntEnum):
     MAX = 4
     COUNT_VALID = 5
     COUNT_ALL = 6
+    SUM_OF_SQUARES = 9
     MEAN = 10
+    M2 = 11
+    VARIANCE = 12
+    STD = 13
 
 
 class Aggregation:
-    __slots__ = ("_kind",)
+    __slots__ = ("_kind", "_ddof")
 
-    def __init__(self, kind: Kind):
+    def __init__(self, kind: Kind, ddof: int | None = None):
         self._kind = Kind(kind)
+        self._ddof = ddof
 
     def kind(self) -> Kind:
         return self._kind
+
+    def abi_kind(self) -> int:
+        """The kind word of the C ABI: B2_AGG_WITH_DDOF(kind, ddof) for VARIANCE / STD (include/cudf_b200.h)."""
+        if self._ddof is None:
+            return int(self._kind)
+        return int(self._kind) | (1 << 30) | ((int(self._ddof) & 0xFFFF) << 8)
 
     def __repr__(self):
         return f"Aggregation({self._kind.name})"
@@ -52,3 +63,19 @@ def mean() -> Aggregation:
 
 def count(null_handling: NullPolicy = NullPolicy.EXCLUDE) -> Aggregation:
     return Aggregation(Kind.COUNT_VALID if null_handling == NullPolicy.EXCLUDE else Kind.COUNT_ALL)
+
+
+def sum_of_squares() -> Aggregation:
+    return Aggregation(Kind.SUM_OF_SQUARES)
+
+
+def m2() -> Aggregation:
+    return Aggregation(Kind.M2)
+
+
+def variance(ddof: int = 1) -> Aggregation:
+    return Aggregation(Kind.VARIANCE, ddof)
+
+
+def std(ddof: int = 1) -> Aggregation:
+    return Aggregation(Kind.STD, ddof)

@@ -34,7 +34,7 @@ class GroupBy:
         arr = (AggRequest * max(n, 1))()
         keep = []
         for i, r in enumerate(requests):
-            kinds = (C.c_int32 * max(len(r._aggregations), 1))(*[int(a.kind()) for a in r._aggregations])
+            kinds = (C.c_int32 * max(len(r._aggregations), 1))(*[a.abi_kind() for a in r._aggregations])
             keep.append(kinds)
             arr[i] = AggRequest(r._values._view(), kinds, len(r._aggregations))
         ko, ro = C.c_void_p(), C.c_void_p()

@@ -286,10 +286,14 @@ class numeric_scalar : public scalar {
 // ------------------------------------------------------------------------------------------------
 class aggregation {
  public:
-  enum Kind : int32_t { SUM = 0, PRODUCT = 2, MIN = 3, MAX = 4, COUNT_VALID = 5, COUNT_ALL = 6, MEAN = 10 };
+  enum Kind : int32_t { SUM = 0, PRODUCT = 2, MIN = 3, MAX = 4, COUNT_VALID = 5, COUNT_ALL = 6, SUM_OF_SQUARES = 9, MEAN = 10, M2 = 11,
+                        VARIANCE = 12, STD = 13 };
   explicit aggregation(Kind k) : kind{k} {}
   virtual ~aggregation() = default;
   Kind kind;
+  size_type _ddof{-1};  // VARIANCE / STD: delta degrees of freedom (aggregation.hpp:231-260); -1 = not applicable
+  // the kind word of the C ABI (B2_AGG_WITH_DDOF)
+  [[nodiscard]] int32_t abi_kind() const { return _ddof < 0 ? static_cast<int32_t>(kind) : B2_AGG_WITH_DDOF(kind, _ddof); }
 };
 class groupby_aggregation : public virtual aggregation { public: groupby_aggregation() : aggregation(SUM) {} };
 class groupby_scan_aggregation : public virtual aggregation { public: groupby_scan_aggregation() : aggregation(SUM) {} };
@@ -306,6 +310,20 @@ template <typename Base = aggregation> std::unique_ptr<Base> make_product_aggreg
 template <typename Base = aggregation> std::unique_ptr<Base> make_min_aggregation() { return detail::make_agg<Base>(aggregation::MIN); }
 template <typename Base = aggregation> std::unique_ptr<Base> make_max_aggregation() { return detail::make_agg<Base>(aggregation::MAX); }
 template <typename Base = aggregation> std::unique_ptr<Base> make_mean_aggregation() { return detail::make_agg<Base>(aggregation::MEAN); }
+template <typename Base = aggregation> std::unique_ptr<Base> make_sum_of_squares_aggregation() { return detail::make_agg<Base>(aggregation::SUM_OF_SQUARES); }
+template <typename Base = aggregation> std::unique_ptr<Base> make_m2_aggregation() { return detail::make_agg<Base>(aggregation::M2); }
+template <typename Base = aggregation> std::unique_ptr<Base> make_variance_aggregation(size_type ddof = 1)
+{
+  auto a = detail::make_agg<Base>(aggregation::VARIANCE);
+  a->_ddof = ddof;
+  return a;
+}
+template <typename Base = aggregation> std::unique_ptr<Base> make_std_aggregation(size_type ddof = 1)
+{
+  auto a = detail::make_agg<Base>(aggregation::STD);
+  a->_ddof = ddof;
+  return a;
+}
 template <typename Base = aggregation>
 std::unique_ptr<Base> make_count_aggregation(null_policy null_handling = null_policy::EXCLUDE)
 {
@@ -556,7 +574,7 @@ class groupby {
     std::vector<std::vector<int32_t>> kinds(requests.size());
     std::vector<b2_agg_request> raw;
     for (std::size_t i = 0; i < requests.size(); ++i) {
-      for (auto const& a : requests[i].aggregations) kinds[i].push_back(static_cast<int32_t>(a->kind));
+      for (auto const& a : requests[i].aggregations) kinds[i].push_back(a->abi_kind());
       raw.push_back(b2_agg_request{requests[i].values.native(), kinds[i].data(), (int32_t)kinds[i].size()});
     }
     b2_table *ko = nullptr, *ro = nullptr;

@@ -10,6 +10,7 @@ import numpy as np
 from . import sort as osort
 
 SUM, PRODUCT, MIN, MAX, COUNT_VALID, COUNT_ALL, MEAN = 0, 2, 3, 4, 5, 6, 10
+SUM_OF_SQUARES, M2, VARIANCE, STD = 9, 11, 12, 13  # a kind may also be the pair (VARIANCE | STD, ddof); ddof defaults to 1
 EXCLUDE, INCLUDE = 0, 1
 
 
@@ -37,7 +38,11 @@ def _group_ids(key_cols, include_nulls):
 
 def result_dtype(kind, in_dtype):
     in_dtype = np.dtype(in_dtype)
-    if kind == SUM or kind == PRODUCT:
+    if isinstance(kind, tuple):
+        kind = kind[0]
+    if kind in (M2, VARIANCE, STD):
+        return np.dtype(np.float64)  # aggregation.hpp:997-1013
+    if kind == SUM or kind == PRODUCT or kind == SUM_OF_SQUARES:
         if in_dtype.kind in "iu" or in_dtype == np.bool_:
             return np.dtype(np.int64)  # aggregation.hpp:935-939: every integral source sums into int64
         return in_dtype
@@ -72,7 +77,34 @@ def aggregate(key_cols, requests, null_handling=EXCLUDE):
         per = []
         vc = np.bincount(gid[m], minlength=ng).astype(np.int64) if ng else np.empty(0, np.int64)
         for kind in kinds:
+            ddof = 1
+            if isinstance(kind, tuple):
+                kind, ddof = kind
             rdt = result_dtype(kind, vals.dtype)
+            if kind in (SUM_OF_SQUARES, M2, VARIANCE, STD):
+                # device_aggregators.cuh:309-321 (value * value in the SUM target type) and
+                # cpp/src/groupby/common/m2_var_std.cu:35-62,150-196
+                xv, xg = v[m], gid[m]
+                sdt = np.dtype(np.float64) if vals.dtype.kind == "f" else np.dtype(np.int64)
+                with np.errstate(over="ignore", invalid="ignore"):
+                    sq = np.zeros(ng, dtype=sdt)
+                    np.add.at(sq, xg, xv.astype(sdt) * xv.astype(sdt))
+                    sm = np.zeros(ng, dtype=sdt)
+                    np.add.at(sm, xg, xv.astype(sdt))
+                    if kind == SUM_OF_SQUARES:
+                        per.append((sq.astype(rdt), (vc > 0) if has_nulls else None))
+                        continue
+                    cnt = np.maximum(vc, 1).astype(np.float64)
+                    m2v = np.where(vc == 0, 0.0, sq.astype(np.float64) - sm.astype(np.float64) * sm.astype(np.float64) / cnt)
+                    if kind == M2:
+                        per.append((m2v, None))
+                        continue
+                    df = vc - ddof
+                    ok = (vc != 0) & (df > 0)
+                    var = np.where(ok, m2v / np.where(ok, df, 1), 0.0)
+                    out = var if kind == VARIANCE else np.sqrt(np.where(ok, var, 0.0))
+                per.append((out, None if ok.all() else ok))
+                continue
             if kind == COUNT_ALL:
                 per.append((np.bincount(gid, minlength=ng).astype(np.int32), None))
                 continue

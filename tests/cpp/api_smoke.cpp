@@ -11,6 +11,7 @@
 #include <cuda_runtime_api.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <vector>
 
@@ -76,6 +77,8 @@ int main()
   reqs[0].values = gvc;
   reqs[0].aggregations.push_back(make_sum_aggregation<groupby_aggregation>());
   reqs[0].aggregations.push_back(make_count_aggregation<groupby_aggregation>());
+  reqs[0].aggregations.push_back(make_variance_aggregation<groupby_aggregation>());      // var_tests.cpp:30-41: {9, 131/12, 31/3}
+  reqs[0].aggregations.push_back(make_std_aggregation<groupby_aggregation>(0));
   auto [gkeys, gres] = gb.aggregate(reqs);
   EXPECT(gkeys->num_rows() == 3);
   auto hk = to_host(gkeys->get_column(0).view().data<int32_t>(), 3);
@@ -85,6 +88,15 @@ int main()
     double es = hk[i] == 1 ? 9 : (hk[i] == 2 ? 19 : 17);
     int ec = hk[i] == 2 ? 4 : 3;
     EXPECT(hs[i] == es && hc[i] == ec);
+  }
+  {
+    auto hv = to_host(gres[0].results[2]->view().data<double>(), 3);
+    auto hd = to_host(gres[0].results[3]->view().data<double>(), 3);
+    for (int i = 0; i < 3; ++i) {
+      double ev = hk[i] == 1 ? 9.0 : (hk[i] == 2 ? 131.0 / 12 : 31.0 / 3);
+      int n = hk[i] == 2 ? 4 : 3;
+      EXPECT(std::abs(hv[i] - ev) < 1e-9 && std::abs(hd[i] * hd[i] - ev * (n - 1) / n) < 1e-9);
+    }
   }
   // reduce + scan
   auto s = reduce(gvc, *make_sum_aggregation<reduce_aggregation>(), data_type{type_id::FLOAT64});

@@ -14,6 +14,8 @@
 #include <cstring>
 #include <functional>
 #include <type_traits>
+#include <cmath>
+using std::sqrt;
 
 // ---- qualifiers ---------------------------------------------------------------------------------------
 #define __global__
