@@ -1,0 +1,152 @@
+// segmented_sort.cu — segmented_sorted_order / segmented_sort_by_key and top_k / top_k_order on top of the radix machinery.
+//
+// Replaces cpp/src/sort/segmented_sort.cu + segmented_sort_impl.cuh (public API cpp/include/cudf/sorting.hpp:232-366)
+// and cpp/src/sort/top_k.cu:100-150 (sorting.hpp:370-416). SURVEY §8f.4 ("next" rows; written after the round-1 GPU
+// budget was spent: checked on the oracle and on the CPU emulator, tests/test_zzzz_segmented_sort.py).
+//
+// Segmented order = one stable lexicographic LSD sort of (segment id, position-outside-segments, keys...):
+//   * a row inside segment s gets (s, 0): rows of one segment stay together and are ordered by the keys;
+//   * a row before the first / after the last offset gets (-1, row) / (num_segments, row): the position column
+//     keeps those rows where they are ("indices outside the specified segments will not be sorted").
+// The two helper columns cost no radix pass for their constant bytes (trivial passes are skipped on the device).
+// top_k = stable sorted order (nulls last for ASCENDING, first for DESCENDING, as top_k.cu:121-123), first k rows.
+#include "common.cuh"
+#include "device_utils.cuh"
+
+#include <algorithm>
+
+namespace b2 {
+namespace {
+
+__global__ void __launch_bounds__(256) segment_ids_kernel(const int32_t* __restrict__ offsets, int32_t num_offsets, int64_t n,
+                                                          int32_t* __restrict__ seg, int32_t* __restrict__ pos)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    // ub = number of offsets <= i
+    int lo = 0, hi = num_offsets;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if ((int64_t)offsets[mid] <= i) lo = mid + 1;
+      else hi = mid;
+    }
+    const int s = lo - 1;
+    const bool outside = num_offsets < 2 || s < 0 || s >= num_offsets - 1;
+    seg[i] = outside ? (s < 0 ? -1 : num_offsets) : s;
+    pos[i] = outside ? (int32_t)i : 0;
+  }
+}
+
+int grid_for(int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, NUM_SMS_B200 * 16)); }
+
+}  // namespace
+
+// cudf::detail::segmented_sorted_order — cpp/src/sort/segmented_sort.cu, sorting.hpp:232-296
+column_ptr segmented_sorted_order(const std::vector<b2_column_view>& keys, const b2_column_view& offsets, const std::vector<uint8_t>& order,
+                                  const std::vector<uint8_t>& nprec, bool stable, cudaStream_t stream)
+{
+  B2_EXPECTS(offsets.type_id == B2_INT32, B2_ERR_LOGIC, "segment offsets should be size_type");
+  B2_EXPECTS(!has_nulls(offsets), B2_ERR_LOGIC, "segment offsets must not contain nulls");
+  if (keys.empty()) return make_column(B2_INT32, 0, false, stream);  // zero-column keys: empty result
+  B2_EXPECTS(order.empty() || order.size() == keys.size(), B2_ERR_LOGIC, "Mismatch between number of columns and column order.");
+  B2_EXPECTS(nprec.empty() || nprec.size() == keys.size(), B2_ERR_LOGIC, "Mismatch between number of columns and null precedence.");
+  const int64_t n = keys[0].size;
+  if (n == 0) return make_column(B2_INT32, 0, false, stream);
+  dbuf seg(sizeof(int32_t) * n, stream), pos(sizeof(int32_t) * n, stream);
+  B2_LAUNCH(segment_ids_kernel, grid_for(n), 256, 0, stream, static_cast<const int32_t*>(offsets.data) + offsets.offset, offsets.size, n,
+            seg.as<int32_t>(), pos.as<int32_t>());
+  std::vector<b2_column_view> all;
+  all.push_back(b2_column_view{B2_INT32, (int32_t)n, seg.ptr, nullptr, 0, 0});
+  all.push_back(b2_column_view{B2_INT32, (int32_t)n, pos.ptr, nullptr, 0, 0});
+  for (auto& k : keys) all.push_back(k);
+  std::vector<uint8_t> ord{B2_ASCENDING, B2_ASCENDING}, np{B2_NULL_BEFORE, B2_NULL_BEFORE};
+  for (size_t c = 0; c < keys.size(); ++c) {
+    ord.push_back(order.empty() ? (uint8_t)B2_ASCENDING : order[c]);
+    np.push_back(nprec.empty() ? (uint8_t)B2_NULL_BEFORE : nprec[c]);
+  }
+  (void)stable;  // the LSD sort is stable either way
+  return sorted_order(all, ord, np, true, stream);
+}
+
+// cudf::top_k_order — top_k.cu:143-170 (the reference's unsorted fast path may return the k rows in any order)
+column_ptr top_k_order(const b2_column_view& col, int32_t k, int32_t topk_order, cudaStream_t stream)
+{
+  B2_EXPECTS(k >= 0, B2_ERR_INVALID_ARGUMENT, "k must be non-negative");
+  if (k == 0 || col.size == 0) return make_column(B2_INT32, 0, false, stream);
+  const bool asc = topk_order == B2_ASCENDING;
+  std::vector<uint8_t> ord{(uint8_t)(asc ? B2_ASCENDING : B2_DESCENDING)}, np{(uint8_t)(asc ? B2_NULL_AFTER : B2_NULL_BEFORE)};
+  auto order = sorted_order({col}, ord, np, true, stream);
+  if (k >= col.size) return order;
+  auto out = make_column(B2_INT32, k, false, stream);
+  B2_CUDA_TRY(cudaMemcpyAsync(out->data.ptr, order->data.ptr, sizeof(int32_t) * (size_t)k, cudaMemcpyDeviceToDevice, stream));
+  return out;
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+#define B2_TRY_BEGIN try {
+#define B2_TRY_END                                                                 \
+  }                                                                                \
+  catch (const b2::error& e) { b2::set_last_error(e.what()); return e.code; }      \
+  catch (const std::bad_alloc& e) { b2::set_last_error(e.what()); return B2_ERR_BAD_ALLOC; } \
+  catch (const std::exception& e) { b2::set_last_error(e.what()); return B2_ERR_LOGIC; }     \
+  return B2_OK;
+
+static std::vector<uint8_t> u8v(const uint8_t* p, int32_t n) { return (p && n > 0) ? std::vector<uint8_t>(p, p + n) : std::vector<uint8_t>{}; }
+
+extern "C" {
+
+b2_status b2_segmented_sorted_order(const b2_table_view* keys, const b2_column_view* segment_offsets, const uint8_t* column_order,
+                                    int32_t n_order, const uint8_t* null_precedence, int32_t n_null_prec, int32_t stable, b2_stream stream,
+                                    b2_column** out)
+{
+  B2_TRY_BEGIN
+  B2_EXPECTS(out && segment_offsets, B2_ERR_INVALID_ARGUMENT, "null argument");
+  std::vector<b2_column_view> k;
+  validate_table(keys, k);
+  *out = segmented_sorted_order(k, *segment_offsets, u8v(column_order, n_order), u8v(null_precedence, n_null_prec), stable != 0,
+                                static_cast<cudaStream_t>(stream))
+           .release();
+  B2_TRY_END
+}
+
+b2_status b2_segmented_sort_by_key(const b2_table_view* values, const b2_table_view* keys, const b2_column_view* segment_offsets,
+                                   const uint8_t* column_order, int32_t n_order, const uint8_t* null_precedence, int32_t n_null_prec,
+                                   int32_t stable, b2_stream stream, b2_table** out)
+{
+  B2_TRY_BEGIN
+  B2_EXPECTS(out && segment_offsets, B2_ERR_INVALID_ARGUMENT, "null argument");
+  std::vector<b2_column_view> v, k;
+  validate_table(values, v);
+  validate_table(keys, k);
+  const int32_t vrows = v.empty() ? 0 : v[0].size, krows = k.empty() ? 0 : k[0].size;
+  B2_EXPECTS(vrows == krows, B2_ERR_LOGIC, "Mismatch in number of rows for values and keys");
+  auto s = static_cast<cudaStream_t>(stream);
+  auto order = segmented_sorted_order(k, *segment_offsets, u8v(column_order, n_order), u8v(null_precedence, n_null_prec), stable != 0, s);
+  *out = gather_table(v, order->data.as<int32_t>(), order->size, false, s).release();
+  B2_TRY_END
+}
+
+b2_status b2_top_k_order(const b2_column_view* col, int32_t k, int32_t topk_order, b2_stream stream, b2_column** out)
+{
+  B2_TRY_BEGIN
+  B2_EXPECTS(out && col, B2_ERR_INVALID_ARGUMENT, "null argument");
+  validate_column(*col);
+  *out = top_k_order(*col, k, topk_order, static_cast<cudaStream_t>(stream)).release();
+  B2_TRY_END
+}
+
+b2_status b2_top_k(const b2_column_view* col, int32_t k, int32_t topk_order, b2_stream stream, b2_column** out)
+{
+  B2_TRY_BEGIN
+  B2_EXPECTS(out && col, B2_ERR_INVALID_ARGUMENT, "null argument");
+  validate_column(*col);
+  auto s = static_cast<cudaStream_t>(stream);
+  auto order = top_k_order(*col, k, topk_order, s);
+  *out = gather_column(*col, order->data.as<int32_t>(), order->size, false, s).release();
+  B2_TRY_END
+}
+
+}  // extern "C"

@@ -376,7 +376,51 @@ inline std::unique_ptr<table> sort_by_key_impl(table_view const& values, table_v
 }
 inline std::unique_ptr<table> sort_by_key(table_view const& values, table_view const& keys, CUDF_B2_SORT_ARGS) { return sort_by_key_impl(values, keys, column_order, null_precedence, false, stream); }
 inline std::unique_ptr<table> stable_sort_by_key(table_view const& values, table_view const& keys, CUDF_B2_SORT_ARGS) { return sort_by_key_impl(values, keys, column_order, null_precedence, true, stream); }
+// segmented sort (sorting.hpp:232-366)
+inline std::unique_ptr<column> segmented_sorted_order_impl(table_view const& keys, column_view const& segment_offsets,
+                                                           std::vector<order> const& co, std::vector<null_order> const& np, bool stable,
+                                                           rmm::cuda_stream_view stream)
+{
+  auto o = detail::u8(co); auto p = detail::u8(np);
+  auto kv = keys.native();
+  b2_column* out = nullptr;
+  detail::check(b2_segmented_sorted_order(&kv, &segment_offsets.native(), o.data(), (int32_t)o.size(), p.data(), (int32_t)p.size(), stable,
+                                          stream.value(), &out));
+  return std::make_unique<column>(out);
+}
+inline std::unique_ptr<column> segmented_sorted_order(table_view const& keys, column_view const& segment_offsets, CUDF_B2_SORT_ARGS) { return segmented_sorted_order_impl(keys, segment_offsets, column_order, null_precedence, false, stream); }
+inline std::unique_ptr<column> stable_segmented_sorted_order(table_view const& keys, column_view const& segment_offsets, CUDF_B2_SORT_ARGS) { return segmented_sorted_order_impl(keys, segment_offsets, column_order, null_precedence, true, stream); }
+inline std::unique_ptr<table> segmented_sort_by_key_impl(table_view const& values, table_view const& keys, column_view const& segment_offsets,
+                                                         std::vector<order> const& co, std::vector<null_order> const& np, bool stable,
+                                                         rmm::cuda_stream_view stream)
+{
+  auto o = detail::u8(co); auto p = detail::u8(np);
+  auto vv = values.native(); auto kv = keys.native();
+  b2_table* out = nullptr;
+  detail::check(b2_segmented_sort_by_key(&vv, &kv, &segment_offsets.native(), o.data(), (int32_t)o.size(), p.data(), (int32_t)p.size(),
+                                         stable, stream.value(), &out));
+  return table::from_handle(out);
+}
+inline std::unique_ptr<table> segmented_sort_by_key(table_view const& values, table_view const& keys, column_view const& segment_offsets, CUDF_B2_SORT_ARGS) { return segmented_sort_by_key_impl(values, keys, segment_offsets, column_order, null_precedence, false, stream); }
+inline std::unique_ptr<table> stable_segmented_sort_by_key(table_view const& values, table_view const& keys, column_view const& segment_offsets, CUDF_B2_SORT_ARGS) { return segmented_sort_by_key_impl(values, keys, segment_offsets, column_order, null_precedence, true, stream); }
 #undef CUDF_B2_SORT_ARGS
+// top-k (sorting.hpp:370-416)
+inline std::unique_ptr<column> top_k(column_view const& col, size_type k, order topk_order = order::DESCENDING,
+                                     rmm::cuda_stream_view stream = cudf::get_default_stream(),
+                                     rmm::device_async_resource_ref = cudf::get_current_device_resource_ref())
+{
+  b2_column* out = nullptr;
+  detail::check(b2_top_k(&col.native(), k, static_cast<int32_t>(topk_order), stream.value(), &out));
+  return std::make_unique<column>(out);
+}
+inline std::unique_ptr<column> top_k_order(column_view const& col, size_type k, order topk_order = order::DESCENDING,
+                                           rmm::cuda_stream_view stream = cudf::get_default_stream(),
+                                           rmm::device_async_resource_ref = cudf::get_current_device_resource_ref())
+{
+  b2_column* out = nullptr;
+  detail::check(b2_top_k_order(&col.native(), k, static_cast<int32_t>(topk_order), stream.value(), &out));
+  return std::make_unique<column>(out);
+}
 
 inline std::unique_ptr<table> gather(table_view const& source_table, column_view const& gather_map,
                                      out_of_bounds_policy bounds_policy = out_of_bounds_policy::DONT_CHECK,

@@ -177,6 +177,23 @@ B2_API b2_status b2_sort_by_key(const b2_table_view* values, const b2_table_view
                                 const uint8_t* null_precedence, int32_t n_null_prec, int32_t stable,
                                 b2_stream stream, b2_table** out);
 
+/* cudf::{stable_,}segmented_sorted_order / segmented_sort_by_key (sorting.hpp:232-366): segment_offsets is an INT32
+ * column of start offsets (the last entry ends the last segment); rows outside [offsets[0], offsets[last]) keep their
+ * place; fewer than two offsets sort nothing; a non-INT32 offsets column -> LOGIC error. */
+B2_API b2_status b2_segmented_sorted_order(const b2_table_view* keys, const b2_column_view* segment_offsets,
+                                           const uint8_t* column_order, int32_t n_order,
+                                           const uint8_t* null_precedence, int32_t n_null_prec, int32_t stable,
+                                           b2_stream stream, b2_column** out);
+B2_API b2_status b2_segmented_sort_by_key(const b2_table_view* values, const b2_table_view* keys,
+                                          const b2_column_view* segment_offsets, const uint8_t* column_order,
+                                          int32_t n_order, const uint8_t* null_precedence, int32_t n_null_prec,
+                                          int32_t stable, b2_stream stream, b2_table** out);
+/* cudf::top_k / top_k_order (sorting.hpp:370-416, top_k.cu:100-170): the k first rows of the stable sorted order
+ * (nulls last for ASCENDING, first for DESCENDING); k >= size returns all rows; k < 0 -> INVALID_ARGUMENT. */
+B2_API b2_status b2_top_k(const b2_column_view* col, int32_t k, int32_t topk_order, b2_stream stream, b2_column** out);
+B2_API b2_status b2_top_k_order(const b2_column_view* col, int32_t k, int32_t topk_order, b2_stream stream,
+                                b2_column** out);
+
 /* ---- hash join: cpp/include/cudf/join/join.hpp:127-249, join/hash_join.hpp ---------------- */
 /* Results are two INT32 columns of equal length (cudf returns device_uvector<size_type>), row
  * order unspecified (join.hpp:130-136). */

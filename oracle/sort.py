@@ -94,3 +94,45 @@ def sort_by_key(values, keys, column_order=None, null_precedence=None):
 def sort(columns, column_order=None, null_precedence=None):
     """cudf::sort (sort.cu:52-67)."""
     return sort_by_key(columns, columns, column_order, null_precedence)
+
+
+def segmented_sorted_order(columns, segment_offsets, column_order=None, null_precedence=None) -> np.ndarray:
+    """cudf::{stable_,}segmented_sorted_order (cpp/include/cudf/sorting.hpp:232-296): every segment
+    [offsets[i], offsets[i+1]) is sorted on its own; rows outside the segments keep their place; fewer than two offsets
+    sort nothing. Ties are broken stably (the unstable variant leaves them unspecified)."""
+    if not columns:
+        return np.empty(0, dtype=np.int32)
+    offs = np.asarray(segment_offsets)
+    if offs.dtype != np.int32:
+        raise RuntimeError("segment offsets should be size_type")  # cudf::logic_error
+    n = len(columns[0][0])
+    out = np.arange(n, dtype=np.int32)
+    for b, e in zip(offs[:-1], offs[1:]):
+        b, e = int(b), int(e)
+        if e - b > 1:
+            seg = [(np.asarray(v)[b:e], None if m is None else np.asarray(m)[b:e]) for v, m in columns]
+            out[b:e] = b + sorted_order(seg, column_order, null_precedence)
+    return out
+
+
+def segmented_sort_by_key(values, keys, segment_offsets, column_order=None, null_precedence=None):
+    nv = len(values[0][0]) if values else 0
+    nk = len(keys[0][0]) if keys else 0
+    if nv != nk:
+        raise RuntimeError("Mismatch in number of rows for values and keys")
+    return gather(values, segmented_sorted_order(keys, segment_offsets, column_order, null_precedence))
+
+
+def top_k_order(column, k, order=DESCENDING) -> np.ndarray:
+    """cudf::top_k_order (cpp/src/sort/top_k.cu:143-170): the first k rows of the stable sorted order, nulls last for
+    ASCENDING and first for DESCENDING; the reference may return them in any order."""
+    if k < 0:
+        raise ValueError("k must be non-negative")
+    if k == 0 or len(column[0]) == 0:
+        return np.empty(0, dtype=np.int32)
+    o = sorted_order([column], [order], [AFTER if order == ASCENDING else BEFORE])
+    return o[: min(k, len(o))]
+
+
+def top_k(column, k, order=DESCENDING):
+    return gather([column], top_k_order(column, k, order))[0]

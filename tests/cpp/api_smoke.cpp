@@ -38,6 +38,16 @@ int main()
   auto sorted = sort_by_key(table_view{{kc}}, table_view{{kc}}, {order::DESCENDING});
   EXPECT((to_host(sorted->get_column(0).view().data<int64_t>(), 6) == std::vector<int64_t>{8, 5, 5, 5, 4, 3}));
   try { sorted_order(table_view{{kc, kc}}, {order::ASCENDING}); EXPECT(false); } catch (cudf::logic_error const&) {}
+  {  // segmented sort (sorting.hpp:238-244) and top-k
+    dev_vec<int32_t> sk({9, 8, 7, 6, 5, 4, 3, 2, 1, 0}), so({0, 3, 7, 10});
+    column_view skc{data_type{type_id::INT32}, 10, sk.p}, soc{data_type{type_id::INT32}, 4, so.p};
+    auto seg = segmented_sorted_order(table_view{{skc}}, soc);
+    EXPECT((to_host(seg->view().data<int32_t>(), 10) == std::vector<int32_t>{2, 1, 0, 6, 5, 4, 3, 9, 8, 7}));
+    auto top = top_k(skc, 3);
+    auto ht  = to_host(top->view().data<int32_t>(), 3);
+    std::sort(ht.begin(), ht.end());
+    EXPECT((ht == std::vector<int32_t>{7, 8, 9}));
+  }
   // hash join gold maps (join_tests.cpp:2316-2337)
   dev_vec<int32_t> l({3, 1, 2, 0, 2}), r({2, 2, 0, 4, 3});
   column_view lc{data_type{type_id::INT32}, 5, l.p}, rc{data_type{type_id::INT32}, 5, r.p};

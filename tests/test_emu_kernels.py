@@ -222,9 +222,10 @@ def test_emu_cpp_api(emu_lib, tmp_path):
 
 def test_emu_late_suites(emu_lib):
     """The gpu-marked cases of tests/test_zzzz_match_context.py (match context, partitioned probes, finalize) and
-    tests/test_zzzz_var_std.py (SUM_OF_SQUARES / M2 / VARIANCE / STD) on the emulator."""
+    tests/test_zzzz_var_std.py (SUM_OF_SQUARES / M2 / VARIANCE / STD) and tests/test_zzzz_segmented_sort.py on the emulator."""
     e = dict(os.environ, B2_EMU_RUN="1")
-    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_zzzz_match_context.py", "tests/test_zzzz_var_std.py", "-q", "-m", "gpu",
+    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_zzzz_match_context.py", "tests/test_zzzz_var_std.py",
+                        "tests/test_zzzz_segmented_sort.py", "-q", "-m", "gpu",
                         "-p", "no:cacheprovider"],
                        capture_output=True, text=True, env=e, cwd=ROOT, timeout=900)
     assert r.returncode == 0 and " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
