@@ -127,32 +127,7 @@ int32_t b2_column::resolve_null_count() const
 
 using namespace b2;
 
-#define B2_TRY_BEGIN try {
-#define B2_TRY_END                                            \
-  }                                                           \
-  catch (const b2::error& e)                                  \
-  {                                                           \
-    b2::set_last_error(e.what());                             \
-    return e.code;                                            \
-  }                                                           \
-  catch (const std::bad_alloc& e)                             \
-  {                                                           \
-    b2::set_last_error(e.what());                             \
-    return B2_ERR_BAD_ALLOC;                                  \
-  }                                                           \
-  catch (const std::exception& e)                             \
-  {                                                           \
-    b2::set_last_error(e.what());                             \
-    return B2_ERR_LOGIC;                                      \
-  }                                                           \
-  return B2_OK;
-
 static cudaStream_t S(b2_stream s) { return static_cast<cudaStream_t>(s); }
-
-static std::vector<uint8_t> vec_u8(const uint8_t* p, int32_t n)
-{
-  return (p && n > 0) ? std::vector<uint8_t>(p, p + n) : std::vector<uint8_t>{};
-}
 
 extern "C" {
 

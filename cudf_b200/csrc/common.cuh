@@ -49,6 +49,16 @@ struct error : std::exception {
 
 void set_last_error(const char* msg);
 
+// The extern "C" boundary: every entry point body sits between these two (status code + thread-local message).
+#define B2_TRY_BEGIN try {
+#define B2_TRY_END                                                                           \
+  }                                                                                          \
+  catch (const ::b2::error& e) { ::b2::set_last_error(e.what()); return e.code; }            \
+  catch (const std::bad_alloc& e) { ::b2::set_last_error(e.what()); return B2_ERR_BAD_ALLOC; } \
+  catch (const std::exception& e) { ::b2::set_last_error(e.what()); return B2_ERR_LOGIC; }   \
+  return B2_OK;
+inline std::vector<uint8_t> vec_u8(const uint8_t* p, int32_t n) { return (p && n > 0) ? std::vector<uint8_t>(p, p + n) : std::vector<uint8_t>{}; }
+
 // every kernel launch goes through this so bench.py can report gpu_launches
 extern std::atomic<uint64_t> g_launch_count;
 #ifdef B2_EMU  // tests/emu: the kernels run on the CPU emulator (test infrastructure, never part of the product build)

@@ -791,14 +791,6 @@ void groupby_scan(const b2_groupby& gb, const std::vector<request_view>& reqs, c
 }  // namespace b2
 
 // ---- C ABI -----------------------------------------------------------------------------------------
-#define B2_TRY_BEGIN try {
-#define B2_TRY_END                                                                 \
-  }                                                                                \
-  catch (const b2::error& e) { b2::set_last_error(e.what()); return e.code; }      \
-  catch (const std::bad_alloc& e) { b2::set_last_error(e.what()); return B2_ERR_BAD_ALLOC; } \
-  catch (const std::exception& e) { b2::set_last_error(e.what()); return B2_ERR_LOGIC; }     \
-  return B2_OK;
-
 extern "C" {
 
 b2_status b2_groupby_create(const b2_table_view* keys, int32_t null_handling, int32_t keys_are_sorted, const uint8_t* column_order,

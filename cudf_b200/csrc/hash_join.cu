@@ -761,14 +761,6 @@ void hash_join_finalize_full(const std::vector<b2_column_view>& lparts, const st
 }  // namespace b2
 
 // ---- C ABI -----------------------------------------------------------------------------------------
-#define B2_TRY_BEGIN try {
-#define B2_TRY_END                                                                 \
-  }                                                                                \
-  catch (const b2::error& e) { b2::set_last_error(e.what()); return e.code; }      \
-  catch (const std::bad_alloc& e) { b2::set_last_error(e.what()); return B2_ERR_BAD_ALLOC; } \
-  catch (const std::exception& e) { b2::set_last_error(e.what()); return B2_ERR_LOGIC; }     \
-  return B2_OK;
-
 static cudaStream_t S(b2_stream s) { return static_cast<cudaStream_t>(s); }
 
 // free functions: cpp/src/join/join.cu:27-110

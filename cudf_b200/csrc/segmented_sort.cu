@@ -86,16 +86,6 @@ column_ptr top_k_order(const b2_column_view& col, int32_t k, int32_t topk_order,
 
 using namespace b2;
 
-#define B2_TRY_BEGIN try {
-#define B2_TRY_END                                                                 \
-  }                                                                                \
-  catch (const b2::error& e) { b2::set_last_error(e.what()); return e.code; }      \
-  catch (const std::bad_alloc& e) { b2::set_last_error(e.what()); return B2_ERR_BAD_ALLOC; } \
-  catch (const std::exception& e) { b2::set_last_error(e.what()); return B2_ERR_LOGIC; }     \
-  return B2_OK;
-
-static std::vector<uint8_t> u8v(const uint8_t* p, int32_t n) { return (p && n > 0) ? std::vector<uint8_t>(p, p + n) : std::vector<uint8_t>{}; }
-
 extern "C" {
 
 b2_status b2_segmented_sorted_order(const b2_table_view* keys, const b2_column_view* segment_offsets, const uint8_t* column_order,
@@ -106,7 +96,7 @@ b2_status b2_segmented_sorted_order(const b2_table_view* keys, const b2_column_v
   B2_EXPECTS(out && segment_offsets, B2_ERR_INVALID_ARGUMENT, "null argument");
   std::vector<b2_column_view> k;
   validate_table(keys, k);
-  *out = segmented_sorted_order(k, *segment_offsets, u8v(column_order, n_order), u8v(null_precedence, n_null_prec), stable != 0,
+  *out = segmented_sorted_order(k, *segment_offsets, vec_u8(column_order, n_order), vec_u8(null_precedence, n_null_prec), stable != 0,
                                 static_cast<cudaStream_t>(stream))
            .release();
   B2_TRY_END
@@ -124,7 +114,7 @@ b2_status b2_segmented_sort_by_key(const b2_table_view* values, const b2_table_v
   const int32_t vrows = v.empty() ? 0 : v[0].size, krows = k.empty() ? 0 : k[0].size;
   B2_EXPECTS(vrows == krows, B2_ERR_LOGIC, "Mismatch in number of rows for values and keys");
   auto s = static_cast<cudaStream_t>(stream);
-  auto order = segmented_sorted_order(k, *segment_offsets, u8v(column_order, n_order), u8v(null_precedence, n_null_prec), stable != 0, s);
+  auto order = segmented_sorted_order(k, *segment_offsets, vec_u8(column_order, n_order), vec_u8(null_precedence, n_null_prec), stable != 0, s);
   *out = gather_table(v, order->data.as<int32_t>(), order->size, false, s).release();
   B2_TRY_END
 }
