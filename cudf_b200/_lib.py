@@ -125,6 +125,7 @@ _sig("b2_segmented_sorted_order", [P(TableView), P(ColumnView), u8p, i32, u8p, i
 _sig("b2_segmented_sort_by_key", [P(TableView), P(TableView), P(ColumnView), u8p, i32, u8p, i32, i32, b2_stream, P(vp)])
 _sig("b2_top_k", [P(ColumnView), i32, i32, b2_stream, P(vp)])
 _sig("b2_top_k_order", [P(ColumnView), i32, i32, b2_stream, P(vp)])
+_sig("b2_rank", [P(ColumnView), i32, i32, i32, i32, i32, b2_stream, P(vp)])
 for _j in ("inner", "left", "full"):
     _sig(f"b2_{_j}_join", [P(TableView), P(TableView), i32, b2_stream, P(vp), P(vp)])
     _sig(f"b2_hash_join_{_j}_join", [vp, P(TableView), i32, C.c_size_t, b2_stream, P(vp), P(vp)])
@@ -161,7 +162,7 @@ DECLARED_SYMBOLS = [
     "b2_scalar_device_data", "b2_scalar_get", "b2_scalar_free", "b2_bitmask_allocation_size_bytes",
     "b2_create_null_mask", "b2_set_null_mask", "b2_copy_bitmask", "b2_count_set_bits", "b2_null_count",
     "b2_bitmask_and", "b2_gather", "b2_sorted_order", "b2_sort", "b2_sort_by_key", "b2_segmented_sorted_order",
-    "b2_segmented_sort_by_key", "b2_top_k", "b2_top_k_order", "b2_inner_join", "b2_left_join",
+    "b2_segmented_sort_by_key", "b2_top_k", "b2_top_k_order", "b2_rank", "b2_inner_join", "b2_left_join",
     "b2_full_join", "b2_hash_join_create", "b2_hash_join_destroy", "b2_hash_join_inner_join",
     "b2_hash_join_left_join", "b2_hash_join_full_join", "b2_hash_join_inner_join_size",
     "b2_hash_join_left_join_size", "b2_hash_join_full_join_size", "b2_hash_join_match_counts",

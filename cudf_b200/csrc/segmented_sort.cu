@@ -1,4 +1,4 @@
-// segmented_sort.cu — segmented_sorted_order / segmented_sort_by_key and top_k / top_k_order on top of the radix machinery.
+// segmented_sort.cu — segmented_sorted_order / segmented_sort_by_key, top_k / top_k_order and rank on top of the radix machinery.
 //
 // Replaces cpp/src/sort/segmented_sort.cu + segmented_sort_impl.cuh (public API cpp/include/cudf/sorting.hpp:232-366)
 // and cpp/src/sort/top_k.cu:100-150 (sorting.hpp:370-416). SURVEY §8f.4 ("next" rows; written after the round-1 GPU
@@ -10,8 +10,12 @@
 //     keeps those rows where they are ("indices outside the specified segments will not be sorted").
 // The two helper columns cost no radix pass for their constant bytes (trivial passes are skipped on the device).
 // top_k = stable sorted order (nulls last for ASCENDING, first for DESCENDING, as top_k.cu:121-123), first k rows.
+// rank (cpp/src/sort/rank.cu:236-356, sorting.hpp:165-230) = sorted order -> dense rank of the sorted rows (row equality
+// with null == null, NaN == NaN) -> per tie group first / last position -> FIRST / AVERAGE / MIN / MAX / DENSE value
+// scattered to the row, optionally divided by the row (or group) count.
 #include "common.cuh"
 #include "device_utils.cuh"
+#include "key_pack.cuh"
 
 #include <algorithm>
 
@@ -34,6 +38,57 @@ __global__ void __launch_bounds__(256) segment_ids_kernel(const int32_t* __restr
     const bool outside = num_offsets < 2 || s < 0 || s >= num_offsets - 1;
     seg[i] = outside ? (s < 0 ? -1 : num_offsets) : s;
     pos[i] = outside ? (int32_t)i : 0;
+  }
+}
+
+// head[i] = 1 when sorted row i differs from sorted row i - 1 (rank.cu:40-97 unique_functor)
+__global__ void __launch_bounds__(256) rank_heads_kernel(key_cols kc, const int32_t* __restrict__ order, int64_t n, int32_t* __restrict__ head)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    int32_t h = 1;
+    if (i > 0) {
+      uint64_t k0, k1;
+      uint32_t n0, n1;
+      pack_row(kc, order[i - 1], k0, n0);
+      pack_row(kc, order[i], k1, n1);
+      h = (k0 != k1 || n0 != n1) ? 1 : 0;
+    }
+    head[i] = h;
+  }
+}
+
+// first / last sorted position of every tie group (dense rank d -> gfirst[d - 1], glast[d - 1])
+__global__ void __launch_bounds__(256) rank_groups_kernel(const int32_t* __restrict__ dense, int64_t n, int32_t* __restrict__ gfirst,
+                                                          int32_t* __restrict__ glast)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int32_t d = dense[i];
+    if (i == 0 || dense[i - 1] != d) gfirst[d - 1] = (int32_t)i;
+    if (i == n - 1 || dense[i + 1] != d) glast[d - 1] = (int32_t)i;
+  }
+}
+
+// method: 0 FIRST, 1 AVERAGE, 2 MIN, 3 MAX, 4 DENSE (cudf::rank_method). count > 0: percentage (rank.cu:338-354).
+__global__ void __launch_bounds__(256) rank_scatter_kernel(const int32_t* __restrict__ order, const int32_t* __restrict__ dense,
+                                                           const int32_t* __restrict__ gfirst, const int32_t* __restrict__ glast, int64_t n,
+                                                           int method, bool as_double, int64_t count, void* __restrict__ out)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    double r;
+    if (method == 0) {
+      r = (double)(i + 1);
+    } else {
+      const int32_t d = dense[i];
+      const double lo = (double)gfirst[d - 1] + 1.0, cnt = (double)(glast[d - 1] - gfirst[d - 1] + 1);
+      r = method == 4 ? (double)d : (method == 2 ? lo : (method == 3 ? lo + cnt - 1.0 : lo + (cnt - 1.0) / 2.0));
+    }
+    if (count > 0) r = method == 4 ? r / (double)dense[count - 1] : r / (double)count;
+    const int32_t row = order[i];
+    if (as_double) static_cast<double*>(out)[row] = r;
+    else static_cast<int32_t*>(out)[row] = (int32_t)r;
   }
 }
 
@@ -82,6 +137,44 @@ column_ptr top_k_order(const b2_column_view& col, int32_t k, int32_t topk_order,
   return out;
 }
 
+// cudf::rank — cpp/src/sort/rank.cu:236-356
+column_ptr rank_column(const b2_column_view& input, int32_t method, int32_t column_order, int32_t null_handling, int32_t null_precedence,
+                       bool percentage, cudaStream_t stream)
+{
+  B2_EXPECTS(method >= 0 && method <= 4, B2_ERR_LOGIC, "Unexpected rank_method for rank()");
+  const bool as_double = percentage || method == 1;
+  const int64_t n = input.size;
+  const bool exclude = null_handling == B2_NULL_EXCLUDE;
+  // EXCLUDE: the result carries the input's validity (ranks of null rows are computed but masked)
+  auto out = make_column(as_double ? B2_FLOAT64 : B2_INT32, (int32_t)n, exclude && has_nulls(input), stream);
+  if (n == 0) return out;
+  if (exclude && has_nulls(input)) {
+    dbuf m = copy_bitmask(input.null_mask, input.offset, input.offset + n, stream);
+    B2_CUDA_TRY(cudaMemcpyAsync(out->mask.ptr, m.ptr, std::min(out->mask.bytes, m.bytes), cudaMemcpyDeviceToDevice, stream));
+    out->null_count = input.null_count;
+  }
+  std::vector<uint8_t> ord{(uint8_t)column_order}, np{(uint8_t)null_precedence};
+  auto order = sorted_order({input}, ord, np, true, stream);
+  const int32_t* o = order->data.as<int32_t>();
+  dbuf heads, gfirst, glast;
+  column_ptr dense;
+  if (method != 0) {
+    const key_cols kc = make_key_cols({input});
+    heads = dbuf(sizeof(int32_t) * n, stream);
+    B2_LAUNCH(rank_heads_kernel, grid_for(n), 256, 0, stream, kc, o, n, heads.as<int32_t>());
+    b2_column_view hv{B2_INT32, (int32_t)n, heads.ptr, nullptr, 0, 0};
+    dense  = scan(hv, B2_AGG_SUM, B2_SCAN_INCLUSIVE, B2_NULL_EXCLUDE, stream);
+    gfirst = dbuf(sizeof(int32_t) * n, stream);
+    glast  = dbuf(sizeof(int32_t) * n, stream);
+    B2_LAUNCH(rank_groups_kernel, grid_for(n), 256, 0, stream, dense->data.as<int32_t>(), n, gfirst.as<int32_t>(), glast.as<int32_t>());
+  }
+  const int64_t count = percentage ? (exclude ? n - input.null_count : n) : 0;
+  // all rows null under EXCLUDE: every rank is masked; avoid dividing by a zero count
+  B2_LAUNCH(rank_scatter_kernel, grid_for(n), 256, 0, stream, o, dense ? dense->data.as<int32_t>() : nullptr, gfirst.as<int32_t>(),
+            glast.as<int32_t>(), n, method, as_double, (percentage && count == 0) ? n : count, out->data.ptr);
+  return out;
+}
+
 }  // namespace b2
 
 using namespace b2;
@@ -116,6 +209,16 @@ b2_status b2_segmented_sort_by_key(const b2_table_view* values, const b2_table_v
   auto s = static_cast<cudaStream_t>(stream);
   auto order = segmented_sorted_order(k, *segment_offsets, vec_u8(column_order, n_order), vec_u8(null_precedence, n_null_prec), stable != 0, s);
   *out = gather_table(v, order->data.as<int32_t>(), order->size, false, s).release();
+  B2_TRY_END
+}
+
+b2_status b2_rank(const b2_column_view* input, int32_t method, int32_t column_order, int32_t null_handling, int32_t null_precedence,
+                  int32_t percentage, b2_stream stream, b2_column** out)
+{
+  B2_TRY_BEGIN
+  B2_EXPECTS(out && input, B2_ERR_INVALID_ARGUMENT, "null argument");
+  validate_column(*input);
+  *out = rank_column(*input, method, column_order, null_handling, null_precedence, percentage != 0, static_cast<cudaStream_t>(stream)).release();
   B2_TRY_END
 }
 

@@ -1,10 +1,10 @@
 """pylibcudf-named API of the B200 hot path (sorting, join, groupby, reduce, copying, aggregation, null_mask)."""
 from . import aggregation, copying, groupby, join, null_mask, reduce, sorting, types
 from .column import Column, DeviceSpan, Scalar, Table
-from .types import DataType, MaskState, NullEquality, NullOrder, NullPolicy, Order, OutOfBoundsPolicy, Sorted, TypeId
+from .types import DataType, MaskState, NullEquality, NullOrder, NullPolicy, Order, OutOfBoundsPolicy, RankMethod, Sorted, TypeId
 
 __all__ = [
     "aggregation", "copying", "groupby", "join", "null_mask", "reduce", "sorting", "types",
     "Column", "DeviceSpan", "Scalar", "Table", "DataType", "MaskState", "NullEquality", "NullOrder", "NullPolicy",
-    "Order", "OutOfBoundsPolicy", "Sorted", "TypeId",
+    "Order", "OutOfBoundsPolicy", "RankMethod", "Sorted", "TypeId",
 ]

@@ -116,3 +116,14 @@ def top_k_order(col: Column, k: int, sort_order=1, stream=None, mr=None) -> Colu
     cv = col._view()
     check(lib.b2_top_k_order(C.byref(cv), int(k), int(sort_order), _lib.stream_arg(stream), C.byref(out)))
     return Column._from_handle(out.value)
+
+
+def rank(input_view: Column, method: int, column_order: int, null_handling: int, null_precedence: int, percentage: bool, stream=None,
+         mr=None) -> Column:
+    """cudf::rank (python/pylibcudf/pylibcudf/sorting.pyx rank; cpp/include/cudf/sorting.hpp:165-230).
+    method: RankMethod (0 FIRST, 1 AVERAGE, 2 MIN, 3 MAX, 4 DENSE)."""
+    out = C.c_void_p()
+    cv = input_view._view()
+    check(lib.b2_rank(C.byref(cv), int(method), int(column_order), int(null_handling), int(null_precedence), 1 if percentage else 0,
+                      _lib.stream_arg(stream), C.byref(out)))
+    return Column._from_handle(out.value)

@@ -49,6 +49,14 @@ class NullPolicy(enum.IntEnum):
     INCLUDE = 1
 
 
+class RankMethod(enum.IntEnum):  # cudf::rank_method (cpp/include/cudf/aggregation.hpp:37-43)
+    FIRST = 0
+    AVERAGE = 1
+    MIN = 2
+    MAX = 3
+    DENSE = 4
+
+
 class NullEquality(enum.IntEnum):
     EQUAL = 0
     UNEQUAL = 1

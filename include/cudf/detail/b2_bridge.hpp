@@ -404,6 +404,17 @@ inline std::unique_ptr<table> segmented_sort_by_key_impl(table_view const& value
 inline std::unique_ptr<table> segmented_sort_by_key(table_view const& values, table_view const& keys, column_view const& segment_offsets, CUDF_B2_SORT_ARGS) { return segmented_sort_by_key_impl(values, keys, segment_offsets, column_order, null_precedence, false, stream); }
 inline std::unique_ptr<table> stable_segmented_sort_by_key(table_view const& values, table_view const& keys, column_view const& segment_offsets, CUDF_B2_SORT_ARGS) { return segmented_sort_by_key_impl(values, keys, segment_offsets, column_order, null_precedence, true, stream); }
 #undef CUDF_B2_SORT_ARGS
+// rank (sorting.hpp:165-230; rank_method: aggregation.hpp:37-43)
+enum class rank_method : int32_t { FIRST, AVERAGE, MIN, MAX, DENSE };
+inline std::unique_ptr<column> rank(column_view const& input, rank_method method, order column_order, null_policy null_handling,
+                                    null_order null_precedence, bool percentage, rmm::cuda_stream_view stream = cudf::get_default_stream(),
+                                    rmm::device_async_resource_ref = cudf::get_current_device_resource_ref())
+{
+  b2_column* out = nullptr;
+  detail::check(b2_rank(&input.native(), static_cast<int32_t>(method), static_cast<int32_t>(column_order), static_cast<int32_t>(null_handling),
+                        static_cast<int32_t>(null_precedence), percentage ? 1 : 0, stream.value(), &out));
+  return std::make_unique<column>(out);
+}
 // top-k (sorting.hpp:370-416)
 inline std::unique_ptr<column> top_k(column_view const& col, size_type k, order topk_order = order::DESCENDING,
                                      rmm::cuda_stream_view stream = cudf::get_default_stream(),

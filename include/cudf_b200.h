@@ -193,6 +193,12 @@ B2_API b2_status b2_segmented_sort_by_key(const b2_table_view* values, const b2_
 B2_API b2_status b2_top_k(const b2_column_view* col, int32_t k, int32_t topk_order, b2_stream stream, b2_column** out);
 B2_API b2_status b2_top_k_order(const b2_column_view* col, int32_t k, int32_t topk_order, b2_stream stream,
                                 b2_column** out);
+/* cudf::rank (sorting.hpp:165-230, cpp/src/sort/rank.cu:236-356). method = cudf::rank_method (0 FIRST, 1 AVERAGE,
+ * 2 MIN, 3 MAX, 4 DENSE); the result is FLOAT64 for AVERAGE or percentage, INT32 otherwise; under
+ * null_handling = EXCLUDE the result carries the input's validity; percentage divides by the row count (DENSE: by
+ * the number of distinct values). */
+B2_API b2_status b2_rank(const b2_column_view* input, int32_t method, int32_t column_order, int32_t null_handling,
+                         int32_t null_precedence, int32_t percentage, b2_stream stream, b2_column** out);
 
 /* ---- hash join: cpp/include/cudf/join/join.hpp:127-249, join/hash_join.hpp ---------------- */
 /* Results are two INT32 columns of equal length (cudf returns device_uvector<size_type>), row

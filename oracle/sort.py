@@ -136,3 +136,38 @@ def top_k_order(column, k, order=DESCENDING) -> np.ndarray:
 
 def top_k(column, k, order=DESCENDING):
     return gather([column], top_k_order(column, k, order))[0]
+
+
+def rank(column, method, column_order=ASCENDING, null_handling=1, null_precedence=AFTER, percentage=False):
+    """cudf::rank (cpp/src/sort/rank.cu:236-356, sorting.hpp:165-230). method: 0 FIRST, 1 AVERAGE, 2 MIN, 3 MAX, 4 DENSE;
+    null_handling: 0 EXCLUDE (result carries the input validity), 1 INCLUDE. -> (values, valid | None)."""
+    values, valid = column
+    values = np.asarray(values)
+    n = len(values)
+    as_double = percentage or method == 1
+    if n == 0:
+        return np.empty(0, np.float64 if as_double else np.int32), None
+    m = np.ones(n, bool) if valid is None else np.asarray(valid, bool)
+    o = sorted_order([(values, None if valid is None else m)], [column_order], [null_precedence]).astype(np.int64)
+    sv, sm = values[o], m[o]
+    same = np.zeros(n, bool)
+    if n > 1:
+        a, b = sv[1:], sv[:-1]
+        eqv = (a == b) | ((a != a) & (b != b)) if values.dtype.kind == "f" else (a == b)
+        same[1:] = (sm[1:] & sm[:-1] & eqv) | (~sm[1:] & ~sm[:-1])
+    dense = np.cumsum(~same)
+    starts = np.nonzero(~same)[0]
+    ends = np.concatenate([starts[1:], [n]]) - 1
+    gfirst, glast = starts[dense - 1], ends[dense - 1]
+    pos = np.arange(n)
+    r = {0: pos + 1.0, 1: gfirst + 1 + (glast - gfirst) / 2.0, 2: gfirst + 1.0, 3: glast + 1.0, 4: dense.astype(np.float64)}[method]
+    if percentage:
+        count = int(m.sum()) if null_handling == 0 else n
+        count = count if count > 0 else n
+        r = r / (dense[count - 1] if method == 4 else count)
+    out = np.empty(n, np.float64 if as_double else np.int32)
+    out[o] = r if as_double else r.astype(np.int32)
+    ov = None
+    if null_handling == 0 and valid is not None and not m.all():
+        ov = m.copy()
+    return out, ov

@@ -43,6 +43,10 @@ int main()
     column_view skc{data_type{type_id::INT32}, 10, sk.p}, soc{data_type{type_id::INT32}, 4, so.p};
     auto seg = segmented_sorted_order(table_view{{skc}}, soc);
     EXPECT((to_host(seg->view().data<int32_t>(), 10) == std::vector<int32_t>{2, 1, 0, 6, 5, 4, 3, 9, 8, 7}));
+    dev_vec<int32_t> rk({3, 4, 5, 4, 1, 2});  // sorting.hpp:172-179: AVERAGE = {3, 4.5, 6, 4.5, 1, 2}
+    column_view rkc{data_type{type_id::INT32}, 6, rk.p};
+    auto avg = cudf::rank(rkc, rank_method::AVERAGE, order::ASCENDING, null_policy::INCLUDE, null_order::AFTER, false);
+    EXPECT((to_host(avg->view().data<double>(), 6) == std::vector<double>{3, 4.5, 6, 4.5, 1, 2}));
     auto top = top_k(skc, 3);
     auto ht  = to_host(top->view().data<int32_t>(), 3);
     std::sort(ht.begin(), ht.end());
