@@ -270,8 +270,8 @@ __global__ void __launch_bounds__(256) finalize_kernel(const slot_t* __restrict_
       }
     }
     if (o.mode == 1) {
-      double sum = o.acc == ACC_F64 ? __longlong_as_double((long long)raw)
-                                    : (o.acc == ACC_I64 ? (double)(long long)raw : (double)raw);
+      // SUM of any integral source is an int64 (aggregation.hpp:950-956): unsigned sources are read back as signed too
+      double sum = o.acc == ACC_F64 ? __longlong_as_double((long long)raw) : (double)(long long)raw;
       static_cast<double*>(o.out)[g] = nvalid > 0 ? sum / (double)nvalid : 0.0;
     } else {
       double fv = 0;

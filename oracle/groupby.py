@@ -115,9 +115,12 @@ def aggregate(key_cols, requests, null_handling=EXCLUDE):
             xv, xg = v[m], gid[m]
             with np.errstate(over="ignore", invalid="ignore"):
                 if kind in (SUM, MEAN):
-                    acc = np.zeros(ng, dtype=np.float64 if (rdt.kind == "f") else rdt)
+                    # MEAN = SUM / COUNT_VALID with SUM in its own target type (hash_compound_agg_finalizer.cu:95-131):
+                    # integer sources accumulate in (wrapping) int64, floats in their type (float32 kept as float64 here)
+                    sdt = result_dtype(SUM, vals.dtype)
+                    acc = np.zeros(ng, dtype=np.float64 if sdt.kind == "f" else sdt)
                     np.add.at(acc, xg, xv.astype(acc.dtype))
-                    out = (acc / np.maximum(vc, 1)).astype(rdt) if kind == MEAN else acc.astype(rdt)
+                    out = (acc.astype(np.float64) / np.maximum(vc, 1)).astype(rdt) if kind == MEAN else acc.astype(rdt)
                 elif kind == PRODUCT:
                     acc = np.ones(ng, dtype=rdt)
                     np.multiply.at(acc, xg, xv.astype(rdt))

@@ -91,3 +91,16 @@ def test_var_std_random(impl, vdtype):
                 np.testing.assert_allclose(np.asarray(g[0], np.float64)[em], np.asarray(e[0], np.float64)[em], rtol=rtol, atol=rtol * 9e4)
             else:
                 assert np.array_equal(np.asarray(g[0])[em], np.asarray(e[0])[em]), kind
+
+
+def test_mean_of_wrapping_integer_sums(impl):
+    """MEAN = SUM / COUNT with SUM in int64 for every integral source (aggregation.hpp:950-956,
+    hash_compound_agg_finalizer.cu:95-131): sums that wrap, and unsigned sums above 2^63, read back as signed."""
+    keys = make_col([0, 0, 1, 1, 2], np.int32)
+    vals = (np.array([2**64 - 1, 0, 2**63, 2**63, 7], np.uint64), None)
+    k, r = run(impl, keys, vals, ["sum", "mean"])
+    assert np.asarray(r[0][0]).dtype == np.int64 and np.asarray(r[0][0]).tolist() == [-1, 0, 7]
+    np.testing.assert_allclose(np.asarray(r[1][0]), [-0.5, 0.0, 7.0])
+    vals = (np.array([2**63 - 1, 1, 5, 6, 7], np.int64), None)
+    k, r = run(impl, keys, vals, ["mean"])
+    np.testing.assert_allclose(np.asarray(r[0][0]), [-(2.0**63) / 2, 5.5, 7.0])
