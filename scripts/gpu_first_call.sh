@@ -16,8 +16,12 @@ step() {  # step <name> <timeout-seconds> <command...>
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > "$O/gpu.txt" 2>&1
 
 # 1. the validated suite first, then the files that never ran on hardware (each on its own so that one cannot hide another)
+NEW="tests/test_zzzz_match_context.py tests/test_zzzz_var_std.py tests/test_zzzz_segmented_sort.py tests/test_zzzz_rank.py tests/test_zzzz_partitioning.py"
+IGN=""; for f in $NEW; do IGN="$IGN --ignore $f"; done
 step tests_validated 1500 python -m pytest tests -q -m gpu -x --ignore tests/test_zz_experimental_gpu.py \
-  --ignore tests/test_zz_full_size_gpu.py --ignore tests/test_zzz_cpp_api.py --ignore tests/test_zy_more_golden.py
+  --ignore tests/test_zz_full_size_gpu.py --ignore tests/test_zzz_cpp_api.py --ignore tests/test_zy_more_golden.py $IGN
+# written on the emulator, never on hardware: match context / partitioned probes, VAR / STD, segmented sort / top-k, rank, partitioning
+step tests_emulator_born 900 python -m pytest $NEW -q -m gpu
 step tests_more_golden 300 python -m pytest tests/test_zy_more_golden.py -q -m gpu
 step tests_cpp_api 300 python -m pytest tests/test_zzz_cpp_api.py -q -m gpu
 B2_RUN_EXPERIMENTAL=1 step tests_experimental 1000 python -m pytest tests/test_zz_experimental_gpu.py -q -m gpu -rxX
