@@ -14,6 +14,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 os.chdir(ROOT)
 
+# --mode selects an opt-in path for the whole run (the switches are read by the library, some of them only once)
+_MODES = {"default": {}, "carry": {"B2_SORT_CARRY": "1"}, "alias": {"B2_SORT_ALIAS": "1"}, "radix": {"B2_JOIN_RADIX_ROWS": "1"},
+          "rmw": {"B2_SORT_CFG": "11"}, "portion": {"B2_SORT_PORTION": "6144"}, "mixed": {"B2_JOIN_PARTITION_ROWS": "64"}}
+for _i, _a in enumerate(sys.argv):
+    if _a == "--mode" and _i + 1 < len(sys.argv):
+        os.environ.update(_MODES[sys.argv[_i + 1]])
+
 from tests.emu.harness import install  # noqa: E402
 
 install()
@@ -75,9 +82,18 @@ def fuzz_sort(rng):
         assert np.array_equal(got, exp), ("sorted_order", n, [c[0].dtype for c in cols], order, prec, use_slices)
     else:
         assert np.array_equal(got, exp), ("sorted_order multi", n, [c[0].dtype for c in cols], order, prec, use_slices)
-    vals = (rng.integers(0, 1 << 30, n).astype(np.int32), None)
+    vdt = [np.int32, np.int64, np.float64][int(rng.integers(3))]
+    vals = (rng.integers(0, 1 << 30, n).astype(vdt), None)
     g = plc.sorting.sort_by_key(plc.Table([plc.Column.from_numpy(*vals)]), plc.Table(pc), order, prec).columns()[0].to_numpy()[0]
-    assert np.array_equal(g, vals[0][exp]), ("sort_by_key", n)
+    assert np.array_equal(g, vals[0][exp]), ("sort_by_key", n, vdt)
+    if ncol == 1:
+        t = plc.Table([pc[0]])
+        g, gm = plc.sorting.sort_by_key(t, t, order, prec).columns()[0].to_numpy()       # aliased values = keys
+        e, em = osort.sort_by_key([cols[0]], [cols[0]], order, prec)[0]
+        ok = np.ones(n, bool) if em is None else np.asarray(em, bool)
+        assert np.array_equal(np.asarray(g)[ok].view(np.uint8), np.asarray(e)[ok].view(np.uint8)), ("aliased sort_by_key", n, cols[0][0].dtype)
+        g, gm = plc.sorting.sort(t, order, prec).columns()[0].to_numpy()
+        assert np.array_equal(np.asarray(g)[ok].view(np.uint8), np.asarray(e)[ok].view(np.uint8)), ("sort", n, cols[0][0].dtype)
 
 
 def fuzz_join(rng):
@@ -176,9 +192,13 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seconds", type=float, default=120)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--mode", default="default", choices=sorted(_MODES))
+    ap.add_argument("--only", default="", help="comma-separated subset of: sort,join,groupby,reduce_scan,seg_rank")
     a = ap.parse_args()
     rng = np.random.default_rng(a.seed)
     fns = [fuzz_sort, fuzz_join, fuzz_groupby, fuzz_reduce_scan, fuzz_seg_rank]
+    if a.only:
+        fns = [f for f in fns if f.__name__[5:] in a.only.split(",")]
     counts = {f.__name__: 0 for f in fns}
     t0 = time.time()
     it = 0
