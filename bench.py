@@ -270,20 +270,29 @@ def run_ours(args):
     # algorithmic bytes of THIS implementation's 8 passes over (int64 key, int32 row id):
     # pass 1: 8 read + 12 write; passes 2-7: 12 + 12; pass 8: 12 read + 4 write (row ids only) = 180 B/row
     rows_local = n  # per rank; at N > 1 the received shard differs from n by < 1 % (sample-sort splitters)
+    # opt-in sort paths (README "Environment switches") move different bytes per pass; the default is the row-id path
+    if os.environ.get("B2_SORT_ALIAS", "0") not in ("", "0"):
+        sort_path, bytes_8_passes, kernel_name = "aliased keys-only radix (B2_SORT_ALIAS)", 128.0, "onesweep_kernel<uint64, keys only>"
+    elif os.environ.get("B2_SORT_CARRY", "0") not in ("", "0"):
+        sort_path, bytes_8_passes, kernel_name = "payload-carrying radix (B2_SORT_CARRY)", 248.0, "onesweep_kernel<uint64,(key,8-byte payload)>"
+    else:
+        sort_path, bytes_8_passes, kernel_name = "row ids + gather (default)", 180.0, "onesweep_kernel<uint64,(key,row id)>"
+    default_path = bytes_8_passes == 180.0
     roofline = None
     if os_cnt and rows_local:
-        per_launch_bytes = 180.0 * rows_local / 8.0
+        per_launch_bytes = bytes_8_passes * rows_local / 8.0
         # the n-row sort runs 8 passes per step (uniform 64-bit keys: no trivial digit); at N > 1 the splitter sample sort
         # adds a few microsecond-scale launches per step, whose time stays in the numerator and is negligible
         big_launches = 8 * args.steps
         avg_ms = os_ms / big_launches
         achieved = per_launch_bytes / (avg_ms / 1e3) / 1e9
         roofline = {
-            "bound": "hbm", "kernel": "onesweep_kernel<uint64,(key,row id)>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "bound": "hbm", "kernel": kernel_name, "sort_path": sort_path, "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak,
             # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the ncu --set full capture at 2^27 rows
             # (profiles/r1_onesweep_ncu_e.txt: 1.612 + 1.582 GB per launch = 23.8 B/row), scaled to this launch size
-            "traffic": 23.8 * rows_local, "traffic_source": "ncu capture at 2^27 rows, per-row figure scaled",
+            "traffic": 23.8 * rows_local if default_path else None,
+            "traffic_source": "ncu capture at 2^27 rows, per-row figure scaled" if default_path else "no ncu capture of this path yet",
             "peak_source": peak_src, "rank": rank,
             "algorithmic_bytes_per_launch": per_launch_bytes, "avg_launch_ms": avg_ms, "launches": big_launches, "launches_incl_sample_sort": os_cnt,
             "kernel_share_of_step": os_ms / ms_total,
