@@ -30,7 +30,7 @@ namespace {
 constexpr int MAX_OPS = 24;
 
 enum acc_kind : int8_t { ACC_I64 = 0, ACC_U64 = 1, ACC_F64 = 2 };
-enum op_kind : int8_t { OPK_SUM = 0, OPK_MIN = 1, OPK_MAX = 2, OPK_SUMSQ = 3 };
+enum op_kind : int8_t { OPK_SUM = 0, OPK_MIN = 1, OPK_MAX = 2, OPK_SUMSQ = 3, OPK_PROD = 4 };
 
 struct value_op {
   const void* src;
@@ -128,7 +128,8 @@ __device__ __forceinline__ void load_value(const value_op& op, int64_t e, long l
 // WIDE (keys wider than 8 bytes): the slot holds a 64-bit hash of the row; a hash hit is confirmed by comparing the
 // key columns of this row with the slot's representative row (key_pack.cuh).
 // SQ: the request contains SUM_OF_SQUARES accumulators (M2 / VARIANCE / STD are derived from SUM, SUM_OF_SQUARES and
-// COUNT in the finalize step: cpp/src/groupby/common/m2_var_std.cu:35-62).
+// COUNT in the finalize step: cpp/src/groupby/common/m2_var_std.cu:35-62) or PRODUCT accumulators (a CAS loop per
+// update: device_aggregators.cuh:323-335 atomic_mul).
 template <bool WIDE = false, bool SQ = false>
 __global__ void __launch_bounds__(256) groupby_kernel(key_cols kc, int64_t n, bool skip_null_keys, slot_t* __restrict__ table,
                                                       uint32_t mask, uint32_t cap, int32_t* __restrict__ gsize,
@@ -191,6 +192,18 @@ __global__ void __launch_bounds__(256) groupby_kernel(key_cols kc, int64_t n, bo
           if (op.acc == ACC_F64) atomicAdd(reinterpret_cast<double*>(a), fv * fv);
           else if (op.acc == ACC_I64) atomicAdd(a, (unsigned long long)iv * (unsigned long long)iv);
           else atomicAdd(a, uv * uv);
+          continue;
+        }
+        if (op.op == OPK_PROD) {
+          unsigned long long seen = *reinterpret_cast<volatile unsigned long long*>(a), want;
+          do {
+            const unsigned long long cur = seen;
+            if (op.acc == ACC_F64) want = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)cur) * fv);
+            else if (op.acc == ACC_I64) want = cur * (unsigned long long)iv;
+            else want = cur * uv;
+            seen = atomicCAS(a, cur, want);
+            if (seen == cur) break;
+          } while (true);
           continue;
         }
       }
@@ -307,12 +320,12 @@ int grid_for(int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>((n 
 int32_t result_type(int32_t kind, int32_t src)
 {
   switch (kind) {
-    case B2_AGG_SUM: case B2_AGG_SUM_OF_SQUARES: return is_float_id(src) ? src : B2_INT64;
+    case B2_AGG_SUM: case B2_AGG_SUM_OF_SQUARES: case B2_AGG_PRODUCT: return is_float_id(src) ? src : B2_INT64;
     case B2_AGG_M2: case B2_AGG_VARIANCE: case B2_AGG_STD: return B2_FLOAT64;
     case B2_AGG_MIN: case B2_AGG_MAX: return src;
     case B2_AGG_COUNT_VALID: case B2_AGG_COUNT_ALL: return B2_INT32;
     case B2_AGG_MEAN: return B2_FLOAT64;
-    default: B2_FAIL(B2_ERR_INVALID_ARGUMENT, "unsupported groupby aggregation on the hash path (SUM/MIN/MAX/COUNT/MEAN/SUM_OF_SQUARES/M2/VARIANCE/STD)");
+    default: B2_FAIL(B2_ERR_INVALID_ARGUMENT, "unsupported groupby aggregation on the hash path (SUM/PRODUCT/MIN/MAX/COUNT/MEAN/SUM_OF_SQUARES/M2/VARIANCE/STD)");
   }
 }
 
@@ -324,6 +337,7 @@ inline bool needs_sumsq(int32_t kind) { return kind == B2_AGG_SUM_OF_SQUARES || 
 unsigned long long acc_init(int8_t acc, int8_t op)
 {
   if (op == OPK_SUM || op == OPK_SUMSQ) return 0ull;
+  if (op == OPK_PROD) return acc == ACC_F64 ? 0x3FF0000000000000ull /* 1.0 */ : 1ull;
   if (acc == ACC_U64) return op == OPK_MIN ? ~0ull : 0ull;
   // I64, and F64 in ordered-int64 space
   return op == OPK_MIN ? (unsigned long long)INT64_MAX : (unsigned long long)INT64_MIN;
@@ -370,8 +384,8 @@ void groupby_aggregate(const b2_groupby& gb, const std::vector<request_view>& re
     for (int32_t raw_kind : r.kinds) {
       const int32_t kind = base_kind(raw_kind);
       (void)result_type(kind, r.values.type_id);
-      if (kind == B2_AGG_SUM || kind == B2_AGG_MEAN || needs_sumsq(kind))
-        B2_EXPECTS(is_numeric(r.values.type_id), B2_ERR_LOGIC, "SUM/MEAN/SUM_OF_SQUARES/M2/VARIANCE/STD need a numeric values column");
+      if (kind == B2_AGG_SUM || kind == B2_AGG_MEAN || kind == B2_AGG_PRODUCT || needs_sumsq(kind))
+        B2_EXPECTS(is_numeric(r.values.type_id), B2_ERR_LOGIC, "SUM/PRODUCT/MEAN/SUM_OF_SQUARES/M2/VARIANCE/STD need a numeric values column");
     }
   }
   if (n == 0) return empty_results(gb, reqs, stream, keys_out, res_out);
@@ -420,7 +434,7 @@ void groupby_aggregate(const b2_groupby& gb, const std::vector<request_view>& re
         op.mask     = nullable ? v.null_mask : nullptr;
         op.offset   = v.offset;
         op.src_type = (int8_t)st;
-        const bool sumlike = opk == OPK_SUM || opk == OPK_SUMSQ;
+        const bool sumlike = opk == OPK_SUM || opk == OPK_SUMSQ || opk == OPK_PROD;
         op.acc      = is_float_id(st) ? ACC_F64 : ((is_signed_id(st) || sumlike) ? ACC_I64 : ACC_U64);
         if (sumlike && !is_float_id(st) && !is_signed_id(st)) op.acc = ACC_U64;  // same bits as int64 sums
         op.op       = opk;
@@ -435,6 +449,12 @@ void groupby_aggregate(const b2_groupby& gb, const std::vector<request_view>& re
         if (kind == B2_AGG_MIN || kind == B2_AGG_MAX) {
           op_of[q].push_back(new_op(kind == B2_AGG_MIN ? OPK_MIN : OPK_MAX));
           op2_of[q].push_back(-1);
+          continue;
+        }
+        if (kind == B2_AGG_PRODUCT) {
+          op_of[q].push_back(new_op(OPK_PROD));
+          op2_of[q].push_back(-1);
+          any_sumsq = true;  // the extended kernel instantiation also carries the PRODUCT update
           continue;
         }
         const bool want_sum = kind != B2_AGG_SUM_OF_SQUARES;  // SUM, MEAN, M2, VARIANCE, STD
@@ -513,7 +533,7 @@ void groupby_aggregate(const b2_groupby& gb, const std::vector<request_view>& re
             const value_op& op = ops.op[op_of[q][j]];
             o.accum = op.accum;
             o.acc   = op.acc;
-            o.op    = op.op == OPK_SUMSQ ? (int8_t)OPK_SUM : op.op;  // finalize: "plain accumulator bits", like SUM
+            o.op    = (op.op == OPK_SUMSQ || op.op == OPK_PROD) ? (int8_t)OPK_SUM : op.op;  // finalize: "plain accumulator bits", like SUM
             o.mode  = kind == B2_AGG_MEAN ? 1 : (kind == B2_AGG_M2 ? 5 : (kind == B2_AGG_VARIANCE ? 6 : (kind == B2_AGG_STD ? 7 : 0)));
             if (ext) {
               o.accum2 = ops.op[op2_of[q][j]].accum;

@@ -122,9 +122,9 @@ def aggregate(key_cols, requests, null_handling=EXCLUDE):
                     np.add.at(acc, xg, xv.astype(acc.dtype))
                     out = (acc.astype(np.float64) / np.maximum(vc, 1)).astype(rdt) if kind == MEAN else acc.astype(rdt)
                 elif kind == PRODUCT:
-                    acc = np.ones(ng, dtype=rdt)
-                    np.multiply.at(acc, xg, xv.astype(rdt))
-                    out = acc
+                    acc = np.ones(ng, dtype=np.float64 if rdt.kind == "f" else rdt)
+                    np.multiply.at(acc, xg, xv.astype(acc.dtype))
+                    out = acc.astype(rdt)
                 elif kind == MIN:
                     big = np.full(ng, np.inf if rdt.kind == "f" else (np.iinfo(rdt).max if rdt != np.bool_ else True), dtype=rdt)
                     np.minimum.at(big, xg, xv)

@@ -60,6 +60,19 @@ def test_var_std_golden(impl, vdtype):
         assert np.asarray(c[1]).tolist() == [False]
 
 
+@pytest.mark.parametrize("vdtype", [np.int8, np.int32, np.int64, np.float32, np.float64])
+def test_product_golden(impl, vdtype):
+    # product_tests.cpp:31-44,90-112
+    k, r = run(impl, make_col(KEYS, np.int32), make_col(VALS, vdtype), ["product"])
+    assert np.asarray(r[0][0]).dtype == (np.int64 if np.dtype(vdtype).kind == "i" else np.dtype(vdtype))
+    check(r[0], [0.0, 180.0, 112.0])
+    keys = (np.array(NKEYS[0], np.int32), np.array(NKEYS[1], bool))
+    vals = (np.array([0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 3], vdtype), np.array([0, 1, 1, 1, 1, 0, 1, 1, 1, 1, 0], bool))
+    k, r = run(impl, keys, vals, ["product", "sum"])
+    check(r[0], [18.0, 36.0, 16.0, 3.0], [1, 1, 1, 0])
+    check(r[1], [9.0, 14.0, 10.0, 0.0], [1, 1, 1, 0])
+
+
 def test_var_std_empty_and_all_null_keys(impl):
     k, r = run(impl, make_col([], np.int32), make_col([], np.float64), ["var", "std", "m2"])
     assert len(k[0]) == 0 and all(len(c[0]) == 0 for c in r)
@@ -76,6 +89,8 @@ def test_var_std_random(impl, vdtype):
         raw = rng.integers(0, 200, n) if np.dtype(vdtype).kind == "u" else rng.integers(-300, 300, n)
         vals = (raw.astype(vdtype), (rng.random(n) >= nf) if nf else None)
         kinds = ["sum", "sum_of_squares", "m2", "var", "std", "var0", "std2", "mean", "count"]
+        if np.dtype(vdtype).kind != "f":
+            kinds.append("product")  # integer products wrap identically; float products depend on the multiplication order
         gk, gr = sort_groups(*impl.groupby([keys], [(vals, kinds)]))
         ek, er = sort_groups(*o.groupby([keys], [(vals, kinds)]))
         assert_columns_equal(gk[0], ek[0], what="keys")
