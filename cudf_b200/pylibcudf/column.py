@@ -176,6 +176,23 @@ class Column:
             return torch.as_tensor(span, device="cuda").bool()
         return torch.as_tensor(span, device="cuda")
 
+    # ---- DLPack (python/pylibcudf/pylibcudf/interop.pyx to_dlpack / from_dlpack; data only, like the reference) -----
+    def __dlpack__(self, stream=None):
+        if self._null_count:
+            raise ValueError("DLPack cannot carry a null mask (cudf::to_dlpack rejects columns with nulls)")
+        return self.to_torch().__dlpack__(stream=stream) if stream is not None else self.to_torch().__dlpack__()
+
+    def __dlpack_device__(self):
+        return self.to_torch().__dlpack_device__()
+
+    @classmethod
+    def from_dlpack(cls, obj) -> "Column":
+        """Zero-copy import of a 1-D contiguous CUDA DLPack producer (anything with __dlpack__)."""
+        t = _torch().from_dlpack(obj)
+        if t.dim() != 1 or not t.is_contiguous():
+            raise ValueError("from_dlpack: a contiguous 1-D tensor is required")
+        return cls.from_torch(t)
+
     def to_numpy(self):
         """(values, valid) on the host; valid is None when the column has no mask."""
         torch = _torch()

@@ -48,3 +48,18 @@ def test_hash_partition_contract(plc):
             assert part_of.setdefault(int(key), p) == p                                       # equal keys -> same partition
     with pytest.raises(ValueError):
         plc.partitioning.hash_partition(t, [0, 1], P)
+
+
+def test_dlpack_roundtrip(plc):
+    """Column.__dlpack__ / from_dlpack (pylibcudf interop to_dlpack / from_dlpack): zero-copy both ways, nulls rejected."""
+    import torch
+
+    x = torch.arange(1000, dtype=torch.int64, device="cuda") * 3
+    c = plc.Column.from_dlpack(x)
+    assert c.size() == 1000 and c.type().id() == plc.TypeId.INT64
+    out = plc.sorting.sort(plc.Table([c]), [plc.Order.DESCENDING], []).columns()[0]
+    y = torch.from_dlpack(out)
+    assert y.data_ptr() == out.data().ptr and bool((y == torch.flip(x, [0])).all())
+    masked = plc.Column.from_numpy(np.arange(4, dtype=np.int32), np.array([1, 0, 1, 1], bool))
+    with pytest.raises(ValueError):
+        torch.from_dlpack(masked)
