@@ -30,7 +30,7 @@ namespace {
 constexpr int MAX_OPS = 24;
 
 enum acc_kind : int8_t { ACC_I64 = 0, ACC_U64 = 1, ACC_F64 = 2 };
-enum op_kind : int8_t { OPK_SUM = 0, OPK_MIN = 1, OPK_MAX = 2, OPK_SUMSQ = 3, OPK_PROD = 4 };
+enum op_kind : int8_t { OPK_SUM = 0, OPK_MIN = 1, OPK_MAX = 2, OPK_SUMSQ = 3, OPK_PROD = 4, OPK_ARGMIN = 5, OPK_ARGMAX = 6 };
 
 struct value_op {
   const void* src;
@@ -194,6 +194,31 @@ __global__ void __launch_bounds__(256) groupby_kernel(key_cols kc, int64_t n, bo
           else atomicAdd(a, uv * uv);
           continue;
         }
+        if (op.op == OPK_ARGMIN || op.op == OPK_ARGMAX) {
+          // global_memory_aggregator.cuh:155-200: the accumulator holds a row index (sentinel -1); a row replaces the
+          // holder when its value is strictly better — or equal with a smaller row index, which makes ties
+          // deterministic (the reference keeps whichever tied row arrived first)
+          const bool want_max = op.op == OPK_ARGMAX;
+          unsigned long long seen = *reinterpret_cast<volatile unsigned long long*>(a);
+          while (true) {
+            bool better = seen == ~0ull;
+            if (!better) {
+              const int64_t held = (int64_t)seen;
+              long long hi_ = 0;
+              unsigned long long hu = 0;
+              double hf = 0;
+              load_value(op, held + op.offset, hi_, hu, hf);
+              if (op.acc == ACC_F64) better = (want_max ? fv > hf : fv < hf) || (fv == hf && r < held);
+              else if (op.acc == ACC_I64) better = (want_max ? iv > hi_ : iv < hi_) || (iv == hi_ && r < held);
+              else better = (want_max ? uv > hu : uv < hu) || (uv == hu && r < held);
+            }
+            if (!better) break;
+            const unsigned long long prev = atomicCAS(a, seen, (unsigned long long)r);
+            if (prev == seen) break;
+            seen = prev;
+          }
+          continue;
+        }
         if (op.op == OPK_PROD) {
           unsigned long long seen = *reinterpret_cast<volatile unsigned long long*>(a), want;
           do {
@@ -323,9 +348,9 @@ int32_t result_type(int32_t kind, int32_t src)
     case B2_AGG_SUM: case B2_AGG_SUM_OF_SQUARES: case B2_AGG_PRODUCT: return is_float_id(src) ? src : B2_INT64;
     case B2_AGG_M2: case B2_AGG_VARIANCE: case B2_AGG_STD: return B2_FLOAT64;
     case B2_AGG_MIN: case B2_AGG_MAX: return src;
-    case B2_AGG_COUNT_VALID: case B2_AGG_COUNT_ALL: return B2_INT32;
+    case B2_AGG_COUNT_VALID: case B2_AGG_COUNT_ALL: case B2_AGG_ARGMAX: case B2_AGG_ARGMIN: return B2_INT32;
     case B2_AGG_MEAN: return B2_FLOAT64;
-    default: B2_FAIL(B2_ERR_INVALID_ARGUMENT, "unsupported groupby aggregation on the hash path (SUM/PRODUCT/MIN/MAX/COUNT/MEAN/SUM_OF_SQUARES/M2/VARIANCE/STD)");
+    default: B2_FAIL(B2_ERR_INVALID_ARGUMENT, "unsupported groupby aggregation on the hash path (SUM/PRODUCT/MIN/MAX/ARGMIN/ARGMAX/COUNT/MEAN/SUM_OF_SQUARES/M2/VARIANCE/STD)");
   }
 }
 
@@ -338,6 +363,7 @@ unsigned long long acc_init(int8_t acc, int8_t op)
 {
   if (op == OPK_SUM || op == OPK_SUMSQ) return 0ull;
   if (op == OPK_PROD) return acc == ACC_F64 ? 0x3FF0000000000000ull /* 1.0 */ : 1ull;
+  if (op == OPK_ARGMIN || op == OPK_ARGMAX) return ~0ull;  // ARG*_SENTINEL
   if (acc == ACC_U64) return op == OPK_MIN ? ~0ull : 0ull;
   // I64, and F64 in ordered-int64 space
   return op == OPK_MIN ? (unsigned long long)INT64_MAX : (unsigned long long)INT64_MIN;
@@ -451,6 +477,12 @@ void groupby_aggregate(const b2_groupby& gb, const std::vector<request_view>& re
           op2_of[q].push_back(-1);
           continue;
         }
+        if (kind == B2_AGG_ARGMIN || kind == B2_AGG_ARGMAX) {
+          op_of[q].push_back(new_op(kind == B2_AGG_ARGMIN ? OPK_ARGMIN : OPK_ARGMAX));
+          op2_of[q].push_back(-1);
+          any_sumsq = true;  // handled by the extended kernel instantiation
+          continue;
+        }
         if (kind == B2_AGG_PRODUCT) {
           op_of[q].push_back(new_op(OPK_PROD));
           op2_of[q].push_back(-1);
@@ -534,6 +566,7 @@ void groupby_aggregate(const b2_groupby& gb, const std::vector<request_view>& re
             o.accum = op.accum;
             o.acc   = op.acc;
             o.op    = (op.op == OPK_SUMSQ || op.op == OPK_PROD) ? (int8_t)OPK_SUM : op.op;  // finalize: "plain accumulator bits", like SUM
+            if (op.op == OPK_ARGMIN || op.op == OPK_ARGMAX) { o.acc = ACC_I64; o.op = OPK_SUM; }  // a row index, stored as INT32
             o.mode  = kind == B2_AGG_MEAN ? 1 : (kind == B2_AGG_M2 ? 5 : (kind == B2_AGG_VARIANCE ? 6 : (kind == B2_AGG_STD ? 7 : 0)));
             if (ext) {
               o.accum2 = ops.op[op2_of[q][j]].accum;

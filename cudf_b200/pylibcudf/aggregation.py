@@ -19,6 +19,8 @@ class Kind(enum.IntEnum):
     M2 = 11
     VARIANCE = 12
     STD = 13
+    ARGMAX = 16
+    ARGMIN = 17
 
 
 class Aggregation:
@@ -79,3 +81,11 @@ def variance(ddof: int = 1) -> Aggregation:
 
 def std(ddof: int = 1) -> Aggregation:
     return Aggregation(Kind.STD, ddof)
+
+
+def argmax() -> Aggregation:
+    return Aggregation(Kind.ARGMAX)
+
+
+def argmin() -> Aggregation:
+    return Aggregation(Kind.ARGMIN)

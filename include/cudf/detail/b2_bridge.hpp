@@ -287,7 +287,7 @@ class numeric_scalar : public scalar {
 class aggregation {
  public:
   enum Kind : int32_t { SUM = 0, PRODUCT = 2, MIN = 3, MAX = 4, COUNT_VALID = 5, COUNT_ALL = 6, SUM_OF_SQUARES = 9, MEAN = 10, M2 = 11,
-                        VARIANCE = 12, STD = 13 };
+                        VARIANCE = 12, STD = 13, ARGMAX = 16, ARGMIN = 17 };
   explicit aggregation(Kind k) : kind{k} {}
   virtual ~aggregation() = default;
   Kind kind;
@@ -312,6 +312,8 @@ template <typename Base = aggregation> std::unique_ptr<Base> make_max_aggregatio
 template <typename Base = aggregation> std::unique_ptr<Base> make_mean_aggregation() { return detail::make_agg<Base>(aggregation::MEAN); }
 template <typename Base = aggregation> std::unique_ptr<Base> make_sum_of_squares_aggregation() { return detail::make_agg<Base>(aggregation::SUM_OF_SQUARES); }
 template <typename Base = aggregation> std::unique_ptr<Base> make_m2_aggregation() { return detail::make_agg<Base>(aggregation::M2); }
+template <typename Base = aggregation> std::unique_ptr<Base> make_argmax_aggregation() { return detail::make_agg<Base>(aggregation::ARGMAX); }
+template <typename Base = aggregation> std::unique_ptr<Base> make_argmin_aggregation() { return detail::make_agg<Base>(aggregation::ARGMIN); }
 template <typename Base = aggregation> std::unique_ptr<Base> make_variance_aggregation(size_type ddof = 1)
 {
   auto a = detail::make_agg<Base>(aggregation::VARIANCE);

@@ -70,7 +70,8 @@ enum { B2_MASK_UNALLOCATED = 0, B2_MASK_UNINITIALIZED = 1, B2_MASK_ALL_VALID = 2
 enum {
   B2_AGG_SUM = 0, B2_AGG_PRODUCT = 2, B2_AGG_MIN = 3, B2_AGG_MAX = 4,
   B2_AGG_COUNT_VALID = 5, B2_AGG_COUNT_ALL = 6, B2_AGG_SUM_OF_SQUARES = 9, B2_AGG_MEAN = 10, B2_AGG_M2 = 11,
-  B2_AGG_VARIANCE = 12, B2_AGG_STD = 13 /* groupby only; ddof = 1 unless given with B2_AGG_WITH_DDOF */
+  B2_AGG_VARIANCE = 12, B2_AGG_STD = 13, /* groupby only; ddof = 1 unless given with B2_AGG_WITH_DDOF */
+  B2_AGG_ARGMAX = 16, B2_AGG_ARGMIN = 17 /* groupby only: INT32 row index of the extreme value (first row among ties) */
 };
 /* make_variance_aggregation(ddof) / make_std_aggregation(ddof) (aggregation.hpp:231-260): the kind word carries ddof */
 #define B2_AGG_WITH_DDOF(kind, ddof) ((int32_t)(kind) | (1 << 30) | (((int32_t)(ddof) & 0xFFFF) << 8))

@@ -10,6 +10,7 @@ import numpy as np
 from . import sort as osort
 
 SUM, PRODUCT, MIN, MAX, COUNT_VALID, COUNT_ALL, MEAN = 0, 2, 3, 4, 5, 6, 10
+ARGMAX, ARGMIN = 16, 17  # row index of the extreme value; the first row among ties (the reference leaves ties open)
 SUM_OF_SQUARES, M2, VARIANCE, STD = 9, 11, 12, 13  # a kind may also be the pair (VARIANCE | STD, ddof); ddof defaults to 1
 EXCLUDE, INCLUDE = 0, 1
 
@@ -46,7 +47,7 @@ def result_dtype(kind, in_dtype):
         if in_dtype.kind in "iu" or in_dtype == np.bool_:
             return np.dtype(np.int64)  # aggregation.hpp:935-939: every integral source sums into int64
         return in_dtype
-    if kind in (COUNT_VALID, COUNT_ALL):
+    if kind in (COUNT_VALID, COUNT_ALL, ARGMAX, ARGMIN):
         return np.dtype(np.int32)
     if kind == MEAN:
         return np.dtype(np.float64)
@@ -104,6 +105,20 @@ def aggregate(key_cols, requests, null_handling=EXCLUDE):
                     var = np.where(ok, m2v / np.where(ok, df, 1), 0.0)
                     out = var if kind == VARIANCE else np.sqrt(np.where(ok, var, 0.0))
                 per.append((out, None if ok.all() else ok))
+                continue
+            if kind in (ARGMAX, ARGMIN):
+                # global_memory_aggregator.cuh:155-200 (strict > / < comparisons: a NaN never displaces a holder)
+                out = np.full(ng, -1, np.int32)
+                xv, xg, xr = v[m], gid[m], rows[m]
+                for val, g, r in zip(xv.tolist(), xg.tolist(), xr.tolist()):
+                    h = out[g]
+                    if h < 0:
+                        out[g] = r
+                        continue
+                    hv = vals[h].item()
+                    if (val > hv if kind == ARGMAX else val < hv) or (val == hv and r < h):
+                        out[g] = r
+                per.append((out, (vc > 0) if has_nulls else None))
                 continue
             if kind == COUNT_ALL:
                 per.append((np.bincount(gid, minlength=ng).astype(np.int32), None))

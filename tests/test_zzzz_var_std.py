@@ -119,3 +119,34 @@ def test_mean_of_wrapping_integer_sums(impl):
     vals = (np.array([2**63 - 1, 1, 5, 6, 7], np.int64), None)
     k, r = run(impl, keys, vals, ["mean"])
     np.testing.assert_allclose(np.asarray(r[0][0]), [-(2.0**63) / 2, 5.5, 7.0])
+
+
+@pytest.mark.parametrize("vdtype", [np.int8, np.int32, np.int64, np.uint16, np.float32, np.float64])
+def test_argmin_argmax(impl, vdtype):
+    # argmax_tests.cpp:28-40,82-100 and argmin_tests.cpp:30-35,83-100
+    keys, vals = make_col(KEYS, np.int32), make_col([9, 8, 7, 6, 5, 4, 3, 2, 1, 0], vdtype)
+    k, r = run(impl, keys, vals, ["argmax", "argmin"])
+    assert np.asarray(r[0][0]).dtype == np.int32
+    assert np.asarray(r[0][0]).tolist() == [0, 1, 2] and np.asarray(r[1][0]).tolist() == [6, 9, 8]
+    keys = (np.array(NKEYS[0], np.int32), np.array([1, 1, 0, 1, 1, 1, 1, 1, 1, 1, 1], bool))
+    vals = (np.array([9, 8, 7, 6, 5, 4, 3, 2, 1, 0, 4], vdtype), np.array([0, 0, 1, 1, 1, 1, 1, 1, 1, 1, 0], bool))
+    k, r = run(impl, keys, vals, ["argmax"])
+    check((np.asarray(r[0][0], np.float64), r[0][1]), [3, 4, 7, 0], [1, 1, 1, 0])
+    keys = (np.array(NKEYS[0], np.int32), np.array(NKEYS[1], bool))
+    vals = (np.array([9, 8, 7, 6, 5, 4, 3, 2, 1, 0, 4], vdtype), np.array([1, 1, 1, 1, 1, 0, 0, 1, 1, 1, 0], bool))
+    k, r = run(impl, keys, vals, ["argmin"])
+    check((np.asarray(r[0][0], np.float64), r[0][1]), [3, 9, 8, 0], [1, 1, 1, 0])
+    # random with ties: the first row among equal extremes (a valid outcome of the reference, which leaves ties open)
+    rng = np.random.default_rng(77)
+    o = OracleImpl()
+    n = 30_000
+    keys = (rng.integers(0, 500, n).astype(np.int64), None)
+    raw = rng.integers(0, 40, n) if np.dtype(vdtype).kind == "u" else rng.integers(-20, 20, n)
+    vals = (raw.astype(vdtype), rng.random(n) < 0.9)
+    gk, gr = sort_groups(*impl.groupby([keys], [(vals, ["argmin", "argmax", "min", "max"])]))
+    ek, er = sort_groups(*o.groupby([keys], [(vals, ["argmin", "argmax", "min", "max"])]))
+    for j in range(4):
+        assert_columns_equal(gr[0][j], er[0][j], what=str(j))
+    ok = np.asarray(gr[0][0][1], bool) if gr[0][0][1] is not None else np.ones(len(gk[0][0]), bool)
+    assert np.array_equal(vals[0][np.asarray(gr[0][0][0])[ok]], np.asarray(gr[0][2][0])[ok])   # values at argmin are the minima
+    assert np.array_equal(vals[0][np.asarray(gr[0][1][0])[ok]], np.asarray(gr[0][3][0])[ok])
