@@ -226,6 +226,7 @@ def test_emu_late_suites(emu_lib):
     e = dict(os.environ, B2_EMU_RUN="1")
     r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_zzzz_match_context.py", "tests/test_zzzz_var_std.py",
                         "tests/test_zzzz_segmented_sort.py", "tests/test_zzzz_rank.py", "tests/test_zzzz_partitioning.py", "-q", "-m", "gpu",
+                        "--deselect", "tests/test_zzzz_partitioning.py::test_dlpack_roundtrip",  # needs torch.cuda tensors
                         "-p", "no:cacheprovider"],
                        capture_output=True, text=True, env=e, cwd=ROOT, timeout=900)
     assert r.returncode == 0 and " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
