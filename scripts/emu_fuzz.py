@@ -129,7 +129,9 @@ def fuzz_groupby(rng):
     vals = rnd_col(rng, n, vd, float(rng.choice([0, 0.3])), 200)
     if np.dtype(vd).kind == "f" and n:
         vals = (np.nan_to_num(vals[0], nan=1.0, posinf=2.0), vals[1])
-    kinds = ["sum", "min", "max", "count", "count_all", "mean", "sum_of_squares", "var", "std0", "m2"]
+    kinds = ["sum", "min", "max", "count", "count_all", "mean", "sum_of_squares", "var", "std0", "m2", "argmin", "argmax"]
+    if np.dtype(vd).kind != "f":
+        kinds.append("product")  # float products depend on the multiplication order
     inc = bool(rng.integers(2))
     gk, gr = sort_groups(*cu.groupby(keys, [(vals, kinds)], include_nulls=inc))
     ek, er = sort_groups(*o.groupby(keys, [(vals, kinds)], include_nulls=inc))
