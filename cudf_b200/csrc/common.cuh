@@ -135,6 +135,18 @@ inline int type_width(int32_t id)
   }
 }
 inline bool is_fixed_width(int32_t id) { return type_width(id) != 0; }
+// f(T{}) with the unsigned integer type of `width` bytes (the kernels move fixed-width values as plain bits)
+template <typename F>
+inline void dispatch_width(int width, F&& f)
+{
+  switch (width) {
+    case 1: f(uint8_t{}); break;
+    case 2: f(uint16_t{}); break;
+    case 4: f(uint32_t{}); break;
+    case 8: f(uint64_t{}); break;
+    default: throw ::b2::error(B2_ERR_DATA_TYPE, "unsupported (non fixed-width) column type");
+  }
+}
 // storage type of chrono ids (dispatch_storage_type): timestamps/durations are signed ints
 inline int32_t storage_type(int32_t id)
 {

@@ -239,13 +239,11 @@ table_ptr partition_table(const std::vector<b2_column_view>& input, const b2_col
     {
       prof_scope ps("partition_bucket", stream);
       const unsigned grid = (unsigned)ntiles;
-      switch (type_width(keys.type_id)) {
-        case 1: B2_LAUNCH((bucket_kernel<uint8_t>), grid, 256, 0, stream, static_cast<const uint8_t*>(keys.data) + keys.offset, n, mode, kind, static_cast<const uint8_t*>(splitters), P, ids.as<uint8_t>(), tile_counts.as<uint32_t>()); break;
-        case 2: B2_LAUNCH((bucket_kernel<uint16_t>), grid, 256, 0, stream, static_cast<const uint16_t*>(keys.data) + keys.offset, n, mode, kind, static_cast<const uint16_t*>(splitters), P, ids.as<uint8_t>(), tile_counts.as<uint32_t>()); break;
-        case 4: B2_LAUNCH((bucket_kernel<uint32_t>), grid, 256, 0, stream, static_cast<const uint32_t*>(keys.data) + keys.offset, n, mode, kind, static_cast<const uint32_t*>(splitters), P, ids.as<uint8_t>(), tile_counts.as<uint32_t>()); break;
-        case 8: B2_LAUNCH((bucket_kernel<uint64_t>), grid, 256, 0, stream, static_cast<const uint64_t*>(keys.data) + keys.offset, n, mode, kind, static_cast<const uint64_t*>(splitters), P, ids.as<uint8_t>(), tile_counts.as<uint32_t>()); break;
-        default: B2_FAIL(B2_ERR_DATA_TYPE, "partition: unsupported key type");
-      }
+      dispatch_width(type_width(keys.type_id), [&](auto tag) {
+        using T = decltype(tag);
+        B2_LAUNCH((bucket_kernel<T>), grid, 256, 0, stream, static_cast<const T*>(keys.data) + keys.offset, n, mode, kind, static_cast<const T*>(splitters), P,
+                  ids.as<uint8_t>(), tile_counts.as<uint32_t>());
+      });
     }
     B2_LAUNCH(tile_scan_kernel, 1, 1024, 0, stream, tile_counts.as<uint32_t>(), ntiles, P, totals.as<unsigned long long>());
     bool any_nullable = false;
@@ -260,12 +258,10 @@ table_ptr partition_table(const std::vector<b2_column_view>& input, const b2_col
       const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, NUM_SMS_B200 * 16));
       for (auto& c : input) {
         auto oc = make_column(c.type_id, (int32_t)n, false, stream);
-        switch (type_width(c.type_id)) {
-          case 1: B2_LAUNCH((scatter_kernel<uint8_t>), grid, 256, 0, stream, static_cast<const uint8_t*>(c.data) + c.offset, dest.as<int32_t>(), n, oc->data.as<uint8_t>()); break;
-          case 2: B2_LAUNCH((scatter_kernel<uint16_t>), grid, 256, 0, stream, static_cast<const uint16_t*>(c.data) + c.offset, dest.as<int32_t>(), n, oc->data.as<uint16_t>()); break;
-          case 4: B2_LAUNCH((scatter_kernel<uint32_t>), grid, 256, 0, stream, static_cast<const uint32_t*>(c.data) + c.offset, dest.as<int32_t>(), n, oc->data.as<uint32_t>()); break;
-          default: B2_LAUNCH((scatter_kernel<uint64_t>), grid, 256, 0, stream, static_cast<const uint64_t*>(c.data) + c.offset, dest.as<int32_t>(), n, oc->data.as<uint64_t>()); break;
-        }
+        dispatch_width(type_width(c.type_id), [&](auto tag) {
+          using T = decltype(tag);
+          B2_LAUNCH((scatter_kernel<T>), grid, 256, 0, stream, static_cast<const T*>(c.data) + c.offset, dest.as<int32_t>(), n, oc->data.as<T>());
+        });
         out->cols.push_back(std::move(oc));
       }
     } else {
@@ -290,20 +286,13 @@ table_ptr partition_table(const std::vector<b2_column_view>& input, const b2_col
 extern "C" b2_status b2_partition(const b2_table_view* input, const b2_column_view* keys, int32_t mode, const void* splitters,
                                   int32_t num_partitions, b2_stream stream, b2_table** out, int32_t* out_offsets)
 {
-  try {
+  B2_TRY_BEGIN
     B2_EXPECTS(input && keys && out && out_offsets, B2_ERR_INVALID_ARGUMENT, "null argument");
     std::vector<b2_column_view> cols;
     b2::validate_table(input, cols);
     b2::validate_column(*keys);
     *out = b2::partition_table(cols, *keys, mode, splitters, num_partitions, out_offsets, static_cast<cudaStream_t>(stream)).release();
-  } catch (const b2::error& e) {
-    b2::set_last_error(e.what());
-    return e.code;
-  } catch (const std::exception& e) {
-    b2::set_last_error(e.what());
-    return B2_ERR_LOGIC;
-  }
-  return B2_OK;
+  B2_TRY_END
 }
 
 // ---- two-phase partition (plan + scatter to arbitrary destinations) and CUDA-IPC buffers --------------------
@@ -343,13 +332,11 @@ static std::unique_ptr<b2_partition_plan> make_plan(const b2_column_view& keys, 
   {
     prof_scope ps("partition_bucket", stream);
     const unsigned grid = (unsigned)ntiles;
-    switch (type_width(keys.type_id)) {
-      case 1: B2_LAUNCH((bucket_kernel<uint8_t>), grid, 256, 0, stream, static_cast<const uint8_t*>(keys.data) + keys.offset, n, mode, kind, static_cast<const uint8_t*>(splitters), P, plan->ids.as<uint8_t>(), tile_counts.as<uint32_t>()); break;
-      case 2: B2_LAUNCH((bucket_kernel<uint16_t>), grid, 256, 0, stream, static_cast<const uint16_t*>(keys.data) + keys.offset, n, mode, kind, static_cast<const uint16_t*>(splitters), P, plan->ids.as<uint8_t>(), tile_counts.as<uint32_t>()); break;
-      case 4: B2_LAUNCH((bucket_kernel<uint32_t>), grid, 256, 0, stream, static_cast<const uint32_t*>(keys.data) + keys.offset, n, mode, kind, static_cast<const uint32_t*>(splitters), P, plan->ids.as<uint8_t>(), tile_counts.as<uint32_t>()); break;
-      case 8: B2_LAUNCH((bucket_kernel<uint64_t>), grid, 256, 0, stream, static_cast<const uint64_t*>(keys.data) + keys.offset, n, mode, kind, static_cast<const uint64_t*>(splitters), P, plan->ids.as<uint8_t>(), tile_counts.as<uint32_t>()); break;
-      default: B2_FAIL(B2_ERR_DATA_TYPE, "partition: unsupported key type");
-    }
+    dispatch_width(type_width(keys.type_id), [&](auto tag) {
+      using T = decltype(tag);
+      B2_LAUNCH((bucket_kernel<T>), grid, 256, 0, stream, static_cast<const T*>(keys.data) + keys.offset, n, mode, kind, static_cast<const T*>(splitters), P,
+                plan->ids.as<uint8_t>(), tile_counts.as<uint32_t>());
+    });
   }
   B2_LAUNCH(tile_scan_kernel, 1, 1024, 0, stream, tile_counts.as<uint32_t>(), ntiles, P, totals.as<unsigned long long>());
   {
@@ -372,18 +359,16 @@ extern "C" {
 b2_status b2_partition_plan_create(const b2_column_view* keys, int32_t mode, const void* splitters, int32_t num_partitions,
                                    b2_stream stream, b2_partition_plan** out, int64_t* out_counts)
 {
-  try {
+  B2_TRY_BEGIN
     B2_EXPECTS(keys && out && out_counts, B2_ERR_INVALID_ARGUMENT, "null argument");
     b2::validate_column(*keys);
     *out = b2::make_plan(*keys, mode, splitters, num_partitions, out_counts, static_cast<cudaStream_t>(stream)).release();
-  } catch (const b2::error& e) { b2::set_last_error(e.what()); return e.code;
-  } catch (const std::exception& e) { b2::set_last_error(e.what()); return B2_ERR_LOGIC; }
-  return B2_OK;
+  B2_TRY_END
 }
 
 b2_status b2_partition_scatter(const b2_partition_plan* plan, const b2_column_view* column, void* const* dest_ptrs, b2_stream stream)
 {
-  try {
+  B2_TRY_BEGIN
     B2_EXPECTS(plan && column && dest_ptrs, B2_ERR_INVALID_ARGUMENT, "null argument");
     b2::validate_column(*column);
     B2_EXPECTS(column->size == plan->n, B2_ERR_LOGIC, "Column size mismatch.");
@@ -395,22 +380,19 @@ b2_status b2_partition_scatter(const b2_partition_plan* plan, const b2_column_vi
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, b2::NUM_SMS_B200 * 16));
     auto s = static_cast<cudaStream_t>(stream);
     b2::prof_scope ps("partition_scatter_p2p", s);
-    switch (b2::type_width(column->type_id)) {
-      case 1: B2_LAUNCH((b2::scatter_to_kernel<uint8_t>), grid, 256, 0, s, static_cast<const uint8_t*>(column->data) + column->offset, plan->ids.as<uint8_t>(), plan->dest.as<int32_t>(), n, dt); break;
-      case 2: B2_LAUNCH((b2::scatter_to_kernel<uint16_t>), grid, 256, 0, s, static_cast<const uint16_t*>(column->data) + column->offset, plan->ids.as<uint8_t>(), plan->dest.as<int32_t>(), n, dt); break;
-      case 4: B2_LAUNCH((b2::scatter_to_kernel<uint32_t>), grid, 256, 0, s, static_cast<const uint32_t*>(column->data) + column->offset, plan->ids.as<uint8_t>(), plan->dest.as<int32_t>(), n, dt); break;
-      default: B2_LAUNCH((b2::scatter_to_kernel<uint64_t>), grid, 256, 0, s, static_cast<const uint64_t*>(column->data) + column->offset, plan->ids.as<uint8_t>(), plan->dest.as<int32_t>(), n, dt); break;
-    }
-  } catch (const b2::error& e) { b2::set_last_error(e.what()); return e.code;
-  } catch (const std::exception& e) { b2::set_last_error(e.what()); return B2_ERR_LOGIC; }
-  return B2_OK;
+    b2::dispatch_width(b2::type_width(column->type_id), [&](auto tag) {
+      using T = decltype(tag);
+      B2_LAUNCH((b2::scatter_to_kernel<T>), grid, 256, 0, s, static_cast<const T*>(column->data) + column->offset, plan->ids.as<uint8_t>(),
+                plan->dest.as<int32_t>(), n, dt);
+    });
+  B2_TRY_END
 }
 
 void b2_partition_plan_free(b2_partition_plan* plan) { delete plan; }
 
 b2_status b2_ipc_alloc(size_t bytes, void** out_ptr, uint8_t* out_handle64)
 {
-  try {
+  B2_TRY_BEGIN
     B2_EXPECTS(out_ptr && out_handle64, B2_ERR_INVALID_ARGUMENT, "null argument");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     void* p = nullptr;
@@ -420,28 +402,28 @@ b2_status b2_ipc_alloc(size_t bytes, void** out_ptr, uint8_t* out_handle64)
     if (e != cudaSuccess) { cudaFree(p); B2_CUDA_TRY(e); }
     memcpy(out_handle64, &h, 64);
     *out_ptr = p;
-  } catch (const b2::error& e) { b2::set_last_error(e.what()); return e.code; }
-  return B2_OK;
+  B2_TRY_END
 }
 b2_status b2_ipc_open(const uint8_t* handle64, void** out_ptr)
 {
-  try {
+  B2_TRY_BEGIN
     B2_EXPECTS(out_ptr && handle64, B2_ERR_INVALID_ARGUMENT, "null argument");
     cudaIpcMemHandle_t h;
     memcpy(&h, handle64, 64);
     B2_CUDA_TRY(cudaIpcOpenMemHandle(out_ptr, h, cudaIpcMemLazyEnablePeerAccess));
-  } catch (const b2::error& e) { b2::set_last_error(e.what()); return e.code; }
-  return B2_OK;
+  B2_TRY_END
 }
 b2_status b2_ipc_close(void* ptr)
 {
-  try { if (ptr) B2_CUDA_TRY(cudaIpcCloseMemHandle(ptr)); } catch (const b2::error& e) { b2::set_last_error(e.what()); return e.code; }
-  return B2_OK;
+  B2_TRY_BEGIN
+  if (ptr) B2_CUDA_TRY(cudaIpcCloseMemHandle(ptr));
+  B2_TRY_END
 }
 b2_status b2_ipc_free(void* ptr)
 {
-  try { if (ptr) B2_CUDA_TRY(cudaFree(ptr)); } catch (const b2::error& e) { b2::set_last_error(e.what()); return e.code; }
-  return B2_OK;
+  B2_TRY_BEGIN
+  if (ptr) B2_CUDA_TRY(cudaFree(ptr));
+  B2_TRY_END
 }
 
 }  // extern "C"
@@ -450,7 +432,7 @@ b2_status b2_ipc_free(void* ptr)
 extern "C" b2_status b2_partition_scatter_staged(const b2_partition_plan* plan, const b2_column_view* column, void* const* dest_ptrs,
                                                  b2_stream stream)
 {
-  try {
+  B2_TRY_BEGIN
     B2_EXPECTS(plan && column && dest_ptrs, B2_ERR_INVALID_ARGUMENT, "null argument");
     b2::validate_column(*column);
     B2_EXPECTS(column->size == plan->n, B2_ERR_LOGIC, "Column size mismatch.");
@@ -464,13 +446,10 @@ extern "C" b2_status b2_partition_scatter_staged(const b2_partition_plan* plan, 
     auto s = static_cast<cudaStream_t>(stream);
     b2::prof_scope ps("partition_scatter_p2p_staged", s);
     const uint32_t* ts = plan->tile_starts.as<uint32_t>();
-    switch (b2::type_width(column->type_id)) {
-      case 1: B2_LAUNCH((b2::scatter_to_staged_kernel<uint8_t>), (unsigned)ntiles, 256, 0, s, static_cast<const uint8_t*>(column->data) + column->offset, plan->ids.as<uint8_t>(), plan->dest.as<int32_t>(), ts, n, plan->P, ntiles, dt); break;
-      case 2: B2_LAUNCH((b2::scatter_to_staged_kernel<uint16_t>), (unsigned)ntiles, 256, 0, s, static_cast<const uint16_t*>(column->data) + column->offset, plan->ids.as<uint8_t>(), plan->dest.as<int32_t>(), ts, n, plan->P, ntiles, dt); break;
-      case 4: B2_LAUNCH((b2::scatter_to_staged_kernel<uint32_t>), (unsigned)ntiles, 256, 0, s, static_cast<const uint32_t*>(column->data) + column->offset, plan->ids.as<uint8_t>(), plan->dest.as<int32_t>(), ts, n, plan->P, ntiles, dt); break;
-      default: B2_LAUNCH((b2::scatter_to_staged_kernel<uint64_t>), (unsigned)ntiles, 256, 0, s, static_cast<const uint64_t*>(column->data) + column->offset, plan->ids.as<uint8_t>(), plan->dest.as<int32_t>(), ts, n, plan->P, ntiles, dt); break;
-    }
-  } catch (const b2::error& e) { b2::set_last_error(e.what()); return e.code;
-  } catch (const std::exception& e) { b2::set_last_error(e.what()); return B2_ERR_LOGIC; }
-  return B2_OK;
+    b2::dispatch_width(b2::type_width(column->type_id), [&](auto tag) {
+      using T = decltype(tag);
+      B2_LAUNCH((b2::scatter_to_staged_kernel<T>), (unsigned)ntiles, 256, 0, s, static_cast<const T*>(column->data) + column->offset,
+                plan->ids.as<uint8_t>(), plan->dest.as<int32_t>(), ts, n, plan->P, ntiles, dt);
+    });
+  B2_TRY_END
 }
