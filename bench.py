@@ -39,6 +39,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-rows", type=int, default=10_000_000)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-alias", action="store_true", help="skip the secondary measurement of the opt-in aliased (keys-only) sort path")
     ap.add_argument("--extra", action="store_true", help="also time join / groupby / scan / reduce (extra JSON keys)")
     return ap.parse_args()
 
@@ -359,6 +360,38 @@ def run_ours(args):
         except Exception as ex:  # e.g. not enough pinnable host memory
             e2e = {"value": None, "unit": UNIT, "error": repr(ex)[:200]}
 
+    # ---- secondary, N = 1 only: the opt-in aliased path (sort_by_key(T, T) of one null-free integer column routed to the
+    # keys-only radix, README "Environment switches"). Reported next to the headline, never as the headline; its output is
+    # compared with the default path's output first.
+    alias = None
+    if world == 1 and not args.no_alias and os.environ.get("B2_SORT_ALIAS", "0") in ("", "0"):
+        try:
+            ref_out = step().columns()[0].to_torch()
+            os.environ["B2_SORT_ALIAS"] = "1"
+            try:
+                got = step().columns()[0].to_torch()
+                same = bool(torch.equal(got, ref_out))
+                del got, ref_out
+                for _ in range(2):
+                    o = step()
+                    del o
+                torch.cuda.synchronize()
+                k = max(1, min(args.steps, 3))
+                e0.record(stream)
+                for _ in range(k):
+                    o = step()
+                    del o
+                e1.record(stream)
+                torch.cuda.synchronize()
+                ams = e0.elapsed_time(e1) / k
+                alias = {"path": "B2_SORT_ALIAS=1: keys-only radix, no row ids, no gather (opt-in, not the headline)", "ms_per_step": ams,
+                         "rows_per_s": n / (ams / 1e3), "output_equals_default_path": same,
+                         "algorithmic_bytes_per_row": 136, "achieved_GBps": 136.0 * n / (ams / 1e3) / 1e9}
+            finally:
+                os.environ.pop("B2_SORT_ALIAS", None)
+        except Exception as ex:
+            alias = {"error": repr(ex)[:200]}
+
     extra = None
     if args.extra and world == 1:
         import bench_extra
@@ -376,6 +409,8 @@ def run_ours(args):
             "roofline": roofline, "cpu_baseline": cpu_base, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks.summary(),
         }
+        if alias:
+            line["aliased_keys_only_path"] = alias
         if extra:
             line["extra"] = extra
         print(json.dumps(line), flush=True)
