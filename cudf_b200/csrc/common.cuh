@@ -240,8 +240,11 @@ void radix_partition_top16_mix(const uint64_t* packed_keys, int64_t n, uint64_t*
 
 // radix_join.cu (experimental, opt-in: B2_JOIN_RADIX_ROWS)
 bool radix_join_applicable(const std::vector<b2_column_view>& a, const std::vector<b2_column_view>& b);
-void radix_inner_join(const std::vector<b2_column_view>& build, const std::vector<b2_column_view>& probe, cudaStream_t stream,
-                      column_ptr& out_probe, column_ptr& out_build);
+void radix_join(const std::vector<b2_column_view>& build, const std::vector<b2_column_view>& probe, bool left, cudaStream_t stream,
+                column_ptr& out_probe, column_ptr& out_build);
+// hash_join.cu: concatenates partial full-join results and appends (JoinNoMatch, r) for every unmatched build row r
+void hash_join_finalize_full(const std::vector<b2_column_view>& lparts, const std::vector<b2_column_view>& rparts, int32_t left_rows,
+                             int32_t right_rows, cudaStream_t stream, column_ptr& out_left, column_ptr& out_right);
 
 // scan_reduce.cu
 std::unique_ptr<b2_scalar> reduce(const b2_column_view& col, int32_t kind, int32_t out_type,

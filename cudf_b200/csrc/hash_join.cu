@@ -778,10 +778,21 @@ static b2_status free_join(const b2_table_view* left, const b2_table_view* right
   const bool nulls = table_has_nulls(l) || table_has_nulls(r);
   column_ptr lo, ro;
   // inner join builds on the smaller table and swaps the outputs back (join.cu:52-59)
-  if (kind == JOIN_INNER && radix_join_applicable(l, r)) {  // opt-in partitioned path (radix_join.cu), off by default
+  if (radix_join_applicable(l, r)) {  // opt-in partitioned path (radix_join.cu), off by default
     make_key_cols(l, true);  // same argument checks as the hash path
-    if (r[0].size > l[0].size) radix_inner_join(l, r, S(stream), ro, lo);
-    else radix_inner_join(r, l, S(stream), lo, ro);
+    if (kind == JOIN_INNER) {
+      if (r[0].size > l[0].size) radix_join(l, r, false, S(stream), ro, lo);
+      else radix_join(r, l, false, S(stream), lo, ro);
+    } else {
+      radix_join(r, l, true, S(stream), lo, ro);  // the left table is the probe side
+      if (kind == JOIN_FULL) {
+        const b2_column_view lv{B2_INT32, lo->size, lo->data.ptr, nullptr, 0, 0}, rv{B2_INT32, ro->size, ro->data.ptr, nullptr, 0, 0};
+        column_ptr fl, fr;
+        hash_join_finalize_full({lv}, {rv}, l[0].size, r[0].size, S(stream), fl, fr);
+        lo = std::move(fl);
+        ro = std::move(fr);
+      }
+    }
   } else if (kind == JOIN_INNER && r[0].size > l[0].size) {
     std::unique_ptr<b2_hash_join> hj(hash_join_create(l, nulls, compare_nulls, 0.5, S(stream)));
     hash_join_probe(hj.get(), r, JOIN_INNER, false, 0, S(stream), ro, lo);

@@ -1,8 +1,8 @@
 // radix_join.cu — partitioned ("radix") inner join for large null-free key tables.
 //
 // EXPERIMENTAL in round 1: written after the round's GPU budget was spent, compiled for sm_100a but not yet run on
-// hardware; OFF by default (B2_JOIN_RADIX_ROWS=<rows> routes cudf::inner_join calls whose two sides both have at
-// least that many rows through it).  DESIGN.md §7.4.
+// hardware; OFF by default (B2_JOIN_RADIX_ROWS=<rows> routes cudf::inner_join / left_join / full_join calls whose two
+// sides both have at least that many rows through it).  DESIGN.md §7.4.
 //
 // Same contract as the hash path it stands in for (cpp/src/join/join.cu:27-110 inner_join over
 // cpp/src/join/hash_join/hash_join.cu:32-299): all (probe row, build row) pairs with equal keys, in unspecified
@@ -63,8 +63,9 @@ __global__ void __launch_bounds__(256) rj_bounds_kernel(const uint64_t* __restri
   off[p] = (int32_t)lo;
 }
 
-// pieces[p] = number of work items of partition p (0 when either side is empty there); pieces[RJ_PARTS] = 0
-__global__ void __launch_bounds__(256) rj_pieces_kernel(const int32_t* __restrict__ boff, const int32_t* __restrict__ poff,
+// pieces[p] = number of work items of partition p (0 when either side is empty there; LEFT joins also visit probe rows
+// whose partition has no build rows); pieces[RJ_PARTS] = 0
+__global__ void __launch_bounds__(256) rj_pieces_kernel(const int32_t* __restrict__ boff, const int32_t* __restrict__ poff, bool left,
                                                         int32_t* __restrict__ pieces)
 {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -72,7 +73,7 @@ __global__ void __launch_bounds__(256) rj_pieces_kernel(const int32_t* __restric
   int32_t v = 0;
   if (p < RJ_PARTS) {
     const int64_t nb = (int64_t)boff[p + 1] - boff[p], np = (int64_t)poff[p + 1] - poff[p];
-    if (nb > 0 && np > 0) v = (int32_t)((np + RJ_PIECE - 1) / RJ_PIECE);
+    if (np > 0 && (nb > 0 || left)) v = (int32_t)((np + RJ_PIECE - 1) / RJ_PIECE);
   }
   pieces[p] = v;
 }
@@ -83,7 +84,9 @@ __device__ __forceinline__ uint32_t rj_slot(uint64_t h) { return (uint32_t)(h >>
 // (exclusive scan of rj_pieces_kernel's output, item_first[RJ_PARTS] = number of items).
 // RETRIEVE = false: item_counts[item] = number of pairs, *total += it.
 // RETRIEVE = true: pairs are written to out_probe / out_build starting at item_offsets[item].
-template <bool RETRIEVE>
+// LEFT: a probe row without any match (over all build chunks) yields one pair (row, JoinNoMatch); a thread owns the same
+// <= 64 probe rows in every chunk round, so one 64-bit register remembers which of them have matched.
+template <bool RETRIEVE, bool LEFT = false>
 __global__ void __launch_bounds__(RJ_THREADS, 1)
 rj_join_kernel(const uint64_t* __restrict__ bh, const int32_t* __restrict__ bid, const int32_t* __restrict__ boff,
                const uint64_t* __restrict__ ph, const int32_t* __restrict__ pid, const int32_t* __restrict__ poff,
@@ -121,7 +124,8 @@ rj_join_kernel(const uint64_t* __restrict__ bh, const int32_t* __restrict__ bid,
   const int b0 = boff[part], b1 = boff[part + 1];
   const int64_t p0 = (int64_t)poff[part] + (int64_t)(item - item_first[part]) * RJ_PIECE;
   const int64_t p1 = min(p0 + RJ_PIECE, (int64_t)poff[part + 1]);
-  unsigned long long local = 0;
+  static_assert(RJ_PIECE / RJ_THREADS <= 64, "one bit per probe row of a thread");
+  unsigned long long local = 0, matched = 0;
   for (int64_t c0 = b0; c0 < b1; c0 += RJ_CAP) {  // 64-bit: row numbers go up to 2^31 - 1
     const int cn = (int)min((int64_t)RJ_CAP, (int64_t)b1 - c0);
     __syncthreads();  // the previous chunk's probes are done before the table is reset
@@ -145,13 +149,15 @@ rj_join_kernel(const uint64_t* __restrict__ bh, const int32_t* __restrict__ bid,
       }
     }
     __syncthreads();
-    for (int64_t i = p0 + tid; i < p1; i += RJ_THREADS) {
+    int k = 0;
+    for (int64_t i = p0 + tid; i < p1; i += RJ_THREADS, ++k) {
       const uint64_t h = ld_stream(ph + i);
       uint32_t s = rj_slot(h);
       while (true) {
         const uint32_t e = tab16[s];
         if (e == 0xFFFFu) break;
         if (bk[e] == h) {
+          if (LEFT) matched |= 1ull << k;
           if (RETRIEVE) {
             const unsigned int pos = atomicAdd(&s_cursor, 1u);
             out_probe[pos] = pid[i];
@@ -161,6 +167,19 @@ rj_join_kernel(const uint64_t* __restrict__ bh, const int32_t* __restrict__ bid,
           }
         }
         s = (s + 1) & (uint32_t)(RJ_SLOTS - 1);
+      }
+    }
+  }
+  if (LEFT) {
+    int k = 0;
+    for (int64_t i = p0 + tid; i < p1; i += RJ_THREADS, ++k) {
+      if ((matched >> k) & 1ull) continue;
+      if (RETRIEVE) {
+        const unsigned int pos = atomicAdd(&s_cursor, 1u);
+        out_probe[pos] = pid[i];
+        out_build[pos] = B2_JOIN_NO_MATCH;
+      } else {
+        ++local;
       }
     }
   }
@@ -220,13 +239,16 @@ bool radix_join_applicable(const std::vector<b2_column_view>& a, const std::vect
   return a[0].size >= thr && b[0].size >= thr && !any_nulls(a) && !any_nulls(b) && !keys_are_wide(a);
 }
 
-// pairs (probe row, build row) with equal keys; both tables null-free and non-empty
-void radix_inner_join(const std::vector<b2_column_view>& build, const std::vector<b2_column_view>& probe, cudaStream_t stream,
-                      column_ptr& out_probe, column_ptr& out_build)
+// pairs (probe row, build row) with equal keys; both tables null-free and non-empty. left: probe rows without a match
+// are kept with JoinNoMatch as their build row (left join; the caller appends the unmatched build rows for a full join).
+void radix_join(const std::vector<b2_column_view>& build, const std::vector<b2_column_view>& probe, bool left, cudaStream_t stream,
+                column_ptr& out_probe, column_ptr& out_build)
 {
   static bool attr_set = [] {
-    cudaFuncSetAttribute(rj_join_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RJ_SMEM);
-    cudaFuncSetAttribute(rj_join_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RJ_SMEM);
+    cudaFuncSetAttribute(rj_join_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RJ_SMEM);
+    cudaFuncSetAttribute(rj_join_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RJ_SMEM);
+    cudaFuncSetAttribute(rj_join_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RJ_SMEM);
+    cudaFuncSetAttribute(rj_join_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RJ_SMEM);
     return true;
   }();
   (void)attr_set;
@@ -238,7 +260,7 @@ void radix_inner_join(const std::vector<b2_column_view>& build, const std::vecto
   const int64_t n_probe = probe[0].size;
   const int32_t max_items = (int32_t)(RJ_PARTS + n_probe / RJ_PIECE + 1);
   dbuf pieces(sizeof(int32_t) * (RJ_PARTS + 1), stream);
-  B2_LAUNCH(rj_pieces_kernel, (RJ_PARTS + 1 + 255) / 256, 256, 0, stream, bs.off.as<int32_t>(), ps.off.as<int32_t>(), pieces.as<int32_t>());
+  B2_LAUNCH(rj_pieces_kernel, (RJ_PARTS + 1 + 255) / 256, 256, 0, stream, bs.off.as<int32_t>(), ps.off.as<int32_t>(), left, pieces.as<int32_t>());
   b2_column_view pv{B2_INT32, (int32_t)(RJ_PARTS + 1), pieces.ptr, nullptr, 0, 0};
   auto item_first = scan(pv, B2_AGG_SUM, B2_SCAN_EXCLUSIVE, B2_NULL_EXCLUDE, stream);
 
@@ -246,9 +268,11 @@ void radix_inner_join(const std::vector<b2_column_view>& build, const std::vecto
   B2_CUDA_TRY(cudaMemsetAsync(tot.ptr, 0, sizeof(unsigned long long), stream));
   {
     prof_scope sc("rjoin_count", stream);
-    B2_LAUNCH((rj_join_kernel<false>), max_items, RJ_THREADS, RJ_SMEM, stream, bs.h.as<uint64_t>(), bs.ids.as<int32_t>(),
-              bs.off.as<int32_t>(), ps.h.as<uint64_t>(), ps.ids.as<int32_t>(), ps.off.as<int32_t>(), item_first->data.as<int32_t>(),
-              counts.as<int32_t>(), (const int32_t*)nullptr, tot.as<unsigned long long>(), (int32_t*)nullptr, (int32_t*)nullptr);
+#define B2_RJ(R, L, ...) B2_LAUNCH((rj_join_kernel<R, L>), max_items, RJ_THREADS, RJ_SMEM, stream, bs.h.as<uint64_t>(), bs.ids.as<int32_t>(), \
+                                   bs.off.as<int32_t>(), ps.h.as<uint64_t>(), ps.ids.as<int32_t>(), ps.off.as<int32_t>(),                    \
+                                   item_first->data.as<int32_t>(), __VA_ARGS__)
+    if (left) B2_RJ(false, true, counts.as<int32_t>(), (const int32_t*)nullptr, tot.as<unsigned long long>(), (int32_t*)nullptr, (int32_t*)nullptr);
+    else B2_RJ(false, false, counts.as<int32_t>(), (const int32_t*)nullptr, tot.as<unsigned long long>(), (int32_t*)nullptr, (int32_t*)nullptr);
   }
   unsigned long long m = 0;
   B2_CUDA_TRY(cudaMemcpyAsync(&m, tot.ptr, sizeof(m), cudaMemcpyDeviceToHost, stream));
@@ -261,10 +285,9 @@ void radix_inner_join(const std::vector<b2_column_view>& build, const std::vecto
   b2_column_view cv{B2_INT32, max_items, counts.ptr, nullptr, 0, 0};
   auto offs = scan(cv, B2_AGG_SUM, B2_SCAN_EXCLUSIVE, B2_NULL_EXCLUDE, stream);
   prof_scope sr("rjoin_retrieve", stream);
-  B2_LAUNCH((rj_join_kernel<true>), max_items, RJ_THREADS, RJ_SMEM, stream, bs.h.as<uint64_t>(), bs.ids.as<int32_t>(),
-            bs.off.as<int32_t>(), ps.h.as<uint64_t>(), ps.ids.as<int32_t>(), ps.off.as<int32_t>(), item_first->data.as<int32_t>(),
-            (int32_t*)nullptr, offs->data.as<int32_t>(), (unsigned long long*)nullptr, out_probe->data.as<int32_t>(),
-            out_build->data.as<int32_t>());
+  if (left) B2_RJ(true, true, (int32_t*)nullptr, offs->data.as<int32_t>(), (unsigned long long*)nullptr, out_probe->data.as<int32_t>(), out_build->data.as<int32_t>());
+  else B2_RJ(true, false, (int32_t*)nullptr, offs->data.as<int32_t>(), (unsigned long long*)nullptr, out_probe->data.as<int32_t>(), out_build->data.as<int32_t>());
+#undef B2_RJ
 }
 
 }  // namespace b2

@@ -126,17 +126,19 @@ def test_emu_radix_inner_join(emu_lib):
     """Partitioned shared-memory join incl. the MIX partition kernels, multi-chunk partitions and packed / float keys."""
     run(r"""
 rng = np.random.default_rng(78)
-def check(l, r, tag):
-    got, exp = cu.inner_join(l, r), ojoin.inner_join(l, r)
-    assert np.array_equal(got[0], exp[0]) and np.array_equal(got[1], exp[1]), tag
+def check(l, r, tag, kinds=("inner_join",)):
+    for kind in kinds:
+        got, exp = getattr(cu, kind)(l, r), getattr(ojoin, kind)(l, r)
+        assert np.array_equal(got[0], exp[0]) and np.array_equal(got[1], exp[1]), (tag, kind)
 check([(rng.integers(0, 5000, 20_000), None)], [(rng.integers(0, 5000, 8_000), None)], 'int64')
+check([(rng.integers(0, 90_000, 7_000), None)], [(rng.integers(0, 90_000, 9_000), None)], 'sparse', ("left_join", "full_join"))
 b = rng.integers(0, 1000, 60_000); b[:40_000] = 424242
 p = rng.integers(0, 1000, 80_000); p[:30] = 424242
 check([(p, None)], [(b, None)], 'three chunks')
-l = [(rng.integers(0, 50, 20000).astype(np.int32), None), (rng.integers(0, 9, 20000).astype(np.int16), None)]
-r = [(rng.integers(0, 50, 9000).astype(np.int32), None), (rng.integers(0, 9, 9000).astype(np.int16), None)]
-check(l, r, 'two columns')
-check([(np.array([0.0, -0.0, np.nan, 1.5, np.nan]), None)], [(np.array([-0.0, np.nan, 2.5, 0.0]), None)], 'float specials')
+# packed two-column float key with -0 / NaN (row equality of the reference)
+l = [(rng.integers(0, 50, 2000).astype(np.int32), None), (np.where(rng.random(2000) < 0.3, np.nan, -0.0).astype(np.float32), None)]
+r = [(rng.integers(0, 50, 900).astype(np.int32), None), (np.where(rng.random(900) < 0.3, np.nan, 0.0).astype(np.float32), None)]
+check(l, r, 'two columns, float specials')
 # probe-side hot key: 150000 probe rows of one key -> its partition is split into three work items
 p = rng.integers(0, 100_000, 200_000); p[:150_000] = 777
 b = rng.integers(0, 100_000, 30_000); b[:5] = 777

@@ -73,8 +73,9 @@ from tests.impls import PlcImpl
 cu = PlcImpl(plc)
 rng = np.random.default_rng(78)
 def check(l, r, tag):
-    got = cu.inner_join(l, r); exp = ojoin.inner_join(l, r)
-    assert np.array_equal(got[0], exp[0]) and np.array_equal(got[1], exp[1]), tag
+    for kind in ("inner_join", "left_join", "full_join"):
+        got = getattr(cu, kind)(l, r); exp = getattr(ojoin, kind)(l, r)
+        assert np.array_equal(got[0], exp[0]) and np.array_equal(got[1], exp[1]), (tag, kind)
 for dtype in (np.int64, np.int32, np.float64, np.int8):
     for nl, nr in [(1, 1), (1000, 700), (50_000, 20_000), (300, 90_000), (200_000, 150_000)]:
         if dtype == np.int8 and nl > 50_000:
