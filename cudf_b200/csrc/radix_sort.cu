@@ -312,8 +312,11 @@ constexpr bool EMU_BUILD = false;
 #endif
 // RMW: the leader advances the warp's running digit offset with one ATOMS.ADD (returning the old value) instead of
 // LDS + STS — one shared-memory operation less per key in a kernel bound by shared-memory wavefronts (B2_SORT_CFG=11).
+// BULK: full, 16-byte aligned key tiles arrive in shared memory through ONE bulk async copy (cp.async.bulk, the 1-D TMA
+// path: UBLKCP in SASS) signalled by an mbarrier, and the ranking warps pick their keys up from there instead of issuing
+// IPT global loads each (B2_SORT_CFG=12; other tiles take the ordinary loads).
 template <typename UK, int THREADS, int IPT, int MINB, typename VT = uint32_t, bool CARRY = false, bool MIX = false, bool SAFE = false,
-          bool RMW = false>
+          bool RMW = false, bool BULK = false>
 __global__ void __launch_bounds__(THREADS + 32 * LBW, MINB) onesweep_kernel(pass_args a)
 {
   constexpr int TILE   = THREADS * IPT;
@@ -339,6 +342,13 @@ __global__ void __launch_bounds__(THREADS + 32 * LBW, MINB) onesweep_kernel(pass
   const bool ranker = warp < NWARPS;
 
   if (tid == 0) s_misc[0] = atomicAdd(a.tile_counter, 1u);
+  if constexpr (BULK && !EMU_BUILD) {
+    if (tid == 0) {
+      const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(s_misc + 12);  // 8-byte aligned slot behind the scan scratch (s_misc[1..8])
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+  }
   if (ranker) {
 #pragma unroll
     for (int j = 0; j < RADIX / 32; ++j) {
@@ -429,7 +439,32 @@ __global__ void __launch_bounds__(THREADS + 32 * LBW, MINB) onesweep_kernel(pass
   const uint32_t wbase = tile_base + warp * (32 * IPT) + lane;
   {
     const UK* src = static_cast<const UK*>(pl.key_src == 0 ? a.key_bufs[0] : (pl.key_src == 1 ? a.key_bufs[1] : a.key_bufs[2])) + a.portion_start;
-    if (full) {
+    bool via_smem = false;
+    if constexpr (BULK) via_smem = full && (reinterpret_cast<uintptr_t>(src + tile_base) & 15) == 0;  // uniform over the CTA
+    if (via_smem) {
+      if constexpr (BULK) {
+        constexpr uint32_t BYTES = (uint32_t)(sizeof(UK) * TILE);
+        static_assert(!BULK || BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
+        if constexpr (EMU_BUILD) {  // emulator: the same data movement with ordinary loads
+          for (int q = tid; q < TILE; q += THREADS) s_keys[q] = src[tile_base + q];
+          ranker_barrier(THREADS);
+        } else {
+          const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(s_misc + 12);
+          if (tid == 0) {
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_keys);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(BYTES) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                         "l"(src + tile_base), "r"(BYTES), "r"(mbar)
+                         : "memory");
+          }
+          asm volatile(
+            "{\n .reg .pred p;\n BULK_WAIT:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n @p bra BULK_DONE;\n bra BULK_WAIT;\n BULK_DONE:\n}" ::"r"(mbar)
+            : "memory");
+        }
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) key[i] = s_keys[warp * (32 * IPT) + i * 32 + lane];
+      }
+    } else if (full) {
 #pragma unroll
       for (int i = 0; i < IPT; ++i) key[i] = ld_stream(src + wbase + i * 32);
     } else {
@@ -787,7 +822,7 @@ int64_t portion_limit()
 //  raw_keys == nullptr : keys are pre-twiddled in bufA with explicit row ids in idx buffer pre_idx_buf
 //  pairs: idx_out receives the permutation ; keys-only: bufA is the OUTPUT, bufB the temp.
 template <typename UK, int T, int I, int MINB, typename VT = uint32_t, bool CARRY = false, bool MIX = false, bool SAFE = false,
-          bool RMW = false>
+          bool RMW = false, bool BULK = false>
 void run_radix_cfg(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int32_t* idx_tmp, int32_t* idx_tmp2, int pre_idx_buf, int64_t n,
                    int kind, bool descending, bool pairs, cudaStream_t stream, int first_pass = 0, int last_pass = 7,
                    bool keep_keys = false, const void* val_in = nullptr)
@@ -824,7 +859,7 @@ void run_radix_cfg(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int
   B2_LAUNCH(plan_kernel, 1, RADIX, 0, stream, ghist, NP, (uint32_t)n, raw ? 1 : 0, pre_idx_buf, ctl, first_pass, last_pass);
 
   static bool attr_set = [] {
-    cudaFuncSetAttribute(onesweep_kernel<UK, T, I, MINB, VT, CARRY, MIX, SAFE, RMW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncSetAttribute(onesweep_kernel<UK, T, I, MINB, VT, CARRY, MIX, SAFE, RMW, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)onesweep_smem<UK, T, I, VT>());
     return true;
   }();
@@ -857,7 +892,7 @@ void run_radix_cfg(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int
       const int64_t ntiles = (pn + TILE - 1) / TILE;
       const size_t smem_bytes = onesweep_smem<UK, T, I, VT>();
       prof_scope ps("onesweep", stream);
-      B2_LAUNCH((onesweep_kernel<UK, T, I, MINB, VT, CARRY, MIX, SAFE, RMW>), (unsigned)ntiles, T + 32 * LBW, smem_bytes, stream, a);
+      B2_LAUNCH((onesweep_kernel<UK, T, I, MINB, VT, CARRY, MIX, SAFE, RMW, BULK>), (unsigned)ntiles, T + 32 * LBW, smem_bytes, stream, a);
     }
   }
   {
@@ -898,6 +933,10 @@ void run_radix(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int32_t
       case 10:  // default shape, formally race-free bitmap ranking
         run_radix_cfg<UK, 384, 16, 2, uint32_t, false, false, true>(raw_keys, bufA, bufB, idx_out, idx_tmp, idx_tmp2, pre_idx_buf, n, kind,
                                                                     descending, pairs, stream);
+        break;
+      case 12:  // default shape, key tiles by one bulk async copy (TMA 1-D) + mbarrier
+        run_radix_cfg<UK, 384, 16, 2, uint32_t, false, false, false, false, true>(raw_keys, bufA, bufB, idx_out, idx_tmp, idx_tmp2, pre_idx_buf,
+                                                                                  n, kind, descending, pairs, stream);
         break;
       case 11:  // default shape, running digit offsets advanced by one ATOMS.ADD
         run_radix_cfg<UK, 384, 16, 2, uint32_t, false, false, false, true>(raw_keys, bufA, bufB, idx_out, idx_tmp, idx_tmp2, pre_idx_buf, n,

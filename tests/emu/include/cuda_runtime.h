@@ -107,6 +107,7 @@ template <typename F> inline cudaError_t cudaFuncSetAttribute(F, int, int) { ret
 // ---- device intrinsics -----------------------------------------------------------------------------------
 inline void __syncthreads() { ::emu::sync_threads(); }
 inline void __threadfence() {}
+inline size_t __cvta_generic_to_shared(const void* p) { return reinterpret_cast<size_t>(p); }  // only named in discarded branches
 inline void __nanosleep(unsigned) { ::emu::yield(); }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }

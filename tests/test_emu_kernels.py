@@ -97,9 +97,10 @@ print('VALIDATED_OK')
 """, "VALIDATED_OK", env={"B2_SORT_PORTION": "12288"})
 
 
-@pytest.mark.parametrize("cfg", ["3", "10", "11"])
+@pytest.mark.parametrize("cfg", ["3", "10", "11", "12"])
 def test_emu_sort_tile_variants(emu_lib, cfg):
-    """B2_SORT_CFG variants of the 64-bit one-sweep kernel (another tile shape, the race-free and the ATOMS.ADD ranking)."""
+    """B2_SORT_CFG variants of the 64-bit one-sweep kernel (another tile shape, the race-free and the ATOMS.ADD ranking, the
+    bulk-copy key load — whose data movement the emulator replays with ordinary loads)."""
     run(SORT_PAYLOAD, "SORT_PAYLOAD_OK", env={"B2_SORT_CFG": cfg})
 
 
