@@ -178,8 +178,26 @@ def fuzz_seg_rank(rng):
     if n:
         offs = np.sort(rng.integers(0, n + 1, int(rng.integers(0, 12)))).astype(np.int32)
         keys = [col, (np.arange(n, dtype=np.int32), None)]
-        got = plc.sorting.segmented_sorted_order(plc.Table([plc.Column.from_numpy(*c) for c in keys]), plc.Column.from_numpy(offs),
-                                                 [int(rng.integers(2)), 0], []).to_numpy()[0]
+    if n:
+        order0 = int(rng.integers(2))
+        exp = osort.segmented_sorted_order(keys, offs, [order0, 0], None)
+        got = plc.sorting.segmented_sorted_order(plc.Table([plc.Column.from_numpy(*c) for c in keys]), plc.Column.from_numpy(offs), [order0, 0],
+                                                 []).to_numpy()[0]
+        assert np.array_equal(got, exp), ("segmented_sorted_order", n, dt, order0, offs.tolist())
+        # top-k: any k rows whose multiset of values equals the oracle's
+        k = int(rng.integers(0, n + 3))
+        tk_order = int(rng.integers(2))
+        gv, gm = plc.sorting.top_k(plc.Column.from_numpy(*col), k, tk_order).to_numpy()
+        ev, em = osort.top_k(col, k, tk_order)
+        canon = lambda v, m: sorted((bool(a), (float(b) if b == b else float("inf")) if a else 0.0)
+                                    for a, b in zip(np.ones(len(v), bool) if m is None else np.asarray(m, bool), np.asarray(v, np.float64)))
+        assert canon(gv, gm) == canon(ev, em), ("top_k", n, dt, k, tk_order)
+        # cudf::partition through the pylibcudf twin: stable partition by an explicit map
+        P = int(rng.integers(1, 40))
+        pmap = rng.integers(0, P, n).astype(np.int32)
+        out, poffs = plc.partitioning.partition(plc.Table([plc.Column.from_numpy(np.arange(n, dtype=np.int64))]), plc.Column.from_numpy(pmap), P)
+        assert np.array_equal(out.columns()[0].to_numpy()[0], np.argsort(pmap, kind="stable")), ("partition", n, P)
+        assert poffs == np.concatenate([[0], np.cumsum(np.bincount(pmap, minlength=P))[:-1]]).tolist()
     for method in range(5):
         order, policy, nprec = int(rng.integers(2)), int(rng.integers(2)), int(rng.integers(2))
         pct = bool(rng.integers(2))
