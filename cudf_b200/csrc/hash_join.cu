@@ -409,7 +409,8 @@ b2_hash_join* hash_join_create(const std::vector<b2_column_view>& build, int has
   if (hj->build_rows == 0) return hj.release();
   const double want = std::ceil((double)hj->build_rows / load_factor);
   uint64_t slots = 16;
-  while ((double)slots < want) slots <<= 1;
+  // at least one slot must stay empty: every probe loop ends on an empty slot (load_factor 1.0 with a power-of-two row count)
+  while ((double)slots < want || slots <= (uint64_t)hj->build_rows) slots <<= 1;
   B2_EXPECTS(slots <= (1ull << 31), B2_ERR_INVALID_ARGUMENT, "hash join: build table too large for this load factor");
   hj->mask  = (uint32_t)(slots - 1);
   hj->table = dbuf(slots * sizeof(slot_t), stream);

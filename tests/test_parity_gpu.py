@@ -82,6 +82,15 @@ def test_hash_join_object_reuse_and_errors(plc):
     for lf in (-0.1, 0.0, 1.5):  # InvalidLoadFactor (join_tests.cpp:346-366) -> std::invalid_argument
         with pytest.raises(ValueError):
             plc.join.HashJoin(t, plc.NullEquality.EQUAL, has_nulls=False, load_factor=lf)
+    # load_factor 1.0 is legal (join_tests.cpp:346-366 rejects only <= 0 and > 1): a power-of-two build must not fill the table
+    for nb in (16, 1024):
+        b = np.arange(nb, dtype=np.int64)
+        hj1 = plc.join.HashJoin(plc.Table([plc.Column.from_numpy(b)]), plc.NullEquality.EQUAL, has_nulls=False, load_factor=1.0)
+        pr = np.array([0, nb - 1, nb, -5, 7], np.int64)
+        l, r = hj1.inner_join(plc.Table([plc.Column.from_numpy(pr)]))
+        got = ojoin.canonical(l.to_numpy()[0], r.to_numpy()[0])
+        exp = ojoin.inner_join([(pr, None)], [(b, None)])
+        assert np.array_equal(got[0], exp[0]) and np.array_equal(got[1], exp[1])
     with pytest.raises(TypeError):  # cudf::data_type_error: mismatched key types
         plc.join.inner_join(t, plc.Table([plc.Column.from_numpy(np.array([1.0, 2.0]))]), plc.NullEquality.EQUAL)
     with pytest.raises(ValueError):  # std::invalid_argument: column count mismatch
