@@ -323,7 +323,7 @@ static table_ptr sort_by_key_impl(const std::vector<b2_column_view>& values, con
   B2_EXPECTS(vrows == krows, B2_ERR_LOGIC, "Mismatch in number of rows for values and keys");
   if (keys.size() == 1 && values.size() == 1 && order.size() <= 1 && nprec.size() <= 1) {
     const bool asc = order.empty() ? true : order[0] == B2_ASCENDING;
-    if (sort_carry_applicable(keys[0], values[0], asc)) {  // opt-in experimental path, off by default
+    if (sort_carry_applicable(keys[0], values[0], asc)) {  // single fixed-width payload: carried through the passes
       auto t = std::make_unique<b2_table>();
       t->cols.push_back(sort_by_key_carry(keys[0], values[0], asc, stream));
       return t;

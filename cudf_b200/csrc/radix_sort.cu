@@ -42,7 +42,8 @@ struct pass_plan {
   int32_t idx_src;  // -1 implicit iota, 0 buffer X (output), 1 buffer Y (temp)
   int32_t idx_dst;  // 0 / 1
   int32_t last;     // 1: last executed pass
-  int32_t pad[2];
+  int32_t hybrid;   // 1: partial LSD (top digits only) + segment fix-up follows; this pass keeps its keys and does not untwiddle
+  int32_t pad;
 };
 
 struct sort_ctl {
@@ -50,6 +51,13 @@ struct sort_ctl {
   uint32_t base[2][8][RADIX];  // [portion parity][pass][digit] global start offset of digit
   int32_t any_pass;            // number of executed passes
   uint32_t nan_count;          // FLOAT keys only
+  // hybrid sort (see segment_fix_kernel): the executed passes cover only the digits >= fix_shift / 8; rows whose keys agree
+  // on those bits form short segments that the fix-up orders by the remaining low bits
+  int32_t hybrid;              // decided by the plan kernel
+  int32_t fix_shift;           // segment prefix = key >> fix_shift
+  int32_t fix_key_buf;         // key buffer (1 / 2) written by the last executed pass
+  int32_t fix_idx_buf;         // payload / row-id buffer (0 / 1 / 2) written by the last executed pass
+  uint32_t overflow;           // set by the fix-up when a segment is too long for it: the host reruns the full LSD sort
 };
 
 template <typename UK>
@@ -189,16 +197,34 @@ __global__ void __launch_bounds__(512) histogram_kernel(const UK* __restrict__ k
 // mode_pairs: 1 sorted_order (indices), 0 keys-only.  raw: 1 keys come from the user's column
 // (implicit indices), 0 keys already twiddled in buffer A with explicit indices in idx buffer
 // `pre_idx_buf`.
+// hyb_allowed: the caller can run the segment fix-up (and rerun without it on overflow), so the plan may stop the LSD
+// passes early. The number of top digits that has to be sorted is chosen from the digit histograms: if the digits
+// were independent, rows would share a given combination of the chosen digits with probability prod_p sum_d (c_pd / n)^2,
+// i.e. a segment would hold about n * prod rows. The estimate only selects the plan; the fix-up verifies it.
+constexpr double HYB_MAX_EXPECTED_SEGMENT = 4.0;
+constexpr int HYB_MIN_SAVED_PASSES = 2;
+
 __global__ void plan_kernel(const uint32_t* __restrict__ ghist, int npass, uint32_t n, int raw, int pre_idx_buf,
-                            sort_ctl* ctl, int first_pass, int last_pass)
+                            sort_ctl* ctl, int first_pass, int last_pass, int hyb_allowed)
 {
   __shared__ uint32_t warp_tot[8];
   __shared__ int triv[8];
+  __shared__ double sq[RADIX];
+  __shared__ double coll[8];  // sum_d (c_d / n)^2 of each pass
   const int d = threadIdx.x;  // 256 threads
   for (int p = 0; p < npass; ++p) {
     uint32_t c = ghist[p * RADIX + d];
     if (d == 0) triv[p] = 0;
+    {
+      const double f = (double)c / (double)n;
+      sq[d] = f * f;
+    }
     __syncthreads();
+    if (d == 0) {
+      double t = 0;
+      for (int j = 0; j < RADIX; ++j) t += sq[j];
+      coll[p] = t;
+    }
     if (c == n || p < first_pass || p > last_pass) triv[p] = 1;  // passes outside [first,last] are skipped
     uint32_t inc = warp_inclusive_sum(c);
     if ((d & 31) == 31) warp_tot[d >> 5] = inc;
@@ -211,6 +237,26 @@ __global__ void plan_kernel(const uint32_t* __restrict__ ghist, int npass, uint3
   if (d == 0) {
     int nexec = 0;
     for (int p = 0; p < npass; ++p) nexec += triv[p] ? 0 : 1;
+    int hybrid = 0, low = 0;
+    if (hyb_allowed && nexec > HYB_MIN_SAVED_PASSES) {
+      double e = (double)n;
+      int k = 0;
+      low = npass;
+      for (int p = npass - 1; p >= 0 && (k == 0 || e > HYB_MAX_EXPECTED_SEGMENT); --p) {  // at least one pass
+        if (triv[p]) continue;
+        e *= coll[p];
+        ++k;
+        low = p;
+      }
+      if (e <= HYB_MAX_EXPECTED_SEGMENT && nexec - k >= HYB_MIN_SAVED_PASSES) {
+        hybrid = 1;
+        for (int p = 0; p < low; ++p) triv[p] = 1;
+        nexec = k;
+      }
+    }
+    ctl->hybrid    = hybrid;
+    ctl->fix_shift = low * RADIX_BITS;
+    ctl->overflow  = 0;
     // idx buffers: 0 = output, 1 = temp. the last executed pass must write 0.
     // key buffers: 1 = A, 2 = B (keys-only: 1 = output, 2 = temp; last executed pass must write 1)
     int k = 0;
@@ -228,9 +274,17 @@ __global__ void plan_kernel(const uint32_t* __restrict__ ghist, int npass, uint3
         // (keys in A, row ids in idx buffer 1): keys alternate A/B (their final home is irrelevant,
         // pairs mode never returns keys); row ids go to 0 whenever an even number of passes remains,
         // else to a non-zero buffer other than the source (third buffer only for the first pass).
-        pl.key_dst = raw ? ((remaining_after % 2 == 0) ? 1 : 2) : (key_cur == 1 ? 2 : 1);
-        pl.idx_dst = (remaining_after % 2 == 0) ? 0 : (idx_cur == 1 ? 2 : 1);
+        // Hybrid (raw input only): the last pass must land in the TEMP buffers (key 2 / idx 1), because the fix-up writes
+        // the output buffers (key 1 / idx 0) from them.
+        const int par = (remaining_after + hybrid) % 2;
+        pl.key_dst = raw ? (par == 0 ? 1 : 2) : (key_cur == 1 ? 2 : 1);
+        pl.idx_dst = par == 0 ? 0 : (idx_cur == 1 ? 2 : 1);
         pl.last    = remaining_after == 0;
+        pl.hybrid  = hybrid;
+        if (pl.last) {
+          ctl->fix_key_buf = pl.key_dst;
+          ctl->fix_idx_buf = pl.idx_dst;
+        }
         key_cur = pl.key_dst;
         idx_cur = pl.idx_dst;
         ++k;
@@ -617,7 +671,7 @@ __global__ void __launch_bounds__(THREADS + 32 * LBW, MINB) onesweep_kernel(pass
   }
   __syncthreads();  // (S4) keys staged, scatter offsets ready
 
-  const bool write_keys = !(a.pairs && pl.last) || a.keep_keys;
+  const bool write_keys = !(a.pairs && pl.last) || a.keep_keys || pl.hybrid;
   UK* kdst = static_cast<UK*>(const_cast<void*>(pl.key_dst == 1 ? a.key_bufs[1] : a.key_bufs[2]));
   uint32_t dst[IPT];
 #pragma unroll
@@ -627,7 +681,7 @@ __global__ void __launch_bounds__(THREADS + 32 * LBW, MINB) onesweep_kernel(pass
     const unsigned d = (unsigned)(k >> shift) & 255u;
     dst[j] = s_off[d] + q;
     if (write_keys && q < tile_n) {
-      if (!a.pairs && pl.last) k = untwiddle_rt<UK>(k, a.kind, desc);
+      if (!a.pairs && pl.last && !pl.hybrid) k = untwiddle_rt<UK>(k, a.kind, desc);
       kdst[dst[j]] = k;
     }
   }
@@ -671,6 +725,82 @@ __global__ void finalize_kernel(pass_args a, int64_t n, int raw, int pre_idx_buf
     } else {
       // keys-only (always raw): copy input to output
       static_cast<UK*>(const_cast<void*>(a.key_bufs[1]))[i] = static_cast<const UK*>(a.key_bufs[0])[i];
+    }
+  }
+}
+
+// Hybrid sort, second half.  The executed LSD passes ordered the rows by the key bits >= fix_shift (stable), so rows that
+// agree on those bits ("segments") are contiguous and still in input order.  Each row finds its segment by walking
+// outwards over the neighbouring keys in shared memory and takes its final place = segment start + number of segment
+// rows that precede it in (key, input position) order.  With the plan kernel's choice of digits a segment holds a
+// handful of rows (n / 2^32 = 0.23 on average for 1e9 uniform 64-bit keys after four passes), so this is one
+// streaming pass: read key + payload, write payload (or the untwiddled key) a few places away.
+// A walk stops after FIX_HALO rows.  A row whose walk was cut short keeps its place if every key it saw equals its own
+// (a run of duplicates longer than the window: windows of neighbouring rows overlap, so if nobody objects the whole
+// run is one value and already in order); otherwise it raises ctl->overflow and the host reruns the full LSD sort.
+constexpr int FIX_THREADS = 256;
+constexpr int FIX_IPT     = 8;
+constexpr int FIX_TILE    = FIX_THREADS * FIX_IPT;
+constexpr int FIX_HALO    = 64;
+
+template <typename UK, typename VT>
+__global__ void __launch_bounds__(FIX_THREADS) segment_fix_kernel(pass_args a, int64_t n)
+{
+  if (!a.ctl->hybrid) return;
+  __shared__ UK sk[FIX_TILE + 2 * FIX_HALO];
+  const int shift = a.ctl->fix_shift;
+  const UK* __restrict__ keys = static_cast<const UK*>(a.ctl->fix_key_buf == 1 ? a.key_bufs[1] : a.key_bufs[2]);
+  const VT* __restrict__ vin  = reinterpret_cast<const VT*>(a.ctl->fix_idx_buf == 1 ? a.idx_bufs[1] : a.idx_bufs[2]);
+  VT* __restrict__ vout = reinterpret_cast<VT*>(a.idx_bufs[0]);
+  UK* __restrict__ kout = static_cast<UK*>(const_cast<void*>(a.key_bufs[1]));
+  const UK desc = (UK)a.desc_mask;
+  const int64_t ntiles = (n + FIX_TILE - 1) / FIX_TILE;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t base = tile * FIX_TILE;
+    __syncthreads();  // the previous tile's walks are done
+    for (int q = threadIdx.x; q < FIX_TILE + 2 * FIX_HALO; q += FIX_THREADS) {
+      const int64_t g = base - FIX_HALO + q;
+      sk[q] = (g >= 0 && g < n) ? ld_stream(keys + g) : UK(0);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < FIX_IPT; ++j) {
+      const int i = j * FIX_THREADS + threadIdx.x;
+      const int64_t gi = base + i;
+      if (gi >= n) continue;
+      VT v{};
+      if (a.pairs) v = ld_stream(vin + gi);
+      const UK k  = sk[FIX_HALO + i];
+      const UK pf = k >> shift;
+      // rows to the left / right that exist (array ends are segment ends)
+      const int lmax = (int)(gi < FIX_HALO ? gi : (int64_t)FIX_HALO);
+      const int rmax = (int)(n - 1 - gi < FIX_HALO ? n - 1 - gi : (int64_t)FIX_HALO);
+      int left = 0, before = 0;
+      bool all_equal = true, cut = false;
+      for (;;) {
+        if (left == lmax) { cut = lmax == FIX_HALO; break; }
+        const UK o = sk[FIX_HALO + i - left - 1];
+        if ((UK)(o >> shift) != pf) break;
+        ++left;
+        before += o <= k ? 1 : 0;   // earlier rows win ties
+        all_equal = all_equal && o == k;
+      }
+      int right = 0;
+      for (;;) {
+        if (right == rmax) { cut = cut || rmax == FIX_HALO; break; }
+        const UK o = sk[FIX_HALO + i + right + 1];
+        if ((UK)(o >> shift) != pf) break;
+        ++right;
+        before += o < k ? 1 : 0;
+        all_equal = all_equal && o == k;
+      }
+      int64_t dst = gi - left + before;
+      if (cut) {
+        dst = gi;
+        if (!all_equal) atomicOr(&a.ctl->overflow, 1u);
+      }
+      if (a.pairs) vout[dst] = v;
+      else kout[dst] = untwiddle_rt<UK>(k, a.kind, desc);
     }
   }
 }
@@ -817,6 +947,19 @@ int64_t portion_limit()
   return lim;
 }
 
+// B2_SORT_HYBRID=0 switches the partial-LSD + fix-up plan off; B2_SORT_HYBRID_MIN=<rows> moves its lower size limit
+// (tests run it on small inputs).
+int64_t hybrid_min_rows()
+{
+  static int64_t v = [] {
+    const char* off = std::getenv("B2_SORT_HYBRID");
+    if (off && std::atoi(off) == 0) return INT64_MAX;
+    const char* e = std::getenv("B2_SORT_HYBRID_MIN");
+    return e ? (int64_t)std::atoll(e) : (int64_t(1) << 16);
+  }();
+  return v;
+}
+
 // Sort `n` keys.
 //  raw_keys != nullptr : keys are the user's raw column (twiddled on load, implicit row ids)
 //  raw_keys == nullptr : keys are pre-twiddled in bufA with explicit row ids in idx buffer pre_idx_buf
@@ -843,20 +986,10 @@ void run_radix_cfg(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int
   const size_t status_per  = sizeof(uint32_t) * RADIX * (size_t)tiles_per_portion;
   const size_t status_bytes = status_per * NP * nportions;
   dbuf work(ctl_bytes + hist_bytes + cnt_bytes + status_bytes, stream);
-  B2_CUDA_TRY(cudaMemsetAsync(work.ptr, 0, work.bytes, stream));
   auto* ctl       = reinterpret_cast<sort_ctl*>(work.ptr);
   auto* ghist     = reinterpret_cast<uint32_t*>(static_cast<char*>(work.ptr) + ctl_bytes);
   auto* counters  = reinterpret_cast<uint32_t*>(static_cast<char*>(work.ptr) + ctl_bytes + hist_bytes);
   auto* status    = reinterpret_cast<uint32_t*>(static_cast<char*>(work.ptr) + ctl_bytes + hist_bytes + cnt_bytes);
-
-  {
-    int grid = (int)std::min<int64_t>((n + 512 * 16 - 1) / (512 * 16), NUM_SMS_B200 * 4);
-    grid = std::max(grid, 1);
-    prof_scope ps("histogram", stream);
-    B2_LAUNCH((histogram_kernel<UK, MIX>), grid, 512, 0, stream, raw ? raw_keys : bufA, n, raw ? 1 : 0, kind, desc_mask, ghist,
-              (raw && kind == (int)key_kind::FLOAT) ? &ctl->nan_count : nullptr);
-  }
-  B2_LAUNCH(plan_kernel, 1, RADIX, 0, stream, ghist, NP, (uint32_t)n, raw ? 1 : 0, pre_idx_buf, ctl, first_pass, last_pass);
 
   static bool attr_set = [] {
     cudaFuncSetAttribute(onesweep_kernel<UK, T, I, MINB, VT, CARRY, MIX, SAFE, RMW, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -865,39 +998,70 @@ void run_radix_cfg(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int
   }();
   (void)attr_set;
 
-  pass_args a{};
-  a.key_bufs[0] = raw_keys;
-  a.key_bufs[1] = bufA;
-  a.key_bufs[2] = bufB;
-  a.idx_bufs[0] = idx_out;
-  a.idx_bufs[1] = idx_tmp;
-  a.idx_bufs[2] = idx_tmp2;
-  a.ctl = ctl;
-  a.kind = kind;
-  a.pairs = pairs ? 1 : 0;
-  a.keep_keys = keep_keys ? 1 : 0;
-  a.val_in = val_in;
-  a.desc_mask = (uint64_t)desc_mask;
-  for (int p = std::max(0, first_pass); p < NP && p <= last_pass; ++p) {
-    for (int64_t q = 0; q < nportions; ++q) {
-      const int64_t start = q * plim;
-      const int64_t pn = std::min(plim, n - start);
-      a.pass = p;
-      a.portion_start = start;
-      a.portion_n = (uint32_t)pn;
-      a.portion_parity = (int)(q & 1);
-      a.has_next_portion = q + 1 < nportions;
-      a.status = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(status) + (size_t)(p * nportions + q) * status_per);
-      a.tile_counter = counters + p * nportions + q;
-      const int64_t ntiles = (pn + TILE - 1) / TILE;
-      const size_t smem_bytes = onesweep_smem<UK, T, I, VT>();
-      prof_scope ps("onesweep", stream);
-      B2_LAUNCH((onesweep_kernel<UK, T, I, MINB, VT, CARRY, MIX, SAFE, RMW, BULK>), (unsigned)ntiles, T + 32 * LBW, smem_bytes, stream, a);
+  // Hybrid plan (64-bit raw keys, full sort): LSD passes over the top digits only, then segment_fix_kernel. The plan
+  // kernel decides on the device; the host learns the outcome from one 4-byte read-back after the fix-up.
+  bool try_hybrid = sizeof(UK) == 8 && !MIX && raw && first_pass == 0 && last_pass >= NP - 1 && !keep_keys && n >= hybrid_min_rows();
+
+  for (;;) {
+    B2_CUDA_TRY(cudaMemsetAsync(work.ptr, 0, work.bytes, stream));
+    {
+      int grid = (int)std::min<int64_t>((n + 512 * 16 - 1) / (512 * 16), NUM_SMS_B200 * 4);
+      grid = std::max(grid, 1);
+      prof_scope ps("histogram", stream);
+      B2_LAUNCH((histogram_kernel<UK, MIX>), grid, 512, 0, stream, raw ? raw_keys : bufA, n, raw ? 1 : 0, kind, desc_mask, ghist,
+                (raw && kind == (int)key_kind::FLOAT) ? &ctl->nan_count : nullptr);
     }
-  }
-  {
-    int grid = (int)std::min<int64_t>((n + 255) / 256, NUM_SMS_B200 * 8);
-    B2_LAUNCH((finalize_kernel<UK, MIX>), std::max(grid, 1), 256, 0, stream, a, n, raw ? 1 : 0, pre_idx_buf, CARRY ? (int)sizeof(VT) : 0);
+    B2_LAUNCH(plan_kernel, 1, RADIX, 0, stream, ghist, NP, (uint32_t)n, raw ? 1 : 0, pre_idx_buf, ctl, first_pass, last_pass,
+              try_hybrid ? 1 : 0);
+
+    pass_args a{};
+    a.key_bufs[0] = raw_keys;
+    a.key_bufs[1] = bufA;
+    a.key_bufs[2] = bufB;
+    a.idx_bufs[0] = idx_out;
+    a.idx_bufs[1] = idx_tmp;
+    a.idx_bufs[2] = idx_tmp2;
+    a.ctl = ctl;
+    a.kind = kind;
+    a.pairs = pairs ? 1 : 0;
+    a.keep_keys = keep_keys ? 1 : 0;
+    a.val_in = val_in;
+    a.desc_mask = (uint64_t)desc_mask;
+    for (int p = std::max(0, first_pass); p < NP && p <= last_pass; ++p) {
+      for (int64_t q = 0; q < nportions; ++q) {
+        const int64_t start = q * plim;
+        const int64_t pn = std::min(plim, n - start);
+        a.pass = p;
+        a.portion_start = start;
+        a.portion_n = (uint32_t)pn;
+        a.portion_parity = (int)(q & 1);
+        a.has_next_portion = q + 1 < nportions;
+        a.status = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(status) + (size_t)(p * nportions + q) * status_per);
+        a.tile_counter = counters + p * nportions + q;
+        const int64_t ntiles = (pn + TILE - 1) / TILE;
+        const size_t smem_bytes = onesweep_smem<UK, T, I, VT>();
+        prof_scope ps("onesweep", stream);
+        B2_LAUNCH((onesweep_kernel<UK, T, I, MINB, VT, CARRY, MIX, SAFE, RMW, BULK>), (unsigned)ntiles, T + 32 * LBW, smem_bytes, stream, a);
+      }
+    }
+    if constexpr (sizeof(UK) == 8 && !MIX) {
+      if (try_hybrid) {
+        const int64_t ntiles = (n + FIX_TILE - 1) / FIX_TILE;
+        const int grid = (int)std::min<int64_t>(ntiles, NUM_SMS_B200 * 8);
+        prof_scope ps("segment_fix", stream);
+        B2_LAUNCH((segment_fix_kernel<UK, VT>), grid, FIX_THREADS, 0, stream, a, n);
+      }
+    }
+    {
+      int grid = (int)std::min<int64_t>((n + 255) / 256, NUM_SMS_B200 * 8);
+      B2_LAUNCH((finalize_kernel<UK, MIX>), std::max(grid, 1), 256, 0, stream, a, n, raw ? 1 : 0, pre_idx_buf, CARRY ? (int)sizeof(VT) : 0);
+    }
+    if (!try_hybrid) break;
+    uint32_t overflow = 0;
+    B2_CUDA_TRY(cudaMemcpyAsync(&overflow, &ctl->overflow, sizeof(overflow), cudaMemcpyDeviceToHost, stream));
+    B2_CUDA_TRY(cudaStreamSynchronize(stream));
+    if (!overflow) break;
+    try_hybrid = false;  // a segment was longer than the fix-up window (digits not independent): full LSD sort of the untouched input
   }
   if (pairs && raw && kind == (int)key_kind::FLOAT && descending) {
     B2_LAUNCH(reverse_nan_prefix_kernel, NUM_SMS_B200 * 4, 256, 0, stream, idx_out, &ctl->nan_count);
@@ -1180,13 +1344,14 @@ column_ptr sorted_order(const std::vector<b2_column_view>& keys, const std::vect
   return out;
 }
 
-// EXPERIMENTAL (B2_SORT_CARRY=1): sort_by_key of ONE non-null 4- or 8-byte values column by ONE non-null
-// fixed-width key column, carrying the payload through the passes instead of row ids (no gather).
+// sort_by_key of ONE non-null 4- or 8-byte values column by ONE non-null fixed-width key column carries the payload
+// through the passes instead of row ids: no random-access gather afterwards (B200 fetches 128 bytes per random 8-byte
+// read: 26 ms per 1e9 rows). B2_SORT_CARRY=0 selects the row-id + gather path for every shape.
 bool sort_carry_enabled()
 {
   static bool v = [] {
     const char* e = std::getenv("B2_SORT_CARRY");
-    return e && std::atoi(e) != 0;
+    return !e || std::atoi(e) != 0;
   }();
   return v;
 }
