@@ -238,6 +238,9 @@ column_ptr sort_by_key_carry(const b2_column_view& keys, const b2_column_view& v
 void radix_partition_top16(const uint64_t* keys_in, int64_t n, uint64_t* keys_out, int32_t* idx_out, cudaStream_t stream);
 void radix_partition_top16_mix(const uint64_t* packed_keys, int64_t n, uint64_t* keys_out, int32_t* idx_out, cudaStream_t stream);
 
+void radix_partition_mix_carry(const uint64_t* keys, const void* vals, int val_bytes, int64_t n, uint64_t* mixed_keys_out, void* vals_out,
+                               uint32_t* part_base, cudaStream_t stream);
+
 // radix_join.cu (experimental, opt-in: B2_JOIN_RADIX_ROWS)
 bool radix_join_applicable(const std::vector<b2_column_view>& a, const std::vector<b2_column_view>& b);
 void radix_join(const std::vector<b2_column_view>& build, const std::vector<b2_column_view>& probe, bool left, cudaStream_t stream,

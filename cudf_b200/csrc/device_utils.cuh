@@ -105,6 +105,16 @@ __host__ __device__ __forceinline__ uint64_t mix64(uint64_t k)
   return k;
 }
 
+// inverse of mix64 (each xor-shift by 33 is an involution; the multipliers are odd): lets a kernel carry mix64(key)
+// through a partition pass and recover the key afterwards
+__host__ __device__ __forceinline__ uint64_t unmix64(uint64_t k)
+{
+  k ^= k >> 33; k *= 0x9cb4b2f8129337dbull;
+  k ^= k >> 33; k *= 0x4f74430c22a54005ull;
+  k ^= k >> 33;
+  return k;
+}
+
 // ---- order-preserving twiddles: value -> unsigned radix key ---------------------------------------
 // Integers: flip the sign bit.  Floats (sorted_order_radix.cu:41-50 + cub float ordering): -0 == +0,
 // every NaN (either sign) maps to the all-ones key so NaNs sort last and tie (stable => input order).

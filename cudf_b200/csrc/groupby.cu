@@ -23,6 +23,7 @@
 #include "key_pack.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace b2 {
 namespace {
@@ -249,6 +250,211 @@ __global__ void __launch_bounds__(256) groupby_kernel(key_cols kc, int64_t n, bo
   }
 }
 
+// ---- partitioned path (large inputs, one 8-byte integer key column, one value column) ---------------------------------
+// The L2-atomic kernel above tops out near 60 G atomics/s: 49 ms per 1e9 rows at 1e6 groups. Here the rows are first
+// partitioned by the top byte of mix64(key) (one one-sweep pass carrying the value: radix_sort.cu), so that all rows of a
+// group sit in one of 256 contiguous partitions; a CTA then aggregates a chunk of ONE partition in a shared-memory table
+// (mixed key, row count, up to three accumulators) and merges each of its groups into the global table once — the
+// role of the reference's shared-memory pre-aggregation (cpp/src/groupby/hash/compute_shared_memory_aggs.cu:261-355),
+// which on its own gives up at this many groups (compute_mapping_indices.cuh:92-152 cardinality limit).
+// Groups that do not fit in the shared table (more than ~4.9 K groups in a partition) go to the global table row by row.
+constexpr int PGB_THREADS = 1024;
+constexpr int PGB_MAX_OPS = 3;
+constexpr uint64_t PGB_EMPTY = ~0ull;
+
+struct pgb_args {
+  const uint64_t* mkeys;     // mix64(key), partitioned
+  const void* vals;          // carried value bits (val_bytes each) or null
+  int32_t val_bytes;
+  int32_t src_type;          // storage type id of the value column
+  const uint32_t* part_base; // [256] first row of each partition
+  uint32_t n;
+  const uint32_t* item_start;  // [257] first work item of each partition (exclusive scan of chunk counts)
+  uint32_t* item_counter;
+  uint32_t chunk;            // rows per work item
+  uint32_t smem_slots;       // power of two
+  uint32_t smem_limit;       // groups accepted in the shared table
+  int32_t nops;
+  int8_t op[PGB_MAX_OPS];    // op_kind
+  int8_t acc[PGB_MAX_OPS];   // acc_kind
+  unsigned long long* accum[PGB_MAX_OPS];  // global accumulators [slots]
+  unsigned long long init[PGB_MAX_OPS];
+};
+
+// find or claim the global slot of `key` (same protocol as groupby_kernel); -1: table overflow signalled
+__device__ __forceinline__ int64_t global_slot(slot_t* __restrict__ table, uint32_t mask, uint32_t cap, uint64_t key, int32_t* __restrict__ slot_gid,
+                                               gb_ctl* ctl)
+{
+  slot_t empty;
+  memset(&empty, 0xff, sizeof(empty));
+  uint32_t i = slot_hash(key, 0u, mask);
+  int probes = 0;
+  while (true) {
+    if (((++probes) & 127) == 0 && *reinterpret_cast<volatile unsigned int*>(&ctl->overflow)) return -1;
+    slot_t cur = load_slot_volatile(&table[i]);
+    if (cur.row == -1) {
+      const slot_t want{key, 0, 0u};
+      cur = cas128(&table[i], empty, want);
+      if (cur.row == -1) {
+        const unsigned int g = atomicAdd(&ctl->ngroups, 1u);
+        if (g >= cap) { atomicExch(&ctl->overflow, 1u); return -1; }
+        slot_gid[i] = (int32_t)g;
+        return i;
+      }
+    }
+    if (cur.key == key && cur.nullbits == 0u) return i;
+    i = (i + 1) & mask;
+  }
+}
+
+__device__ __forceinline__ unsigned long long pgb_value_bits(const pgb_args& a, uint32_t r)
+{
+  // accumulator-typed bits of the row's value: int64 / uint64 sums wrap identically, so integers share one form
+  if (a.val_bytes == 8) {
+    const unsigned long long b = __ldcs(static_cast<const unsigned long long*>(a.vals) + r);
+    return b;  // INT64 / UINT64 / FLOAT64 bits
+  }
+  const unsigned int b = __ldcs(static_cast<const unsigned int*>(a.vals) + r);
+  if (a.src_type == B2_FLOAT32) {
+    float f;
+    memcpy(&f, &b, 4);
+    return (unsigned long long)__double_as_longlong((double)f);
+  }
+  if (a.src_type == B2_INT32) return (unsigned long long)(long long)(int)b;
+  return (unsigned long long)b;
+}
+
+template <bool SHARED>
+__device__ __forceinline__ void pgb_combine(unsigned long long* a, int8_t op, int8_t acc, unsigned long long v)
+{
+  // v: partial result in accumulator form (SUM: plain bits; MIN / MAX of floats: order-preserving int64)
+  if (op == OPK_SUM) {
+    if (acc == ACC_F64) atomicAdd(reinterpret_cast<double*>(a), __longlong_as_double((long long)v));
+    else atomicAdd(a, v);
+  } else if (acc == ACC_U64) {
+    if (op == OPK_MIN) atomicMin(a, v); else atomicMax(a, v);
+  } else {
+    if (op == OPK_MIN) atomicMin(reinterpret_cast<long long*>(a), (long long)v);
+    else atomicMax(reinterpret_cast<long long*>(a), (long long)v);
+  }
+}
+
+__global__ void pgb_items_kernel(const uint32_t* __restrict__ part_base, uint32_t n, uint32_t chunk, uint32_t* __restrict__ item_start)
+{
+  // 256 threads: chunks per partition, exclusive scan
+  __shared__ uint32_t wt[8];
+  const int d = threadIdx.x;
+  const uint32_t b = part_base[d], e = d == 255 ? n : part_base[d + 1];
+  const uint32_t c = (e - b + chunk - 1) / chunk;
+  const uint32_t inc = warp_inclusive_sum(c);
+  if ((d & 31) == 31) wt[d >> 5] = inc;
+  __syncthreads();
+  uint32_t off = 0;
+  for (int w = 0; w < (d >> 5); ++w) off += wt[w];
+  item_start[d] = off + inc - c;
+  if (d == 255) item_start[256] = off + inc;
+}
+
+__global__ void __launch_bounds__(PGB_THREADS, 1) pgb_agg_kernel(pgb_args a, slot_t* __restrict__ table, uint32_t mask, uint32_t cap,
+                                                                 int32_t* __restrict__ gsize, int32_t* __restrict__ slot_gid, gb_ctl* ctl)
+{
+  B2_DYNAMIC_SMEM(smem_raw);
+  const uint32_t S = a.smem_slots;
+  unsigned long long* s_key = reinterpret_cast<unsigned long long*>(smem_raw);
+  unsigned long long* s_acc = s_key + S;                                       // [nops][S]
+  uint32_t* s_cnt = reinterpret_cast<uint32_t*>(s_acc + (size_t)a.nops * S);   // [S]
+  __shared__ uint32_t s_item, s_fill;
+  __shared__ uint32_t s_start[257];
+  for (int i = threadIdx.x; i < 257; i += PGB_THREADS) s_start[i] = a.item_start[i];
+  __syncthreads();
+  const uint32_t total = s_start[256];
+  while (true) {
+    if (threadIdx.x == 0) {
+      s_item = *reinterpret_cast<volatile unsigned int*>(&ctl->overflow) ? 0xffffffffu : atomicAdd(a.item_counter, 1u);
+      s_fill = 0;
+    }
+    for (uint32_t i = threadIdx.x; i < S; i += PGB_THREADS) {
+      s_key[i] = PGB_EMPTY;
+      s_cnt[i] = 0;
+      for (int k = 0; k < a.nops; ++k) s_acc[(size_t)k * S + i] = a.init[k];
+    }
+    __syncthreads();
+    const uint32_t item = s_item;
+    if (item >= total) return;  // also: global table overflow seen by thread 0 (the host grows the table and reruns)
+    // partition of this item: last d with s_start[d] <= item
+    int lo = 0, hi = 255;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (s_start[mid] <= item) lo = mid; else hi = mid - 1;
+    }
+    const uint32_t pb = a.part_base[lo], pe = lo == 255 ? a.n : a.part_base[lo + 1];
+    const uint32_t r0 = pb + (item - s_start[lo]) * a.chunk;
+    const uint32_t r1 = min(pe, r0 + a.chunk);
+    constexpr int U = 4;  // rows in flight per thread
+    for (uint32_t rb = r0 + threadIdx.x; rb < r1; rb += U * PGB_THREADS) {
+      unsigned long long mks[U], vbs[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint32_t r = rb + u * PGB_THREADS;
+        mks[u] = r < r1 ? __ldcs(a.mkeys + r) : 0ull;
+        vbs[u] = (r < r1 && a.nops) ? pgb_value_bits(a, r) : 0ull;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+      if (rb + u * PGB_THREADS >= r1) break;
+      const unsigned long long mk = mks[u];
+      const unsigned long long vb = vbs[u];
+      // accumulator form of the value for MIN / MAX of floats
+      const unsigned long long vo = (a.nops && a.acc[0] == ACC_F64) ? (unsigned long long)f64_to_ordered(__longlong_as_double((long long)vb)) : vb;
+      int64_t slot = -1;
+      if (mk != PGB_EMPTY) {
+        uint32_t i = (uint32_t)mk & (S - 1);
+        for (int probes = 0; probes < 64; ++probes) {
+          unsigned long long k = *reinterpret_cast<volatile unsigned long long*>(&s_key[i]);
+          if (k == PGB_EMPTY) {
+            if (*reinterpret_cast<volatile uint32_t*>(&s_fill) >= a.smem_limit) break;
+            k = atomicCAS(&s_key[i], PGB_EMPTY, mk);
+            if (k == PGB_EMPTY) { atomicAdd(&s_fill, 1u); k = mk; }
+          }
+          if (k == mk) { slot = i; break; }
+          i = (i + 1) & (S - 1);
+        }
+      }
+      if (slot >= 0) {
+        atomicAdd(&s_cnt[slot], 1u);
+        for (int k = 0; k < a.nops; ++k) pgb_combine<true>(&s_acc[(size_t)k * S + slot], a.op[k], a.acc[k], a.op[k] == OPK_SUM ? vb : vo);
+      } else {
+        // shared table full (or the reserved key value): this row goes to the global table directly
+        const int64_t g = global_slot(table, mask, cap, unmix64(mk), slot_gid, ctl);
+        if (g >= 0) {
+          atomicAdd(&gsize[g], 1);
+          for (int k = 0; k < a.nops; ++k) pgb_combine<false>(a.accum[k] + g, a.op[k], a.acc[k], a.op[k] == OPK_SUM ? vb : vo);
+        }
+      }
+      }
+    }
+    __syncthreads();
+    // merge this item's groups into the global table
+    for (uint32_t i = threadIdx.x; i < S; i += PGB_THREADS) {
+      const unsigned long long mk = s_key[i];
+      if (mk == PGB_EMPTY) continue;
+      const int64_t g = global_slot(table, mask, cap, unmix64(mk), slot_gid, ctl);
+      if (g < 0) continue;
+      atomicAdd(&gsize[g], (int32_t)s_cnt[i]);
+      for (int k = 0; k < a.nops; ++k) pgb_combine<false>(a.accum[k] + g, a.op[k], a.acc[k], s_acc[(size_t)k * S + i]);
+    }
+    __syncthreads();
+  }
+}
+
+// keys of the partitioned path: group g's key is the packed key stored in its slot (one 8-byte integer column)
+__global__ void pgb_keys_kernel(const slot_t* __restrict__ table, int64_t slots, const int32_t* __restrict__ slot_gid, uint64_t* __restrict__ out)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < slots; s += stride)
+    if (table[s].row != -1) out[slot_gid[s]] = table[s].key;
+}
+
 __global__ void fill_u64_kernel(unsigned long long* p, int64_t n, unsigned long long v)
 {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -422,6 +628,58 @@ void groupby_aggregate(const b2_groupby& gb, const std::vector<request_view>& re
   for (auto& k : gb.keys) keys_nullable |= has_nulls(k);
   const bool skip_null_keys = keys_nullable && gb.null_handling == B2_NULL_EXCLUDE;
 
+  // ---- partitioned path? (one null-free 8-byte integer key column, all value data from ONE null-free 4- / 8-byte column,
+  // SUM / MIN / MAX / MEAN / COUNT only, large input) ----
+  bool use_pgb = false;
+  const b2_column_view* pgb_val = nullptr;
+  {
+    static const int64_t min_rows = [] {
+      const char* e = std::getenv("B2_GROUPBY_PARTITION_ROWS");  // 0 switches the path off
+      const int64_t v = e ? std::atoll(e) : (int64_t(1) << 24);
+      return v <= 0 ? INT64_MAX : v;
+    }();
+    bool ok = n >= min_rows && gb.keys.size() == 1 && type_width(gb.keys[0].type_id) == 8 && !is_float_id(storage_type(gb.keys[0].type_id)) &&
+              !keys_nullable;
+    int data_ops = 0;
+    for (auto& r : reqs) {
+      if (!ok) break;
+      if (has_nulls(r.values)) { ok = false; break; }
+      bool needs_data = false;
+      bool has_sum = false;
+      for (int32_t raw_kind : r.kinds) {
+        const int32_t kind = base_kind(raw_kind);
+        if (kind == B2_AGG_COUNT_VALID || kind == B2_AGG_COUNT_ALL) continue;
+        if (kind == B2_AGG_SUM || kind == B2_AGG_MEAN) { needs_data = true; if (!has_sum) { has_sum = true; ++data_ops; } continue; }
+        if (kind == B2_AGG_MIN || kind == B2_AGG_MAX) { needs_data = true; ++data_ops; continue; }
+        ok = false;
+      }
+      if (!needs_data) continue;
+      const int w = type_width(r.values.type_id);
+      if (w != 4 && w != 8) ok = false;
+      if (pgb_val && (pgb_val->data != r.values.data || pgb_val->offset != r.values.offset || pgb_val->type_id != r.values.type_id)) ok = false;
+      if (pgb_val && ok) ok = false;  // one request carries the data column (keeps the op bookkeeping below one-to-one)
+      pgb_val = &r.values;
+    }
+    use_pgb = ok && data_ops <= PGB_MAX_OPS;
+  }
+  dbuf pgb_keys, pgb_vals, pgb_base, pgb_items;
+  if (use_pgb) {
+    prof_scope ps("groupby_partition", stream);
+    const int vb = pgb_val ? type_width(pgb_val->type_id) : 0;
+    pgb_keys  = dbuf(sizeof(uint64_t) * n, stream);
+    pgb_base  = dbuf(sizeof(uint32_t) * 256, stream);
+    pgb_items = dbuf(sizeof(uint32_t) * 258, stream);
+    const uint64_t* kin = static_cast<const uint64_t*>(gb.keys[0].data) + gb.keys[0].offset;
+    if (vb) {
+      pgb_vals = dbuf((size_t)vb * n, stream);
+      radix_partition_mix_carry(kin, static_cast<const char*>(pgb_val->data) + (size_t)pgb_val->offset * vb, vb, n, pgb_keys.as<uint64_t>(),
+                                pgb_vals.ptr, pgb_base.as<uint32_t>(), stream);
+    } else {  // counts only: the key column doubles as the carried payload
+      pgb_vals = dbuf(sizeof(uint64_t) * n, stream);
+      radix_partition_mix_carry(kin, kin, 8, n, pgb_keys.as<uint64_t>(), pgb_vals.ptr, pgb_base.as<uint32_t>(), stream);
+    }
+  }
+
   // ---- plan the accumulators ----
   struct col_plan { int32_t* vcount = nullptr; bool bumped = false; };
   uint64_t max_slots = 16;
@@ -519,7 +777,44 @@ void groupby_aggregate(const b2_groupby& gb, const std::vector<request_view>& re
       }
     }
 
-    {
+    if (use_pgb) {
+      prof_scope ps("groupby_aggregate", stream);
+      pgb_args pa{};
+      pa.mkeys = pgb_keys.as<uint64_t>();
+      pa.vals  = pgb_val ? pgb_vals.ptr : nullptr;
+      pa.val_bytes = pgb_val ? type_width(pgb_val->type_id) : 0;
+      pa.src_type  = pgb_val ? storage_type(pgb_val->type_id) : B2_INT64;
+      pa.part_base = pgb_base.as<uint32_t>();
+      pa.n = (uint32_t)n;
+      pa.item_start = pgb_items.as<uint32_t>();
+      pa.item_counter = pgb_items.as<uint32_t>() + 257;
+      pa.chunk = 1u << 18;
+      pa.nops = ops.n;
+      for (int k = 0; k < ops.n; ++k) {
+        pa.op[k] = ops.op[k].op; pa.acc[k] = ops.op[k].acc; pa.accum[k] = ops.op[k].accum; pa.init[k] = acc_init(ops.op[k].acc, ops.op[k].op);
+      }
+      pa.smem_slots = ops.n <= 1 ? 8192u : 4096u;
+      {
+        static const uint32_t forced = [] {  // test hook: a tiny shared table exercises the spill to the global table
+          const char* e = std::getenv("B2_GROUPBY_SMEM_SLOTS");
+          uint32_t v = e ? (uint32_t)std::atoi(e) : 0u;
+          while (v & (v - 1)) v &= v - 1;  // power of two
+          return v;
+        }();
+        if (forced >= 16 && forced < pa.smem_slots) pa.smem_slots = forced;
+      }
+      pa.smem_limit = pa.smem_slots * 6 / 10;
+      const size_t smem = (size_t)pa.smem_slots * (8 + 8 * (size_t)ops.n + 4);
+      static bool attr = [] {
+        cudaFuncSetAttribute(pgb_agg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 20);
+        return true;
+      }();
+      (void)attr;
+      B2_CUDA_TRY(cudaMemsetAsync(pa.item_counter, 0, sizeof(uint32_t), stream));
+      B2_LAUNCH(pgb_items_kernel, 1, 256, 0, stream, pa.part_base, pa.n, pa.chunk, pgb_items.as<uint32_t>());
+      B2_LAUNCH(pgb_agg_kernel, NUM_SMS_B200, PGB_THREADS, smem, stream, pa, table.as<slot_t>(), (uint32_t)(slots - 1), cap,
+                gsize.as<int32_t>(), slot_gid.as<int32_t>(), ctl.as<gb_ctl>());
+    } else {
       prof_scope ps("groupby_aggregate", stream);
 #define B2_GB(W, Q)                                                                                                                    \
   B2_LAUNCH((groupby_kernel<W, Q>), grid_for(n), 256, 0, stream, kc, n, skip_null_keys, table.as<slot_t>(), (uint32_t)(slots - 1), cap, \
@@ -539,7 +834,15 @@ void groupby_aggregate(const b2_groupby& gb, const std::vector<request_view>& re
     const int32_t G = (int32_t)h.ngroups;
 
     // ---- outputs ----
-    keys_out = gather_table(gb.keys, rep_rows.as<int32_t>(), G, false, stream);
+    if (use_pgb) {
+      keys_out = std::make_unique<b2_table>();
+      keys_out->cols.push_back(make_column(gb.keys[0].type_id, G, false, stream));
+      if (G > 0)
+        B2_LAUNCH(pgb_keys_kernel, grid_for((int64_t)slots), 256, 0, stream, table.as<slot_t>(), (int64_t)slots, slot_gid.as<int32_t>(),
+                  keys_out->cols[0]->data.as<uint64_t>());
+    } else {
+      keys_out = gather_table(gb.keys, rep_rows.as<int32_t>(), G, false, stream);
+    }
     res_out  = std::make_unique<b2_table>();
     for (size_t q = 0; q < reqs.size(); ++q) {
       const auto& v = reqs[q].values;

@@ -709,6 +709,11 @@ __global__ void finalize_kernel(pass_args a, int64_t n, int raw, int pre_idx_buf
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
       if (carry_bytes == 8) reinterpret_cast<uint64_t*>(a.idx_bufs[0])[i] = static_cast<const uint64_t*>(a.val_in)[i];
       else reinterpret_cast<uint32_t*>(a.idx_bufs[0])[i] = static_cast<const uint32_t*>(a.val_in)[i];
+      if (a.keep_keys && raw) {  // partition passes keep the (mixed) keys next to the payload
+        UK k = static_cast<const UK*>(a.key_bufs[0])[i];
+        if constexpr (MIX) k = (UK)mix64((uint64_t)k);
+        static_cast<UK*>(const_cast<void*>(a.key_bufs[1]))[i] = k;
+      }
     }
     return;
   }
@@ -968,7 +973,7 @@ template <typename UK, int T, int I, int MINB, typename VT = uint32_t, bool CARR
           bool RMW = false, bool BULK = false>
 void run_radix_cfg(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int32_t* idx_tmp, int32_t* idx_tmp2, int pre_idx_buf, int64_t n,
                    int kind, bool descending, bool pairs, cudaStream_t stream, int first_pass = 0, int last_pass = 7,
-                   bool keep_keys = false, const void* val_in = nullptr)
+                   bool keep_keys = false, const void* val_in = nullptr, uint32_t* top_digit_base_out = nullptr)
 {
   constexpr int NP = sizeof(UK);
   constexpr int TILE = T * I;
@@ -1066,6 +1071,8 @@ void run_radix_cfg(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int
   if (pairs && raw && kind == (int)key_kind::FLOAT && descending) {
     B2_LAUNCH(reverse_nan_prefix_kernel, NUM_SMS_B200 * 4, 256, 0, stream, idx_out, &ctl->nan_count);
   }
+  if (top_digit_base_out)  // start offset of every value of the most significant digit (partition boundaries)
+    B2_CUDA_TRY(cudaMemcpyAsync(top_digit_base_out, &ctl->base[0][NP - 1][0], sizeof(uint32_t) * RADIX, cudaMemcpyDeviceToDevice, stream));
 }
 
 int sort_cfg_env()
@@ -1133,6 +1140,23 @@ void radix_partition_top16_mix(const uint64_t* packed_keys, int64_t n, uint64_t*
   dbuf b(sizeof(uint64_t) * n, stream), it(sizeof(int32_t) * n, stream);
   run_radix_cfg<uint64_t, 384, 16, 2, uint32_t, false, true>(packed_keys, keys_out, b.as<uint64_t>(), idx_out, it.as<int32_t>(), nullptr, 0,
                                                              n, (int)key_kind::UNSIGNED, false, true, stream, 6, 7, true);
+}
+
+// One stable partition pass by the top byte of mix64(key), carrying one 4- or 8-byte payload column next to the mixed
+// keys (hash groupby: rows of a group meet in one of 256 partitions; mix64 is undone with unmix64). part_base[d] =
+// first row of partition d.
+void radix_partition_mix_carry(const uint64_t* keys, const void* vals, int val_bytes, int64_t n, uint64_t* mixed_keys_out, void* vals_out,
+                               uint32_t* part_base, cudaStream_t stream)
+{
+  dbuf b(sizeof(uint64_t) * n, stream), vt((size_t)val_bytes * n, stream);
+  if (val_bytes == 8)
+    run_radix_cfg<uint64_t, 384, 16, 2, uint64_t, true, true>(keys, mixed_keys_out, b.as<uint64_t>(), static_cast<int32_t*>(vals_out),
+                                                               vt.as<int32_t>(), nullptr, 0, n, (int)key_kind::UNSIGNED, false, true, stream,
+                                                               7, 7, true, vals, part_base);
+  else
+    run_radix_cfg<uint64_t, 384, 16, 2, uint32_t, true, true>(keys, mixed_keys_out, b.as<uint64_t>(), static_cast<int32_t*>(vals_out),
+                                                               vt.as<int32_t>(), nullptr, 0, n, (int)key_kind::UNSIGNED, false, true, stream,
+                                                               7, 7, true, vals, part_base);
 }
 
 namespace {

@@ -42,7 +42,7 @@ def emu_lib():
 
 def run(code: str, marker: str, env=None, timeout=900):
     e = dict(os.environ)
-    for k in ("B2_SORT_HYBRID", "B2_SORT_HYBRID_MIN", "B2_SORT_CARRY", "B2_SORT_ALIAS", "B2_JOIN_RADIX_ROWS", "B2_JOIN_PARTITION_ROWS", "B2_SORT_CFG", "B2_SORT_PORTION"):
+    for k in ("B2_GROUPBY_PARTITION_ROWS", "B2_GROUPBY_SMEM_SLOTS", "B2_SORT_HYBRID", "B2_SORT_HYBRID_MIN", "B2_SORT_CARRY", "B2_SORT_ALIAS", "B2_JOIN_RADIX_ROWS", "B2_JOIN_PARTITION_ROWS", "B2_SORT_CFG", "B2_SORT_PORTION"):
         e.pop(k, None)
     e.update(env or {})
     r = subprocess.run([sys.executable, "-c", PRELUDE + code], capture_output=True, text=True, env=e, cwd=ROOT, timeout=timeout)
@@ -114,6 +114,15 @@ def test_emu_sort_hybrid(emu_lib):
 
     for env in ({}, {"B2_SORT_CARRY": "0"}):
         run("SIZES = (3, 100, 2047, 2049, 6145, 20011)\n" + CODE, "HYBRID_OK", env=dict(env, B2_SORT_HYBRID_MIN="0"))
+
+
+def test_emu_groupby_partitioned(emu_lib):
+    """Partition + shared-memory aggregation path of the hash groupby, with and without shared-table overflow."""
+    from tests.snippets.partitioned_groupby import CODE
+
+    cases = "CASES = [(1, 1), (100, 7), (5000, 300), (40_000, 20_000), (60_000, 3)]\n"
+    for env in ({}, {"B2_GROUPBY_SMEM_SLOTS": "64"}):
+        run(cases + CODE, "PGB_OK", env=dict(env, B2_GROUPBY_PARTITION_ROWS="1"))
 
 
 def test_emu_sort_alias(emu_lib):
