@@ -1,15 +1,19 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of the hot path (BASELINE.json): rows/s of cudf::sort_by_key on a
-1e9-row int64 column (configs[1]) per GPU, through the pylibcudf-named shim over the C ABI.
+"""bench.py — benchmark of the hot path (BASELINE.json): rows/s of cudf::sort_by_key on a 1e9-row int64 column
+(configs[1]) per GPU through the pylibcudf-named shim over the C ABI, plus (N = 1) the other operations BASELINE's metric
+names — hash inner_join (configs[2]), groupby (configs[3]), scan / reduce — as sub-objects under `ops`, and (N > 1) the
+sharded inner_join (configs[4]) under `sharded_inner_join`.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--rows R] [--impl ours|reference]
 
-One "step" = one sort_by_key(values=T, keys=T) over a resident synthetic column (splitmix64 keys,
-SURVEY §8d).  `value` is device-resident throughput; `e2e` includes the pinned-host -> device copy of
-the keys and the device -> pinned-host copy of the sorted column inside the timed region.
+One "step" = one sort_by_key(values=T, keys=T) over a resident synthetic column (splitmix64 keys); at N > 1
+the sharded sort (sample -> splitters -> range partition -> bucket exchange over NVLink -> local sort).
+`value` is device-resident throughput.  `e2e` is the same call fed from PINNED HOST memory with the sorted column copied
+back to pinned host memory, every step, inside the timed region; the steps are software-pipelined over three streams
+(H2D of step i+1 and D2H of step i-1 overlap the sort of step i; PCIe is full duplex).
 `roofline` is measured live with CUDA events around the one-sweep pass launches (b2_profile_*).
-`cpu_baseline` / `--impl reference` time pandas sort_values (configs[0], the reference's CPU-runnable
-case) on a bounded 1e7-row sample of the same key stream on the host cores.
+`cpu_baseline` / `--impl reference` time pandas (configs[0], the reference's CPU-runnable case) on a bounded 1e7-row
+sample of the same key stream on the host cores.
 Inputs (8 GB per GPU) are far larger than the 126 MB L2, so no explicit L2 flush is needed.
 """
 from __future__ import annotations
@@ -28,6 +32,7 @@ sys.path.insert(0, str(ROOT))
 
 METRIC = "sort_by_key_rows_per_s"
 UNIT = "rows/s"
+SEED_KEYS = 0x5EED0001  # SURVEY §8d seed of the key stream (same constant as oracle/datagen.py; the GPU arm does not import oracle)
 
 
 def parse_args():
@@ -39,13 +44,13 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-rows", type=int, default=10_000_000)
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-alias", action="store_true", help="skip the secondary measurement of the opt-in aliased (keys-only) sort path")
-    ap.add_argument("--extra", action="store_true", help="also time join / groupby / scan / reduce (extra JSON keys)")
+    ap.add_argument("--no-ops", action="store_true", help="skip the per-operation measurements (join / groupby / scan / reduce) at N = 1")
+    ap.add_argument("--no-join", action="store_true", help="skip the sharded inner_join measurement at N > 1")
     return ap.parse_args()
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU baseline (pandas; the oracle's host-side twin of the workload)
+# CPU baseline (pandas; the oracle's host-side twin of the workload) — the one leg that may import oracle/
 # ------------------------------------------------------------------------------------------------
 def cpu_sort_sample(cpu_rows: int, steps: int, warmup: int):
     import numpy as np
@@ -95,8 +100,8 @@ def cpu_sort_sample(cpu_rows: int, steps: int, warmup: int):
 def workload_config(n: int, world: int) -> dict:
     return {"workload": f"{n}-row single int64 column sort_by_key(values=T, keys=T), no nulls, ASCENDING, per GPU "
                         "(BASELINE.json configs[1])" + ("" if world == 1 else f"; sharded over {world} GPUs: sample-sort splitters, stable range "
-                        "partition, bucket exchange (fused peer-memory scatter over NVLink at 2 ranks, NCCL all-to-all-v "
-                        "above), local LSD sort (configs[4])"),
+                        "partition, bucket exchange over NVLink peer memory (fused scatter at 2 ranks, partition + contiguous peer "
+                        "copies above), local radix sort (configs[4])"),
             "rows_per_gpu": n, "l2_flush": "inputs (8 GB/GPU) exceed the 126 MB L2; no explicit flush",
             "generator": "splitmix64(seed 0x5EED0001 + i)"}
 
@@ -179,6 +184,18 @@ class ClockSampler:
         return {"sm_mhz": load[len(load) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def measured_traffic(kernel_key: str):
+    """DRAM bytes per row of one launch of the dominant kernel, from this round's `ncu --set full` capture
+    (profiles/r2_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum at 2^27 rows)."""
+    p = ROOT / "profiles" / "r2_traffic.json"
+    try:
+        e = json.loads(p.read_text())[kernel_key]
+        return float(e["dram_bytes_per_row"]), (f"profiles/r2_traffic.json[{kernel_key}] ({e.get('source', 'ncu --set full')}), "
+                                                "per-row figure x rows of one launch")
+    except Exception:
+        return None, "no ncu capture of this kernel under profiles/ yet"
+
+
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
@@ -201,16 +218,16 @@ def run_ours(args):
     g.build()
     import cudf_b200.pylibcudf as plc
     from cudf_b200 import _lib
-    from oracle import datagen
 
     n = args.rows
     dev = torch.device("cuda", local_rank)
     stream = torch.cuda.current_stream()
     keys = torch.empty(n, dtype=torch.int64, device=dev)
     # disjoint counter range per rank: rank r draws x_i for i in [r*n, (r+1)*n)
-    _lib.check(_lib.lib.b2_fill_splitmix64(C.c_void_p(keys.data_ptr()), n, datagen.SEED_KEYS, rank * n, 0, 0, _lib.stream_arg(None)))
+    _lib.check(_lib.lib.b2_fill_splitmix64(C.c_void_p(keys.data_ptr()), n, SEED_KEYS, rank * n, 0, 0, _lib.stream_arg(None)))
     torch.cuda.synchronize()
 
+    sharded = None
     if world > 1:
         from cudf_b200 import sharded
 
@@ -227,6 +244,12 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     for _ in range(max(args.warmup, 3)):
         out = step()
@@ -247,12 +270,8 @@ def run_ours(args):
         e1.record(stream)
         barrier()
     _lib.lib.b2_profile_enable(0)
-    ms = e0.elapsed_time(e1)
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches = _lib.kernel_launch_count() - launches0
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
     ms_step = ms_total / args.steps
     value = world * n / (ms_step / 1e3)
 
@@ -265,46 +284,71 @@ def run_ours(args):
             peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
         except Exception:
             pass
-    os_ms, os_cnt = _lib.profile_get("onesweep")
-    hist_ms, hist_cnt = _lib.profile_get("histogram")
-    ga_ms, ga_cnt = _lib.profile_get("gather")
-    fix_ms, fix_cnt = _lib.profile_get("segment_fix")
-    # algorithmic bytes of THIS implementation's 8 passes over (int64 key, int32 row id):
-    # pass 1: 8 read + 12 write; passes 2-7: 12 + 12; pass 8: 12 read + 4 write (row ids only) = 180 B/row
+    os_all_ms, os_all_cnt = _lib.profile_get("onesweep")
+    # the host launches one kernel per digit; passes the plan skipped (hybrid plan: the low digits; trivial digits) return at
+    # once — only launches of at least 0.2 ms (at >= 1e8 rows) are executed passes
+    min_ms = 0.2 if n >= 100_000_000 else 0.0
+    os_ms, os_cnt = _lib.profile_get_over("onesweep", min_ms)
+    hist_ms, _ = _lib.profile_get("histogram")
+    ga_ms, _ = _lib.profile_get("gather")
+    fix_ms, fix_cnt = _lib.profile_get_over("segment_fix", min_ms)
     rows_local = n  # per rank; at N > 1 the received shard differs from n by < 1 % (sample-sort splitters)
-    # opt-in sort paths (README "Environment switches") move different bytes per pass; the default is the row-id path
-    if os.environ.get("B2_SORT_ALIAS", "0") not in ("", "0"):
-        sort_path, bytes_8_passes, kernel_name = "aliased keys-only radix (B2_SORT_ALIAS)", 128.0, "onesweep_kernel<uint64, keys only>"
-    elif os.environ.get("B2_SORT_CARRY", "0") not in ("", "0"):
-        sort_path, bytes_8_passes, kernel_name = "payload-carrying radix (B2_SORT_CARRY)", 248.0, "onesweep_kernel<uint64,(key,8-byte payload)>"
+    carry = os.environ.get("B2_SORT_CARRY", "1") != "0"
+    hybrid = fix_cnt > 0
+    if carry:
+        sort_path, pass_bytes_row, kernel_name, tkey = ("(key, 8-byte payload) carried through the passes", 32.0,
+                                                        "onesweep_kernel<uint64,(key,8-byte payload)>", "onesweep_carry")
     else:
-        sort_path, bytes_8_passes, kernel_name = "row ids + gather (default)", 180.0, "onesweep_kernel<uint64,(key,row id)>"
-    default_path = bytes_8_passes == 180.0
+        sort_path, pass_bytes_row, kernel_name, tkey = "(key, row id) passes + gather", 24.0, "onesweep_kernel<uint64,(key,row id)>", "onesweep_rowid"
+    sort_path += "; hybrid plan: LSD passes over the top digits, then the segment fix-up" if hybrid else "; full LSD"
     roofline = None
     if os_cnt and rows_local:
-        per_launch_bytes = bytes_8_passes * rows_local / 8.0
-        # the n-row sort runs 8 passes per step (uniform 64-bit keys: no trivial digit); at N > 1 the splitter sample sort
-        # adds a few microsecond-scale launches per step, whose time stays in the numerator and is negligible
-        big_launches = 8 * args.steps
-        avg_ms = os_ms / big_launches
+        passes_per_step = os_cnt / args.steps
+        per_launch_bytes = pass_bytes_row * rows_local
+        avg_ms = os_ms / os_cnt
         achieved = per_launch_bytes / (avg_ms / 1e3) / 1e9
+        tr_row, tr_src = measured_traffic(tkey)
+        # algorithmic bytes of THIS implementation per row: histogram 8 + executed passes + fix-up (key + payload in, payload out) / gather
+        impl_bytes_row = 8 + passes_per_step * pass_bytes_row + (24 if hybrid and carry else (16 if hybrid else 0)) + (0 if carry else 20)
         roofline = {
             "bound": "hbm", "kernel": kernel_name, "sort_path": sort_path, "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak,
-            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the ncu --set full capture at 2^27 rows
-            # (profiles/r1_onesweep_ncu_e.txt: 1.612 + 1.582 GB per launch = 23.8 B/row), scaled to this launch size
-            "traffic": 23.8 * rows_local if default_path else None,
-            "traffic_source": "ncu capture at 2^27 rows, per-row figure scaled" if default_path else "no ncu capture of this path yet",
+            "traffic": tr_row * rows_local if tr_row else None, "traffic_source": tr_src,
             "peak_source": peak_src, "rank": rank,
-            "algorithmic_bytes_per_launch": per_launch_bytes, "avg_launch_ms": avg_ms, "launches": big_launches, "launches_incl_sample_sort": os_cnt,
+            "algorithmic_bytes_per_launch": per_launch_bytes, "algorithmic_bytes_per_row_per_launch": pass_bytes_row,
+            "avg_launch_ms": avg_ms, "launches": os_cnt, "executed_passes_per_step": passes_per_step,
+            "launches_incl_skipped_and_sample_sort": os_all_cnt,
             "kernel_share_of_step": os_ms / ms_total,
             "whole_op": {"algorithmic_bytes_per_row_contract": 216, "achieved_GBps_contract": 216.0 * rows_local / (ms_step / 1e3) / 1e9,
-                         "frac_contract": 216.0 * rows_local / (ms_step / 1e3) / 1e9 / peak},
+                         "frac_contract": 216.0 * rows_local / (ms_step / 1e3) / 1e9 / peak,
+                         "algorithmic_bytes_per_row_this_algorithm": impl_bytes_row,
+                         "frac_this_algorithm": impl_bytes_row * rows_local / (ms_step / 1e3) / 1e9 / peak,
+                         "note": "contract = SURVEY §8d C2 formula (8-bit LSD, row ids + gather: 216 B/row); this algorithm moves fewer bytes "
+                                 "(BASELINE.md §2 restates its formula)"},
             "other_kernels_ms_per_step": {"histogram": hist_ms / args.steps, "gather": ga_ms / args.steps, "segment_fix": fix_ms / args.steps,
-                                          "onesweep_total": os_ms / args.steps},
+                                          "onesweep_total": os_all_ms / args.steps},
         }
 
-    # ---- e2e: pinned host -> device -> sort_by_key -> pinned host ----
+    # ---- N > 1: per-phase device times of the sharded step (CUDA events inside sharded.py), max over ranks ----
+    phases_ms = None
+    if world > 1:
+        sharded.enable_phase_timing(True)
+        acc = {}
+        reps = 3
+        for _ in range(reps):
+            barrier()
+            out = step()
+            ph = sharded.phases()
+            del out
+            for k_, v_ in ph.items():
+                acc[k_] = acc.get(k_, 0.0) + v_ / reps
+        sharded.enable_phase_timing(False)
+        names = sorted(acc)
+        vals = torch.tensor([acc[k_] for k_ in names], dtype=torch.float64, device=dev)
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        phases_ms = {k_: float(v_) for k_, v_ in zip(names, vals.tolist())}
+
+    # ---- e2e: pinned host -> device -> sort_by_key -> pinned host, software-pipelined over three streams ----
     e2e = None
     if not args.no_e2e:
         try:
@@ -312,8 +356,8 @@ def run_ours(args):
             alloc_err = None
             try:
                 h_in = torch.empty(n, dtype=torch.int64, pin_memory=True)
-                h_out = torch.empty(cap, dtype=torch.int64, pin_memory=True)
-                d_in = torch.empty(n, dtype=torch.int64, device=dev)
+                h_out = [torch.empty(cap, dtype=torch.int64, pin_memory=True) for _ in range(2)]
+                d_in = [torch.empty(n, dtype=torch.int64, device=dev) for _ in range(2)]
             except Exception as ex:  # e.g. not enough pinnable host memory on this rank
                 alloc_err = ex
             ok = torch.tensor([0 if alloc_err else 1], dtype=torch.int32, device=dev)
@@ -323,82 +367,90 @@ def run_ours(args):
                 raise RuntimeError(f"e2e buffers could not be allocated on every rank: {alloc_err!r}")
             h_in.copy_(keys)
             torch.cuda.synchronize()
+            s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
 
-            if world == 1:
-                def e2e_step():
-                    d_in.copy_(h_in, non_blocking=True)
-                    c = plc.Column.from_torch(d_in)
-                    o = plc.sorting.sort_by_key(plc.Table([c]), plc.Table([c]), [plc.Order.ASCENDING], [])
-                    h_out.copy_(o.columns()[0].to_torch(), non_blocking=True)
-                    return o
-            else:
-                def e2e_step():
-                    d_in.copy_(h_in, non_blocking=True)
-                    o = sharded.sort_by_key_sharded(d_in, d_in)
-                    m = min(o.numel(), cap)
-                    h_out[:m].copy_(o[:m], non_blocking=True)
-                    return o
+            def pipeline(k):
+                """k steps; step i: H2D (copy-in stream) -> sort (compute stream) -> D2H (copy-out stream). Buffers are
+                double-buffered; events order the three streams. Every step's copies are issued inside the timed region."""
+                in_ready = [None, None]
+                in_free = [None, None]
+                out_done = [None, None]
+                outs = [None, None]
+                for i in range(k):
+                    b = i & 1
+                    with torch.cuda.stream(s_in):
+                        if in_free[b] is not None:
+                            s_in.wait_event(in_free[b])       # the sort that read this buffer two steps ago has finished
+                        d_in[b].copy_(h_in, non_blocking=True)
+                        in_ready[b] = torch.cuda.Event()
+                        in_ready[b].record(s_in)
+                    stream.wait_event(in_ready[b])
+                    if out_done[b] is not None:
+                        # D2H of step i-2 has finished: pinned buffer b is free, and that step's device output may be released
+                        # (its stream-ordered free lands on the compute stream behind this wait)
+                        stream.wait_event(out_done[b])
+                        outs[b] = None
+                    if world == 1:
+                        c = plc.Column.from_torch(d_in[b])
+                        o = plc.sorting.sort_by_key(plc.Table([c]), plc.Table([c]), [plc.Order.ASCENDING], [])
+                        res = o.columns()[0].to_torch()
+                    else:
+                        o = sharded.sort_by_key_sharded(d_in[b], d_in[b])
+                        res = o
+                    in_free[b] = torch.cuda.Event()
+                    in_free[b].record(stream)
+                    with torch.cuda.stream(s_out):
+                        s_out.wait_event(in_free[b])
+                        m = min(res.numel(), cap)
+                        h_out[b][:m].copy_(res[:m], non_blocking=True)
+                        out_done[b] = torch.cuda.Event()
+                        out_done[b].record(s_out)
+                    outs[b] = (o, res)
+                for ev in out_done:
+                    if ev is not None:
+                        stream.wait_event(ev)
+                return outs
 
-            o = e2e_step()
+            keep = pipeline(2)
             torch.cuda.synchronize()
-            del o
-            k = max(1, min(args.steps, 3))
+            del keep
+            k = max(2, min(args.steps, 6))
             barrier()
             e0.record(stream)
-            for _ in range(k):
-                o = e2e_step()
-                del o
+            keep = pipeline(k)
             e1.record(stream)
             barrier()
-            te = torch.tensor([e0.elapsed_time(e1) / k], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(te, op=dist.ReduceOp.MAX)
-            ems = float(te.item())
-            assert bool((h_out[1:1000001] >= h_out[:1000000]).all())
+            ems = max_over_ranks(e0.elapsed_time(e1) / k)
+            del keep
+            assert bool((h_out[0][1:1000001] >= h_out[0][:1000000]).all()) and bool((h_out[1][1:1000001] >= h_out[1][:1000000]).all())
             e2e = {"value": world * n / (ems / 1e3), "unit": UNIT, "h2d_bytes_per_step": 8 * n * world,
-                   "d2h_bytes_per_step": 8 * n * world, "ms_per_step": ems}
+                   "d2h_bytes_per_step": 8 * n * world, "ms_per_step": ems, "steps": k,
+                   "pipeline": "three streams, double-buffered: H2D(i+1) | sort(i) | D2H(i-1); every step copies its 8 GB/GPU input from "
+                               "pinned host memory and its sorted 8 GB/GPU output back to pinned host memory inside the timed region"}
             del h_in, h_out, d_in
         except Exception as ex:  # e.g. not enough pinnable host memory
             e2e = {"value": None, "unit": UNIT, "error": repr(ex)[:200]}
 
-    # ---- secondary, N = 1 only: the opt-in aliased path (sort_by_key(T, T) of one null-free integer column routed to the
-    # keys-only radix, README "Environment switches"). Reported next to the headline, never as the headline; its output is
-    # compared with the default path's output first.
-    alias = None
-    if world == 1 and not args.no_alias and os.environ.get("B2_SORT_ALIAS", "0") in ("", "0"):
+    # ---- N > 1: sharded inner_join (BASELINE configs[4]) ----
+    sjoin = None
+    if world > 1 and not args.no_join:
         try:
-            ref_out = step().columns()[0].to_torch()
-            os.environ["B2_SORT_ALIAS"] = "1"
-            try:
-                got = step().columns()[0].to_torch()
-                same = bool(torch.equal(got, ref_out))
-                del got, ref_out
-                for _ in range(2):
-                    o = step()
-                    del o
-                torch.cuda.synchronize()
-                k = max(1, min(args.steps, 3))
-                e0.record(stream)
-                for _ in range(k):
-                    o = step()
-                    del o
-                e1.record(stream)
-                torch.cuda.synchronize()
-                ams = e0.elapsed_time(e1) / k
-                alias = {"path": "B2_SORT_ALIAS=1: keys-only radix, no row ids, no gather (opt-in, not the headline)", "ms_per_step": ams,
-                         "rows_per_s": n / (ams / 1e3), "output_equals_default_path": same,
-                         "algorithmic_bytes_per_row": 136, "achieved_GBps": 136.0 * n / (ams / 1e3) / 1e9}
-            finally:
-                os.environ.pop("B2_SORT_ALIAS", None)
+            del keys
+            _lib.check(_lib.lib.b2_trim_pool())
+            sjoin = bench_sharded_join(args, torch, dist, sharded, _lib, C, n, world, rank, dev, barrier, max_over_ranks)
         except Exception as ex:
-            alias = {"error": repr(ex)[:200]}
+            sjoin = {"error": repr(ex)[:300]}
 
-    extra = None
-    if args.extra and world == 1:
+    ops = None
+    if world == 1 and not args.no_ops:
         import bench_extra
 
-        del keys
-        extra = bench_extra.run(plc, _lib, n, peak)
+        del keys, col, tbl
+        _lib.check(_lib.lib.b2_trim_pool())
+        try:
+            ops = bench_extra.run(plc, _lib, n, peak, cpu_rows=args.cpu_rows)
+        except Exception as ex:
+            ops = {"error": repr(ex)[:300]}
 
     if rank == 0:
         cpu_base, _ = cpu_sort_sample(args.cpu_rows, 3, 1)
@@ -410,13 +462,74 @@ def run_ours(args):
             "roofline": roofline, "cpu_baseline": cpu_base, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks.summary(),
         }
-        if alias:
-            line["aliased_keys_only_path"] = alias
-        if extra:
-            line["extra"] = extra
+        if phases_ms is not None:
+            line["phases_ms"] = phases_ms
+        if sjoin is not None:
+            line["sharded_inner_join"] = sjoin
+        if ops is not None:
+            line["ops"] = ops
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_sharded_join(args, torch, dist, sharded, _lib, C, n, world, rank, dev, barrier, max_over_ranks):
+    """configs[4]: inner_join of two row-sharded int64 key columns, n rows per GPU and side, 10 % of the probe rows match a
+    build row (of another rank) exactly once: hash partition of (key, global row id) on both sides -> bucket exchange ->
+    local join -> global row-id pairs. Row-id consistency is checked on the result (as scripts/sharded_check.py does)."""
+    def fill(t, seed, first):
+        _lib.check(_lib.lib.b2_fill_splitmix64(C.c_void_p(t.data_ptr()), t.numel(), seed, first, 0, 0, _lib.stream_arg(None)))
+        return t
+
+    m = n
+    rk = fill(torch.empty(m, dtype=torch.int64, device=dev), 0x5EED0002, rank * m)
+    # probe rank r: every 10th row copies the key of the same row of build rank (r+1) % world; the other rows are fresh keys
+    lk = fill(torch.empty(m, dtype=torch.int64, device=dev), 0x5EED0009, (1 << 45) + rank * m)
+    nxt = (rank + 1) % world
+    chunk = 50_000_000  # multiple of 10: the strided rows line up with the chunk starts
+    for c0 in range(0, m, chunk):
+        c1 = min(m, c0 + chunk)
+        tmp = fill(torch.empty(c1 - c0, dtype=torch.int64, device=dev), 0x5EED0002, nxt * m + c0)
+        lk[c0:c1:10] = tmp[::10]
+        del tmp
+    expected_local = len(range(0, m, 10))
+
+    def step():
+        return sharded.inner_join_sharded(lk, rk)
+
+    jl, jr = step()
+    torch.cuda.synchronize()
+    tot = torch.tensor([jl.numel()], dtype=torch.int64, device=dev)
+    dist.all_reduce(tot)
+    lrank, lrow = jl // m, jl % m
+    consistent = bool((lrow % 10 == 0).all()) and bool((jr == ((lrank + 1) % world) * m + lrow).all())
+    okc = torch.tensor([1 if consistent else 0], dtype=torch.int32, device=dev)
+    dist.all_reduce(okc, op=dist.ReduceOp.MIN)
+    del jl, jr, lrank, lrow
+    k = max(1, min(args.steps, 3))
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(k):
+        o = step()
+        del o
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1) / k)
+    sharded.enable_phase_timing(True)
+    barrier()
+    o = step()
+    ph = sharded.phases()
+    del o
+    sharded.enable_phase_timing(False)
+    names = sorted(ph)
+    vals = torch.tensor([ph[k_] for k_ in names], dtype=torch.float64, device=dev)
+    dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+    return {"metric": "sharded_inner_join_probe_rows_per_s", "value": world * m / (ms / 1e3), "unit": "probe rows/s", "ms_per_step": ms, "steps": k,
+            "rows_per_gpu_per_side": m, "pairs": int(tot.item()), "pairs_expected": world * expected_local,
+            "row_ids_consistent": bool(int(okc.item())), "phases_ms": {k_: float(v_) for k_, v_ in zip(names, vals.tolist())},
+            "workload": f"inner_join of two int64 key columns, {m} rows per GPU and side, 10 % of probe rows match once; (key, global row id) "
+                        "hash-partitioned and exchanged over NVLink peer memory, local join, global row-id pairs (BASELINE configs[4])"}
 
 
 def main():

@@ -110,6 +110,7 @@ _sig("b2_trim_pool", [])
 _sig("b2_profile_enable", [i32], None)
 _sig("b2_profile_reset", [], None)
 _sig("b2_profile_get", [C.c_char_p, P(C.c_double), P(C.c_int64)])
+_sig("b2_profile_get_over", [C.c_char_p, C.c_double, P(C.c_double), P(C.c_int64)])
 _sig("b2_bitmask_allocation_size_bytes", [i32], C.c_size_t)
 _sig("b2_create_null_mask", [i32, i32, b2_stream, P(vp)])
 _sig("b2_set_null_mask", [vp, i32, i32, i32, b2_stream])
@@ -151,6 +152,7 @@ _sig("b2_ipc_alloc", [C.c_size_t, P(vp), u8p])
 _sig("b2_ipc_open", [u8p, P(vp)])
 _sig("b2_ipc_close", [vp])
 _sig("b2_ipc_free", [vp])
+_sig("b2_peer_copy", [vp, vp, C.c_size_t, b2_stream])
 _sig("b2_fill_splitmix64", [vp, C.c_int64, C.c_uint64, C.c_int64, i32, C.c_uint64, b2_stream])
 
 # every symbol the header declares, for the loader test
@@ -169,7 +171,7 @@ DECLARED_SYMBOLS = [
     "b2_hash_join_partitioned_join", "b2_hash_join_finalize_full_join", "b2_groupby_create", "b2_groupby_destroy",
     "b2_groupby_aggregate", "b2_groupby_scan", "b2_reduce", "b2_segmented_reduce", "b2_scan", "b2_partition",
     "b2_partition_plan_create", "b2_partition_scatter", "b2_partition_scatter_staged", "b2_partition_plan_free", "b2_ipc_alloc", "b2_ipc_open", "b2_ipc_close",
-    "b2_ipc_free",
+    "b2_ipc_free", "b2_peer_copy", "b2_profile_get_over",
     "b2_fill_splitmix64",
 ]
 
@@ -199,4 +201,11 @@ def kernel_launch_count() -> int:
 def profile_get(name: str):
     ms, cnt = C.c_double(0), C.c_int64(0)
     check(lib.b2_profile_get(name.encode(), C.byref(ms), C.byref(cnt)))
+    return ms.value, cnt.value
+
+
+def profile_get_over(name: str, min_ms: float):
+    """(total ms, count) of the profiled scopes `name` that lasted at least min_ms."""
+    ms, cnt = C.c_double(0), C.c_int64(0)
+    check(lib.b2_profile_get_over(name.encode(), float(min_ms), C.byref(ms), C.byref(cnt)))
     return ms.value, cnt.value

@@ -157,6 +157,23 @@ b2_status b2_profile_get(const char* name, double* total_ms, int64_t* launches)
   *total_ms = t; *launches = c;
   B2_TRY_END
 }
+b2_status b2_profile_get_over(const char* name, double min_ms, double* total_ms, int64_t* launches)
+{
+  B2_TRY_BEGIN
+  B2_EXPECTS(name && total_ms && launches, B2_ERR_INVALID_ARGUMENT, "null argument");
+  B2_CUDA_TRY(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  double t = 0; int64_t c = 0;
+  for (auto& r : g_prof) {
+    if (r.name != name) continue;
+    float ms = 0;
+    B2_CUDA_TRY(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    if (ms < min_ms) continue;
+    t += ms; ++c;
+  }
+  *total_ms = t; *launches = c;
+  B2_TRY_END
+}
 b2_status b2_trim_pool(void)
 {
   B2_TRY_BEGIN

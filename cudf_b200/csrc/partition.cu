@@ -428,6 +428,37 @@ b2_status b2_ipc_free(void* ptr)
 
 }  // extern "C"
 
+namespace b2 {
+namespace {
+// grid-stride copy: 16-byte vectors when both ends are 16-byte aligned, bytes for the ragged ends
+__global__ void __launch_bounds__(256) peer_copy_kernel(char* __restrict__ dst, const char* __restrict__ src, size_t bytes)
+{
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t head = (16 - (reinterpret_cast<uintptr_t>(src) & 15)) & 15;
+  if (head > bytes) head = bytes;
+  const bool vec = ((reinterpret_cast<uintptr_t>(dst) + head) & 15) == 0;
+  const size_t nvec = vec ? (bytes - head) / 16 : 0;
+  for (size_t i = tid; i < head; i += stride) dst[i] = src[i];
+  const int4* s4 = reinterpret_cast<const int4*>(src + head);
+  int4* d4 = reinterpret_cast<int4*>(dst + head);
+  for (size_t i = tid; i < nvec; i += stride) st_na_v4(d4 + i, ld_nc_v4(s4 + i));
+  for (size_t i = head + nvec * 16 + tid; i < bytes; i += stride) dst[i] = src[i];
+}
+}  // namespace
+}  // namespace b2
+
+extern "C" b2_status b2_peer_copy(void* dst, const void* src, size_t bytes, b2_stream stream)
+{
+  B2_TRY_BEGIN
+    B2_EXPECTS(bytes == 0 || (dst && src), B2_ERR_INVALID_ARGUMENT, "null argument");
+    if (bytes == 0) return B2_OK;
+    const int grid = (int)std::max<size_t>(1, std::min<size_t>((bytes / 16 + 255) / 256, (size_t)b2::NUM_SMS_B200 * 8));
+    b2::prof_scope ps("peer_copy", static_cast<cudaStream_t>(stream));
+    B2_LAUNCH(b2::peer_copy_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream), static_cast<char*>(dst), static_cast<const char*>(src), bytes);
+  B2_TRY_END
+}
+
 // EXPERIMENTAL (see scatter_to_staged_kernel): same contract as b2_partition_scatter.
 extern "C" b2_status b2_partition_scatter_staged(const b2_partition_plan* plan, const b2_column_view* column, void* const* dest_ptrs,
                                                  b2_stream stream)

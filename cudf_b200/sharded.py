@@ -23,29 +23,60 @@ import torch
 import torch.distributed as dist
 
 _TIMING = os.environ.get("B2_SHARD_TIMING", "0") == "1"
+last_phases_ms: dict = {}   # phases of the most recent sharded call on this rank (filled when timing is on)
+
+
+def enable_phase_timing(on: bool = True):
+    """bench.py switches this on: phases are bracketed by CUDA events on the current stream (no extra synchronisation
+    inside the step); `last_phases_ms` is resolved by phases() after the caller has synchronised."""
+    global _TIMING
+    _TIMING = bool(on)
 
 
 class _Phase:
-    """Optional wall-clock phase timing (B2_SHARD_TIMING=1): synchronises the device around each phase."""
+    """Phase timing of a sharded call: CUDA events on the current stream when a GPU is present, wall clock on CPU."""
 
     def __init__(self):
-        self.t = {}
-        self._last = None
+        self.marks = []
 
     def mark(self, name):
         if not _TIMING:
             return
         if torch.cuda.is_available():
-            torch.cuda.synchronize()
-        now = time.perf_counter()
-        if self._last is not None:
-            self.t[self._last[0]] = self.t.get(self._last[0], 0.0) + (now - self._last[1]) * 1e3
-        self._last = (name, now)
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self.marks.append((name, e))
+        else:
+            self.marks.append((name, time.perf_counter()))
 
     def done(self, tag):
         self.mark("_end")
-        if _TIMING and dist.get_rank() == 0:
-            print(f"[{tag}] " + " ".join(f"{k}={v:.1f}ms" for k, v in self.t.items() if k != "_end"), flush=True)
+        if not _TIMING:
+            return
+        global _pending
+        _pending = (tag, self.marks)
+
+
+_pending = None
+
+
+def phases() -> dict:
+    """Resolve the phase times of the last sharded call (synchronises the device)."""
+    global _pending, last_phases_ms
+    if _pending is None:
+        return last_phases_ms
+    tag, marks = _pending
+    _pending = None
+    out = {}
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    for (name, a), (_, b) in zip(marks[:-1], marks[1:]):
+        ms = a.elapsed_time(b) if torch.cuda.is_available() else (b - a) * 1e3
+        out[name] = out.get(name, 0.0) + ms
+    last_phases_ms = out
+    if os.environ.get("B2_SHARD_TIMING", "0") == "1" and dist.get_rank() == 0:
+        print(f"[{tag}] " + " ".join(f"{k}={v:.1f}ms" for k, v in out.items()), flush=True)
+    return out
 
 
 class CudaOps:
@@ -94,7 +125,8 @@ class CudaOps:
             recv_total = int(cm[:, rank].sum())
             max_recv = int(cm.sum(dim=0).max())
             esz = column.element_size()
-            ex = PeerExchange.get(lib, int(max(max_recv, key.numel()) * esz * 1.05) + (1 << 20), group)
+            max_send = int(cm.sum(dim=1).max())                    # every rank sees the same matrix: the capacity is agreed
+            ex = PeerExchange.get(lib, int(max(max_recv, max_send) * esz * 1.05) + (1 << 20), group)
             my_off = cm[:rank, :].sum(dim=0)                          # rows written before mine in each destination
             dest = (C.c_void_p * world)(*[ex.peer_ptrs[d] + int(my_off[d]) * esz for d in range(world)])
             dist.barrier(group=group)                                 # peers are done reading the previous contents
@@ -170,13 +202,29 @@ class PeerExchange:
         dist.barrier(group=group)
 
     @classmethod
-    def get(cls, lib, capacity_bytes: int, group=None) -> "PeerExchange":
-        key = (id(group), dist.get_world_size(group))
+    def get(cls, lib, capacity_bytes: int, group=None, slot: int = 0) -> "PeerExchange":
+        """`capacity_bytes` must be computed from values every rank agrees on (the all-gathered count matrix): the
+        constructor runs collectives, so all ranks have to take the same branch here."""
+        key = (id(group), dist.get_world_size(group), slot)
         cur = cls._cache.get(key)
         if cur is None or cur.capacity < capacity_bytes:
-            cur = cls(lib, capacity_bytes, group)  # a larger buffer replaces the cached one (the old mapping stays alive)
+            if cur is not None:
+                cur.close()
+            cur = cls(lib, capacity_bytes, group)
             cls._cache[key] = cur
         return cur
+
+    def close(self):
+        """Unmap the peers' buffers and free ours (all ranks call this together, before the replacement is built)."""
+        rank = dist.get_rank(self.group)
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)  # nobody still writes into the old buffers
+        for r, p in enumerate(self.peer_ptrs):
+            if r != rank and p:
+                self._lib.lib.b2_ipc_close(C.c_void_p(p))
+        dist.barrier(group=self.group)  # every mapping is closed before the owner frees
+        self._lib.lib.b2_ipc_free(C.c_void_p(self.local_ptr))
+        self.peer_ptrs, self.local_ptr = [], None
 
     def view(self, nelems: int, dtype: torch.dtype) -> torch.Tensor:
         import numpy as np
@@ -197,6 +245,43 @@ def _exchange(buckets: torch.Tensor, offsets, group=None) -> torch.Tensor:
     out = torch.empty(sum(recv_l), dtype=buckets.dtype, device=buckets.device)
     dist.all_to_all_single(out, buckets, output_split_sizes=recv_l, input_split_sizes=send_l, group=group)
     return out
+
+
+def _exchange_peer(cols, offsets, lib, group=None, slot_base: int = 0):
+    """all-to-all-v of the contiguous buckets of several columns over peer memory: every rank copies bucket d straight into
+    rank d's receive buffer (CUDA-IPC mapped, b2_peer_copy: one contiguous run per destination, so NVLink sees large
+    sequential writes). Returns the received columns (views of the exchange buffers of slots slot_base.., valid until
+    the next exchange that uses the same slot)."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = cols[0].device
+    mine = torch.tensor([offsets[i + 1] - offsets[i] for i in range(world)], dtype=torch.int64, device=dev)
+    allc = torch.empty(world * world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(allc, mine, group=group)
+    cm = allc.view(world, world).cpu()                          # cm[r][d] = rows rank r sends to rank d
+    recv_total = int(cm[:, rank].sum())
+    cap_rows = max(int(cm.sum(dim=0).max()), int(cm.sum(dim=1).max()))
+    my_off = cm[:rank, :].sum(dim=0)                              # rows written before mine in each destination
+    exs = [PeerExchange.get(lib, int(cap_rows * c.element_size() * 1.05) + (1 << 20), group, slot=slot_base + j) for j, c in enumerate(cols)]
+    dist.barrier(group=group)                                     # peers are done reading the previous contents
+    st = lib.stream_arg(None)
+    for j, c in enumerate(cols):
+        esz = c.element_size()
+        for step in range(world):                                 # staggered: at any time every rank writes to a different peer
+            d = (rank + step) % world
+            cnt = int(cm[rank][d])
+            if cnt:
+                lib.check(lib.lib.b2_peer_copy(C.c_void_p(exs[j].peer_ptrs[d] + int(my_off[d]) * esz),
+                                               C.c_void_p(c.data_ptr() + int(offsets[d]) * esz), cnt * esz, st))
+    dist.barrier(group=group)                                     # stream-ordered after the copies: all buckets landed
+    return [ex.view(recv_total, c.dtype) for ex, c in zip(exs, cols)]
+
+
+def _exchange_cols(cols, offsets, ops, group=None, slot_base: int = 0):
+    """Bucket exchange of partitioned columns: peer copies on GPUs (B2_SHARD_XCHG=nccl selects all_to_all_single), the
+    process group's all-to-all on CPU (gloo tests)."""
+    if cols[0].is_cuda and hasattr(ops, "_lib") and os.environ.get("B2_SHARD_XCHG", "peer") != "nccl":
+        return _exchange_peer(cols, offsets, ops._lib, group, slot_base)
+    return [_exchange(c, offsets, group) for c in cols]
 
 
 def choose_splitters(samples_sorted: torch.Tensor, world: int) -> torch.Tensor:
@@ -241,8 +326,9 @@ def sort_by_key_sharded(values: torch.Tensor, keys: torch.Tensor, ops=None, grou
         ph.mark("partition")
         cols, offsets = ops.partition([keys] if same else [keys, values], keys, 0, splitters, world)
         ph.mark("exchange")
-        rk = _exchange(cols[0], offsets, group)
-        rv = rk if same else _exchange(cols[1], offsets, group)
+        recv = _exchange_cols(cols, offsets, ops, group)
+        rk = recv[0]
+        rv = rk if same else recv[1]
         del cols
     ph.mark("local_sort")
     out = ops.sort_by_key(rv, rk)
@@ -262,17 +348,25 @@ def inner_join_sharded(left_keys: torch.Tensor, right_keys: torch.Tensor, ops=No
         base = int(sum(int(c.item()) for c in allc[:rank]))
         return torch.arange(base, base + t.numel(), dtype=torch.int64, device=t.device)
 
-    def shuffle(keys):
+    def shuffle(keys, slot_base):
         gid = global_ids(keys)
         if world == 1:
             return keys, gid
+        ph.mark("partition")
         cols, offsets = ops.partition([keys, gid], keys, 1, None, world)
-        return _exchange(cols[0], offsets, group), _exchange(cols[1], offsets, group)
+        ph.mark("exchange")
+        got = _exchange_cols(cols, offsets, ops, group, slot_base)  # each side has its own pair of exchange buffers
+        return got[0], got[1]
 
-    lk, lg = shuffle(left_keys)
-    rk, rg = shuffle(right_keys)
+    ph = _Phase()
+    lk, lg = shuffle(left_keys, 0)
+    rk, rg = shuffle(right_keys, 2)
+    ph.mark("local_join")
     li, ri = ops.inner_join(lk, rk)
-    return lg[li.long()], rg[ri.long()]
+    ph.mark("row_ids")
+    out = lg[li.long()], rg[ri.long()]
+    ph.done("inner_join_sharded")
+    return out
 
 
 def reduce_sharded(col: torch.Tensor, kind: str = "sum", ops=None, group=None):

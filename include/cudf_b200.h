@@ -119,6 +119,8 @@ B2_API uint64_t b2_kernel_launch_count(void);
 B2_API void      b2_profile_enable(int32_t on);
 B2_API void      b2_profile_reset(void);
 B2_API b2_status b2_profile_get(const char* name, double* total_ms, int64_t* launches);
+/* same, restricted to the scopes that took at least `min_ms` (separates executed radix passes from skipped ones) */
+B2_API b2_status b2_profile_get_over(const char* name, double min_ms, double* total_ms, int64_t* launches);
 /* Trim the stream-ordered pool back to the driver (rmm pool release analogue). */
 B2_API b2_status b2_trim_pool(void);
 
@@ -310,6 +312,10 @@ B2_API b2_status b2_ipc_alloc(size_t bytes, void** out_ptr, uint8_t* out_handle6
 B2_API b2_status b2_ipc_open(const uint8_t* handle64, void** out_ptr);
 B2_API b2_status b2_ipc_close(void* ptr);
 B2_API b2_status b2_ipc_free(void* ptr);
+/* Copy `bytes` (any alignment) from local device memory to `dst`, which may be PEER memory mapped with b2_ipc_open: a
+ * plain copy kernel whose stores travel over NVLink (the bucket exchange after b2_partition: one contiguous run per
+ * destination rank). Stream-ordered. */
+B2_API b2_status b2_peer_copy(void* dst, const void* src, size_t bytes, b2_stream stream);
 
 /* ---- synthetic data (SURVEY §8d generator): x_i = splitmix64(seed + first + i) -------------- */
 /* kind 0: raw uint64 -> int64 ; 1: float64 uniform [0,1) ; 2: x mod modulus as int64 ;

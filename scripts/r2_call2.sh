@@ -11,15 +11,15 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > 
 step tests_hybrid 600 python -m pytest tests/test_sort_hybrid_gpu.py -q -m gpu -x
 B2_RUN_EXPERIMENTAL=1 step tests_experimental 900 python -m pytest tests/test_zz_experimental_gpu.py -q -m gpu -rxX
 step tests_all 1200 python -m pytest tests -q -m gpu -x --ignore tests/test_zz_experimental_gpu.py --ignore tests/test_sort_hybrid_gpu.py
-step bench 600 python bench.py --no-e2e --no-alias
-B2_SORT_HYBRID=0 B2_SORT_CARRY=0 step bench_r1path 400 python bench.py --no-e2e --no-alias --steps 3 --cpu-rows 100000
-B2_SORT_HYBRID=0 B2_SORT_CARRY=1 step bench_carry_only 400 python bench.py --no-e2e --no-alias --steps 3 --cpu-rows 100000
-B2_SORT_HYBRID=1 B2_SORT_CARRY=0 step bench_hybrid_only 400 python bench.py --no-e2e --no-alias --steps 3 --cpu-rows 100000
-B2_SORT_CFG=10 step bench_cfg10 400 python bench.py --no-e2e --no-alias --steps 3 --cpu-rows 100000
-B2_SORT_CFG=11 step bench_cfg11 400 python bench.py --no-e2e --no-alias --steps 3 --cpu-rows 100000
-step bench_extra 900 python bench.py --extra --no-e2e --no-alias --steps 3 --cpu-rows 100000
+step bench 600 python bench.py --no-e2e --no-ops
+B2_SORT_HYBRID=0 B2_SORT_CARRY=0 step bench_r1path 400 python bench.py --no-e2e --no-ops --steps 3 --cpu-rows 100000
+B2_SORT_HYBRID=0 B2_SORT_CARRY=1 step bench_carry_only 400 python bench.py --no-e2e --no-ops --steps 3 --cpu-rows 100000
+B2_SORT_HYBRID=1 B2_SORT_CARRY=0 step bench_hybrid_only 400 python bench.py --no-e2e --no-ops --steps 3 --cpu-rows 100000
+B2_SORT_CFG=10 step bench_cfg10 400 python bench.py --no-e2e --no-ops --steps 3 --cpu-rows 100000
+B2_SORT_CFG=11 step bench_cfg11 400 python bench.py --no-e2e --no-ops --steps 3 --cpu-rows 100000
+step bench_extra 900 python bench.py --no-e2e --steps 3
 step ncu_launches 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file "$O/bench_launches.csv" \
-  python bench.py --steps 2 --warmup 1 --no-e2e --no-alias --cpu-rows 100000
+  python bench.py --steps 2 --warmup 1 --no-e2e --no-ops --cpu-rows 100000
 R=134217728
 cap() {  # cap <name> <kernel regex> <skip> <count> <env...> -- <op>
   local name=$1 rx=$2 skip=$3 cnt=$4; shift 4
