@@ -70,7 +70,7 @@ def _build_locked(force: bool, verbose: bool) -> Path:
 
     with ThreadPoolExecutor(max_workers=min(8, len(sources))) as ex:
         objs = list(ex.map(compile_one, sources))
-    cmd = [NVCC, "-shared", "-o", str(LIB), *map(str, objs), "-lcudart"]
+    cmd = [NVCC, "-shared", "-o", str(LIB), *map(str, objs), "-lcudart", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

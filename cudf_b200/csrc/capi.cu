@@ -38,21 +38,22 @@ prof_scope::~prof_scope()
 }
 
 // ---- allocator ----------------------------------------------------------------------------------
+// Per device, on first allocation: keep freed blocks cached in the stream-ordered pool (like an rmm pool resource).
+// B2_L2_FETCH=<32|64|128> additionally sets cudaLimitMaxL2FetchGranularity — opt-in, because it is a device-wide setting
+// shared with every other library in the process (measured: no effect on the random-access kernels of this library).
 static void init_pool_once()
 {
-  static std::once_flag once;
-  std::call_once(once, [] {
+  static std::atomic<uint64_t> done{0};
+  once_per_device(done, [] {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return;
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-      uint64_t thr = UINT64_MAX;  // keep freed blocks cached in the pool (like an rmm pool resource)
+      uint64_t thr = UINT64_MAX;
       cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
-    // Random 8-byte accesses (gather, hash probes) otherwise pull 128 B per miss from HBM (measured:
-    // 122 B/row in the sort_by_key gather); streaming kernels use whole lines either way.
     const char* e = std::getenv("B2_L2_FETCH");
-    size_t gran = e ? (size_t)std::atoi(e) : 32;
+    const size_t gran = e ? (size_t)std::atoi(e) : 0;
     if (gran) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
   });
 }

@@ -49,8 +49,36 @@ struct error : std::exception {
 
 void set_last_error(const char* msg);
 
+// NVTX range over every C-ABI entry point (role of CUDF_FUNC_RANGE, cpp/include/cudf/detail/nvtx/ranges.hpp:50): header-only
+// NVTX v3, a no-op unless a profiler is attached.
+#ifndef B2_EMU
+}  // namespace b2
+#include <nvtx3/nvToolsExt.h>
+namespace b2 {
+struct nvtx_range {
+  explicit nvtx_range(const char* name) { nvtxRangePushA(name); }
+  ~nvtx_range() { nvtxRangePop(); }
+};
+#else
+struct nvtx_range {
+  explicit nvtx_range(const char*) {}
+};
+#endif
+
+// One-time per-device setup (function attributes, pool / limit settings): `done` is a bit mask over device ordinals.
+template <typename F>
+inline void once_per_device(std::atomic<uint64_t>& done, F&& f)
+{
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return;
+  const uint64_t bit = 1ull << (dev & 63);
+  if (done.load(std::memory_order_acquire) & bit) return;
+  f();
+  done.fetch_or(bit, std::memory_order_release);
+}
+
 // The extern "C" boundary: every entry point body sits between these two (status code + thread-local message).
-#define B2_TRY_BEGIN try {
+#define B2_TRY_BEGIN try { ::b2::nvtx_range b2_nvtx_range__(__func__);
 #define B2_TRY_END                                                                           \
   }                                                                                          \
   catch (const ::b2::error& e) { ::b2::set_last_error(e.what()); return e.code; }            \

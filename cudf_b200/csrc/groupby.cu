@@ -805,11 +805,8 @@ void groupby_aggregate(const b2_groupby& gb, const std::vector<request_view>& re
       }
       pa.smem_limit = pa.smem_slots * 6 / 10;
       const size_t smem = (size_t)pa.smem_slots * (8 + 8 * (size_t)ops.n + 4);
-      static bool attr = [] {
-        cudaFuncSetAttribute(pgb_agg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 20);
-        return true;
-      }();
-      (void)attr;
+      static std::atomic<uint64_t> attr_done{0};
+      once_per_device(attr_done, [] { B2_CUDA_TRY(cudaFuncSetAttribute(pgb_agg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 20)); });
       B2_CUDA_TRY(cudaMemsetAsync(pa.item_counter, 0, sizeof(uint32_t), stream));
       B2_LAUNCH(pgb_items_kernel, 1, 256, 0, stream, pa.part_base, pa.n, pa.chunk, pgb_items.as<uint32_t>());
       B2_LAUNCH(pgb_agg_kernel, NUM_SMS_B200, PGB_THREADS, smem, stream, pa, table.as<slot_t>(), (uint32_t)(slots - 1), cap,

@@ -244,14 +244,13 @@ bool radix_join_applicable(const std::vector<b2_column_view>& a, const std::vect
 void radix_join(const std::vector<b2_column_view>& build, const std::vector<b2_column_view>& probe, bool left, cudaStream_t stream,
                 column_ptr& out_probe, column_ptr& out_build)
 {
-  static bool attr_set = [] {
-    cudaFuncSetAttribute(rj_join_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RJ_SMEM);
-    cudaFuncSetAttribute(rj_join_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RJ_SMEM);
-    cudaFuncSetAttribute(rj_join_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RJ_SMEM);
-    cudaFuncSetAttribute(rj_join_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RJ_SMEM);
-    return true;
-  }();
-  (void)attr_set;
+  static std::atomic<uint64_t> attr_done{0};
+  once_per_device(attr_done, [] {
+    B2_CUDA_TRY(cudaFuncSetAttribute(rj_join_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RJ_SMEM));
+    B2_CUDA_TRY(cudaFuncSetAttribute(rj_join_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RJ_SMEM));
+    B2_CUDA_TRY(cudaFuncSetAttribute(rj_join_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RJ_SMEM));
+    B2_CUDA_TRY(cudaFuncSetAttribute(rj_join_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RJ_SMEM));
+  });
   rj_side bs, ps;
   rj_partition(build, stream, bs);
   rj_partition(probe, stream, ps);

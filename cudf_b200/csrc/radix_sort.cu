@@ -996,12 +996,11 @@ void run_radix_cfg(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int
   auto* counters  = reinterpret_cast<uint32_t*>(static_cast<char*>(work.ptr) + ctl_bytes + hist_bytes);
   auto* status    = reinterpret_cast<uint32_t*>(static_cast<char*>(work.ptr) + ctl_bytes + hist_bytes + cnt_bytes);
 
-  static bool attr_set = [] {
-    cudaFuncSetAttribute(onesweep_kernel<UK, T, I, MINB, VT, CARRY, MIX, SAFE, RMW, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)onesweep_smem<UK, T, I, VT>());
-    return true;
-  }();
-  (void)attr_set;
+  static std::atomic<uint64_t> attr_done{0};  // per device: the opt-in to > 48 KB of dynamic shared memory is a per-context setting
+  once_per_device(attr_done, [] {
+    B2_CUDA_TRY(cudaFuncSetAttribute(onesweep_kernel<UK, T, I, MINB, VT, CARRY, MIX, SAFE, RMW, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)onesweep_smem<UK, T, I, VT>()));
+  });
 
   // Hybrid plan (64-bit raw keys, full sort): LSD passes over the top digits only, then segment_fix_kernel. The plan
   // kernel decides on the device; the host learns the outcome from one 4-byte read-back after the fix-up.

@@ -91,3 +91,95 @@ def test_inner_join_1e9_properties(plc):
     assert nhit <= l.numel() <= nhit + 1000
     assert bool((lk[l] == rk[r]).all())
     _lib.check(_lib.lib.b2_trim_pool())
+
+
+# ---- oracle-exact comparisons at SURVEY §8c sizes (numpy on the host cores; tens of seconds each) ----------------------
+def test_sort_1e8_exact_vs_numpy_stable(plc):
+    """sorted_order and sort_by_key of 1e8 uniform int64 keys, bit-exact against np.argsort(kind='stable')."""
+    import numpy as np
+    import torch
+
+    from cudf_b200 import _lib
+
+    n = 100_000_000
+    keys = _fill(_lib, torch.empty(n, dtype=torch.int64, device="cuda"), n, 0)
+    vals = _fill(_lib, torch.empty(n, dtype=torch.float64, device="cuda"), n, 8, kind=1)
+    kt = plc.Table([plc.Column.from_torch(keys)])
+    order = plc.sorting.sorted_order(kt, [plc.Order.ASCENDING], []).to_torch().cpu().numpy()
+    got = plc.sorting.sort_by_key(plc.Table([plc.Column.from_torch(vals)]), kt, [plc.Order.ASCENDING], []).columns()[0].to_torch().cpu().numpy()
+    hk, hv = keys.cpu().numpy(), vals.cpu().numpy()
+    exp = np.argsort(hk, kind="stable")
+    assert order.dtype == np.int32 and np.array_equal(order, exp.astype(np.int32))
+    assert np.array_equal(got, hv[exp])
+    # a duplicate-heavy column of the same size (ties keep input order): keys mod 1000
+    dk = _fill(_lib, torch.empty(n, dtype=torch.int64, device="cuda"), n, 9, kind=2, modulus=1000)
+    order = plc.sorting.sorted_order(plc.Table([plc.Column.from_torch(dk)]), [plc.Order.DESCENDING], []).to_torch().cpu().numpy()
+    hd = dk.cpu().numpy()
+    exp = np.argsort(-hd, kind="stable")
+    assert np.array_equal(order, exp.astype(np.int32))
+    _lib.check(_lib.lib.b2_trim_pool())
+
+
+@pytest.mark.parametrize("path", ["default", "hash_table", "partitioned"])
+def test_inner_join_3e7_canonical_pairs_exact(plc, path):
+    """BASELINE configs[2] shape at 3e7 x 3e7 rows: canonical-sorted (left, right) pairs equal the oracle's, for the default
+    path choice and for each join path forced."""
+    import os
+
+    import numpy as np
+    import torch
+
+    from cudf_b200 import _lib
+    from oracle import join as ojoin
+
+    n = 30_000_000
+    rk = _fill(_lib, torch.empty(n, dtype=torch.int64, device="cuda"), n, 1)
+    lk = _fill(_lib, torch.empty(n, dtype=torch.int64, device="cuda"), n, 6)
+    u = _fill(_lib, torch.empty(n, dtype=torch.float64, device="cuda"), n, 5, kind=1)
+    sel = _fill(_lib, torch.empty(n, dtype=torch.int64, device="cuda"), n, 4, kind=2, modulus=n)
+    hit = u < 0.10
+    lk[hit] = rk[sel[hit]]
+    lk[::1000] = lk[7]  # a probe-side hot key as well
+    prev = os.environ.get("B2_JOIN_RADIX_ROWS")
+    if path != "default":
+        os.environ["B2_JOIN_RADIX_ROWS"] = "0" if path == "hash_table" else "1000000"
+    try:
+        li, ri = plc.join.inner_join(plc.Table([plc.Column.from_torch(lk)]), plc.Table([plc.Column.from_torch(rk)]), plc.NullEquality.EQUAL)
+    finally:
+        if prev is None:
+            os.environ.pop("B2_JOIN_RADIX_ROWS", None)
+        else:
+            os.environ["B2_JOIN_RADIX_ROWS"] = prev
+    got = ojoin.canonical(li.to_torch().cpu().numpy(), ri.to_torch().cpu().numpy())
+    exp = ojoin.inner_join([(lk.cpu().numpy(), None)], [(rk.cpu().numpy(), None)])
+    assert np.array_equal(got[0], exp[0]) and np.array_equal(got[1], exp[1])
+    _lib.check(_lib.lib.b2_trim_pool())
+
+
+def test_groupby_1e9_per_group_exact(plc):
+    """BASELINE configs[3] at full size: every group's COUNT bit-exact and SUM(float64) within 1e-9 relative of np.bincount."""
+    import numpy as np
+    import torch
+
+    from cudf_b200 import _lib
+
+    if not _enough_memory(torch, 60):
+        pytest.skip("needs ~60 GB of free HBM")
+    G = 1_000_000
+    k = _fill(_lib, torch.empty(N, dtype=torch.int64, device="cuda"), N, 9, kind=2, modulus=G)
+    v = _fill(_lib, torch.empty(N, dtype=torch.float64, device="cuda"), N, 8, kind=1)
+    c = _fill(_lib, torch.empty(N, dtype=torch.int32, device="cuda"), N, 10, kind=3)
+    gb = plc.groupby.GroupBy(plc.Table([plc.Column.from_torch(k)]))
+    agg = plc.aggregation
+    keys_out, res = gb.aggregate([plc.groupby.GroupByRequest(plc.Column.from_torch(v), [agg.sum()]),
+                                  plc.groupby.GroupByRequest(plc.Column.from_torch(c), [agg.count()])])
+    gk = keys_out.columns()[0].to_torch().cpu().numpy()
+    gs = res[0].columns()[0].to_torch().cpu().numpy()
+    gc = res[1].columns()[0].to_torch().cpu().numpy()
+    hk, hv = k.cpu().numpy(), v.cpu().numpy()
+    del k, v, c
+    order = np.argsort(gk, kind="stable")
+    assert np.array_equal(gk[order], np.arange(G, dtype=np.int64))
+    assert gc.dtype == np.int32 and np.array_equal(gc[order], np.bincount(hk, minlength=G).astype(np.int32))
+    np.testing.assert_allclose(gs[order], np.bincount(hk, weights=hv, minlength=G), rtol=1e-9)
+    _lib.check(_lib.lib.b2_trim_pool())
