@@ -338,7 +338,11 @@ std::unique_ptr<b2_scalar> reduce(const b2_column_view& col, int32_t kind, int32
 namespace {
 
 constexpr int SC_THREADS = 512;
-constexpr int SC_K       = 4;  // 16-byte vectors per lane per tile
+// 16-byte vectors per lane per tile: 64 KB tiles for 8-byte types (8192 elements), 32 KB otherwise. The look-back consumes
+// SC_LB * 32 predecessor records per global-memory round trip, so tiles/us <= SC_LB * 32 / latency: larger tiles and a
+// wider window lift that ceiling above the HBM rate (round 1: 32 KB tiles, 32 records per round = 0.26 of peak).
+template <typename T> constexpr int sc_k() { return sizeof(T) == 8 ? 8 : 4; }
+constexpr int SC_LB = 4;  // predecessor records per look-back lane and round
 
 __device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v)
 {
@@ -405,6 +409,7 @@ __global__ void __launch_bounds__(SC_THREADS) scan_kernel(const T* __restrict__ 
 {
   using B = binop<T, OP>;
   constexpr int V = 16 / sizeof(T);
+  constexpr int SC_K = sc_k<T>();
   constexpr int NW = SC_THREADS / 32;
   constexpr int64_t WARP_ELEMS = 32 * V * SC_K;
   constexpr int64_t TILE = WARP_ELEMS * NW;
@@ -477,24 +482,43 @@ __global__ void __launch_bounds__(SC_THREADS) scan_kernel(const T* __restrict__ 
     } else {
       if (lane == 0) publish_rec<T>(st.rec + tile, 1u, block_tot);
       T excl = B::identity();
-      int64_t base = tile - 1;
+      int64_t base = tile - 1;  // nearest predecessor not folded yet
       while (true) {
-        const int64_t idx = base - lane;
-        uint32_t f = 2u;  // tiles before the first one act as an inclusive identity
-        T c = B::identity();
-        if (idx >= 0) f = read_rec<T>(st.rec + idx, c);
-        // all lanes must be ready before we can fold the window
-        while (__any_sync(0xffffffffu, f == 0u)) {
-          if (f == 0u) f = read_rec<T>(st.rec + idx, c);
-        }
-        const unsigned incl_mask = __ballot_sync(0xffffffffu, f == 2u);
-        const int first = incl_mask ? (__ffs(incl_mask) - 1) : 32;
-        if (lane > first) c = B::identity();
+        // lane l holds the SC_LB records at distances l * SC_LB + r from `base` (lane 0 = the nearest ones), fetched with
+        // independent 16-byte loads; tiles before the first one act as an inclusive identity
+        uint32_t f[SC_LB];
+        T c[SC_LB];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) c = B::apply(__shfl_xor_sync(0xffffffffu, c, o), c);
-        excl = B::apply(c, excl);
+        for (int r = 0; r < SC_LB; ++r) {
+          const int64_t idx = base - ((int64_t)lane * SC_LB + r);
+          f[r] = 2u;
+          c[r] = B::identity();
+          if (idx >= 0) f[r] = read_rec<T>(st.rec + idx, c[r]);
+        }
+        // leading ready records of this lane, the first inclusive one among them, and their fold (nearest first)
+        int nr = 0, fi = SC_LB;
+        T part = B::identity();
+#pragma unroll
+        for (int r = 0; r < SC_LB; ++r) {
+          if (nr == r && fi == SC_LB && f[r] != 0u) {
+            ++nr;
+            part = B::apply(c[r], part);
+            if (f[r] == 2u) fi = r;
+          }
+        }
+        const bool has_incl = fi < SC_LB;
+        const bool blocked  = !has_incl && nr < SC_LB;  // a record that is still needed has not been published yet
+        const unsigned incl_mask = __ballot_sync(0xffffffffu, has_incl);
+        const unsigned blk_mask  = __ballot_sync(0xffffffffu, blocked);
+        const int first_incl = incl_mask ? (__ffs(incl_mask) - 1) : 32;
+        const int first_blk  = blk_mask ? (__ffs(blk_mask) - 1) : 32;
+        if (first_blk < first_incl) continue;  // poll again (the loads above are volatile)
+        if (lane > first_incl) part = B::identity();
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part = B::apply(__shfl_xor_sync(0xffffffffu, part, o), part);
+        excl = B::apply(part, excl);
         if (incl_mask) break;
-        base -= 32;
+        base -= 32 * SC_LB;
       }
       if (lane == 0) {
         publish_rec<T>(st.rec + tile, 2u, B::apply(excl, block_tot));
@@ -541,7 +565,7 @@ template <typename T, int OP, bool COUNT>
 void launch_scan(const T* in, const uint32_t* mask, int64_t bit_offset, int64_t n, bool exclusive, T* out, cudaStream_t stream)
 {
   constexpr int V = 16 / sizeof(T);
-  constexpr int64_t TILE = (int64_t)32 * V * SC_K * (SC_THREADS / 32);
+  constexpr int64_t TILE = (int64_t)32 * V * sc_k<T>() * (SC_THREADS / 32);
   const int64_t ntiles = (n + TILE - 1) / TILE;
   dbuf work(sizeof(uint4) * (ntiles + 1), stream);
   B2_CUDA_TRY(cudaMemsetAsync(work.ptr, 0, work.bytes, stream));
