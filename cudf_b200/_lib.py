@@ -144,6 +144,8 @@ _sig("b2_reduce", [P(ColumnView), i32, i32, vp, b2_stream, P(vp)])
 _sig("b2_segmented_reduce", [P(ColumnView), vp, i32, i32, i32, i32, vp, b2_stream, P(vp)])
 _sig("b2_scan", [P(ColumnView), i32, i32, i32, b2_stream, P(vp)])
 _sig("b2_partition", [P(TableView), P(ColumnView), i32, vp, i32, b2_stream, P(vp), P(i32)])
+_sig("b2_hash_partition", [P(TableView), P(TableView), i32, i32, C.c_uint32, b2_stream, P(vp), P(i32)])
+_sig("b2_partition_by_map", [P(TableView), P(ColumnView), i32, b2_stream, P(vp), P(i32)])
 _sig("b2_partition_plan_create", [P(ColumnView), i32, vp, i32, b2_stream, P(vp), P(C.c_int64)])
 _sig("b2_partition_scatter", [vp, P(ColumnView), P(vp), b2_stream])
 _sig("b2_partition_scatter_staged", [vp, P(ColumnView), P(vp), b2_stream])
@@ -171,7 +173,7 @@ DECLARED_SYMBOLS = [
     "b2_hash_join_partitioned_join", "b2_hash_join_finalize_full_join", "b2_groupby_create", "b2_groupby_destroy",
     "b2_groupby_aggregate", "b2_groupby_scan", "b2_reduce", "b2_segmented_reduce", "b2_scan", "b2_partition",
     "b2_partition_plan_create", "b2_partition_scatter", "b2_partition_scatter_staged", "b2_partition_plan_free", "b2_ipc_alloc", "b2_ipc_open", "b2_ipc_close",
-    "b2_ipc_free", "b2_peer_copy", "b2_profile_get_over",
+    "b2_ipc_free", "b2_peer_copy", "b2_profile_get_over", "b2_hash_partition", "b2_partition_by_map",
     "b2_fill_splitmix64",
 ]
 

@@ -8,6 +8,7 @@
 // one-pass radix sorted_order of the ids (radix_sort.cu) as gather map, then the fused gather.
 #include "common.cuh"
 #include "device_utils.cuh"
+#include "key_pack.cuh"
 
 #include <algorithm>
 
@@ -55,6 +56,71 @@ __global__ void __launch_bounds__(256) bucket_kernel(const UK* __restrict__ keys
     } else {
       b = (int)(mix64((uint64_t)raw) % (uint64_t)P);
     }
+    ids[i] = (uint8_t)b;
+    atomicAdd(&s_cnt[b], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < P; i += blockDim.x) tile_counts[tile * P + i] = s_cnt[i];
+}
+
+// ---- cudf::hash_partition's row hash (cpp/src/partitioning/partitioning.cu:875-945, row_operator/hashing.cuh:40-140) ----
+// MurmurHash3_x86_32 of a fixed-width value's little-endian bytes (cuco::murmurhash3_32 = the public algorithm; restated
+// from its published description, not from cuCollections, which is not in the reference tree).
+__device__ __forceinline__ uint32_t murmur3_32_fixed(uint64_t bits, int len, uint32_t seed)
+{
+  constexpr uint32_t c1 = 0xcc9e2d51u, c2 = 0x1b873593u;
+  uint32_t h = seed;
+  auto mixk = [&](uint32_t k) {
+    k *= c1;
+    k = (k << 15) | (k >> 17);
+    return k * c2;
+  };
+  if (len >= 4) {
+    h ^= mixk((uint32_t)bits);
+    h = ((h << 13) | (h >> 19)) * 5u + 0xe6546b64u;
+    if (len == 8) {
+      h ^= mixk((uint32_t)(bits >> 32));
+      h = ((h << 13) | (h >> 19)) * 5u + 0xe6546b64u;
+    }
+  } else {
+    h ^= mixk((uint32_t)bits & (len == 1 ? 0xffu : 0xffffu));  // tail bytes only
+  }
+  h ^= (uint32_t)len;
+  h ^= h >> 16; h *= 0x85ebca6bu;
+  h ^= h >> 13; h *= 0xc2b2ae35u;
+  return h ^ (h >> 16);
+}
+
+// hash_fn: 0 = IdentityHash (integral keys only here), 1 = MurmurHash3_x86_32.  Floats hash their normalised value (-0 -> +0,
+// NaN -> canonical quiet NaN: key_col_bits does exactly that), BOOL8 hashes one byte 0 / 1, a null hashes to UINT32_MAX,
+// the columns are folded left to right with hash_combine (hashing.hpp:83-86), the first column's hash being the start.
+__device__ __forceinline__ uint32_t row_hash32(const key_cols& kc, int64_t r, int hash_fn, uint32_t seed, uint32_t bool_cols)
+{
+  uint32_t h = 0;
+#pragma unroll 1
+  for (int c = 0; c < kc.n; ++c) {
+    const int64_t e = r + kc.offset[c];
+    uint32_t hc = 0xffffffffu;
+    if (kc.mask[c] == nullptr || bit_is_set(kc.mask[c], e)) {
+      uint64_t bits = key_col_bits(kc, c, e);
+      if ((bool_cols >> c) & 1u) bits = bits != 0;
+      hc = hash_fn == 0 ? (uint32_t)bits : murmur3_32_fixed(bits, kc.width[c], seed);
+    }
+    h = c == 0 ? hc : (h ^ (hc + 0x9e3779b9u + (h << 6) + (h >> 2)));
+  }
+  return h;
+}
+
+__global__ void __launch_bounds__(256) bucket_rowhash_kernel(key_cols kc, int64_t n, int P, int hash_fn, uint32_t seed, uint32_t bool_cols,
+                                                             uint8_t* __restrict__ ids, uint32_t* __restrict__ tile_counts)
+{
+  __shared__ unsigned int s_cnt[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_cnt[i] = 0;
+  __syncthreads();
+  const int64_t tile = blockIdx.x;
+  const int64_t end = min(n, (tile + 1) * (int64_t)PT_TILE);
+  for (int64_t i = tile * PT_TILE + threadIdx.x; i < end; i += blockDim.x) {
+    const int b = (int)(row_hash32(kc, i, hash_fn, seed, bool_cols) % (uint32_t)P);
     ids[i] = (uint8_t)b;
     atomicAdd(&s_cnt[b], 1u);
   }
@@ -220,30 +286,65 @@ __global__ void __launch_bounds__(256) scatter_kernel(const T* __restrict__ in, 
 
 }  // namespace
 
-table_ptr partition_table(const std::vector<b2_column_view>& input, const b2_column_view& keys, int mode, const void* splitters,
-                          int P, int32_t* out_offsets, cudaStream_t stream)
+// ---- more than 256 partitions: ids as a 32-bit column, stable radix order of the ids (radix_sort.cu), fused gather ----
+__global__ void __launch_bounds__(256) rowhash_ids32_kernel(key_cols kc, int64_t n, uint32_t P, int hash_fn, uint32_t seed, uint32_t bool_cols,
+                                                            uint32_t* __restrict__ ids)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) ids[i] = row_hash32(kc, i, hash_fn, seed, bool_cols) % P;
+}
+template <typename M>
+__global__ void __launch_bounds__(256) map_ids32_kernel(const M* __restrict__ map, int64_t n, uint32_t* __restrict__ ids)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) ids[i] = (uint32_t)map[i];
+}
+// offsets[p] = number of rows whose id is < p (ids read through the sorted order), p in [0, P]
+__global__ void __launch_bounds__(256) id_offsets_kernel(const uint32_t* __restrict__ ids, const int32_t* __restrict__ order, int64_t n, uint32_t P,
+                                                         int32_t* __restrict__ offsets)
+{
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p > (int64_t)P) return;
+  int64_t lo = 0, hi = n;
+  while (lo < hi) {
+    const int64_t mid = lo + (hi - lo) / 2;
+    if (ids[order[mid]] < (uint32_t)p) lo = mid + 1;
+    else hi = mid;
+  }
+  offsets[p] = (int32_t)lo;
+}
+
+static table_ptr partition_by_ids32(const std::vector<b2_column_view>& input, const dbuf& ids, int64_t n, int P, int32_t* out_offsets,
+                                    cudaStream_t stream)
+{
+  b2_column_view idv{B2_UINT32, (int32_t)n, ids.ptr, nullptr, 0, 0};
+  auto order = sorted_order({idv}, {}, {}, true, stream);
+  auto out = gather_table(input, order->data.as<int32_t>(), (int32_t)n, false, stream);
+  dbuf offs(sizeof(int32_t) * ((size_t)P + 1), stream);
+  B2_LAUNCH(id_offsets_kernel, (unsigned)((P + 1 + 255) / 256), 256, 0, stream, ids.as<uint32_t>(), order->data.as<int32_t>(), n, (uint32_t)P,
+            offs.as<int32_t>());
+  B2_CUDA_TRY(cudaMemcpyAsync(out_offsets, offs.ptr, sizeof(int32_t) * ((size_t)P + 1), cudaMemcpyDeviceToHost, stream));
+  B2_CUDA_TRY(cudaStreamSynchronize(stream));
+  return out;
+}
+
+// common tail of every partition flavour: `buckets(ids, tile_counts)` launches the kernel that writes one bucket id per row
+// and the per-tile bucket counts
+template <typename BucketFn>
+static table_ptr partition_rows(const std::vector<b2_column_view>& input, int64_t n, int P, int32_t* out_offsets, cudaStream_t stream,
+                                BucketFn&& buckets)
 {
   B2_EXPECTS(P >= 1 && P <= 256, B2_ERR_INVALID_ARGUMENT, "num_partitions must be in [1, 256]");
-  B2_EXPECTS(!has_nulls(keys), B2_ERR_INVALID_ARGUMENT, "partition key column must not contain nulls");
-  B2_EXPECTS(mode == 1 || P == 1 || splitters != nullptr, B2_ERR_INVALID_ARGUMENT, "range partition needs splitters");
-  const int64_t n = keys.size;
   for (auto& c : input) B2_EXPECTS(c.size == n, B2_ERR_LOGIC, "Column size mismatch.");
   const int64_t ntiles = (n + PT_TILE - 1) / PT_TILE;
   dbuf ids(std::max<int64_t>(n, 1), stream), totals(sizeof(unsigned long long) * 256, stream);
   dbuf tile_counts(sizeof(uint32_t) * std::max<int64_t>(ntiles, 1) * P, stream);
   B2_CUDA_TRY(cudaMemsetAsync(totals.ptr, 0, totals.bytes, stream));
-  const int sid  = storage_type(keys.type_id);
-  const int kind = is_float_id(sid) ? (int)key_kind::FLOAT : (is_signed_id(sid) ? (int)key_kind::SIGNED : (int)key_kind::UNSIGNED);
   auto out = std::make_unique<b2_table>();
   if (n > 0) {
     {
       prof_scope ps("partition_bucket", stream);
-      const unsigned grid = (unsigned)ntiles;
-      dispatch_width(type_width(keys.type_id), [&](auto tag) {
-        using T = decltype(tag);
-        B2_LAUNCH((bucket_kernel<T>), grid, 256, 0, stream, static_cast<const T*>(keys.data) + keys.offset, n, mode, kind, static_cast<const T*>(splitters), P,
-                  ids.as<uint8_t>(), tile_counts.as<uint32_t>());
-      });
+      buckets(ids.as<uint8_t>(), tile_counts.as<uint32_t>(), (unsigned)ntiles);
     }
     B2_LAUNCH(tile_scan_kernel, 1, 1024, 0, stream, tile_counts.as<uint32_t>(), ntiles, P, totals.as<unsigned long long>());
     bool any_nullable = false;
@@ -281,7 +382,103 @@ table_ptr partition_table(const std::vector<b2_column_view>& input, const b2_col
   return out;
 }
 
+table_ptr partition_table(const std::vector<b2_column_view>& input, const b2_column_view& keys, int mode, const void* splitters,
+                          int P, int32_t* out_offsets, cudaStream_t stream)
+{
+  B2_EXPECTS(!has_nulls(keys), B2_ERR_INVALID_ARGUMENT, "partition key column must not contain nulls");
+  B2_EXPECTS(mode == 1 || P == 1 || splitters != nullptr, B2_ERR_INVALID_ARGUMENT, "range partition needs splitters");
+  const int64_t n = keys.size;
+  const int sid  = storage_type(keys.type_id);
+  const int kind = is_float_id(sid) ? (int)key_kind::FLOAT : (is_signed_id(sid) ? (int)key_kind::SIGNED : (int)key_kind::UNSIGNED);
+  return partition_rows(input, n, P, out_offsets, stream, [&](uint8_t* ids, uint32_t* tile_counts, unsigned grid) {
+    dispatch_width(type_width(keys.type_id), [&](auto tag) {
+      using T = decltype(tag);
+      B2_LAUNCH((bucket_kernel<T>), grid, 256, 0, stream, static_cast<const T*>(keys.data) + keys.offset, n, mode, kind, static_cast<const T*>(splitters), P,
+                ids, tile_counts);
+    });
+  });
+}
+
+// cudf::partition(t, partition_map, num_partitions) — cpp/src/partitioning/partitioning.cu:898-915: the map names each row's partition
+table_ptr partition_by_map(const std::vector<b2_column_view>& input, const b2_column_view& map, int P, int32_t* out_offsets, cudaStream_t stream)
+{
+  B2_EXPECTS(is_integral_id(map.type_id) && map.type_id != B2_BOOL8, B2_ERR_LOGIC, "Unexpected, non-integral partition map.");
+  B2_EXPECTS(!has_nulls(map), B2_ERR_LOGIC, "Unexpected null values in partition_map.");
+  const int64_t n = map.size;
+  for (auto& c : input) B2_EXPECTS(c.size == n, B2_ERR_LOGIC, "Size mismatch between table and partition map.");
+  if (P <= 0 || n == 0) {
+    auto out = std::make_unique<b2_table>();
+    for (auto& c : input) out->cols.push_back(make_column(c.type_id, 0, false, stream));
+    for (int b = 0; b <= std::max(P, 0); ++b) out_offsets[b] = 0;
+    return out;
+  }
+  dbuf ids(sizeof(uint32_t) * n, stream);
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, NUM_SMS_B200 * 16));
+  dispatch_width(type_width(map.type_id), [&](auto tag) {
+    using M = decltype(tag);
+    B2_LAUNCH((map_ids32_kernel<M>), grid, 256, 0, stream, static_cast<const M*>(map.data) + map.offset, n, ids.as<uint32_t>());
+  });
+  return partition_by_ids32(input, ids, n, P, out_offsets, stream);
+}
+
+// cudf::hash_partition(input, keys, num_partitions, hash_function, seed) — cpp/src/partitioning/partitioning.cu:875-945
+table_ptr hash_partition_table(const std::vector<b2_column_view>& input, const std::vector<b2_column_view>& keys, int P, int hash_fn,
+                               uint32_t seed, int32_t* out_offsets, cudaStream_t stream)
+{
+  const int64_t n = input.empty() ? 0 : input[0].size;
+  B2_EXPECTS(hash_fn == 0 || hash_fn == 1, B2_ERR_LOGIC, "Unsupported hash function in hash_partition");
+  B2_EXPECTS(keys.empty() || keys[0].size == n, B2_ERR_INVALID_ARGUMENT,
+             "Input table and key table must have same number of rows, or key table should have no columns.");
+  if (P <= 0 || n == 0 || keys.empty()) {  // empty result with num_partitions + 1 zero offsets
+    auto out = std::make_unique<b2_table>();
+    for (auto& c : input) out->cols.push_back(make_column(c.type_id, 0, false, stream));
+    for (int b = 0; b <= std::max(P, 0); ++b) out_offsets[b] = 0;
+    return out;
+  }
+  uint32_t bool_cols = 0;
+  for (size_t c = 0; c < keys.size(); ++c) {
+    if (hash_fn == 0) B2_EXPECTS(is_integral_id(storage_type(keys[c].type_id)), B2_ERR_LOGIC, "IdentityHash does not support this data type");
+    if (keys[c].type_id == B2_BOOL8) bool_cols |= 1u << c;
+  }
+  const key_cols kc = make_key_cols(keys, true);
+  if (P > 256) {
+    dbuf ids(sizeof(uint32_t) * n, stream);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, NUM_SMS_B200 * 16));
+    B2_LAUNCH(rowhash_ids32_kernel, grid, 256, 0, stream, kc, n, (uint32_t)P, hash_fn, seed, bool_cols, ids.as<uint32_t>());
+    return partition_by_ids32(input, ids, n, P, out_offsets, stream);
+  }
+  return partition_rows(input, n, P, out_offsets, stream, [&](uint8_t* ids, uint32_t* tile_counts, unsigned grid) {
+    B2_LAUNCH(bucket_rowhash_kernel, grid, 256, 0, stream, kc, n, P, hash_fn, seed, bool_cols, ids, tile_counts);
+  });
+}
+
 }  // namespace b2
+
+extern "C" b2_status b2_partition_by_map(const b2_table_view* input, const b2_column_view* partition_map, int32_t num_partitions, b2_stream stream,
+                                          b2_table** out, int32_t* out_offsets)
+{
+  B2_TRY_BEGIN
+    B2_EXPECTS(input && partition_map && out && out_offsets, B2_ERR_INVALID_ARGUMENT, "null argument");
+    std::vector<b2_column_view> cols;
+    b2::validate_table(input, cols);
+    b2::validate_column(*partition_map);
+    *out = b2::partition_by_map(cols, *partition_map, num_partitions, out_offsets, static_cast<cudaStream_t>(stream)).release();
+  B2_TRY_END
+}
+
+extern "C" b2_status b2_hash_partition(const b2_table_view* input, const b2_table_view* keys, int32_t num_partitions, int32_t hash_function,
+                                       uint32_t seed, b2_stream stream, b2_table** out, int32_t* out_offsets)
+{
+  B2_TRY_BEGIN
+    B2_EXPECTS(input && keys && out && out_offsets, B2_ERR_INVALID_ARGUMENT, "null argument");
+    std::vector<b2_column_view> cols, kcols;
+    b2::validate_table(input, cols);
+    B2_EXPECTS(keys->num_columns >= 0 && (keys->num_columns == 0 || keys->columns != nullptr), B2_ERR_INVALID_ARGUMENT, "invalid table_view");
+    kcols.assign(keys->columns, keys->columns + keys->num_columns);
+    for (auto& c : kcols) b2::validate_column(c);
+    *out = b2::hash_partition_table(cols, kcols, num_partitions, hash_function, seed, out_offsets, static_cast<cudaStream_t>(stream)).release();
+  B2_TRY_END
+}
 
 extern "C" b2_status b2_partition(const b2_table_view* input, const b2_column_view* keys, int32_t mode, const void* splitters,
                                   int32_t num_partitions, b2_stream stream, b2_table** out, int32_t* out_offsets)

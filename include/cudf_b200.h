@@ -291,6 +291,21 @@ B2_API b2_status b2_partition(const b2_table_view* input, const b2_column_view* 
                               const void* splitters, int32_t num_partitions, b2_stream stream,
                               b2_table** out, int32_t* out_offsets);
 
+/* cudf::hash_partition(input, keys, num_partitions, hash_function, seed) — cpp/include/cudf/partitioning.hpp:103-145,
+ * cpp/src/partitioning/partitioning.cu:875-945.  Row hash as in libcudf (hash_function 1 = HASH_MURMUR3: MurmurHash3_x86_32
+ * per column with `seed`, floats normalised, null = UINT32_MAX, columns folded with hash_combine; 0 = HASH_IDENTITY on
+ * integral keys), partition = hash % num_partitions: a row lands in the same partition as under libcudf, so the output
+ * interoperates with dask_cudf / rapidsmpf style shuffles.  out_offsets: host int32[num_partitions + 1].  Rows keep their
+ * input order inside a partition.  Up to 256 partitions take the tile-based partition kernels, more go through a stable
+ * radix order of the 32-bit partition ids; zero key columns / rows give an empty result. */
+B2_API b2_status b2_hash_partition(const b2_table_view* input, const b2_table_view* keys, int32_t num_partitions,
+                                   int32_t hash_function, uint32_t seed, b2_stream stream, b2_table** out, int32_t* out_offsets);
+
+/* cudf::partition(t, partition_map, num_partitions) for any partition count (cpp/include/cudf/partitioning.hpp:58-101): the
+ * integer map names each row's partition; stable order of the map values + fused gather. out_offsets: int32[P + 1]. */
+B2_API b2_status b2_partition_by_map(const b2_table_view* input, const b2_column_view* partition_map, int32_t num_partitions,
+                                     b2_stream stream, b2_table** out, int32_t* out_offsets);
+
 /* Two-phase form of b2_partition for the fused partition + exchange: the plan holds the bucket id and the
  * stable in-bucket rank of every row; out_counts[b] = rows of bucket b.  b2_partition_scatter then writes one
  * fixed-width column straight to P destination base addresses — local buffers or PEER device memory mapped with

@@ -75,3 +75,37 @@ def test_join_gold_maps():
     # join_tests.cpp:2316-2337 (gold maps) with the InnerJoinNoNulls column 0 (:1163-1237)
     l, r = oracle.join.inner_join([(np.array([3, 1, 2, 0, 2]), None)], [(np.array([2, 2, 0, 4, 3]), None)])
     assert l.tolist() == [0, 2, 2, 3, 4, 4] and r.tolist() == [4, 0, 1, 2, 0, 1]
+
+
+def test_murmur3_row_hash_pinned():
+    """oracle/partition.py: MurmurHash3_x86_32 against the published known answers (SMHasher verification values) and against
+    scikit-learn's C implementation on random fixed-width values; hash_combine and the null hash against hand-computed values
+    (cpp/include/cudf/hashing/detail/hashing.hpp:83-86, row_operator/hashing.cuh:52-56)."""
+    import numpy as np
+
+    from oracle import partition as op
+
+    known = [(np.uint32, 0xFFFFFFFF, 0, 0x76293B50), (np.uint32, 0x87654321, 0, 0xF55B516B), (np.uint32, 0x87654321, 0x5082EDEE, 0x2362F9DE),
+             (np.uint16, 0x4321, 0, 0xA0F7B07A), (np.uint8, 0x21, 0, 0x72661CF4), (np.uint32, 0, 0, 0x2362F9DE)]
+    for dt, v, seed, exp in known:
+        assert int(op.murmur3_32_fixed(np.array([v], dt), seed)[0]) == exp
+    try:
+        from sklearn.utils import murmurhash3_32
+    except Exception:
+        murmurhash3_32 = None
+    if murmurhash3_32 is not None:
+        rng = np.random.default_rng(1)
+        for dt in (np.uint8, np.uint16, np.uint32, np.uint64, np.float32, np.float64):
+            v = rng.integers(0, 2**63 - 1, 300, dtype=np.int64).astype(dt) if np.dtype(dt).kind != "f" else rng.standard_normal(300).astype(dt)
+            for seed in (0, 619):
+                exp = np.array([murmurhash3_32(x.tobytes(), seed, positive=True) for x in v], dtype=np.uint32)
+                assert np.array_equal(op.murmur3_32_fixed(v, seed), exp)
+    # normalisation and nulls: -0.0 hashes like +0.0, every NaN like the canonical one, a null is UINT32_MAX
+    f = np.array([0.0, -0.0, np.nan, -np.nan], np.float64)
+    h = op.row_hash([(f, np.array([True, True, True, True]))])
+    assert h[0] == h[1] and h[2] == h[3]
+    assert int(op.row_hash([(f, np.array([False, True, True, True]))])[0]) == 0xFFFFFFFF
+    a = np.array([1, 2], np.int32)
+    h0, h1 = op.murmur3_32_fixed(a), op.murmur3_32_fixed(a.astype(np.int64))
+    comb = h0 ^ ((h1 + np.uint32(0x9E3779B9) + (h0 << np.uint32(6)) + (h0 >> np.uint32(2))).astype(np.uint32))
+    assert np.array_equal(op.row_hash([(a, None), (a.astype(np.int64), None)]), comb)
