@@ -155,6 +155,10 @@ _sig("b2_ipc_open", [u8p, P(vp)])
 _sig("b2_ipc_close", [vp])
 _sig("b2_ipc_free", [vp])
 _sig("b2_peer_copy", [vp, vp, C.c_size_t, b2_stream])
+_sig("b2_packed_size", [P(TableView), P(C.c_size_t)])
+_sig("b2_pack", [P(TableView), b2_stream, u8p, C.c_size_t, P(C.c_size_t), P(vp)])
+_sig("b2_pack_metadata", [P(TableView), vp, C.c_size_t, u8p, C.c_size_t, P(C.c_size_t)])
+_sig("b2_unpack", [u8p, C.c_size_t, vp, P(ColumnView), i32, P(i32), P(i32)])
 _sig("b2_fill_splitmix64", [vp, C.c_int64, C.c_uint64, C.c_int64, i32, C.c_uint64, b2_stream])
 
 # every symbol the header declares, for the loader test
@@ -173,7 +177,7 @@ DECLARED_SYMBOLS = [
     "b2_hash_join_partitioned_join", "b2_hash_join_finalize_full_join", "b2_groupby_create", "b2_groupby_destroy",
     "b2_groupby_aggregate", "b2_groupby_scan", "b2_reduce", "b2_segmented_reduce", "b2_scan", "b2_partition",
     "b2_partition_plan_create", "b2_partition_scatter", "b2_partition_scatter_staged", "b2_partition_plan_free", "b2_ipc_alloc", "b2_ipc_open", "b2_ipc_close",
-    "b2_ipc_free", "b2_peer_copy", "b2_profile_get_over", "b2_hash_partition", "b2_partition_by_map",
+    "b2_ipc_free", "b2_peer_copy", "b2_profile_get_over", "b2_hash_partition", "b2_partition_by_map", "b2_packed_size", "b2_pack", "b2_pack_metadata", "b2_unpack",
     "b2_fill_splitmix64",
 ]
 

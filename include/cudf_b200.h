@@ -332,6 +332,18 @@ B2_API b2_status b2_ipc_free(void* ptr);
  * destination rank). Stream-ordered. */
 B2_API b2_status b2_peer_copy(void* dst, const void* src, size_t bytes, b2_stream stream);
 
+/* ---- cudf::pack / packed_size / pack_metadata / unpack (cpp/include/cudf/contiguous_split.hpp:233-317, cpp/src/copying/pack.cpp):
+ *      libcudf's contiguous wire format for tables of fixed-width columns. metadata = host bytes (16-byte table header +
+ *      40 bytes per column), gpu_data = one device buffer (validity then data per column, 64-byte padded). -------------- */
+B2_API b2_status b2_packed_size(const b2_table_view* input, size_t* out_bytes);
+B2_API b2_status b2_pack(const b2_table_view* input, b2_stream stream, uint8_t* metadata, size_t metadata_capacity,
+                         size_t* metadata_size, b2_buffer** gpu_data);
+B2_API b2_status b2_pack_metadata(const b2_table_view* input, const uint8_t* contiguous_buffer, size_t buffer_size,
+                                  uint8_t* metadata, size_t metadata_capacity, size_t* metadata_size);
+/* No allocation: out_columns[i] point into gpu_data (the caller keeps it alive). */
+B2_API b2_status b2_unpack(const uint8_t* metadata, size_t metadata_size, const void* gpu_data, b2_column_view* out_columns,
+                           int32_t capacity, int32_t* num_columns, int32_t* num_rows);
+
 /* ---- synthetic data (SURVEY §8d generator): x_i = splitmix64(seed + first + i) -------------- */
 /* kind 0: raw uint64 -> int64 ; 1: float64 uniform [0,1) ; 2: x mod modulus as int64 ;
  * 3: int32 low bits ; 4: validity bitmask words with P(valid)=0.5 (n = number of bits) */
