@@ -742,4 +742,100 @@ inline std::pair<rmm::device_buffer, size_type> bitmask_and(table_view const& vi
   return {rmm::device_buffer{out}, nulls};
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// partitioning.hpp (cpp/include/cudf/partitioning.hpp:32-175)
+// ------------------------------------------------------------------------------------------------
+enum class hash_id : int32_t { HASH_IDENTITY = 0, HASH_MURMUR3 };
+static constexpr uint32_t DEFAULT_HASH_SEED = 0;
+
+inline std::pair<std::unique_ptr<table>, std::vector<size_type>> partition(table_view const& t, column_view const& partition_map,
+                                                                           size_type num_partitions,
+                                                                           rmm::cuda_stream_view stream = cudf::get_default_stream(),
+                                                                           rmm::device_async_resource_ref = cudf::get_current_device_resource_ref())
+{
+  if (t.num_rows() != partition_map.size()) throw cudf::logic_error("Size mismatch between table and partition map.");
+  auto tv = t.native();
+  b2_table* out = nullptr;
+  std::vector<size_type> offsets(static_cast<size_t>(std::max(num_partitions, 0)) + 1, 0);
+  detail::check(b2_partition_by_map(&tv, &partition_map.native(), num_partitions, stream.value(), &out, offsets.data()));
+  return {table::from_handle(out), std::move(offsets)};
+}
+
+inline std::pair<std::unique_ptr<table>, std::vector<size_type>> hash_partition(table_view const& input, table_view const& keys, int num_partitions,
+                                                                                hash_id hash_function = hash_id::HASH_MURMUR3,
+                                                                                uint32_t seed = DEFAULT_HASH_SEED,
+                                                                                rmm::cuda_stream_view stream = cudf::get_default_stream(),
+                                                                                rmm::device_async_resource_ref = cudf::get_current_device_resource_ref())
+{
+  auto tv = input.native();
+  auto kv = keys.native();
+  b2_table* out = nullptr;
+  std::vector<size_type> offsets(static_cast<size_t>(std::max(num_partitions, 0)) + 1, 0);
+  detail::check(b2_hash_partition(&tv, &kv, num_partitions, static_cast<int32_t>(hash_function), seed, stream.value(), &out, offsets.data()));
+  return {table::from_handle(out), std::move(offsets)};
+}
+inline std::pair<std::unique_ptr<table>, std::vector<size_type>> hash_partition(table_view const& input, std::vector<size_type> const& columns_to_hash,
+                                                                                int num_partitions, hash_id hash_function = hash_id::HASH_MURMUR3,
+                                                                                uint32_t seed = DEFAULT_HASH_SEED,
+                                                                                rmm::cuda_stream_view stream = cudf::get_default_stream(),
+                                                                                rmm::device_async_resource_ref mr = cudf::get_current_device_resource_ref())
+{
+  std::vector<column_view> kc;
+  for (auto i : columns_to_hash) kc.push_back(input.column(i));  // std::out_of_range on a bad index, as in libcudf
+  return hash_partition(input, table_view{kc}, num_partitions, hash_function, seed, stream, mr);
+}
+
+// ------------------------------------------------------------------------------------------------
+// contiguous_split.hpp: pack / unpack (cpp/include/cudf/contiguous_split.hpp:100-120,233-317)
+// ------------------------------------------------------------------------------------------------
+struct packed_columns {
+  std::unique_ptr<std::vector<uint8_t>> metadata = std::make_unique<std::vector<uint8_t>>();
+  std::unique_ptr<rmm::device_buffer> gpu_data   = std::make_unique<rmm::device_buffer>();
+};
+inline std::size_t packed_size(table_view const& input, rmm::cuda_stream_view = cudf::get_default_stream(),
+                               rmm::device_async_resource_ref = cudf::get_current_device_resource_ref())
+{
+  auto tv = input.native();
+  std::size_t bytes = 0;
+  detail::check(b2_packed_size(&tv, &bytes));
+  return bytes;
+}
+inline packed_columns pack(table_view const& input, rmm::cuda_stream_view stream = cudf::get_default_stream(),
+                           rmm::device_async_resource_ref = cudf::get_current_device_resource_ref())
+{
+  auto tv = input.native();
+  packed_columns out;
+  out.metadata->resize(16 + 40 * static_cast<size_t>(input.num_columns()));
+  std::size_t md = 0;
+  b2_buffer* buf = nullptr;
+  detail::check(b2_pack(&tv, stream.value(), out.metadata->data(), out.metadata->size(), &md, &buf));
+  out.metadata->resize(md);
+  out.gpu_data = std::make_unique<rmm::device_buffer>(buf);
+  return out;
+}
+inline std::vector<uint8_t> pack_metadata(table_view const& table, uint8_t const* contiguous_buffer, size_t buffer_size)
+{
+  auto tv = table.native();
+  std::vector<uint8_t> md(16 + 40 * static_cast<size_t>(table.num_columns()));
+  std::size_t n = 0;
+  detail::check(b2_pack_metadata(&tv, contiguous_buffer, buffer_size, md.data(), md.size(), &n));
+  md.resize(n);
+  return md;
+}
+inline table_view unpack(uint8_t const* metadata, size_t metadata_size, uint8_t const* gpu_data)
+{
+  std::vector<b2_column_view> raw(metadata_size >= 16 ? (metadata_size - 16) / 40 + 1 : 1);
+  int32_t ncols = 0, nrows = 0;
+  detail::check(b2_unpack(metadata, metadata_size, gpu_data, raw.data(), static_cast<int32_t>(raw.size()), &ncols, &nrows));
+  std::vector<column_view> cols;
+  for (int32_t i = 0; i < ncols; ++i)
+    cols.emplace_back(data_type{static_cast<type_id>(raw[i].type_id)}, raw[i].size, raw[i].data, raw[i].null_mask, raw[i].null_count, 0);
+  return table_view{cols};
+}
+inline table_view unpack(packed_columns const& input)
+{
+  return unpack(input.metadata->data(), input.metadata->size(), static_cast<uint8_t const*>(input.gpu_data->data()));
+}
+
 }  // namespace cudf

@@ -1,6 +1,8 @@
 // Reads like a libcudf gtest (cpp/tests/sort/sort_test.cpp:50-85, cpp/tests/join/join_tests.cpp:2316-2337,
 // cpp/tests/groupby/sum_tests.cpp:68-80): exercises the cudf:: C++ surface in include/cudf over the C ABI.
 #include <cudf/column/column_view.hpp>
+#include <cudf/contiguous_split.hpp>
+#include <cudf/partitioning.hpp>
 #include <cudf/groupby.hpp>
 #include <cudf/join/hash_join.hpp>
 #include <cudf/join/join.hpp>
@@ -117,6 +119,20 @@ int main()
   EXPECT(s->is_valid());
   auto sc = scan(gkc, *make_sum_aggregation<scan_aggregation>(), scan_type::INCLUSIVE);
   EXPECT((to_host(sc->view().data<int32_t>(), 10).back() == 20));
+  {  // partition (partition_test.cpp:166-181 Reverse), hash_partition contract, pack / unpack round trip (pack_tests.cpp:69-75)
+    dev_vec<int32_t> pv({0, 1, 3, 7, 5, 13}), pm({5, 4, 3, 2, 1, 0});
+    column_view pvc{data_type{type_id::INT32}, 6, pv.p}, pmc{data_type{type_id::INT32}, 6, pm.p};
+    auto [pt, poff] = cudf::partition(table_view{{pvc}}, pmc, 6);
+    EXPECT((poff == std::vector<size_type>{0, 1, 2, 3, 4, 5, 6}));
+    EXPECT((to_host(pt->get_column(0).view().data<int32_t>(), 6) == std::vector<int32_t>{13, 5, 7, 3, 1, 0}));
+    auto [ht, hoff] = cudf::hash_partition(table_view{{pvc, pmc}}, std::vector<size_type>{0}, 3);
+    EXPECT(hoff.size() == 4 && hoff.front() == 0 && hoff.back() == 6 && ht->num_rows() == 6);
+    auto packed = cudf::pack(table_view{{pvc, pmc}});
+    EXPECT(packed.gpu_data->size() == cudf::packed_size(table_view{{pvc, pmc}}) && packed.metadata->size() == 16 + 2 * 40);
+    auto un = cudf::unpack(packed);
+    EXPECT(un.num_columns() == 2 && un.num_rows() == 6);
+    EXPECT((to_host(un.column(1).data<int32_t>(), 6) == std::vector<int32_t>{5, 4, 3, 2, 1, 0}));
+  }
   std::printf("CPP_API_OK\n");
   return 0;
 }
