@@ -58,6 +58,11 @@ struct sort_ctl {
   int32_t fix_key_buf;         // key buffer (1 / 2) written by the last executed pass
   int32_t fix_idx_buf;         // payload / row-id buffer (0 / 1 / 2) written by the last executed pass
   uint32_t overflow;           // set by the fix-up when a segment is too long for it: the host reruns the full LSD sort
+  // two-phase histogram of the hybrid plan: phase 1 counts the top four digits only; the low digits are counted (phase 2) only
+  // when the plan cannot stop above them
+  int32_t need_low;            // 1: phase 1 could not decide, the low digits' histograms are required
+  int32_t pad2;
+  unsigned long long vary;     // OR of (key ^ first key) over the input
 };
 
 template <typename UK>
@@ -84,12 +89,19 @@ __device__ __forceinline__ UK untwiddle_rt(UK k, int kind, UK desc_mask)
 // 1. histogram
 // ------------------------------------------------------------------------------------------------
 // MIX (64-bit keys, join partitioning): keys are mix64(raw) and only the digits of passes 6 and 7 are counted.
+// pass_mask: bit p set = count digit p (the hybrid plan first looks at the top digits only; a partition pass needs one).
+// gate: when not null the kernel returns at once unless *gate != 0 (second-phase histogram of the low digits).
+// vary_out: when not null receives the OR over all keys of (key ^ first key): a digit is constant over the input iff its
+// byte of that word is zero (lets the plan know which uncounted digits are trivial).
 template <typename UK, bool MIX = false>
 __global__ void __launch_bounds__(512) histogram_kernel(const UK* __restrict__ keys, int64_t n, int raw, int kind,
                                                        UK desc_mask, uint32_t* __restrict__ ghist,
-                                                       uint32_t* __restrict__ nan_count)
+                                                       uint32_t* __restrict__ nan_count, uint32_t pass_mask = 0xffu,
+                                                       const int32_t* __restrict__ gate = nullptr,
+                                                       unsigned long long* __restrict__ vary_out = nullptr)
 {
   constexpr int NP = sizeof(UK);
+  if (gate != nullptr && *gate == 0) return;
   __shared__ uint32_t sh[NP][RADIX];
   for (int i = threadIdx.x; i < NP * RADIX; i += blockDim.x) (&sh[0][0])[i] = 0;
   __syncthreads();
@@ -103,14 +115,23 @@ __global__ void __launch_bounds__(512) histogram_kernel(const UK* __restrict__ k
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
 
+  // reference key for the vary word: the (transformed) first key of the column
+  UK k_first;
+  {
+    const UK r0 = keys[0];
+    if constexpr (MIX) k_first = (UK)mix64((uint64_t)r0);
+    else k_first = raw ? twiddle_rt<UK>(r0, kind, desc_mask) : r0;
+  }
+  uint64_t vary_acc = 0;
   auto account = [&](UK rawbits, bool active) {
     UK k;
     if constexpr (MIX) k = (UK)mix64((uint64_t)rawbits);
     else k = raw ? twiddle_rt<UK>(rawbits, kind, desc_mask) : rawbits;
     if (active && raw && kind == (int)key_kind::FLOAT && (UK)(k ^ desc_mask) == (UK)~UK(0)) nans++;
+    if (active) vary_acc |= (uint64_t)(k ^ k_first);
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
-      if (MIX && p < 6) continue;
+      if (!((pass_mask >> p) & 1u)) continue;
       unsigned d = (unsigned)(k >> (p * 8)) & 255u;
       unsigned amask = __ballot_sync(0xffffffffu, active);
       if (amask == 0) continue;
@@ -133,14 +154,16 @@ __global__ void __launch_bounds__(512) histogram_kernel(const UK* __restrict__ k
     if constexpr (MIX) k = (UK)mix64((uint64_t)rawbits);
     else k = raw ? twiddle_rt<UK>(rawbits, kind, desc_mask) : rawbits;
     if (raw && kind == (int)key_kind::FLOAT && (UK)(k ^ desc_mask) == (UK)~UK(0)) nans++;
-    const uint64_t k64 = (uint64_t)k;
-    const uint64_t d64 = k64 ^ __shfl_sync(0xffffffffu, k64, 0);
+    // bits in which some lane differs from the column's first key: a digit whose byte is zero here is the same in all 32
+    // lanes (counted once per warp), and the OR over all warps tells which digits are constant over the whole input
+    const uint64_t d64 = (uint64_t)(k ^ k_first);
     uint32_t vary_lo = __reduce_or_sync(0xffffffffu, (uint32_t)d64);
     uint32_t vary_hi = sizeof(UK) > 4 ? __reduce_or_sync(0xffffffffu, (uint32_t)(d64 >> 32)) : 0u;
     const uint64_t vary = ((uint64_t)vary_hi << 32) | vary_lo;
+    vary_acc |= vary;
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
-      if (MIX && p < 6) continue;
+      if (!((pass_mask >> p) & 1u)) continue;
       const unsigned d = (unsigned)(k >> (p * 8)) & 255u;
       if (((vary >> (p * 8)) & 255u) == 0) {
         if (lane_id() == 0) atomicAdd(&sh[p][d], 32u);
@@ -189,6 +212,11 @@ __global__ void __launch_bounds__(512) histogram_kernel(const UK* __restrict__ k
     nans = warp_sum(nans);
     if (lane_id() == 0 && nans) atomicAdd(nan_count, nans);
   }
+  if (vary_out) {
+    const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)vary_acc);
+    const uint32_t hi = __reduce_or_sync(0xffffffffu, (uint32_t)(vary_acc >> 32));
+    if (lane_id() == 0 && (lo | hi)) atomicOr(vary_out, ((unsigned long long)hi << 32) | lo);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -204,16 +232,24 @@ __global__ void __launch_bounds__(512) histogram_kernel(const UK* __restrict__ k
 constexpr double HYB_MAX_EXPECTED_SEGMENT = 4.0;
 constexpr int HYB_MIN_SAVED_PASSES = 2;
 
+// phase 0: every digit was counted. phase 1 (64-bit keys, hybrid allowed): only digits 4..7 were counted; the low digits are
+// known to be constant or not from ctl->vary; if the hybrid plan can stop within the top digits it is final, otherwise
+// ctl->need_low is raised, the gated second histogram counts digits 0..3 and phase 2 plans with everything (phase 2 returns
+// at once when phase 1 was final).
 __global__ void plan_kernel(const uint32_t* __restrict__ ghist, int npass, uint32_t n, int raw, int pre_idx_buf,
-                            sort_ctl* ctl, int first_pass, int last_pass, int hyb_allowed)
+                            sort_ctl* ctl, int first_pass, int last_pass, int hyb_allowed, int phase = 0)
 {
   __shared__ uint32_t warp_tot[8];
   __shared__ int triv[8];
   __shared__ double sq[RADIX];
   __shared__ double coll[8];  // sum_d (c_d / n)^2 of each pass
   const int d = threadIdx.x;  // 256 threads
+  if (phase == 2 && ctl->need_low == 0) return;
+  const int counted_from = phase == 1 ? 4 : 0;  // digits below were not counted
+  const unsigned long long vary = ctl->vary;
   for (int p = 0; p < npass; ++p) {
     uint32_t c = ghist[p * RADIX + d];
+    if (p < counted_from) c = ((vary >> (8 * p)) & 0xffull) == 0 ? (d == 0 ? n : 0u) : 0u;  // all-or-nothing stand-in: constant digit or unknown
     if (d == 0) triv[p] = 0;
     {
       const double f = (double)c / (double)n;
@@ -238,21 +274,33 @@ __global__ void plan_kernel(const uint32_t* __restrict__ ghist, int npass, uint3
     int nexec = 0;
     for (int p = 0; p < npass; ++p) nexec += triv[p] ? 0 : 1;
     int hybrid = 0, low = 0;
+    bool undecided = false;  // phase 1: the decision would need an uncounted digit
     if (hyb_allowed && nexec > HYB_MIN_SAVED_PASSES) {
       double e = (double)n;
       int k = 0;
       low = npass;
       for (int p = npass - 1; p >= 0 && (k == 0 || e > HYB_MAX_EXPECTED_SEGMENT); --p) {  // at least one pass
         if (triv[p]) continue;
+        if (p < counted_from) { undecided = true; break; }
         e *= coll[p];
         ++k;
         low = p;
       }
-      if (e <= HYB_MAX_EXPECTED_SEGMENT && nexec - k >= HYB_MIN_SAVED_PASSES) {
+      if (!undecided && e <= HYB_MAX_EXPECTED_SEGMENT && nexec - k >= HYB_MIN_SAVED_PASSES) {
         hybrid = 1;
         for (int p = 0; p < low; ++p) triv[p] = 1;
         nexec = k;
       }
+    }
+    if (phase == 1) {
+      // final only when the hybrid plan stops within the counted digits, or when no uncounted digit has to be sorted at all
+      bool low_needed = false;
+      for (int p = 0; p < counted_from; ++p) low_needed = low_needed || !triv[p];
+      if (!hybrid && low_needed) {
+        ctl->need_low = 1;
+        return;
+      }
+      ctl->need_low = 0;
     }
     ctl->hybrid    = hybrid;
     ctl->fix_shift = low * RADIX_BITS;
@@ -1011,12 +1059,33 @@ void run_radix_cfg(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int
     {
       int grid = (int)std::min<int64_t>((n + 512 * 16 - 1) / (512 * 16), NUM_SMS_B200 * 4);
       grid = std::max(grid, 1);
-      prof_scope ps("histogram", stream);
-      B2_LAUNCH((histogram_kernel<UK, MIX>), grid, 512, 0, stream, raw ? raw_keys : bufA, n, raw ? 1 : 0, kind, desc_mask, ghist,
-                (raw && kind == (int)key_kind::FLOAT) ? &ctl->nan_count : nullptr);
+      const UK* hkeys = raw ? raw_keys : bufA;
+      uint32_t* nanp = (raw && kind == (int)key_kind::FLOAT) ? &ctl->nan_count : nullptr;
+      // digits that can be executed at all: [first_pass, last_pass]
+      const uint32_t span_mask = ((last_pass >= NP - 1 ? (1u << NP) : (1u << (last_pass + 1))) - 1u) & ~((1u << std::max(first_pass, 0)) - 1u);
+      if (try_hybrid) {
+        // two-phase: the top four digits first (half the shared-memory atomics); the low four only if the plan needs them
+        {
+          prof_scope ps("histogram", stream);
+          B2_LAUNCH((histogram_kernel<UK, MIX>), grid, 512, 0, stream, hkeys, n, raw ? 1 : 0, kind, desc_mask, ghist, nanp, 0xf0u,
+                    (const int32_t*)nullptr, &ctl->vary);
+        }
+        B2_LAUNCH(plan_kernel, 1, RADIX, 0, stream, ghist, NP, (uint32_t)n, raw ? 1 : 0, pre_idx_buf, ctl, first_pass, last_pass, 1, 1);
+        {
+          prof_scope ps("histogram", stream);
+          B2_LAUNCH((histogram_kernel<UK, MIX>), grid, 512, 0, stream, hkeys, n, raw ? 1 : 0, kind, desc_mask, ghist, (uint32_t*)nullptr, 0x0fu,
+                    &ctl->need_low, (unsigned long long*)nullptr);
+        }
+        B2_LAUNCH(plan_kernel, 1, RADIX, 0, stream, ghist, NP, (uint32_t)n, raw ? 1 : 0, pre_idx_buf, ctl, first_pass, last_pass, 1, 2);
+      } else {
+        {
+          prof_scope ps("histogram", stream);
+          B2_LAUNCH((histogram_kernel<UK, MIX>), grid, 512, 0, stream, hkeys, n, raw ? 1 : 0, kind, desc_mask, ghist, nanp, span_mask,
+                    (const int32_t*)nullptr, (unsigned long long*)nullptr);
+        }
+        B2_LAUNCH(plan_kernel, 1, RADIX, 0, stream, ghist, NP, (uint32_t)n, raw ? 1 : 0, pre_idx_buf, ctl, first_pass, last_pass, 0, 0);
+      }
     }
-    B2_LAUNCH(plan_kernel, 1, RADIX, 0, stream, ghist, NP, (uint32_t)n, raw ? 1 : 0, pre_idx_buf, ctl, first_pass, last_pass,
-              try_hybrid ? 1 : 0);
 
     pass_args a{};
     a.key_bufs[0] = raw_keys;
