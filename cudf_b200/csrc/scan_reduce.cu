@@ -403,7 +403,7 @@ __device__ __forceinline__ uint32_t valid_bits_at(const uint32_t* mask, int64_t 
 }
 
 template <typename T, int OP, bool COUNT>
-__global__ void __launch_bounds__(SC_THREADS) scan_kernel(const T* __restrict__ in, const uint32_t* __restrict__ mask,
+__global__ void __launch_bounds__(SC_THREADS, 2) scan_kernel(const T* __restrict__ in, const uint32_t* __restrict__ mask,
                                                           int64_t bit_offset, int64_t n, bool exclusive, bool in_aligned,
                                                           T* __restrict__ out, scan_state st)
 {
