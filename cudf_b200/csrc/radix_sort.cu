@@ -1100,7 +1100,27 @@ void run_radix_cfg(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int
     a.keep_keys = keep_keys ? 1 : 0;
     a.val_in = val_in;
     a.desc_mask = (uint64_t)desc_mask;
+    // Large inputs: read the plan back (one small copy + sync, ~20 us against milliseconds of passes) and launch only the
+    // passes it executes — a skipped pass would otherwise start one CTA per tile just to return (163 K CTAs at 1e9 rows).
+    // Small inputs launch every digit's kernel and stay free of host synchronisation.
+    uint32_t skip_mask = 0;
+    bool plan_hybrid = true;
+    static const int64_t readback_min = [] {
+      const char* e = std::getenv("B2_SORT_PLAN_READBACK_MIN");  // test hook
+      return e ? (int64_t)std::atoll(e) : (int64_t(1) << 22);
+    }();
+    if (n >= readback_min) {
+      pass_plan hp[8];
+      int32_t hflag = 0;
+      B2_CUDA_TRY(cudaMemcpyAsync(hp, &ctl->plan[0], sizeof(pass_plan) * 8, cudaMemcpyDeviceToHost, stream));
+      B2_CUDA_TRY(cudaMemcpyAsync(&hflag, &ctl->hybrid, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+      B2_CUDA_TRY(cudaStreamSynchronize(stream));
+      for (int p = 0; p < NP; ++p)
+        if (hp[p].trivial) skip_mask |= 1u << p;
+      plan_hybrid = hflag != 0;
+    }
     for (int p = std::max(0, first_pass); p < NP && p <= last_pass; ++p) {
+      if ((skip_mask >> p) & 1u) continue;
       for (int64_t q = 0; q < nportions; ++q) {
         const int64_t start = q * plim;
         const int64_t pn = std::min(plim, n - start);
@@ -1118,7 +1138,7 @@ void run_radix_cfg(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int
       }
     }
     if constexpr (sizeof(UK) == 8 && !MIX) {
-      if (try_hybrid) {
+      if (try_hybrid && plan_hybrid) {
         const int64_t ntiles = (n + FIX_TILE - 1) / FIX_TILE;
         const int grid = (int)std::min<int64_t>(ntiles, NUM_SMS_B200 * 8);
         prof_scope ps("segment_fix", stream);
@@ -1129,7 +1149,7 @@ void run_radix_cfg(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int
       int grid = (int)std::min<int64_t>((n + 255) / 256, NUM_SMS_B200 * 8);
       B2_LAUNCH((finalize_kernel<UK, MIX>), std::max(grid, 1), 256, 0, stream, a, n, raw ? 1 : 0, pre_idx_buf, CARRY ? (int)sizeof(VT) : 0);
     }
-    if (!try_hybrid) break;
+    if (!try_hybrid || !plan_hybrid) break;
     uint32_t overflow = 0;
     B2_CUDA_TRY(cudaMemcpyAsync(&overflow, &ctl->overflow, sizeof(overflow), cudaMemcpyDeviceToHost, stream));
     B2_CUDA_TRY(cudaStreamSynchronize(stream));
