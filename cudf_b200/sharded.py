@@ -311,10 +311,12 @@ def sort_by_key_sharded(values: torch.Tensor, keys: torch.Tensor, ops=None, grou
         list(gathered.view(world, -1).unbind(0)), sample, group=group)
     splitters = choose_splitters(ops.sort_keys(gathered), world)
     same = values.data_ptr() == keys.data_ptr() and values.numel() == keys.numel()
-    # Peer-memory scatter vs NCCL: measured on B200 boxes (profiles/r1_multi_gpu.md) the fused scatter wins at
-    # 2 ranks (9.6 ms vs 6.8 + 11.5 ms per 5e8 rows) but at 8 ranks a warp's 32 rows split into ~4-row (32 B)
-    # segments per peer and NVLink runs at ~60 GB/s (114 ms per 1e9 rows), so larger groups use the partition +
-    # NCCL all-to-all-v path until the scatter stages per-peer runs in shared memory. B2_SHARD_P2P=0/1 forces it.
+    # Bucket exchange variants (B2_SHARD_P2P / B2_SHARD_XCHG force one; profiles/ holds the measurements):
+    #   fused scatter ("1"): one kernel writes every row straight into its destination GPU's buffer; best at 2 ranks
+    #     (9.6 ms per 5e8 rows), but at 8 ranks a warp's 32 rows split into ~4-row (32-byte) NVLink writes (114 ms per 1e9 rows)
+    #   fused staged scatter ("staged"): the same with 4 KB per-peer runs staged in shared memory
+    #   partition + contiguous peer copies (B2_SHARD_P2P=0, the default above 2 ranks): b2_partition, then one b2_peer_copy per
+    #     destination — NVLink sees large sequential writes; B2_SHARD_XCHG=nccl swaps the copies for NCCL all_to_all_single
     p2p_env = os.environ.get("B2_SHARD_P2P", "")
     p2p_default = world <= 2
     use_p2p = same and keys.is_cuda and hasattr(ops, "partition_exchange") and (p2p_env in ("1", "staged") or (p2p_env == "" and p2p_default))
