@@ -1,8 +1,7 @@
 // radix_join.cu — partitioned ("radix") inner join for large null-free key tables.
 //
-// EXPERIMENTAL in round 1: written after the round's GPU budget was spent, compiled for sm_100a but not yet run on
-// hardware; OFF by default (B2_JOIN_RADIX_ROWS=<rows> routes cudf::inner_join / left_join / full_join calls whose two
-// sides both have at least that many rows through it).  DESIGN.md §7.4.
+// Default for cudf::inner_join / left_join / full_join calls whose two sides both have at least 2^24 rows
+// (B2_JOIN_RADIX_ROWS=<rows> moves the limit, 0 switches the path off).  Validated on hardware in round 2.
 //
 // Same contract as the hash path it stands in for (cpp/src/join/join.cu:27-110 inner_join over
 // cpp/src/join/hash_join/hash_join.cu:32-299): all (probe row, build row) pairs with equal keys, in unspecified
@@ -230,12 +229,19 @@ void rj_partition(const std::vector<b2_column_view>& cols, cudaStream_t stream, 
 
 }  // namespace
 
-// rows threshold of the experimental path (both sides); unset = off
+// The partitioned join takes over when BOTH sides are large: a build side of 2^24 rows already needs a 512 MB table (beyond
+// the L2), where every build / probe touch of the open-addressing path is a 128-byte DRAM fetch (1e9 x 1e9: 163 ms against
+// 75 ms here, profiles/r2_*). Smaller build sides keep the hash table (L2 resident). B2_JOIN_RADIX_ROWS=<rows> moves the
+// limit (0 = never).
 bool radix_join_applicable(const std::vector<b2_column_view>& a, const std::vector<b2_column_view>& b)
 {
+  if (a.empty() || b.empty()) return false;
   const char* e = std::getenv("B2_JOIN_RADIX_ROWS");
-  if (!e || a.empty() || b.empty()) return false;
-  const int64_t thr = std::max<int64_t>(1, std::atoll(e));
+  int64_t thr = int64_t(1) << 24;
+  if (e) {
+    thr = std::atoll(e);
+    if (thr <= 0) return false;
+  }
   return a[0].size >= thr && b[0].size >= thr && !any_nulls(a) && !any_nulls(b) && !keys_are_wide(a);
 }
 
