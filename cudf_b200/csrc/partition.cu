@@ -627,20 +627,23 @@ b2_status b2_ipc_free(void* ptr)
 
 namespace b2 {
 namespace {
-// grid-stride copy: 16-byte vectors when both ends are 16-byte aligned, bytes for the ragged ends
+// grid-stride copy with the widest vector both ends allow: src and dst are aligned to G bytes RELATIVE to each other
+// (bucket offsets are multiples of the element size, so 8-byte columns usually give G = 8 or 16); the few bytes before the
+// first G-aligned address and after the last whole vector go one by one
+template <typename V>
 __global__ void __launch_bounds__(256) peer_copy_kernel(char* __restrict__ dst, const char* __restrict__ src, size_t bytes)
 {
+  constexpr size_t G = sizeof(V);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  size_t head = (16 - (reinterpret_cast<uintptr_t>(src) & 15)) & 15;
+  size_t head = (G - (reinterpret_cast<uintptr_t>(src) & (G - 1))) & (G - 1);
   if (head > bytes) head = bytes;
-  const bool vec = ((reinterpret_cast<uintptr_t>(dst) + head) & 15) == 0;
-  const size_t nvec = vec ? (bytes - head) / 16 : 0;
+  const size_t nvec = (bytes - head) / G;
   for (size_t i = tid; i < head; i += stride) dst[i] = src[i];
-  const int4* s4 = reinterpret_cast<const int4*>(src + head);
-  int4* d4 = reinterpret_cast<int4*>(dst + head);
-  for (size_t i = tid; i < nvec; i += stride) st_na_v4(d4 + i, ld_nc_v4(s4 + i));
-  for (size_t i = head + nvec * 16 + tid; i < bytes; i += stride) dst[i] = src[i];
+  const V* s = reinterpret_cast<const V*>(src + head);
+  V* d = reinterpret_cast<V*>(dst + head);
+  for (size_t i = tid; i < nvec; i += stride) d[i] = s[i];
+  for (size_t i = head + nvec * G + tid; i < bytes; i += stride) dst[i] = src[i];
 }
 }  // namespace
 }  // namespace b2
@@ -652,7 +655,14 @@ extern "C" b2_status b2_peer_copy(void* dst, const void* src, size_t bytes, b2_s
     if (bytes == 0) return B2_OK;
     const int grid = (int)std::max<size_t>(1, std::min<size_t>((bytes / 16 + 255) / 256, (size_t)b2::NUM_SMS_B200 * 8));
     b2::prof_scope ps("peer_copy", static_cast<cudaStream_t>(stream));
-    B2_LAUNCH(b2::peer_copy_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream), static_cast<char*>(dst), static_cast<const char*>(src), bytes);
+    const uintptr_t rel = reinterpret_cast<uintptr_t>(dst) ^ reinterpret_cast<uintptr_t>(src);  // low bits equal <=> same relative alignment
+    char* d = static_cast<char*>(dst);
+    const char* s = static_cast<const char*>(src);
+    auto st = static_cast<cudaStream_t>(stream);
+    if ((rel & 15) == 0) B2_LAUNCH((b2::peer_copy_kernel<uint4>), grid, 256, 0, st, d, s, bytes);
+    else if ((rel & 7) == 0) B2_LAUNCH((b2::peer_copy_kernel<uint2>), grid, 256, 0, st, d, s, bytes);
+    else if ((rel & 3) == 0) B2_LAUNCH((b2::peer_copy_kernel<uint32_t>), grid, 256, 0, st, d, s, bytes);
+    else B2_LAUNCH((b2::peer_copy_kernel<uint8_t>), grid, 256, 0, st, d, s, bytes);
   B2_TRY_END
 }
 

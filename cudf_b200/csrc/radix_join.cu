@@ -15,9 +15,10 @@
 //      16-bit local row numbers (32768 slots, load factor <= 0.5, slot = bits 33..47 of h); the partition's probe
 //      rows stream through it.  Larger partitions (skew, duplicates, > ~1e9 rows) are handled in chunks of 16384
 //      build rows, re-streaming the probe rows per chunk.
-//   3. count pass (matches per work item) -> exclusive scan -> retrieve pass (same kernel, writes the pairs at the
-//      item's offset; positions inside an item come from a shared-memory cursor).  A work item is (partition, piece of
-//      at most 65536 probe rows), so that a probe-side hot key is spread over many CTAs (each re-builds the table).
+//   3. ONE walk writes the pairs: per (work item, build chunk) count -> one global reservation -> revisit the matching
+//      rows (rj_join_kernel).  A work item is (partition, piece of at most 65536 probe rows), so that a probe-side hot key
+//      is spread over many CTAs (each re-builds the table).  The output buffers are sized by a guess and the walk is
+//      repeated with the exact size when the guess was too small.
 #include "common.cuh"
 #include "device_utils.cuh"
 #include "key_pack.cuh"
@@ -81,31 +82,64 @@ __device__ __forceinline__ uint32_t rj_slot(uint64_t h) { return (uint32_t)(h >>
 
 // One CTA joins work item blockIdx.x = (partition, probe piece); item_first[p] is the first item of partition p
 // (exclusive scan of rj_pieces_kernel's output, item_first[RJ_PARTS] = number of items).
-// RETRIEVE = false: item_counts[item] = number of pairs, *total += it.
-// RETRIEVE = true: pairs are written to out_probe / out_build starting at item_offsets[item].
+// ONE walk produces the pairs: per (item, build chunk) the CTA first probes its rows counting matches (probe keys are
+// fetched RJ_BATCH at a time per thread, so that their global-memory latency overlaps), reserves the output range of the
+// whole chunk with one atomicAdd on the global cursor, and then revisits only the rows that matched to write their pairs —
+// the structure of the reference's partitioned retrieve (cpp/src/join/hash_join/partitioned_retrieve_kernels.cuh:57-206:
+// matches staged per block, one reservation per flush), with the table in shared memory. Pairs beyond `capacity` are counted
+// but not written: the host reruns with the exact size (the cursor's final value) when its guess was too small.
 // LEFT: a probe row without any match (over all build chunks) yields one pair (row, JoinNoMatch); a thread owns the same
 // <= 64 probe rows in every chunk round, so one 64-bit register remembers which of them have matched.
-template <bool RETRIEVE, bool LEFT = false>
+constexpr int RJ_BATCH = 8;
+
+__device__ __forceinline__ unsigned long long rj_block_reserve(unsigned long long mine, unsigned long long* cursor, unsigned long long* s_wsum,
+                                                               unsigned long long* s_base)
+{
+  // exclusive scan of `mine` over the CTA + one global reservation; returns this thread's first output position
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned long long inc = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long nb = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += nb;
+  }
+  if (lane == 31) s_wsum[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned long long w = lane < RJ_THREADS / 32 ? s_wsum[lane] : 0ull;
+    unsigned long long winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long nb = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += nb;
+    }
+    if (lane < RJ_THREADS / 32) s_wsum[lane] = winc - w;  // exclusive offset of each warp
+    if (lane == 31) *s_base = winc ? atomicAdd(cursor, winc) : 0ull;
+  }
+  __syncthreads();
+  const unsigned long long pos = *s_base + s_wsum[warp] + (inc - mine);
+  __syncthreads();  // s_wsum / s_base are reused by the next reservation
+  return pos;
+}
+
+template <bool LEFT = false>
 __global__ void __launch_bounds__(RJ_THREADS, 1)
 rj_join_kernel(const uint64_t* __restrict__ bh, const int32_t* __restrict__ bid, const int32_t* __restrict__ boff,
                const uint64_t* __restrict__ ph, const int32_t* __restrict__ pid, const int32_t* __restrict__ poff,
-               const int32_t* __restrict__ item_first, int32_t* __restrict__ item_counts, const int32_t* __restrict__ item_offsets,
-               unsigned long long* __restrict__ total, int32_t* __restrict__ out_probe, int32_t* __restrict__ out_build)
+               const int32_t* __restrict__ item_first, unsigned long long* __restrict__ cursor, unsigned long long capacity,
+               int32_t* __restrict__ out_probe, int32_t* __restrict__ out_build)
 {
   B2_DYNAMIC_SMEM(rj_smem);
   uint64_t* bk  = reinterpret_cast<uint64_t*>(rj_smem);
   uint32_t* tab = reinterpret_cast<uint32_t*>(rj_smem + (size_t)RJ_CAP * sizeof(uint64_t));  // RJ_SLOTS / 2 words
   const uint16_t* tab16 = reinterpret_cast<const uint16_t*>(tab);
-  __shared__ unsigned int s_cursor;
-  __shared__ unsigned long long s_total;
+  __shared__ unsigned long long s_wsum[RJ_THREADS / 32];
+  __shared__ unsigned long long s_base;
   __shared__ int s_part;
 
   const int item = blockIdx.x;
   const int tid  = threadIdx.x;
-  if (item >= item_first[RJ_PARTS]) {  // the grid is sized for the worst case; uniform over the CTA
-    if (!RETRIEVE && tid == 0) item_counts[item] = 0;
-    return;
-  }
+  if (item >= item_first[RJ_PARTS]) return;  // the grid is sized for the worst case; uniform over the CTA
   if (tid == 0) {
     // partition of this item: the last p with item_first[p] <= item (partitions without items repeat their successor's value)
     int lo = 0, hi = RJ_PARTS;
@@ -114,17 +148,17 @@ rj_join_kernel(const uint64_t* __restrict__ bh, const int32_t* __restrict__ bid,
       if (item_first[mid] <= item) lo = mid;
       else hi = mid;
     }
-    s_part  = lo;
-    s_total = 0;
-    if (RETRIEVE) s_cursor = (unsigned int)item_offsets[item];
+    s_part = lo;
   }
   __syncthreads();
   const int part = s_part;
   const int b0 = boff[part], b1 = boff[part + 1];
   const int64_t p0 = (int64_t)poff[part] + (int64_t)(item - item_first[part]) * RJ_PIECE;
   const int64_t p1 = min(p0 + RJ_PIECE, (int64_t)poff[part + 1]);
-  static_assert(RJ_PIECE / RJ_THREADS <= 64, "one bit per probe row of a thread");
-  unsigned long long local = 0, matched = 0;
+  constexpr int ROUNDS = RJ_PIECE / RJ_THREADS;  // probe rows per thread
+  static_assert(ROUNDS <= 64 && ROUNDS % RJ_BATCH == 0, "one bit per probe row of a thread; whole batches");
+  const int my_rounds = (int)((p1 - p0 - tid + RJ_THREADS - 1) / RJ_THREADS);  // rows p0 + tid + k * RJ_THREADS, k < my_rounds (may be <= 0)
+  unsigned long long matched = 0;
   for (int64_t c0 = b0; c0 < b1; c0 += RJ_CAP) {  // 64-bit: row numbers go up to 2^31 - 1
     const int cn = (int)min((int64_t)RJ_CAP, (int64_t)b1 - c0);
     __syncthreads();  // the previous chunk's probes are done before the table is reset
@@ -148,48 +182,63 @@ rj_join_kernel(const uint64_t* __restrict__ bh, const int32_t* __restrict__ bid,
       }
     }
     __syncthreads();
-    int k = 0;
-    for (int64_t i = p0 + tid; i < p1; i += RJ_THREADS, ++k) {
-      const uint64_t h = ld_stream(ph + i);
+    // ---- walk 1: count this chunk's matches, remember which of my rows matched ----
+    unsigned long long hit = 0, local = 0;
+    for (int kb = 0; kb < ROUNDS; kb += RJ_BATCH) {
+      if (kb >= my_rounds) break;
+      uint64_t h[RJ_BATCH];
+#pragma unroll
+      for (int u = 0; u < RJ_BATCH; ++u) h[u] = (kb + u < my_rounds) ? ld_stream(ph + p0 + tid + (int64_t)(kb + u) * RJ_THREADS) : 0ull;
+#pragma unroll
+      for (int u = 0; u < RJ_BATCH; ++u) {
+        if (kb + u >= my_rounds) break;
+        uint32_t s = rj_slot(h[u]);
+        while (true) {
+          const uint32_t e = tab16[s];
+          if (e == 0xFFFFu) break;
+          if (bk[e] == h[u]) {
+            ++local;
+            hit |= 1ull << (kb + u);
+          }
+          s = (s + 1) & (uint32_t)(RJ_SLOTS - 1);
+        }
+      }
+    }
+    if (LEFT) matched |= hit;
+    // ---- one reservation for the chunk, then walk 2 over the rows that matched ----
+    unsigned long long pos = rj_block_reserve(local, cursor, s_wsum, &s_base);
+    while (hit) {
+      const int k = (uint32_t)hit ? __ffs((int)(uint32_t)hit) - 1 : 32 + __ffs((int)(uint32_t)(hit >> 32)) - 1;
+      hit &= hit - 1;
+      const int64_t i = p0 + tid + (int64_t)k * RJ_THREADS;
+      const uint64_t h = ph[i];
+      const int32_t prow = pid[i];
       uint32_t s = rj_slot(h);
       while (true) {
         const uint32_t e = tab16[s];
         if (e == 0xFFFFu) break;
         if (bk[e] == h) {
-          if (LEFT) matched |= 1ull << k;
-          if (RETRIEVE) {
-            const unsigned int pos = atomicAdd(&s_cursor, 1u);
-            out_probe[pos] = pid[i];
+          if (pos < capacity) {
+            out_probe[pos] = prow;
             out_build[pos] = bid[c0 + e];
-          } else {
-            ++local;
           }
+          ++pos;
         }
         s = (s + 1) & (uint32_t)(RJ_SLOTS - 1);
       }
     }
   }
   if (LEFT) {
-    int k = 0;
-    for (int64_t i = p0 + tid; i < p1; i += RJ_THREADS, ++k) {
+    unsigned long long un = 0;  // my rows that never matched
+    for (int k = 0; k < my_rounds; ++k) un += ((matched >> k) & 1ull) ? 0ull : 1ull;
+    unsigned long long pos = rj_block_reserve(un, cursor, s_wsum, &s_base);
+    for (int k = 0; k < my_rounds; ++k) {
       if ((matched >> k) & 1ull) continue;
-      if (RETRIEVE) {
-        const unsigned int pos = atomicAdd(&s_cursor, 1u);
-        out_probe[pos] = pid[i];
+      if (pos < capacity) {
+        out_probe[pos] = pid[p0 + tid + (int64_t)k * RJ_THREADS];
         out_build[pos] = B2_JOIN_NO_MATCH;
-      } else {
-        ++local;
       }
-    }
-  }
-  if (!RETRIEVE) {
-    local = warp_sum(local);
-    if (lane_id() == 0 && local) atomicAdd(&s_total, local);
-    __syncthreads();
-    if (tid == 0) {
-      const unsigned long long t = s_total;
-      item_counts[item] = (int32_t)min(t, (unsigned long long)INT32_MAX);  // the 64-bit total catches overflow
-      if (t) atomicAdd(total, t);
+      ++pos;
     }
   }
 }
@@ -252,10 +301,8 @@ void radix_join(const std::vector<b2_column_view>& build, const std::vector<b2_c
 {
   static std::atomic<uint64_t> attr_done{0};
   once_per_device(attr_done, [] {
-    B2_CUDA_TRY(cudaFuncSetAttribute(rj_join_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RJ_SMEM));
-    B2_CUDA_TRY(cudaFuncSetAttribute(rj_join_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RJ_SMEM));
-    B2_CUDA_TRY(cudaFuncSetAttribute(rj_join_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RJ_SMEM));
-    B2_CUDA_TRY(cudaFuncSetAttribute(rj_join_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RJ_SMEM));
+    B2_CUDA_TRY(cudaFuncSetAttribute(rj_join_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RJ_SMEM));
+    B2_CUDA_TRY(cudaFuncSetAttribute(rj_join_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RJ_SMEM));
   });
   rj_side bs, ps;
   rj_partition(build, stream, bs);
@@ -269,30 +316,48 @@ void radix_join(const std::vector<b2_column_view>& build, const std::vector<b2_c
   b2_column_view pv{B2_INT32, (int32_t)(RJ_PARTS + 1), pieces.ptr, nullptr, 0, 0};
   auto item_first = scan(pv, B2_AGG_SUM, B2_SCAN_EXCLUSIVE, B2_NULL_EXCLUDE, stream);
 
-  dbuf counts(sizeof(int32_t) * max_items, stream), tot(sizeof(unsigned long long), stream);
-  B2_CUDA_TRY(cudaMemsetAsync(tot.ptr, 0, sizeof(unsigned long long), stream));
-  {
-    prof_scope sc("rjoin_count", stream);
-#define B2_RJ(R, L, ...) B2_LAUNCH((rj_join_kernel<R, L>), max_items, RJ_THREADS, RJ_SMEM, stream, bs.h.as<uint64_t>(), bs.ids.as<int32_t>(), \
-                                   bs.off.as<int32_t>(), ps.h.as<uint64_t>(), ps.ids.as<int32_t>(), ps.off.as<int32_t>(),                    \
-                                   item_first->data.as<int32_t>(), __VA_ARGS__)
-    if (left) B2_RJ(false, true, counts.as<int32_t>(), (const int32_t*)nullptr, tot.as<unsigned long long>(), (int32_t*)nullptr, (int32_t*)nullptr);
-    else B2_RJ(false, false, counts.as<int32_t>(), (const int32_t*)nullptr, tot.as<unsigned long long>(), (int32_t*)nullptr, (int32_t*)nullptr);
-  }
-  unsigned long long m = 0;
-  B2_CUDA_TRY(cudaMemcpyAsync(&m, tot.ptr, sizeof(m), cudaMemcpyDeviceToHost, stream));
-  B2_CUDA_TRY(cudaStreamSynchronize(stream));  // the reference syncs for the output size too (size_impl.cuh:52-61)
-  B2_EXPECTS(m <= (unsigned long long)INT32_MAX, B2_ERR_LOGIC /* std::overflow_error in libcudf */,
-             "join output exceeds size_type (use hash_join::*_join_size and partition the probe side)");
-  out_probe = make_column(B2_INT32, (int32_t)m, false, stream);
-  out_build = make_column(B2_INT32, (int32_t)m, false, stream);
-  if (m == 0) return;
-  b2_column_view cv{B2_INT32, max_items, counts.ptr, nullptr, 0, 0};
-  auto offs = scan(cv, B2_AGG_SUM, B2_SCAN_EXCLUSIVE, B2_NULL_EXCLUDE, stream);
-  prof_scope sr("rjoin_retrieve", stream);
-  if (left) B2_RJ(true, true, (int32_t*)nullptr, offs->data.as<int32_t>(), (unsigned long long*)nullptr, out_probe->data.as<int32_t>(), out_build->data.as<int32_t>());
-  else B2_RJ(true, false, (int32_t*)nullptr, offs->data.as<int32_t>(), (unsigned long long*)nullptr, out_probe->data.as<int32_t>(), out_build->data.as<int32_t>());
+  // The output size is only known after the walk (the reference walks twice: size_impl.cuh then retrieve_impl.cuh). Guess
+  // one pair per probe row (left joins: a quarter more), write what fits, read the true size back, and repeat with the
+  // exact size in the rare case the guess was too small.
+  dbuf tot(sizeof(unsigned long long), stream);
+  unsigned long long capacity = std::min<unsigned long long>((unsigned long long)INT32_MAX, (unsigned long long)n_probe + (left ? (unsigned long long)n_probe / 4 : 0ull));
+  if (const char* e = std::getenv("B2_JOIN_RADIX_CAPACITY")) capacity = std::max<long long>(1, std::atoll(e));  // test hook: force the rerun
+  for (int attempt = 0;; ++attempt) {
+    auto op = make_column(B2_INT32, (int32_t)capacity, false, stream);
+    auto ob = make_column(B2_INT32, (int32_t)capacity, false, stream);
+    B2_CUDA_TRY(cudaMemsetAsync(tot.ptr, 0, sizeof(unsigned long long), stream));
+    {
+      prof_scope sc("rjoin_join", stream);
+#define B2_RJ(L) B2_LAUNCH((rj_join_kernel<L>), max_items, RJ_THREADS, RJ_SMEM, stream, bs.h.as<uint64_t>(), bs.ids.as<int32_t>(),      \
+                           bs.off.as<int32_t>(), ps.h.as<uint64_t>(), ps.ids.as<int32_t>(), ps.off.as<int32_t>(),                        \
+                           item_first->data.as<int32_t>(), tot.as<unsigned long long>(), capacity, op->data.as<int32_t>(), ob->data.as<int32_t>())
+      if (left) B2_RJ(true);
+      else B2_RJ(false);
 #undef B2_RJ
+    }
+    unsigned long long m = 0;
+    B2_CUDA_TRY(cudaMemcpyAsync(&m, tot.ptr, sizeof(m), cudaMemcpyDeviceToHost, stream));
+    B2_CUDA_TRY(cudaStreamSynchronize(stream));  // the reference syncs for the output size too (size_impl.cuh:52-61)
+    B2_EXPECTS(m <= (unsigned long long)INT32_MAX, B2_ERR_LOGIC /* std::overflow_error in libcudf */,
+               "join output exceeds size_type (use hash_join::*_join_size and partition the probe side)");
+    if (m > capacity) {
+      B2_EXPECTS(attempt == 0, B2_ERR_LOGIC, "radix join: output size changed between walks");
+      capacity = m;
+      continue;
+    }
+    if (m == capacity) {
+      out_probe = std::move(op);
+      out_build = std::move(ob);
+    } else {  // hand back right-sized columns (the guess may be ten times the result)
+      out_probe = make_column(B2_INT32, (int32_t)m, false, stream);
+      out_build = make_column(B2_INT32, (int32_t)m, false, stream);
+      if (m) {
+        B2_CUDA_TRY(cudaMemcpyAsync(out_probe->data.ptr, op->data.ptr, sizeof(int32_t) * m, cudaMemcpyDeviceToDevice, stream));
+        B2_CUDA_TRY(cudaMemcpyAsync(out_build->data.ptr, ob->data.ptr, sizeof(int32_t) * m, cudaMemcpyDeviceToDevice, stream));
+      }
+    }
+    return;
+  }
 }
 
 }  // namespace b2

@@ -106,10 +106,14 @@ class CudaOps:
         res = plc.Table._from_handle(out.value)
         return [c.to_torch() for c in res.columns()], list(offs)
 
-    def partition_exchange(self, column: torch.Tensor, key: torch.Tensor, mode: int, splitters, group=None):
-        """Fused partition + all-to-all of ONE column over peer memory. Returns this rank's received rows (a view of
-        the exchange buffer, valid until the next call) or None when P2P is unavailable."""
+    def partition_exchange(self, columns, key: torch.Tensor, mode: int, splitters, group=None, slot_base: int = 0, variant: str = "staged"):
+        """Fused partition + all-to-all of several columns over peer memory: ONE plan (bucket + stable in-bucket rank of every
+        row), then one scatter kernel per column that writes each row straight into its destination GPU's receive buffer
+        (variant "staged": per-peer runs staged in shared memory first; "plain": row by row). Returns this rank's received
+        columns (views of the exchange buffers slot_base.., valid until the next call that uses the same slots)."""
         plc, lib = self.plc, self._lib
+        single = isinstance(columns, torch.Tensor)
+        cols = [columns] if single else list(columns)
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         kcol = plc.Column.from_torch(key)
         kv = kcol._view()
@@ -124,18 +128,21 @@ class CudaOps:
             cm = allc.view(world, world).cpu()                      # cm[r][d] = rows rank r sends to rank d
             recv_total = int(cm[:, rank].sum())
             max_recv = int(cm.sum(dim=0).max())
-            esz = column.element_size()
             max_send = int(cm.sum(dim=1).max())                    # every rank sees the same matrix: the capacity is agreed
-            ex = PeerExchange.get(lib, int(max(max_recv, max_send) * esz * 1.05) + (1 << 20), group)
+            exs = [PeerExchange.get(lib, int(max(max_recv, max_send) * c.element_size() * 1.05) + (1 << 20), group, slot=slot_base + j)
+                   for j, c in enumerate(cols)]
             my_off = cm[:rank, :].sum(dim=0)                          # rows written before mine in each destination
-            dest = (C.c_void_p * world)(*[ex.peer_ptrs[d] + int(my_off[d]) * esz for d in range(world)])
             dist.barrier(group=group)                                 # peers are done reading the previous contents
-            ccol = plc.Column.from_torch(column)
-            cv = ccol._view()
-            scatter = lib.lib.b2_partition_scatter_staged if os.environ.get("B2_SHARD_P2P", "") == "staged" else lib.lib.b2_partition_scatter
-            lib.check(scatter(plan, C.byref(cv), dest, lib.stream_arg(None)))
-            dist.barrier(group=group)                                 # stream-ordered after the scatter: all buckets landed
-            return ex.view(recv_total, column.dtype)
+            scatter = lib.lib.b2_partition_scatter_staged if variant == "staged" else lib.lib.b2_partition_scatter
+            for ex, c in zip(exs, cols):
+                esz = c.element_size()
+                dest = (C.c_void_p * world)(*[ex.peer_ptrs[d] + int(my_off[d]) * esz for d in range(world)])
+                ccol = plc.Column.from_torch(c)
+                cv = ccol._view()
+                lib.check(scatter(plan, C.byref(cv), dest, lib.stream_arg(None)))
+            dist.barrier(group=group)                                 # stream-ordered after the scatters: all buckets landed
+            out = [ex.view(recv_total, c.dtype) for ex, c in zip(exs, cols)]
+            return out[0] if single else out
         finally:
             lib.lib.b2_partition_plan_free(plan)
 
@@ -284,6 +291,23 @@ def _exchange_cols(cols, offsets, ops, group=None, slot_base: int = 0):
     return [_exchange(c, offsets, group) for c in cols]
 
 
+def _exchange_variant(t: torch.Tensor, ops) -> str:
+    """Bucket exchange on GPUs (B2_SHARD_P2P forces one; measurements in profiles/r2_multi_gpu.md):
+      "staged" (default): fused partition + exchange, per-peer runs of a 4096-row tile staged in shared memory before the
+          remote stores (2 GPUs: 14.0 ms per 1e9 rows)
+      "1" / "plain": fused, row-by-row remote stores (2 GPUs: 16.9 ms; at 8 GPUs a warp's rows split into 32-byte writes)
+      "0" / "copy": b2_partition, then one contiguous b2_peer_copy per destination (B2_SHARD_XCHG=nccl: all_to_all_single)
+    CPU tensors (gloo tests) always take the partition + process-group all-to-all path."""
+    if not (t.is_cuda and hasattr(ops, "partition_exchange")):
+        return "copy"
+    env = os.environ.get("B2_SHARD_P2P", "")
+    if env in ("0", "copy"):
+        return "copy"
+    if env in ("1", "plain"):
+        return "plain"
+    return "staged"
+
+
 def choose_splitters(samples_sorted: torch.Tensor, world: int) -> torch.Tensor:
     """P-1 splitters at the i/P quantiles of the gathered, sorted sample."""
     m = samples_sorted.numel()
@@ -311,19 +335,14 @@ def sort_by_key_sharded(values: torch.Tensor, keys: torch.Tensor, ops=None, grou
         list(gathered.view(world, -1).unbind(0)), sample, group=group)
     splitters = choose_splitters(ops.sort_keys(gathered), world)
     same = values.data_ptr() == keys.data_ptr() and values.numel() == keys.numel()
-    # Bucket exchange variants (B2_SHARD_P2P / B2_SHARD_XCHG force one; profiles/ holds the measurements):
-    #   fused scatter ("1"): one kernel writes every row straight into its destination GPU's buffer; best at 2 ranks
-    #     (9.6 ms per 5e8 rows), but at 8 ranks a warp's 32 rows split into ~4-row (32-byte) NVLink writes (114 ms per 1e9 rows)
-    #   fused staged scatter ("staged"): the same with 4 KB per-peer runs staged in shared memory
-    #   partition + contiguous peer copies (B2_SHARD_P2P=0, the default above 2 ranks): b2_partition, then one b2_peer_copy per
-    #     destination — NVLink sees large sequential writes; B2_SHARD_XCHG=nccl swaps the copies for NCCL all_to_all_single
-    p2p_env = os.environ.get("B2_SHARD_P2P", "")
-    p2p_default = world <= 2
-    use_p2p = same and keys.is_cuda and hasattr(ops, "partition_exchange") and (p2p_env in ("1", "staged") or (p2p_env == "" and p2p_default))
-    if use_p2p:
+    variant = _exchange_variant(keys, ops)
+    if variant in ("staged", "plain"):
         ph.mark("partition+exchange(p2p)")
-        rk = ops.partition_exchange(keys, keys, 0, splitters, group)
-        rv = rk
+        if same:
+            rk = ops.partition_exchange(keys, keys, 0, splitters, group, variant=variant)
+            rv = rk
+        else:
+            rk, rv = ops.partition_exchange([keys, values], keys, 0, splitters, group, variant=variant)
     else:
         ph.mark("partition")
         cols, offsets = ops.partition([keys] if same else [keys, values], keys, 0, splitters, world)
@@ -354,6 +373,11 @@ def inner_join_sharded(left_keys: torch.Tensor, right_keys: torch.Tensor, ops=No
         gid = global_ids(keys)
         if world == 1:
             return keys, gid
+        variant = _exchange_variant(keys, ops)
+        if variant in ("staged", "plain"):
+            ph.mark("partition+exchange(p2p)")
+            got = ops.partition_exchange([keys, gid], keys, 1, None, group, slot_base=slot_base, variant=variant)
+            return got[0], got[1]
         ph.mark("partition")
         cols, offsets = ops.partition([keys, gid], keys, 1, None, world)
         ph.mark("exchange")

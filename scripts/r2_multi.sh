@@ -21,10 +21,11 @@ TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr
 nvidia-smi topo -m > "$O/topo.txt" 2>&1
 for v in $VARIANTS; do
   case $v in
-    peer)   E="B2_SHARD_P2P=0 B2_SHARD_XCHG=peer" ;;
+    peer)   E="B2_SHARD_P2P=copy B2_SHARD_XCHG=peer" ;;
     staged) E="B2_SHARD_P2P=staged" ;;
+    copy)   E="B2_SHARD_P2P=copy" ;;
     p2p)    E="B2_SHARD_P2P=1" ;;
-    nccl)   E="B2_SHARD_P2P=0 B2_SHARD_XCHG=nccl" ;;
+    nccl)   E="B2_SHARD_P2P=copy B2_SHARD_XCHG=nccl" ;;
     default) E="X=1" ;;
   esac
   run check_$v 300 $E -- $TR scripts/sharded_check.py --rows 20000000

@@ -42,7 +42,7 @@ def emu_lib():
 
 def run(code: str, marker: str, env=None, timeout=900):
     e = dict(os.environ)
-    for k in ("B2_SORT_PLAN_READBACK_MIN", "B2_GROUPBY_PARTITION_ROWS", "B2_GROUPBY_SMEM_SLOTS", "B2_SORT_HYBRID", "B2_SORT_HYBRID_MIN", "B2_SORT_CARRY", "B2_SORT_ALIAS", "B2_JOIN_RADIX_ROWS", "B2_JOIN_PARTITION_ROWS", "B2_SORT_CFG", "B2_SORT_PORTION"):
+    for k in ("B2_JOIN_RADIX_CAPACITY", "B2_SORT_PLAN_READBACK_MIN", "B2_GROUPBY_PARTITION_ROWS", "B2_GROUPBY_SMEM_SLOTS", "B2_SORT_HYBRID", "B2_SORT_HYBRID_MIN", "B2_SORT_CARRY", "B2_SORT_ALIAS", "B2_JOIN_RADIX_ROWS", "B2_JOIN_PARTITION_ROWS", "B2_SORT_CFG", "B2_SORT_PORTION"):
         e.pop(k, None)
     e.update(env or {})
     r = subprocess.run([sys.executable, "-c", PRELUDE + code], capture_output=True, text=True, env=e, cwd=ROOT, timeout=timeout)
@@ -145,7 +145,7 @@ print('ALIAS_OK')
 
 def test_emu_radix_inner_join(emu_lib):
     """Partitioned shared-memory join incl. the MIX partition kernels, multi-chunk partitions and packed / float keys."""
-    run(r"""
+    code = r"""
 rng = np.random.default_rng(78)
 def check(l, r, tag, kinds=("inner_join",)):
     for kind in kinds:
@@ -164,8 +164,15 @@ check(l, r, 'two columns, float specials')
 p = rng.integers(0, 100_000, 200_000); p[:150_000] = 777
 b = rng.integers(0, 100_000, 30_000); b[:5] = 777
 check([(p, None)], [(b, None)], 'probe pieces')
+# a left join whose hot probe key spans several pieces AND several build chunks
+p = rng.integers(0, 100_000, 90_000); p[:70_000] = 555
+b = rng.integers(0, 100_000, 40_000); b[:20_000] = 555
+check([(p[:3000], None)], [(b, None)], 'dup x chunks', ("inner_join", "left_join"))
 print('RADIX_JOIN_OK')
-""", "RADIX_JOIN_OK", env={"B2_JOIN_RADIX_ROWS": "1"})
+"""
+    run(code, "RADIX_JOIN_OK", env={"B2_JOIN_RADIX_ROWS": "1"})
+    # output-size guess too small: the walk is repeated with the exact size
+    run(code, "RADIX_JOIN_OK", env={"B2_JOIN_RADIX_ROWS": "1", "B2_JOIN_RADIX_CAPACITY": "100"})
 
 
 def test_emu_wide_keys(emu_lib):
