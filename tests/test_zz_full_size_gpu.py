@@ -111,7 +111,8 @@ def test_sort_1e8_exact_vs_numpy_stable(plc):
     exp = np.argsort(hk, kind="stable")
     assert order.dtype == np.int32 and np.array_equal(order, exp.astype(np.int32))
     assert np.array_equal(got, hv[exp])
-    # a duplicate-heavy column of the same size (ties keep input order): keys mod 1000
+    # a duplicate-heavy column (ties keep input order): keys mod 1000
+    n = 30_000_000
     dk = _fill(_lib, torch.empty(n, dtype=torch.int64, device="cuda"), n, 9, kind=2, modulus=1000)
     order = plc.sorting.sorted_order(plc.Table([plc.Column.from_torch(dk)]), [plc.Order.DESCENDING], []).to_torch().cpu().numpy()
     hd = dk.cpu().numpy()
@@ -120,10 +121,9 @@ def test_sort_1e8_exact_vs_numpy_stable(plc):
     _lib.check(_lib.lib.b2_trim_pool())
 
 
-@pytest.mark.parametrize("path", ["default", "hash_table", "partitioned"])
-def test_inner_join_3e7_canonical_pairs_exact(plc, path):
+def test_inner_join_3e7_canonical_pairs_exact(plc):
     """BASELINE configs[2] shape at 3e7 x 3e7 rows: canonical-sorted (left, right) pairs equal the oracle's, for the default
-    path choice and for each join path forced."""
+    path choice and for each join path forced (the oracle runs once)."""
     import os
 
     import numpy as np
@@ -140,19 +140,23 @@ def test_inner_join_3e7_canonical_pairs_exact(plc, path):
     hit = u < 0.10
     lk[hit] = rk[sel[hit]]
     lk[::1000] = lk[7]  # a probe-side hot key as well
+    exp = ojoin.inner_join([(lk.cpu().numpy(), None)], [(rk.cpu().numpy(), None)])
+    L, R = plc.Table([plc.Column.from_torch(lk)]), plc.Table([plc.Column.from_torch(rk)])
     prev = os.environ.get("B2_JOIN_RADIX_ROWS")
-    if path != "default":
-        os.environ["B2_JOIN_RADIX_ROWS"] = "0" if path == "hash_table" else "1000000"
     try:
-        li, ri = plc.join.inner_join(plc.Table([plc.Column.from_torch(lk)]), plc.Table([plc.Column.from_torch(rk)]), plc.NullEquality.EQUAL)
+        for path in ("default", "hash_table", "partitioned"):
+            if path == "default":
+                os.environ.pop("B2_JOIN_RADIX_ROWS", None)
+            else:
+                os.environ["B2_JOIN_RADIX_ROWS"] = "0" if path == "hash_table" else "1000000"
+            li, ri = plc.join.inner_join(L, R, plc.NullEquality.EQUAL)
+            got = ojoin.canonical(li.to_torch().cpu().numpy(), ri.to_torch().cpu().numpy())
+            assert np.array_equal(got[0], exp[0]) and np.array_equal(got[1], exp[1]), path
     finally:
         if prev is None:
             os.environ.pop("B2_JOIN_RADIX_ROWS", None)
         else:
             os.environ["B2_JOIN_RADIX_ROWS"] = prev
-    got = ojoin.canonical(li.to_torch().cpu().numpy(), ri.to_torch().cpu().numpy())
-    exp = ojoin.inner_join([(lk.cpu().numpy(), None)], [(rk.cpu().numpy(), None)])
-    assert np.array_equal(got[0], exp[0]) and np.array_equal(got[1], exp[1])
     _lib.check(_lib.lib.b2_trim_pool())
 
 
