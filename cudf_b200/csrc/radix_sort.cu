@@ -1486,11 +1486,31 @@ column_ptr sort_by_key_carry(const b2_column_view& keys, const b2_column_view& v
     using UK = decltype(ktag);
     using VT = decltype(vtag);
     dbuf a(sizeof(UK) * n, stream), b(sizeof(UK) > 1 ? sizeof(UK) * n : 0, stream);
-    if constexpr (sizeof(UK) == 8)
-      run_radix_cfg<UK, 384, 16, 2, VT, true>(static_cast<const UK*>(keys.data) + keys.offset, a.as<UK>(), b.as<UK>(),
-                                              out->data.as<int32_t>(), vtmp.as<int32_t>(), nullptr, 0, n, kind, !ascending, true,
-                                              stream, 0, 7, false, vin);
-    else
+    if constexpr (sizeof(UK) == 8) {
+      // B2_SORT_CFG on the payload-carrying kernel: 10 = formally race-free ranking (one more __syncwarp), 11 = running
+      // offsets by one ATOMS.ADD, 13 = both
+      switch (sort_cfg_env()) {
+        case 10:
+          run_radix_cfg<UK, 384, 16, 2, VT, true, false, true>(static_cast<const UK*>(keys.data) + keys.offset, a.as<UK>(), b.as<UK>(),
+                                                               out->data.as<int32_t>(), vtmp.as<int32_t>(), nullptr, 0, n, kind, !ascending,
+                                                               true, stream, 0, 7, false, vin);
+          break;
+        case 11:
+          run_radix_cfg<UK, 384, 16, 2, VT, true, false, false, true>(static_cast<const UK*>(keys.data) + keys.offset, a.as<UK>(), b.as<UK>(),
+                                                                      out->data.as<int32_t>(), vtmp.as<int32_t>(), nullptr, 0, n, kind,
+                                                                      !ascending, true, stream, 0, 7, false, vin);
+          break;
+        case 13:
+          run_radix_cfg<UK, 384, 16, 2, VT, true, false, true, true>(static_cast<const UK*>(keys.data) + keys.offset, a.as<UK>(), b.as<UK>(),
+                                                                     out->data.as<int32_t>(), vtmp.as<int32_t>(), nullptr, 0, n, kind,
+                                                                     !ascending, true, stream, 0, 7, false, vin);
+          break;
+        default:
+          run_radix_cfg<UK, 384, 16, 2, VT, true>(static_cast<const UK*>(keys.data) + keys.offset, a.as<UK>(), b.as<UK>(),
+                                                  out->data.as<int32_t>(), vtmp.as<int32_t>(), nullptr, 0, n, kind, !ascending, true,
+                                                  stream, 0, 7, false, vin);
+      }
+    } else
       run_radix_cfg<UK, 512, 16, 1, VT, true>(static_cast<const UK*>(keys.data) + keys.offset, a.as<UK>(), b.as<UK>(),
                                               out->data.as<int32_t>(), vtmp.as<int32_t>(), nullptr, 0, n, kind, !ascending, true,
                                               stream, 0, 7, false, vin);
