@@ -344,6 +344,34 @@ B2_API b2_status b2_pack_metadata(const b2_table_view* input, const uint8_t* con
 B2_API b2_status b2_unpack(const uint8_t* metadata, size_t metadata_size, const void* gpu_data, b2_column_view* out_columns,
                            int32_t capacity, int32_t* num_columns, int32_t* num_rows);
 
+/* ---- Arrow C Data / C Device Data interface (cpp/include/cudf/interop.hpp to_arrow_schema / to_arrow_device / to_arrow_host /
+ *      from_arrow_device_column / from_arrow; cpp/src/interop/*).  The structs are the published Arrow ABI: a pointer to
+ *      b2_arrow_schema / b2_arrow_array / b2_arrow_device_array IS a pointer to ArrowSchema / ArrowArray / ArrowDeviceArray.
+ *      Fixed-width types only (BOOL8 is bit-packed on the Arrow side and converted). --------------------------------------- */
+typedef struct b2_arrow_schema {
+  const char* format; const char* name; const char* metadata; int64_t flags; int64_t n_children;
+  struct b2_arrow_schema** children; struct b2_arrow_schema* dictionary;
+  void (*release)(struct b2_arrow_schema*); void* private_data;
+} b2_arrow_schema;
+typedef struct b2_arrow_array {
+  int64_t length; int64_t null_count; int64_t offset; int64_t n_buffers; int64_t n_children;
+  const void** buffers; struct b2_arrow_array** children; struct b2_arrow_array* dictionary;
+  void (*release)(struct b2_arrow_array*); void* private_data;
+} b2_arrow_array;
+typedef struct b2_arrow_device_array {
+  b2_arrow_array array; int64_t device_id; int32_t device_type; void* sync_event; int64_t reserved[3];
+} b2_arrow_device_array;
+B2_API b2_status b2_to_arrow_schema(const b2_column_view* col, const char* name, b2_arrow_schema* out);
+/* zero copy: the caller keeps the column alive until out->array.release is called; sync_event is recorded on `stream` */
+B2_API b2_status b2_to_arrow_device(const b2_column_view* col, b2_stream stream, b2_arrow_device_array* out);
+B2_API b2_status b2_to_arrow_host(const b2_column_view* col, b2_stream stream, b2_arrow_array* out);
+/* out_view points into the producer's buffers (which must outlive it); BOOL8 input is converted: *out_owner owns the copy */
+B2_API b2_status b2_from_arrow_device(const b2_arrow_schema* schema, const b2_arrow_device_array* in, b2_stream stream,
+                                      b2_column_view* out_view, b2_column** out_owner);
+B2_API b2_status b2_from_arrow_host(const b2_arrow_schema* schema, const b2_arrow_array* in, b2_stream stream, b2_column** out);
+B2_API void      b2_arrow_schema_release(b2_arrow_schema* schema);
+B2_API void      b2_arrow_array_release(b2_arrow_array* array);
+
 /* ---- synthetic data (SURVEY §8d generator): x_i = splitmix64(seed + first + i) -------------- */
 /* kind 0: raw uint64 -> int64 ; 1: float64 uniform [0,1) ; 2: x mod modulus as int64 ;
  * 3: int32 low bits ; 4: validity bitmask words with P(valid)=0.5 (n = number of bits) */

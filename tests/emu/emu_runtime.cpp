@@ -372,6 +372,8 @@ cudaError_t cudaDeviceSetLimit(int, size_t) { return cudaSuccess; }
 struct emu_event { std::chrono::steady_clock::time_point t; };
 cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new emu_event(); return cudaSuccess; }
 cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { return cudaEventCreate(e); }
+cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
 cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { e->t = std::chrono::steady_clock::now(); return cudaSuccess; }
 cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b)
 {

@@ -98,6 +98,9 @@ cudaError_t cudaDeviceSetLimit(int, size_t);
 cudaError_t cudaEventCreate(cudaEvent_t*);
 cudaError_t cudaEventDestroy(cudaEvent_t);
 cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t);
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t*, unsigned);
+cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned);
+constexpr unsigned cudaEventDisableTiming = 2;
 cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t);
 cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t*, void*);
 cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned);
