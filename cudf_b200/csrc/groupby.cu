@@ -604,10 +604,15 @@ static void empty_results(const b2_groupby& gb, const std::vector<request_view>&
     for (int32_t kind : r.kinds) res_out->cols.push_back(make_column(result_type(base_kind(kind), r.values.type_id), 0, false, stream));
 }
 
+bool groupby_needs_sort_path(const b2_groupby& gb, const std::vector<request_view>& reqs);
+void groupby_aggregate_sorted(const b2_groupby& gb, const std::vector<request_view>& reqs, cudaStream_t stream, table_ptr& keys_out,
+                              table_ptr& res_out);
+
 // cudf::groupby::groupby::aggregate — groupby.cu:220-237 -> hash path
 void groupby_aggregate(const b2_groupby& gb, const std::vector<request_view>& reqs, cudaStream_t stream, table_ptr& keys_out,
                        table_ptr& res_out)
 {
+  if (groupby_needs_sort_path(gb, reqs)) return groupby_aggregate_sorted(gb, reqs, stream, keys_out, res_out);
   const int64_t n = gb.keys.empty() ? 0 : gb.keys[0].size;
   for (auto& r : reqs) {
     validate_column(r.values);
@@ -1135,6 +1140,352 @@ void groupby_scan(const b2_groupby& gb, const std::vector<request_view>& reqs, c
         if (flt) run_seg_scan<double, OPK_MAX>(a, stream);
         else if (uns) run_seg_scan<unsigned long long, OPK_MAX>(a, stream);
         else run_seg_scan<long long, OPK_MAX>(a, stream);
+      }
+      res_out->cols.push_back(std::move(col));
+    }
+  }
+}
+
+// ---- sort-based aggregate -----------------------------------------------------------------------------------------------
+// cudf::groupby falls back to its sort-based implementation when the keys are declared pre-sorted or when a requested
+// aggregation has no hash implementation (cpp/src/groupby/groupby.cu:76-99 dispatch_aggregation, cpp/src/groupby/sort/
+// aggregate.cpp, sort_helper.cu; per-aggregation group_*.cu).  Here: stable sorted order of the keys (radix_sort.cu) ->
+// group boundaries -> values gathered into group order -> one segmented reduction per aggregation (scan_reduce.cu); the
+// order-dependent ones (NTH_ELEMENT, NUNIQUE, MEDIAN) read the group order / a second order by (keys, values).
+// Output: one row per group in ascending key order (nulls first), the sort path's order in the reference.
+namespace {
+
+__global__ void gb_offsets_kernel(const uint8_t* __restrict__ head, const int32_t* __restrict__ gid_incl, int64_t n, int32_t G,
+                                  int32_t* __restrict__ offsets)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    if (head[i]) offsets[gid_incl[i] - 1] = (int32_t)i;
+    if (i == 0) offsets[G] = (int32_t)n;
+  }
+}
+__global__ void gb_head32_kernel(const uint8_t* __restrict__ head, int64_t n, int32_t* __restrict__ out)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = head[i];
+}
+__global__ void gb_rep_rows_kernel(const int32_t* __restrict__ order, const int32_t* __restrict__ offsets, int32_t G, int32_t* __restrict__ rep)
+{
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < G) rep[g] = order[offsets[g]];
+}
+__global__ void gb_sizes_kernel(const int32_t* __restrict__ offsets, int32_t G, int32_t* __restrict__ out)
+{
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < G) out[g] = offsets[g + 1] - offsets[g];
+}
+__global__ void gb_valid_flags_kernel(const uint32_t* __restrict__ mask, int64_t n, int32_t* __restrict__ flags)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) flags[i] = (mask == nullptr || bit_is_set(mask, i)) ? 1 : 0;
+}
+// NTH_ELEMENT: gather map into the group-ordered values; out-of-range picks become nulls (INT32_MIN is out of bounds for gather)
+__global__ void gb_nth_map_kernel(const int32_t* __restrict__ offsets, int32_t G, int32_t nth, int32_t* __restrict__ map)
+{
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  const int32_t size = offsets[g + 1] - offsets[g];
+  const int32_t idx = nth >= 0 ? nth : size + nth;
+  map[g] = (idx >= 0 && idx < size) ? offsets[g] + idx : INT32_MIN;
+}
+// values as doubles (and their squares) / as wrapped 64-bit integers squared: inputs of SUM_OF_SQUARES / M2 / VARIANCE / STD
+__global__ void gb_squares_kernel(const void* __restrict__ src, int32_t st, int64_t n, double* __restrict__ x, double* __restrict__ x2,
+                                  long long* __restrict__ i2)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    double d = 0;
+    long long w = 0;
+    switch (st) {
+      case B2_INT8: w = static_cast<const int8_t*>(src)[i]; d = (double)w; break;
+      case B2_INT16: w = static_cast<const int16_t*>(src)[i]; d = (double)w; break;
+      case B2_INT32: w = static_cast<const int32_t*>(src)[i]; d = (double)w; break;
+      case B2_INT64: w = static_cast<const int64_t*>(src)[i]; d = (double)w; break;
+      case B2_UINT8: case B2_BOOL8: w = static_cast<const uint8_t*>(src)[i]; d = (double)w; break;
+      case B2_UINT16: w = static_cast<const uint16_t*>(src)[i]; d = (double)w; break;
+      case B2_UINT32: w = static_cast<const uint32_t*>(src)[i]; d = (double)w; break;
+      case B2_UINT64: { const unsigned long long u = static_cast<const unsigned long long*>(src)[i]; w = (long long)u; d = (double)(long long)u; break; }
+      case B2_FLOAT32: d = static_cast<const float*>(src)[i]; break;
+      default: d = static_cast<const double*>(src)[i]; break;
+    }
+    if (x) x[i] = d;
+    if (x2) x2[i] = d * d;
+    if (i2) i2[i] = (long long)((unsigned long long)w * (unsigned long long)w);
+  }
+}
+// M2 / VARIANCE / STD from per-group sum, sum of squares and valid count (cpp/src/groupby/common/m2_var_std.cu:35-62,150-196)
+__global__ void gb_m2_kernel(const double* __restrict__ s1, const double* __restrict__ s2, const int32_t* __restrict__ cnt, int32_t G, int mode /*5 M2, 6 VAR, 7 STD*/,
+                             int32_t ddof, double* __restrict__ out, uint32_t* __restrict__ out_mask, unsigned long long* __restrict__ valid_count)
+{
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  const int32_t n = cnt[g];
+  const double m2 = n == 0 ? 0.0 : s2[g] - s1[g] * s1[g] / n;
+  double o = m2;
+  bool valid = true;
+  if (mode != 5) {
+    const int df = n - ddof;
+    valid = n != 0 && df > 0;
+    o = valid ? (mode == 6 ? m2 / df : sqrt(m2 / df)) : 0.0;
+  }
+  out[g] = o;
+  if (out_mask && valid) {
+    atomicOr(&out_mask[g >> 5], 1u << (g & 31));
+    atomicAdd(valid_count, 1ull);
+  }
+}
+// NUNIQUE: rows are ordered by (keys, value) with null values last inside a group; a valid row counts when it opens its group
+// or differs from its predecessor (floats: -0 == +0, NaN == NaN as in the reference's equality comparator)
+template <typename T>
+__global__ void gb_distinct_flags_kernel(const T* __restrict__ v, const uint32_t* __restrict__ mask, const int32_t* __restrict__ gid_incl, int64_t n,
+                                         int is_float, int32_t* __restrict__ flags)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  auto norm = [&](T b) -> T {
+    if (!is_float) return b;
+    if constexpr (sizeof(T) == 4) {
+      if ((b << 1) == 0) return 0;
+      if ((b & 0x7fffffffu) > 0x7f800000u) return (T)0x7fc00000u;
+    } else if constexpr (sizeof(T) == 8) {
+      if ((b << 1) == 0) return 0;
+      if ((b & 0x7fffffffffffffffull) > 0x7ff0000000000000ull) return (T)0x7ff8000000000000ull;
+    }
+    return b;
+  };
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const bool valid = mask == nullptr || bit_is_set(mask, i);
+    int32_t f = 0;
+    if (valid) {
+      const bool first = i == 0 || gid_incl[i] != gid_incl[i - 1];
+      f = (first || norm(v[i]) != norm(v[i - 1])) ? 1 : 0;
+    }
+    flags[i] = f;
+  }
+}
+// MEDIAN = 0.5 quantile with linear interpolation over the group's valid values (sorted ascending, nulls last)
+__global__ void gb_median_kernel(const double* __restrict__ x, const int32_t* __restrict__ offsets, const int32_t* __restrict__ valid_cnt, int32_t G,
+                                 double* __restrict__ out, uint32_t* __restrict__ out_mask, unsigned long long* __restrict__ valid_count)
+{
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  const int32_t m = valid_cnt[g];
+  if (m == 0) { out[g] = 0.0; return; }
+  const double pos = (m - 1) * 0.5;
+  const int32_t lo = (int32_t)floor(pos), hi = (int32_t)ceil(pos);
+  const double a = x[offsets[g] + lo], b = x[offsets[g] + hi];
+  out[g] = a + (pos - lo) * (b - a);
+  atomicOr(&out_mask[g >> 5], 1u << (g & 31));
+  atomicAdd(valid_count, 1ull);
+}
+
+constexpr int32_t AGG_MEDIAN = 14, AGG_NUNIQUE = 18, AGG_NTH_ELEMENT = 19;  // aggregation::Kind values (aggregation.hpp:78-121)
+// B2_AGG_WITH_DDOF carries a 16-bit parameter: ddof for VARIANCE / STD, n (signed) for NTH_ELEMENT
+inline int32_t kind_param_signed(int32_t k) { return (k & (1 << 30)) ? (int32_t)(int16_t)((k >> 8) & 0xFFFF) : 0; }
+
+int32_t sorted_result_type(int32_t kind, int32_t src)
+{
+  switch (kind) {
+    case AGG_MEDIAN: return B2_FLOAT64;
+    case AGG_NUNIQUE: return B2_INT32;
+    case AGG_NTH_ELEMENT: return src;
+    default: return result_type(kind, src);
+  }
+}
+
+void mark_pending_valid(b2_column& c, cudaStream_t stream)
+{
+  c.pending = dbuf(sizeof(unsigned long long), stream);
+  c.pending_stream = stream;
+  c.pending_is_valid_count = true;
+  c.null_count = -1;
+  B2_CUDA_TRY(cudaMemsetAsync(c.pending.ptr, 0, sizeof(unsigned long long), stream));
+}
+
+}  // namespace
+
+bool groupby_needs_sort_path(const b2_groupby& gb, const std::vector<request_view>& reqs)
+{
+  if (gb.keys_are_sorted) return true;
+  if (const char* e = std::getenv("B2_GROUPBY_SORT")) if (std::atoi(e) != 0) return true;  // test hook
+  for (auto& r : reqs)
+    for (int32_t raw : r.kinds) {
+      const int32_t k = base_kind(raw);
+      if (k == AGG_MEDIAN || k == AGG_NUNIQUE || k == AGG_NTH_ELEMENT) return true;
+    }
+  return false;
+}
+
+void groupby_aggregate_sorted(const b2_groupby& gb, const std::vector<request_view>& reqs, cudaStream_t stream, table_ptr& keys_out,
+                              table_ptr& res_out)
+{
+  const int64_t n_all = gb.keys.empty() ? 0 : gb.keys[0].size;
+  for (auto& r : reqs) {
+    validate_column(r.values);
+    B2_EXPECTS(r.values.size == n_all, B2_ERR_LOGIC, "Size mismatch between request values and groupby keys.");
+    B2_EXPECTS(!r.kinds.empty(), B2_ERR_LOGIC, "Empty aggregation request");
+    for (int32_t raw : r.kinds) {
+      const int32_t k = base_kind(raw);
+      const bool ok = k == B2_AGG_SUM || k == B2_AGG_PRODUCT || k == B2_AGG_MIN || k == B2_AGG_MAX || k == B2_AGG_MEAN || k == B2_AGG_COUNT_VALID ||
+                      k == B2_AGG_COUNT_ALL || needs_sumsq(k) || k == AGG_MEDIAN || k == AGG_NUNIQUE || k == AGG_NTH_ELEMENT;
+      B2_EXPECTS(ok, B2_ERR_INVALID_ARGUMENT, "unsupported aggregation on the sort-based groupby path");
+      if (k != B2_AGG_MIN && k != B2_AGG_MAX && k != B2_AGG_COUNT_VALID && k != B2_AGG_COUNT_ALL && k != AGG_NUNIQUE && k != AGG_NTH_ELEMENT)
+        B2_EXPECTS(is_numeric(r.values.type_id), B2_ERR_LOGIC, "this aggregation needs a numeric values column");
+    }
+  }
+  auto empty = [&] {
+    keys_out = std::make_unique<b2_table>();
+    for (auto& k : gb.keys) keys_out->cols.push_back(make_column(k.type_id, 0, false, stream));
+    res_out = std::make_unique<b2_table>();
+    for (auto& r : reqs)
+      for (int32_t kind : r.kinds) res_out->cols.push_back(make_column(sorted_result_type(base_kind(kind), r.values.type_id), 0, false, stream));
+  };
+  if (n_all == 0) return empty();
+  key_cols kc = make_key_cols(gb.keys, true);
+
+  // order of the rows by key: ascending, nulls first (or the given order when the caller says the keys are sorted);
+  // rows with a null key are dropped under EXCLUDE (single key column, as in groupby_scan)
+  std::vector<uint8_t> asc(gb.keys.size(), B2_ASCENDING), before(gb.keys.size(), B2_NULL_BEFORE);
+  column_ptr order_col;
+  int64_t n = n_all;
+  int64_t skip = 0;
+  bool keys_nullable = false;
+  for (auto& k : gb.keys) keys_nullable |= has_nulls(k);
+  int32_t null_rows = 0;
+  if (keys_nullable && gb.null_handling == B2_NULL_EXCLUDE) {
+    dbuf m = bitmask_and(gb.keys, (int32_t)n_all, &null_rows, stream);
+    if (null_rows > 0)
+      B2_EXPECTS(gb.keys.size() == 1, B2_ERR_INVALID_ARGUMENT, "sort-based groupby with null keys under EXCLUDE supports a single key column on this path");
+  }
+  order_col = sorted_order(gb.keys, asc, before, true, stream);  // pre-sorted keys sort to the same grouping (stable), no shortcut needed for correctness
+  skip = null_rows;
+  n -= skip;
+  const int32_t* order = order_col->data.as<int32_t>() + skip;
+  if (n == 0) return empty();
+
+  // group boundaries
+  dbuf head(n, stream), head32(sizeof(int32_t) * n, stream);
+  if (keys_are_wide(gb.keys)) B2_LAUNCH((group_heads_kernel<true>), grid_for(n), 256, 0, stream, kc, order, n, head.as<uint8_t>());
+  else B2_LAUNCH((group_heads_kernel<false>), grid_for(n), 256, 0, stream, kc, order, n, head.as<uint8_t>());
+  B2_LAUNCH(gb_head32_kernel, grid_for(n), 256, 0, stream, head.as<uint8_t>(), n, head32.as<int32_t>());
+  b2_column_view hv{B2_INT32, (int32_t)n, head32.ptr, nullptr, 0, 0};
+  auto gid = scan(hv, B2_AGG_SUM, B2_SCAN_INCLUSIVE, B2_NULL_EXCLUDE, stream);  // 1-based group number of every sorted row
+  int32_t G = 0;
+  B2_CUDA_TRY(cudaMemcpyAsync(&G, gid->data.as<int32_t>() + (n - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  B2_CUDA_TRY(cudaStreamSynchronize(stream));
+  dbuf offsets(sizeof(int32_t) * ((size_t)G + 1), stream);
+  B2_LAUNCH(gb_offsets_kernel, grid_for(n), 256, 0, stream, head.as<uint8_t>(), gid->data.as<int32_t>(), n, G, offsets.as<int32_t>());
+  const int32_t* off = offsets.as<int32_t>();
+  const int ggrid = (G + 255) / 256;
+  {
+    dbuf rep(sizeof(int32_t) * (size_t)G, stream);
+    B2_LAUNCH(gb_rep_rows_kernel, ggrid, 256, 0, stream, order, off, G, rep.as<int32_t>());
+    keys_out = gather_table(gb.keys, rep.as<int32_t>(), G, false, stream);
+  }
+  res_out = std::make_unique<b2_table>();
+
+  for (auto& r : reqs) {
+    const auto& v = r.values;
+    const int32_t st = storage_type(v.type_id);
+    const bool nullable = has_nulls(v);
+    auto vs = gather_column(v, order, (int32_t)n, false, stream);  // values in group order (input order inside a group)
+    const b2_column_view vsv = vs->view();
+    // valid count per group (shared by COUNT_VALID, M2 / VARIANCE / STD, MEDIAN)
+    column_ptr vcnt;
+    auto valid_counts = [&]() -> const int32_t* {
+      if (!vcnt) {
+        dbuf flags(sizeof(int32_t) * n, stream);
+        B2_LAUNCH(gb_valid_flags_kernel, grid_for(n), 256, 0, stream, nullable ? vsv.null_mask : nullptr, n, flags.as<int32_t>());
+        b2_column_view fv{B2_INT32, (int32_t)n, flags.ptr, nullptr, 0, 0};
+        vcnt = segmented_reduce(fv, off, G + 1, B2_AGG_SUM, B2_INT32, B2_NULL_EXCLUDE, nullptr, stream);
+        vcnt->mask.reset();
+        vcnt->pending.reset();
+        vcnt->null_count = 0;
+      }
+      return vcnt->data.as<int32_t>();
+    };
+    // the second order, by (keys, values): shares the group boundaries, sorts the values inside each group (nulls last)
+    column_ptr vs2;
+    auto values_sorted_in_group = [&]() -> const b2_column& {
+      if (!vs2) {
+        std::vector<b2_column_view> kv = gb.keys;
+        kv.push_back(v);
+        std::vector<uint8_t> a2(kv.size(), B2_ASCENDING), p2(kv.size(), B2_NULL_BEFORE);
+        p2.back() = B2_NULL_AFTER;
+        auto o2 = sorted_order(kv, a2, p2, true, stream);
+        vs2 = gather_column(v, o2->data.as<int32_t>() + skip, (int32_t)n, false, stream);
+      }
+      return *vs2;
+    };
+    for (int32_t raw : r.kinds) {
+      const int32_t kind = base_kind(raw);
+      const int32_t rt = sorted_result_type(kind, v.type_id);
+      column_ptr col;
+      if (kind == B2_AGG_COUNT_ALL) {
+        col = make_column(B2_INT32, G, false, stream);
+        B2_LAUNCH(gb_sizes_kernel, ggrid, 256, 0, stream, off, G, col->data.as<int32_t>());
+      } else if (kind == B2_AGG_COUNT_VALID) {
+        col = make_column(B2_INT32, G, false, stream);
+        B2_CUDA_TRY(cudaMemcpyAsync(col->data.ptr, valid_counts(), sizeof(int32_t) * (size_t)G, cudaMemcpyDeviceToDevice, stream));
+      } else if (kind == B2_AGG_SUM || kind == B2_AGG_PRODUCT || kind == B2_AGG_MIN || kind == B2_AGG_MAX || kind == B2_AGG_MEAN) {
+        b2_column_view sv = vsv;
+        sv.type_id = (kind == B2_AGG_MIN || kind == B2_AGG_MAX) ? vsv.type_id : st;  // chrono sums go through their integer storage
+        col = segmented_reduce(sv, off, G + 1, kind, (kind == B2_AGG_MIN || kind == B2_AGG_MAX) ? vsv.type_id : rt, B2_NULL_EXCLUDE, nullptr, stream);
+        col->type_id = rt;
+        if (!nullable) { col->pending.reset(); col->mask.reset(); col->null_count = 0; }  // a mask only when the input has nulls (output_utils.cu:67-86)
+      } else if (needs_sumsq(kind)) {
+        const bool want_int = kind == B2_AGG_SUM_OF_SQUARES && !is_float_id(st);
+        dbuf x(want_int ? 0 : sizeof(double) * n, stream), x2(want_int ? 0 : sizeof(double) * n, stream), i2(want_int ? sizeof(long long) * n : 0, stream);
+        B2_LAUNCH(gb_squares_kernel, grid_for(n), 256, 0, stream, vsv.data, st, n, x.as<double>(), x2.as<double>(), i2.as<long long>());
+        if (kind == B2_AGG_SUM_OF_SQUARES) {
+          b2_column_view qv{want_int ? B2_INT64 : B2_FLOAT64, (int32_t)n, want_int ? i2.ptr : x2.ptr, nullable ? vsv.null_mask : nullptr, nullable ? vsv.null_count : 0, 0};
+          col = segmented_reduce(qv, off, G + 1, B2_AGG_SUM, rt, B2_NULL_EXCLUDE, nullptr, stream);
+          if (!nullable) { col->pending.reset(); col->mask.reset(); col->null_count = 0; }
+        } else {
+          b2_column_view xv{B2_FLOAT64, (int32_t)n, x.ptr, nullable ? vsv.null_mask : nullptr, nullable ? vsv.null_count : 0, 0};
+          b2_column_view x2v = xv;
+          x2v.data = x2.ptr;
+          auto s1 = segmented_reduce(xv, off, G + 1, B2_AGG_SUM, B2_FLOAT64, B2_NULL_EXCLUDE, nullptr, stream);
+          auto s2 = segmented_reduce(x2v, off, G + 1, B2_AGG_SUM, B2_FLOAT64, B2_NULL_EXCLUDE, nullptr, stream);
+          const bool var_std = kind != B2_AGG_M2;
+          col = make_column(B2_FLOAT64, G, var_std, stream);
+          if (var_std) mark_pending_valid(*col, stream);
+          const int32_t* vc = valid_counts();  // (evaluated here: launch arguments must not launch kernels themselves)
+          B2_LAUNCH(gb_m2_kernel, ggrid, 256, 0, stream, s1->data.as<double>(), s2->data.as<double>(), vc, G, kind == B2_AGG_M2 ? 5 : (kind == B2_AGG_VARIANCE ? 6 : 7),
+                    kind_ddof(raw), col->data.as<double>(), var_std ? col->mask.as<uint32_t>() : nullptr, var_std ? col->pending.as<unsigned long long>() : nullptr);
+        }
+      } else if (kind == AGG_NTH_ELEMENT) {
+        dbuf map(sizeof(int32_t) * (size_t)G, stream);
+        B2_LAUNCH(gb_nth_map_kernel, ggrid, 256, 0, stream, off, G, kind_param_signed(raw), map.as<int32_t>());
+        col = gather_column(vsv, map.as<int32_t>(), G, true, stream);
+      } else if (kind == AGG_NUNIQUE) {
+        const b2_column& s2c = values_sorted_in_group();
+        const b2_column_view s2v = s2c.view();
+        dbuf flags(sizeof(int32_t) * n, stream);
+        dispatch_width(type_width(v.type_id), [&](auto tag) {
+          using T = decltype(tag);
+          B2_LAUNCH((gb_distinct_flags_kernel<T>), grid_for(n), 256, 0, stream, static_cast<const T*>(s2v.data), has_nulls(s2v) ? s2v.null_mask : nullptr,
+                    gid->data.as<int32_t>(), n, is_float_id(st) ? 1 : 0, flags.as<int32_t>());
+        });
+        b2_column_view fv{B2_INT32, (int32_t)n, flags.ptr, nullptr, 0, 0};
+        col = segmented_reduce(fv, off, G + 1, B2_AGG_SUM, B2_INT32, B2_NULL_EXCLUDE, nullptr, stream);
+        col->pending.reset();
+        col->mask.reset();
+        col->null_count = 0;
+      } else {  // MEDIAN
+        const b2_column& s2c = values_sorted_in_group();
+        const b2_column_view s2v = s2c.view();
+        dbuf x(sizeof(double) * n, stream);
+        B2_LAUNCH(gb_squares_kernel, grid_for(n), 256, 0, stream, s2v.data, st, n, x.as<double>(), (double*)nullptr, (long long*)nullptr);
+        col = make_column(B2_FLOAT64, G, true, stream);
+        mark_pending_valid(*col, stream);
+        const int32_t* vc = valid_counts();
+        B2_LAUNCH(gb_median_kernel, ggrid, 256, 0, stream, x.as<double>(), off, vc, G, col->data.as<double>(), col->mask.as<uint32_t>(),
+                  col->pending.as<unsigned long long>());
       }
       res_out->cols.push_back(std::move(col));
     }

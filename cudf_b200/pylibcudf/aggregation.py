@@ -19,8 +19,11 @@ class Kind(enum.IntEnum):
     M2 = 11
     VARIANCE = 12
     STD = 13
+    MEDIAN = 14
     ARGMAX = 16
     ARGMIN = 17
+    NUNIQUE = 18
+    NTH_ELEMENT = 19
 
 
 class Aggregation:
@@ -34,7 +37,8 @@ class Aggregation:
         return self._kind
 
     def abi_kind(self) -> int:
-        """The kind word of the C ABI: B2_AGG_WITH_DDOF(kind, ddof) for VARIANCE / STD (include/cudf_b200.h)."""
+        """The kind word of the C ABI: B2_AGG_WITH_DDOF(kind, parameter) — ddof for VARIANCE / STD, the (signed) n for
+        NTH_ELEMENT (include/cudf_b200.h)."""
         if self._ddof is None:
             return int(self._kind)
         return int(self._kind) | (1 << 30) | ((int(self._ddof) & 0xFFFF) << 8)
@@ -89,3 +93,25 @@ def argmax() -> Aggregation:
 
 def argmin() -> Aggregation:
     return Aggregation(Kind.ARGMIN)
+
+
+def median() -> Aggregation:
+    """make_median_aggregation (sort-based groupby path)."""
+    return Aggregation(Kind.MEDIAN)
+
+
+def nunique(null_handling: NullPolicy = NullPolicy.EXCLUDE) -> Aggregation:
+    """make_nunique_aggregation: distinct valid values per group (sort-based groupby path; nulls are not counted)."""
+    if null_handling != NullPolicy.EXCLUDE:
+        raise ValueError("nunique: only null_policy::EXCLUDE is supported on this path")
+    return Aggregation(Kind.NUNIQUE)
+
+
+def nth_element(n: int, null_handling: NullPolicy = NullPolicy.INCLUDE) -> Aggregation:
+    """make_nth_element_aggregation(n): the n-th row of each group in input order (negative n counts from the end); a group
+    that is too short gives null (sort-based groupby path; null_policy::INCLUDE)."""
+    if null_handling != NullPolicy.INCLUDE:
+        raise ValueError("nth_element: only null_policy::INCLUDE is supported on this path")
+    if not -32768 <= int(n) <= 32767:
+        raise ValueError("nth_element: n must fit 16 bits on this path")
+    return Aggregation(Kind.NTH_ELEMENT, int(n))

@@ -12,6 +12,8 @@ from . import sort as osort
 SUM, PRODUCT, MIN, MAX, COUNT_VALID, COUNT_ALL, MEAN = 0, 2, 3, 4, 5, 6, 10
 ARGMAX, ARGMIN = 16, 17  # row index of the extreme value; the first row among ties (the reference leaves ties open)
 SUM_OF_SQUARES, M2, VARIANCE, STD = 9, 11, 12, 13  # a kind may also be the pair (VARIANCE | STD, ddof); ddof defaults to 1
+MEDIAN, NUNIQUE, NTH_ELEMENT = 14, 18, 19  # sort-based path only (cpp/src/groupby/sort/aggregate.cpp; group_quantiles.cu, group_nunique.cu,
+# group_nth_element.cu); NTH_ELEMENT is the pair (NTH_ELEMENT, n), null_policy INCLUDE; NUNIQUE skips nulls; MEDIAN = 0.5 quantile, linear
 EXCLUDE, INCLUDE = 0, 1
 
 
@@ -47,8 +49,10 @@ def result_dtype(kind, in_dtype):
         if in_dtype.kind in "iu" or in_dtype == np.bool_:
             return np.dtype(np.int64)  # aggregation.hpp:935-939: every integral source sums into int64
         return in_dtype
-    if kind in (COUNT_VALID, COUNT_ALL, ARGMAX, ARGMIN):
+    if kind in (COUNT_VALID, COUNT_ALL, ARGMAX, ARGMIN, NUNIQUE):
         return np.dtype(np.int32)
+    if kind == MEDIAN:
+        return np.dtype(np.float64)
     if kind == MEAN:
         return np.dtype(np.float64)
     return in_dtype
@@ -105,6 +109,33 @@ def aggregate(key_cols, requests, null_handling=EXCLUDE):
                     var = np.where(ok, m2v / np.where(ok, df, 1), 0.0)
                     out = var if kind == VARIANCE else np.sqrt(np.where(ok, var, 0.0))
                 per.append((out, None if ok.all() else ok))
+                continue
+            if kind in (MEDIAN, NUNIQUE, NTH_ELEMENT):
+                out = np.zeros(ng, dtype=rdt)
+                ok = np.ones(ng, bool)
+                for g in range(ng):
+                    sel = gid == g
+                    gv, gm = v[sel], m[sel]
+                    if kind == NTH_ELEMENT:      # rows in input order inside the group (rows is a stable order)
+                        idx = ddof if ddof >= 0 else len(gv) + ddof
+                        if 0 <= idx < len(gv) and gm[idx]:
+                            out[g] = gv[idx]
+                        else:
+                            ok[g] = False
+                    elif kind == NUNIQUE:
+                        x = gv[gm]
+                        if x.dtype.kind == "f":
+                            x = np.where(x == 0, 0.0, x)          # -0 == +0; np.unique treats NaNs as one value
+                        out[g] = len(np.unique(x))
+                    else:
+                        x = np.sort(gv[gm].astype(np.float64))
+                        if len(x) == 0:
+                            ok[g] = False
+                        else:
+                            pos = (len(x) - 1) * 0.5
+                            lo, hi = int(np.floor(pos)), int(np.ceil(pos))
+                            out[g] = x[lo] + (pos - lo) * (x[hi] - x[lo])
+                per.append((out, None if (kind == NUNIQUE or ok.all()) else ok))
                 continue
             if kind in (ARGMAX, ARGMIN):
                 # global_memory_aggregator.cuh:155-200 (strict > / < comparisons: a NaN never displaces a holder)

@@ -10,7 +10,9 @@ from oracle import join as ojoin
 from oracle import reduce as ored
 
 KINDS = {"sum": 0, "product": 2, "min": 3, "max": 4, "count": 5, "count_all": 6, "mean": 10, "sum_of_squares": 9, "m2": 11,
-         "var": 12, "std": 13, "argmax": 16, "argmin": 17, "var0": (12, 0), "var2": (12, 2), "std0": (13, 0), "std2": (13, 2)}
+         "var": 12, "std": 13, "argmax": 16, "argmin": 17, "var0": (12, 0), "var2": (12, 2), "std0": (13, 0), "std2": (13, 2),
+         "median": 14, "nunique": 18, "nth0": (19, 0), "nth1": (19, 1), "nth2": (19, 2), "nth3": (19, 3), "nth-1": (19, -1), "nth-2": (19, -2),
+         "nth-3": (19, -3), "nth-4": (19, -4)}
 
 
 class OracleImpl:
@@ -103,6 +105,10 @@ class PlcImpl:
         a = self.plc.aggregation
         if name in ("var0", "var2", "std0", "std2"):
             return (a.variance if name[0] == "v" else a.std)(int(name[-1]))
+        if name.startswith("nth"):
+            return a.nth_element(int(name[3:]))
+        if name in ("median", "nunique"):
+            return getattr(a, name)()
         return {"sum": a.sum, "min": a.min, "max": a.max, "mean": a.mean, "product": a.product, "sum_of_squares": a.sum_of_squares,
                 "m2": a.m2, "var": a.variance, "std": a.std, "argmax": a.argmax, "argmin": a.argmin,
                 "count": lambda: a.count(self.plc.NullPolicy.EXCLUDE), "count_all": lambda: a.count(self.plc.NullPolicy.INCLUDE)}[name]()
