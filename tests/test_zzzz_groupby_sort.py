@@ -11,7 +11,6 @@ import pytest
 from tests.helpers import assert_columns_equal
 from tests.impls import OracleImpl, PlcImpl
 
-pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 KEYS = np.array([1, 2, 3, 1, 2, 2, 1, 3, 3, 2], np.int32)
 VALS = np.arange(10)
@@ -22,9 +21,9 @@ def _one(impl, keys, vals, kind, valid=None):
     return k[0], r[0][0]
 
 
-@pytest.mark.parametrize("which", ["oracle", "cuda"])
-def test_golden_median_nunique_nth(plc, which):
-    impl = OracleImpl() if which == "oracle" else PlcImpl(plc)
+@pytest.mark.parametrize("which", ["oracle", pytest.param("cuda", marks=pytest.mark.gpu)])
+def test_golden_median_nunique_nth(request, which):
+    impl = OracleImpl() if which == "oracle" else PlcImpl(request.getfixturevalue("plc"))
     for vdt in (np.int8, np.int32, np.int64, np.float32, np.float64, np.uint16):
         v = VALS.astype(vdt)
         k, (out, m) = _one(impl, KEYS, v, "median")
@@ -47,6 +46,7 @@ def test_golden_median_nunique_nth(plc, which):
     assert len(k[0]) == 0 and len(out) == 0 and out.dtype == np.float64
 
 
+@pytest.mark.gpu
 def test_random_vs_oracle(plc):
     rng = np.random.default_rng(17)
     cu, o = PlcImpl(plc), OracleImpl()
@@ -76,6 +76,7 @@ def test_random_vs_oracle(plc):
         assert_columns_equal(gr[0][0], er[0][0]); assert_columns_equal(gr[0][1], er[0][1])
 
 
+@pytest.mark.gpu
 def test_hash_aggregations_through_the_sort_path():
     """B2_GROUPBY_SORT=1: SUM / MIN / MAX / MEAN / COUNT / PRODUCT / SUM_OF_SQUARES / M2 / VARIANCE / STD on the sort-based path equal
     the oracle (the same checks as the hash path's tests); also keys declared pre-sorted (sorted::YES)."""
