@@ -174,7 +174,7 @@ def run(plc, _lib, n, peak_gbs, cpu_rows=10_000_000, with_cpu=True):
         M = li.size()
         alg = 16 * slots + 24 * n + 24 * n + 8 * M
         res["inner_join_10pct"] = entry(ms, n, alg, "inner_join", unit="probe rows/s", matches=M,
-                                        phases_ms=phases("join_build", "join_count", "join_retrieve", "rjoin_partition", "rjoin_count", "rjoin_retrieve"),
+                                        phases_ms=phases("join_build", "join_count", "join_retrieve", "rjoin_partition", "rjoin_join"),
                                         note="contract bytes (SURVEY §8d C3): 16 B x 2|R| slots + 24|R| + 24|L| + 8M")
         # both join paths forced on the same inputs (B2_JOIN_RADIX_ROWS: 0 = open-addressing table in HBM, <rows> = partitioned
         # shared-memory join for inputs of at least that many rows; unset = the library's default choice, measured above)
@@ -186,7 +186,7 @@ def run(plc, _lib, n, peak_gbs, cpu_rows=10_000_000, with_cpu=True):
                 rms = profiled(lambda: plc.join.inner_join(L, R, plc.NullEquality.EQUAL), steps=2, warmup=1)
                 li2, _ri2 = plc.join.inner_join(L, R, plc.NullEquality.EQUAL)
                 res[label] = entry(rms, n, alg, unit="probe rows/s", matches=li2.size(), same_match_count=bool(li2.size() == M),
-                                   phases_ms=phases("join_build", "join_count", "join_retrieve", "rjoin_partition", "rjoin_count", "rjoin_retrieve"))
+                                   phases_ms=phases("join_build", "join_count", "join_retrieve", "rjoin_partition", "rjoin_join"))
                 del li2, _ri2
             except Exception as ex:
                 res[label] = {"error": repr(ex)[:200]}

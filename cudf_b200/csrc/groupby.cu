@@ -355,6 +355,26 @@ __global__ void pgb_items_kernel(const uint32_t* __restrict__ part_base, uint32_
   if (d == 255) item_start[256] = off + inc;
 }
 
+// MODE: 0 generic (any supported ops, decided at run time), 1 = one SUM of an 8-byte float column, 2 = one SUM of an 8-byte
+// integer column, 3 = no value ops (counts only). The specialised forms drop the per-row dispatch: the generic kernel spends
+// ~150 instructions per row and is issue-bound at 1.8 TB/s (ncu, profiles/r2_groupby_agg_ncu.txt).
+template <int MODE>
+__device__ __forceinline__ void pgb_apply(const pgb_args& a, unsigned long long* acc, size_t stride, uint32_t slot, unsigned long long vb, unsigned long long vo,
+                                          bool shared_mem)
+{
+  if constexpr (MODE == 1) {
+    atomicAdd(reinterpret_cast<double*>(acc + slot), __longlong_as_double((long long)vb));
+  } else if constexpr (MODE == 2) {
+    atomicAdd(acc + slot, vb);
+  } else if constexpr (MODE == 0) {
+    for (int k = 0; k < a.nops; ++k) {
+      if (shared_mem) pgb_combine<true>(acc + (size_t)k * stride + slot, a.op[k], a.acc[k], a.op[k] == OPK_SUM ? vb : vo);
+      else pgb_combine<false>(a.accum[k] + slot, a.op[k], a.acc[k], a.op[k] == OPK_SUM ? vb : vo);
+    }
+  }
+}
+
+template <int MODE>
 __global__ void __launch_bounds__(PGB_THREADS, 1) pgb_agg_kernel(pgb_args a, slot_t* __restrict__ table, uint32_t mask, uint32_t cap,
                                                                  int32_t* __restrict__ gsize, int32_t* __restrict__ slot_gid, gb_ctl* ctl)
 {
@@ -397,15 +417,18 @@ __global__ void __launch_bounds__(PGB_THREADS, 1) pgb_agg_kernel(pgb_args a, slo
       for (int u = 0; u < U; ++u) {
         const uint32_t r = rb + u * PGB_THREADS;
         mks[u] = r < r1 ? __ldcs(a.mkeys + r) : 0ull;
-        vbs[u] = (r < r1 && a.nops) ? pgb_value_bits(a, r) : 0ull;
+        if constexpr (MODE == 1 || MODE == 2) vbs[u] = r < r1 ? __ldcs(static_cast<const unsigned long long*>(a.vals) + r) : 0ull;
+        else if constexpr (MODE == 3) vbs[u] = 0ull;
+        else vbs[u] = (r < r1 && a.nops) ? pgb_value_bits(a, r) : 0ull;
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-      if (rb + u * PGB_THREADS >= r1) break;
+      if (rb + u * PGB_THREADS >= r1) continue;  // (not `break`: keeps the loop fully unrolled and mks / vbs in registers)
       const unsigned long long mk = mks[u];
       const unsigned long long vb = vbs[u];
-      // accumulator form of the value for MIN / MAX of floats
-      const unsigned long long vo = (a.nops && a.acc[0] == ACC_F64) ? (unsigned long long)f64_to_ordered(__longlong_as_double((long long)vb)) : vb;
+      // accumulator form of the value for MIN / MAX of floats (generic kernel only)
+      unsigned long long vo = vb;
+      if constexpr (MODE == 0) vo = (a.nops && a.acc[0] == ACC_F64) ? (unsigned long long)f64_to_ordered(__longlong_as_double((long long)vb)) : vb;
       int64_t slot = -1;
       if (mk != PGB_EMPTY) {
         uint32_t i = (uint32_t)mk & (S - 1);
@@ -422,13 +445,13 @@ __global__ void __launch_bounds__(PGB_THREADS, 1) pgb_agg_kernel(pgb_args a, slo
       }
       if (slot >= 0) {
         atomicAdd(&s_cnt[slot], 1u);
-        for (int k = 0; k < a.nops; ++k) pgb_combine<true>(&s_acc[(size_t)k * S + slot], a.op[k], a.acc[k], a.op[k] == OPK_SUM ? vb : vo);
+        pgb_apply<MODE>(a, s_acc, S, (uint32_t)slot, vb, vo, true);
       } else {
         // shared table full (or the reserved key value): this row goes to the global table directly
         const int64_t g = global_slot(table, mask, cap, unmix64(mk), slot_gid, ctl);
         if (g >= 0) {
           atomicAdd(&gsize[g], 1);
-          for (int k = 0; k < a.nops; ++k) pgb_combine<false>(a.accum[k] + g, a.op[k], a.acc[k], a.op[k] == OPK_SUM ? vb : vo);
+          pgb_apply<MODE>(a, MODE == 0 ? nullptr : a.accum[0], 0, (uint32_t)g, vb, vo, false);
         }
       }
       }
@@ -441,7 +464,11 @@ __global__ void __launch_bounds__(PGB_THREADS, 1) pgb_agg_kernel(pgb_args a, slo
       const int64_t g = global_slot(table, mask, cap, unmix64(mk), slot_gid, ctl);
       if (g < 0) continue;
       atomicAdd(&gsize[g], (int32_t)s_cnt[i]);
-      for (int k = 0; k < a.nops; ++k) pgb_combine<false>(a.accum[k] + g, a.op[k], a.acc[k], s_acc[(size_t)k * S + i]);
+      if constexpr (MODE == 0) {
+        for (int k = 0; k < a.nops; ++k) pgb_combine<false>(a.accum[k] + g, a.op[k], a.acc[k], s_acc[(size_t)k * S + i]);
+      } else {
+        pgb_apply<MODE>(a, a.accum[0], 0, (uint32_t)g, s_acc[i], 0ull, false);
+      }
     }
     __syncthreads();
   }
@@ -811,11 +838,26 @@ void groupby_aggregate(const b2_groupby& gb, const std::vector<request_view>& re
       pa.smem_limit = pa.smem_slots * 6 / 10;
       const size_t smem = (size_t)pa.smem_slots * (8 + 8 * (size_t)ops.n + 4);
       static std::atomic<uint64_t> attr_done{0};
-      once_per_device(attr_done, [] { B2_CUDA_TRY(cudaFuncSetAttribute(pgb_agg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 20)); });
+      once_per_device(attr_done, [] {
+        B2_CUDA_TRY(cudaFuncSetAttribute(pgb_agg_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 20));
+        B2_CUDA_TRY(cudaFuncSetAttribute(pgb_agg_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 20));
+        B2_CUDA_TRY(cudaFuncSetAttribute(pgb_agg_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 20));
+        B2_CUDA_TRY(cudaFuncSetAttribute(pgb_agg_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 20));
+      });
       B2_CUDA_TRY(cudaMemsetAsync(pa.item_counter, 0, sizeof(uint32_t), stream));
       B2_LAUNCH(pgb_items_kernel, 1, 256, 0, stream, pa.part_base, pa.n, pa.chunk, pgb_items.as<uint32_t>());
-      B2_LAUNCH(pgb_agg_kernel, NUM_SMS_B200, PGB_THREADS, smem, stream, pa, table.as<slot_t>(), (uint32_t)(slots - 1), cap,
-                gsize.as<int32_t>(), slot_gid.as<int32_t>(), ctl.as<gb_ctl>());
+      int mode = 0;
+      if (ops.n == 0) mode = 3;
+      else if (ops.n == 1 && pa.op[0] == OPK_SUM && pa.val_bytes == 8) mode = pa.acc[0] == ACC_F64 ? 1 : 2;
+#define B2_PGB(M) B2_LAUNCH((pgb_agg_kernel<M>), NUM_SMS_B200, PGB_THREADS, smem, stream, pa, table.as<slot_t>(), (uint32_t)(slots - 1), cap, \
+                            gsize.as<int32_t>(), slot_gid.as<int32_t>(), ctl.as<gb_ctl>())
+      switch (mode) {
+        case 1: B2_PGB(1); break;
+        case 2: B2_PGB(2); break;
+        case 3: B2_PGB(3); break;
+        default: B2_PGB(0); break;
+      }
+#undef B2_PGB
     } else {
       prof_scope ps("groupby_aggregate", stream);
 #define B2_GB(W, Q)                                                                                                                    \

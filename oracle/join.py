@@ -25,6 +25,12 @@ def _row_ids(left_cols, right_cols, nulls_equal):
         raise ValueError("Mismatch in number of columns to be joined on")  # std::invalid_argument
     nl = len(left_cols[0][0]) if left_cols else 0
     nr = len(right_cols[0][0]) if right_cols else 0
+    if len(left_cols) == 1 and left_cols[0][1] is None and right_cols[0][1] is None and np.asarray(left_cols[0][0]).dtype.kind in "iu" \
+            and np.asarray(left_cols[0][0]).dtype == np.asarray(right_cols[0][0]).dtype and nl + nr > 1_000_000:
+        # large single integer key column without nulls: rank the values directly (same ids, minutes faster than the row-wise unique)
+        v = np.concatenate([np.asarray(left_cols[0][0]), np.asarray(right_cols[0][0])])
+        _, ids = np.unique(v, return_inverse=True)
+        return ids[:nl].astype(np.int64), ids[nl:].astype(np.int64)
     ids = np.zeros(nl + nr, dtype=np.int64)
     dead = np.zeros(nl + nr, dtype=bool)
     for (lv, lm), (rv, rm) in zip(left_cols, right_cols):

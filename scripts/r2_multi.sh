@@ -28,11 +28,11 @@ for v in $VARIANTS; do
     nccl)   E="B2_SHARD_P2P=copy B2_SHARD_XCHG=nccl" ;;
     default) E="X=1" ;;
   esac
-  run check_$v 300 $E -- $TR scripts/sharded_check.py --rows 20000000
-  run bench_$v 500 $E -- $TR bench.py --gpus $N --steps 3 --warmup 3 --no-e2e --no-join --cpu-rows 100000
+  run check_$v 150 $E -- $TR scripts/sharded_check.py --rows 20000000
+  run bench_$v 240 $E -- $TR bench.py --gpus $N --steps 3 --warmup 3 --no-e2e --no-join --cpu-rows 100000
 done
 # the default path with everything (e2e + sharded join) once
-run bench_default 900 X=1 -- $TR bench.py --gpus $N --steps 5 --warmup 3 --cpu-rows 1000000
+run bench_default 420 X=1 -- $TR bench.py --gpus $N --steps 5 --warmup 3 --cpu-rows 1000000
 grep -h '"metric"' "$O"/bench_*.log | python -c "
 import sys, json
 for line in sys.stdin:

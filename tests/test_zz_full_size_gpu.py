@@ -121,8 +121,8 @@ def test_sort_1e8_exact_vs_numpy_stable(plc):
     _lib.check(_lib.lib.b2_trim_pool())
 
 
-def test_inner_join_3e7_canonical_pairs_exact(plc):
-    """BASELINE configs[2] shape at 3e7 x 3e7 rows: canonical-sorted (left, right) pairs equal the oracle's, for the default
+def test_inner_join_2e7_canonical_pairs_exact(plc):
+    """BASELINE configs[2] shape at 2e7 x 2e7 rows (above the 2^24-row limit of the partitioned path): canonical-sorted (left, right) pairs equal the oracle's, for the default
     path choice and for each join path forced (the oracle runs once)."""
     import os
 
@@ -132,7 +132,7 @@ def test_inner_join_3e7_canonical_pairs_exact(plc):
     from cudf_b200 import _lib
     from oracle import join as ojoin
 
-    n = 30_000_000
+    n = 20_000_000
     rk = _fill(_lib, torch.empty(n, dtype=torch.int64, device="cuda"), n, 1)
     lk = _fill(_lib, torch.empty(n, dtype=torch.int64, device="cuda"), n, 6)
     u = _fill(_lib, torch.empty(n, dtype=torch.float64, device="cuda"), n, 5, kind=1)
