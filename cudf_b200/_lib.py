@@ -150,6 +150,8 @@ _sig("b2_partition_plan_create", [P(ColumnView), i32, vp, i32, b2_stream, P(vp),
 _sig("b2_partition_scatter", [vp, P(ColumnView), P(vp), b2_stream])
 _sig("b2_partition_scatter_staged", [vp, P(ColumnView), P(vp), b2_stream])
 _sig("b2_partition_plan_free", [vp], None)
+_sig("b2_range_partition_counts", [P(ColumnView), vp, i32, b2_stream, P(C.c_int64)])
+_sig("b2_range_partition_scatter", [P(ColumnView), P(ColumnView), vp, i32, P(vp), P(vp), b2_stream])
 _sig("b2_ipc_alloc", [C.c_size_t, P(vp), u8p])
 _sig("b2_ipc_open", [u8p, P(vp)])
 _sig("b2_ipc_close", [vp])
@@ -177,7 +179,7 @@ DECLARED_SYMBOLS = [
     "b2_hash_join_partitioned_join", "b2_hash_join_finalize_full_join", "b2_groupby_create", "b2_groupby_destroy",
     "b2_groupby_aggregate", "b2_groupby_scan", "b2_reduce", "b2_segmented_reduce", "b2_scan", "b2_partition",
     "b2_partition_plan_create", "b2_partition_scatter", "b2_partition_scatter_staged", "b2_partition_plan_free", "b2_ipc_alloc", "b2_ipc_open", "b2_ipc_close",
-    "b2_ipc_free", "b2_peer_copy", "b2_profile_get_over", "b2_hash_partition", "b2_partition_by_map", "b2_packed_size", "b2_pack", "b2_pack_metadata", "b2_unpack", "b2_to_arrow_schema", "b2_to_arrow_device", "b2_to_arrow_host", "b2_from_arrow_device",
+    "b2_ipc_free", "b2_peer_copy", "b2_profile_get_over", "b2_hash_partition", "b2_partition_by_map", "b2_range_partition_counts", "b2_range_partition_scatter", "b2_packed_size", "b2_pack", "b2_pack_metadata", "b2_unpack", "b2_to_arrow_schema", "b2_to_arrow_device", "b2_to_arrow_host", "b2_from_arrow_device",
     "b2_from_arrow_host", "b2_arrow_schema_release", "b2_arrow_array_release",
     "b2_fill_splitmix64",
 ]

@@ -269,6 +269,10 @@ void radix_partition_top16_mix(const uint64_t* packed_keys, int64_t n, uint64_t*
 void radix_partition_mix_carry(const uint64_t* keys, const void* vals, int val_bytes, int64_t n, uint64_t* mixed_keys_out, void* vals_out,
                                uint32_t* part_base, cudaStream_t stream);
 
+void range_partition_counts(const b2_column_view& keys, const void* splitters, int P, int64_t* out_counts, cudaStream_t stream);
+void range_partition_scatter(const b2_column_view& keys, const b2_column_view* values, const void* splitters, int P, void* const* key_dst,
+                             void* const* val_dst, cudaStream_t stream);
+
 // radix_join.cu (experimental, opt-in: B2_JOIN_RADIX_ROWS)
 bool radix_join_applicable(const std::vector<b2_column_view>& a, const std::vector<b2_column_view>& b);
 void radix_join(const std::vector<b2_column_view>& build, const std::vector<b2_column_view>& probe, bool left, cudaStream_t stream,

@@ -648,6 +648,42 @@ __global__ void __launch_bounds__(256) peer_copy_kernel(char* __restrict__ dst, 
 }  // namespace
 }  // namespace b2
 
+// Range partition fused with the first radix pass machinery (radix_sort.cu::range_partition_*): counts, then ONE stable pass that
+// writes every bucket's rows to its destination (peer) buffer.
+extern "C" b2_status b2_range_partition_counts(const b2_column_view* keys, const void* splitters, int32_t num_partitions, b2_stream stream,
+                                               int64_t* out_counts)
+{
+  B2_TRY_BEGIN
+    B2_EXPECTS(keys && out_counts, B2_ERR_INVALID_ARGUMENT, "null argument");
+    b2::validate_column(*keys);
+    B2_EXPECTS(num_partitions >= 1 && num_partitions <= 256, B2_ERR_INVALID_ARGUMENT, "num_partitions must be in [1, 256]");
+    B2_EXPECTS(num_partitions == 1 || splitters != nullptr, B2_ERR_INVALID_ARGUMENT, "range partition needs splitters");
+    B2_EXPECTS(b2::type_width(keys->type_id) == 8 && !b2::is_float_id(b2::storage_type(keys->type_id)) && !b2::has_nulls(*keys), B2_ERR_DATA_TYPE,
+               "b2_range_partition_*: one null-free 8-byte integer-like key column");
+    b2::range_partition_counts(*keys, splitters, num_partitions, out_counts, static_cast<cudaStream_t>(stream));
+  B2_TRY_END
+}
+extern "C" b2_status b2_range_partition_scatter(const b2_column_view* keys, const b2_column_view* values, const void* splitters,
+                                                int32_t num_partitions, void* const* key_dst, void* const* val_dst, b2_stream stream)
+{
+  B2_TRY_BEGIN
+    B2_EXPECTS(keys && key_dst, B2_ERR_INVALID_ARGUMENT, "null argument");
+    b2::validate_column(*keys);
+    B2_EXPECTS(num_partitions >= 1 && num_partitions <= 256, B2_ERR_INVALID_ARGUMENT, "num_partitions must be in [1, 256]");
+    B2_EXPECTS(num_partitions == 1 || splitters != nullptr, B2_ERR_INVALID_ARGUMENT, "range partition needs splitters");
+    B2_EXPECTS(b2::type_width(keys->type_id) == 8 && !b2::is_float_id(b2::storage_type(keys->type_id)) && !b2::has_nulls(*keys), B2_ERR_DATA_TYPE,
+               "b2_range_partition_*: one null-free 8-byte integer-like key column");
+    if (values) {
+      b2::validate_column(*values);
+      B2_EXPECTS(val_dst != nullptr, B2_ERR_INVALID_ARGUMENT, "null argument");
+      B2_EXPECTS(values->size == keys->size, B2_ERR_LOGIC, "Column size mismatch.");
+      const int vw = b2::type_width(values->type_id);
+      B2_EXPECTS((vw == 4 || vw == 8) && !b2::has_nulls(*values), B2_ERR_DATA_TYPE, "b2_range_partition_scatter: one null-free 4- or 8-byte payload column");
+    }
+    b2::range_partition_scatter(*keys, values, splitters, num_partitions, key_dst, val_dst, static_cast<cudaStream_t>(stream));
+  B2_TRY_END
+}
+
 extern "C" b2_status b2_peer_copy(void* dst, const void* src, size_t bytes, b2_stream stream)
 {
   B2_TRY_BEGIN

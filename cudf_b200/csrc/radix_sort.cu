@@ -362,6 +362,12 @@ struct pass_args {
   uint64_t desc_mask;
   int32_t keep_keys;        // pairs mode: also write the keys in the last executed pass (partial sorts)
   const void* val_in;       // CARRY kernels: the caller's payload column (first pass source); last member on purpose
+  // RANGE kernels (sharded sort: the range partition IS the exchange): digit = number of splitters <= key; the rows of digit d
+  // are written to range_key_dst[d] / range_val_dst[d] (local or PEER memory) at their rank inside this GPU's digit-d run
+  const void* range_splitters;       // device array of (range_parts - 1) twiddled keys, ascending
+  void* const* range_key_dst;        // device array of range_parts pointers
+  void* const* range_val_dst;        // same for the carried payload (CARRY) or null
+  int32_t range_parts;
 };
 
 __device__ __forceinline__ void ranker_barrier(int nthreads)
@@ -418,12 +424,13 @@ constexpr bool EMU_BUILD = false;
 // path: UBLKCP in SASS) signalled by an mbarrier, and the ranking warps pick their keys up from there instead of issuing
 // IPT global loads each (B2_SORT_CFG=12; other tiles take the ordinary loads).
 template <typename UK, int THREADS, int IPT, int MINB, typename VT = uint32_t, bool CARRY = false, bool MIX = false, bool SAFE = false,
-          bool RMW = false, bool BULK = false>
+          bool RMW = false, bool BULK = false, bool RANGE = false>
 __global__ void __launch_bounds__(THREADS + 32 * LBW, MINB) onesweep_kernel(pass_args a)
 {
   constexpr int TILE   = THREADS * IPT;
   constexpr int NWARPS = THREADS / 32;
   static_assert(THREADS >= RADIX, "need one ranking thread per digit");
+  static_assert(!RANGE || (!MIX && !BULK), "the range-partition pass uses the plain key load");
 
   const pass_plan pl = a.ctl->plan[a.pass];
   if (pl.trivial) return;
@@ -437,6 +444,11 @@ __global__ void __launch_bounds__(THREADS + 32 * LBW, MINB) onesweep_kernel(pass
   uint32_t* s_off     = s_bm + NWARPS * RADIX;     // [256] global offset of digit - tile-local start
   uint32_t* s_cnt     = s_off + RADIX;             // [256] {tile count of digit, tile-local start} pairs
   uint32_t* s_misc    = s_cnt + 2 * RADIX;         // [16]
+  // RANGE only: splitters, per-digit destination pointers, digit of every staged item
+  UK* s_split         = reinterpret_cast<UK*>(s_misc + 16);                  // [256]
+  void** s_kdst       = reinterpret_cast<void**>(s_split + RADIX);           // [256]
+  void** s_vdst       = s_kdst + RADIX;                                      // [256]
+  uint8_t* s_dig      = reinterpret_cast<uint8_t*>(s_vdst + RADIX);          // [TILE]
 
   const int tid  = threadIdx.x;
   const int lane = tid & 31;
@@ -456,6 +468,13 @@ __global__ void __launch_bounds__(THREADS + 32 * LBW, MINB) onesweep_kernel(pass
     for (int j = 0; j < RADIX / 32; ++j) {
       s_whist[warp * RADIX + j * 32 + lane] = 0;
       s_bm[warp * RADIX + j * 32 + lane]    = 0;
+    }
+  }
+  if constexpr (RANGE) {
+    for (int i = tid; i < RADIX; i += THREADS + 32 * LBW) {
+      s_split[i] = i < a.range_parts - 1 ? static_cast<const UK*>(a.range_splitters)[i] : ~UK(0);
+      s_kdst[i]  = i < a.range_parts ? a.range_key_dst[i] : nullptr;
+      s_vdst[i]  = (CARRY && i < a.range_parts) ? a.range_val_dst[i] : nullptr;
     }
   }
   __syncthreads();
@@ -591,10 +610,33 @@ __global__ void __launch_bounds__(THREADS + 32 * LBW, MINB) onesweep_kernel(pass
     }
   }
 
+  // digit of a key: a byte of it, or (RANGE) the number of splitters <= key — padding items (all-ones key) land in the last bucket
+  auto digit_of = [&](UK k) -> unsigned {
+    if constexpr (RANGE) {
+      int lo = 0, hi = a.range_parts - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (s_split[mid] <= k) lo = mid + 1;
+        else hi = mid;
+      }
+      return (unsigned)lo;
+    } else {
+      return (unsigned)(k >> shift) & 255u;
+    }
+  };
+  unsigned dg[RANGE ? IPT : 1];
+  if constexpr (RANGE) {
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) dg[i] = (wbase + i * 32 >= a.portion_n) ? (unsigned)(RADIX - 1) : digit_of(key[i]);  // padding ranks last (digit 255)
+  }
+  auto digit_at = [&](int i) -> unsigned {
+    if constexpr (RANGE) return dg[i];
+    else return (unsigned)(key[i] >> shift) & 255u;
+  };
   // ---- early counts: warp-private digit histogram by shared-memory atomics (no dependency chain) ----
   uint32_t* my_hist = s_whist + warp * RADIX;
 #pragma unroll
-  for (int i = 0; i < IPT; ++i) atomicAdd(&my_hist[(unsigned)(key[i] >> shift) & 255u], 1u);
+  for (int i = 0; i < IPT; ++i) atomicAdd(&my_hist[digit_at(i)], 1u);
   __syncwarp();
   // number of distinct digits in this warp's 32*IPT keys: picks the ranking flavour below
   int distinct = 0;
@@ -644,7 +686,7 @@ __global__ void __launch_bounds__(THREADS + 32 * LBW, MINB) onesweep_kernel(pass
   if (distinct > 4) {
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
-      const unsigned d = (unsigned)(key[i] >> shift) & 255u;
+      const unsigned d = digit_at(i);
       atomicOr(&my_bm[d], 1u << lane);
       __syncwarp();
       const unsigned peers = my_bm[d];
@@ -670,7 +712,7 @@ __global__ void __launch_bounds__(THREADS + 32 * LBW, MINB) onesweep_kernel(pass
   } else {
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
-      const unsigned d = (unsigned)(key[i] >> shift) & 255u;
+      const unsigned d = digit_at(i);
       const unsigned peers = __match_any_sync(0xffffffffu, d);
       const unsigned lt = __popc(peers & lanemask_lt());
       uint32_t prev = 0;
@@ -686,6 +728,10 @@ __global__ void __launch_bounds__(THREADS + 32 * LBW, MINB) onesweep_kernel(pass
   // tile-sorted staging of the keys
 #pragma unroll
   for (int i = 0; i < IPT; ++i) s_keys[pos[i]] = key[i];
+  if constexpr (RANGE) {
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) s_dig[pos[i]] = (uint8_t)dg[i];
+  }
   // row ids are fetched only now (their registers replace the dead key registers); the loads
   // overlap with the key write-out below
   VT idx[IPT];
@@ -722,13 +768,19 @@ __global__ void __launch_bounds__(THREADS + 32 * LBW, MINB) onesweep_kernel(pass
   const bool write_keys = !(a.pairs && pl.last) || a.keep_keys || pl.hybrid;
   UK* kdst = static_cast<UK*>(const_cast<void*>(pl.key_dst == 1 ? a.key_bufs[1] : a.key_bufs[2]));
   uint32_t dst[IPT];
+  uint8_t dstd[RANGE ? IPT : 1];
 #pragma unroll
   for (int j = 0; j < IPT; ++j) {
     const uint32_t q = j * THREADS + tid;
     UK k = s_keys[q];
-    const unsigned d = (unsigned)(k >> shift) & 255u;
+    unsigned d;
+    if constexpr (RANGE) d = s_dig[q];
+    else d = (unsigned)(k >> shift) & 255u;
     dst[j] = s_off[d] + q;
-    if (write_keys && q < tile_n) {
+    if constexpr (RANGE) {
+      dstd[j] = (uint8_t)d;
+      if (q < tile_n) static_cast<UK*>(s_kdst[d])[dst[j]] = untwiddle_rt<UK>(k, a.kind, desc);  // the receiver sorts raw column values
+    } else if (write_keys && q < tile_n) {
       if (!a.pairs && pl.last && !pl.hybrid) k = untwiddle_rt<UK>(k, a.kind, desc);
       kdst[dst[j]] = k;
     }
@@ -742,7 +794,11 @@ __global__ void __launch_bounds__(THREADS + 32 * LBW, MINB) onesweep_kernel(pass
 #pragma unroll
     for (int j = 0; j < IPT; ++j) {
       const uint32_t q = j * THREADS + tid;
-      if (q < tile_n) idst[dst[j]] = s_vals[q];
+      if constexpr (RANGE) {
+        if (q < tile_n) static_cast<VT*>(s_vdst[dstd[j]])[dst[j]] = s_vals[q];
+      } else {
+        if (q < tile_n) idst[dst[j]] = s_vals[q];
+      }
     }
   }
 }
@@ -984,9 +1040,11 @@ struct tile_cfg { int threads; int ipt; };
 
 
 template <typename UK, int T, int I, typename VT = uint32_t>
-size_t onesweep_smem()
+size_t onesweep_smem(bool range = false)
 {
-  return (sizeof(UK) > sizeof(VT) ? sizeof(UK) : sizeof(VT)) * (size_t)T * I + sizeof(uint32_t) * (2 * (T / 32) * RADIX + 3 * RADIX + 16);
+  // every instantiation declares the RANGE arrays behind s_misc, only RANGE launches allocate them
+  return (sizeof(UK) > sizeof(VT) ? sizeof(UK) : sizeof(VT)) * (size_t)T * I + sizeof(uint32_t) * (2 * (T / 32) * RADIX + 3 * RADIX + 16) +
+         (range ? (sizeof(UK) + 2 * sizeof(void*)) * RADIX + (size_t)T * I : 0);
 }
 
 int64_t portion_limit()
@@ -1245,6 +1303,145 @@ void radix_partition_mix_carry(const uint64_t* keys, const void* vals, int val_b
     run_radix_cfg<uint64_t, 384, 16, 2, uint32_t, true, true>(keys, mixed_keys_out, b.as<uint64_t>(), static_cast<int32_t*>(vals_out),
                                                                vt.as<int32_t>(), nullptr, 0, n, (int)key_kind::UNSIGNED, false, true, stream,
                                                                7, 7, true, vals, part_base);
+}
+
+namespace {
+// bucket b of a key = number of splitters <= key (twiddled order); counts[b] += rows of bucket b
+template <typename UK>
+__global__ void __launch_bounds__(512) range_count_kernel(const UK* __restrict__ keys, int64_t n, int kind, const UK* __restrict__ splitters, int P,
+                                                          unsigned long long* __restrict__ counts)
+{
+  __shared__ UK sp[RADIX];
+  __shared__ unsigned int cnt[RADIX];
+  for (int i = threadIdx.x; i < RADIX; i += blockDim.x) {
+    sp[i]  = i < P - 1 ? splitters[i] : ~UK(0);
+    cnt[i] = 0;
+  }
+  __syncthreads();
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const UK k = twiddle_rt<UK>(ld_stream(keys + i), kind, UK(0));
+    int lo = 0, hi = P - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (sp[mid] <= k) lo = mid + 1;
+      else hi = mid;
+    }
+    atomicAdd(&cnt[lo], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < P; i += blockDim.x)
+    if (cnt[i]) atomicAdd(&counts[i], (unsigned long long)cnt[i]);
+}
+template <typename UK>
+__global__ void twiddle_splitters_kernel(const UK* __restrict__ raw, int m, int kind, UK* __restrict__ out)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m) out[i] = twiddle_rt<UK>(raw[i], kind, UK(0));
+}
+}  // namespace
+
+// Range partition of one null-free 8-byte integer-like key column (and optionally one null-free 4- / 8-byte payload column) straight
+// into P destination buffers — local or PEER memory (sharded sort: the partition pass is the bucket exchange).
+// Step 1 (range_partition_counts): rows per bucket, so that the ranks can agree on where each one writes.
+// Step 2 (range_partition_scatter): ONE one-sweep pass (stable; per-(tile, bucket) runs of ~6144 / P rows, i.e. 6 KB NVLink
+// writes at P = 8) whose digit is the bucket; key_dst[b] / val_dst[b] = address of this rank's first row of bucket b.
+void range_partition_counts(const b2_column_view& keys, const void* splitters, int P, int64_t* out_counts, cudaStream_t stream)
+{
+  using UK = uint64_t;
+  const int64_t n = keys.size;
+  const int kind = is_signed_id(storage_type(keys.type_id)) ? (int)key_kind::SIGNED : (int)key_kind::UNSIGNED;
+  for (int b = 0; b < P; ++b) out_counts[b] = 0;
+  if (n == 0) return;
+  dbuf cnt(sizeof(unsigned long long) * RADIX, stream), sp(sizeof(UK) * RADIX, stream);
+  B2_CUDA_TRY(cudaMemsetAsync(cnt.ptr, 0, cnt.bytes, stream));
+  if (P > 1) B2_LAUNCH((twiddle_splitters_kernel<UK>), 1, RADIX, 0, stream, static_cast<const UK*>(splitters), P - 1, kind, sp.as<UK>());
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 511) / 512, NUM_SMS_B200 * 4));
+  {
+    prof_scope ps("range_count", stream);
+    B2_LAUNCH((range_count_kernel<UK>), grid, 512, 0, stream, static_cast<const UK*>(keys.data) + keys.offset, n, kind, sp.as<UK>(), P,
+              cnt.as<unsigned long long>());
+  }
+  unsigned long long h[RADIX];
+  B2_CUDA_TRY(cudaMemcpyAsync(h, cnt.ptr, sizeof(h), cudaMemcpyDeviceToHost, stream));
+  B2_CUDA_TRY(cudaStreamSynchronize(stream));
+  for (int b = 0; b < P; ++b) out_counts[b] = (int64_t)h[b];
+}
+
+template <typename VT, bool CARRY>
+static void range_scatter_impl(const b2_column_view& keys, const void* vals, const void* splitters, int P, void* const* key_dst, void* const* val_dst,
+                               cudaStream_t stream)
+{
+  using UK = uint64_t;
+  constexpr int T = 384, I = 16, TILE = T * I;
+  const int64_t n = keys.size;
+  const int kind = is_signed_id(storage_type(keys.type_id)) ? (int)key_kind::SIGNED : (int)key_kind::UNSIGNED;
+  const int64_t plim = std::max<int64_t>(TILE, portion_limit() / TILE * TILE);
+  const int64_t nportions = (n + plim - 1) / plim;
+  const int64_t tiles_per_portion = (std::min(n, plim) + TILE - 1) / TILE;
+  const size_t ctl_bytes = (sizeof(sort_ctl) + 255) / 256 * 256;
+  const size_t cnt_bytes = (sizeof(uint32_t) * nportions + 255) / 256 * 256;
+  const size_t status_per = sizeof(uint32_t) * RADIX * (size_t)tiles_per_portion;
+  const size_t tab_bytes = sizeof(UK) * RADIX + 2 * sizeof(void*) * RADIX;
+  dbuf work(ctl_bytes + cnt_bytes + status_per * nportions + tab_bytes, stream);
+  B2_CUDA_TRY(cudaMemsetAsync(work.ptr, 0, work.bytes, stream));
+  auto* ctl      = reinterpret_cast<sort_ctl*>(work.ptr);
+  auto* counters = reinterpret_cast<uint32_t*>(static_cast<char*>(work.ptr) + ctl_bytes);
+  auto* status   = static_cast<char*>(work.ptr) + ctl_bytes + cnt_bytes;
+  auto* d_split  = reinterpret_cast<UK*>(status + status_per * nportions);
+  auto* d_kdst   = reinterpret_cast<void**>(d_split + RADIX);
+  auto* d_vdst   = d_kdst + RADIX;
+  if (P > 1) B2_LAUNCH((twiddle_splitters_kernel<UK>), 1, RADIX, 0, stream, static_cast<const UK*>(splitters), P - 1, kind, d_split);
+  B2_CUDA_TRY(cudaMemcpyAsync(d_kdst, key_dst, sizeof(void*) * P, cudaMemcpyHostToDevice, stream));
+  if (CARRY) B2_CUDA_TRY(cudaMemcpyAsync(d_vdst, val_dst, sizeof(void*) * P, cudaMemcpyHostToDevice, stream));
+  // the plan of the single pass 0: executed, raw keys, last pass (keys-only mode untwiddles what it writes); base = 0: positions
+  // count from the start of each bucket's run
+  pass_plan pl{};
+  pl.trivial = 0; pl.key_src = 0; pl.key_dst = 1; pl.idx_src = -1; pl.idx_dst = 0; pl.last = 1; pl.hybrid = 0;
+  B2_CUDA_TRY(cudaMemcpyAsync(&ctl->plan[0], &pl, sizeof(pl), cudaMemcpyHostToDevice, stream));
+
+  static std::atomic<uint64_t> attr_done{0};
+  once_per_device(attr_done, [] {
+    B2_CUDA_TRY(cudaFuncSetAttribute(onesweep_kernel<UK, T, I, 2, VT, CARRY, false, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)onesweep_smem<UK, T, I, VT>(true)));
+  });
+  pass_args a{};
+  a.key_bufs[0] = static_cast<const UK*>(keys.data) + keys.offset;
+  a.ctl = ctl;
+  a.kind = kind;
+  a.pairs = CARRY ? 1 : 0;
+  a.val_in = vals;
+  a.desc_mask = 0;
+  a.range_splitters = d_split;
+  a.range_key_dst = d_kdst;
+  a.range_val_dst = d_vdst;
+  a.range_parts = P;
+  a.pass = 0;
+  for (int64_t q = 0; q < nportions; ++q) {
+    const int64_t start = q * plim;
+    const int64_t pn = std::min(plim, n - start);
+    a.portion_start = start;
+    a.portion_n = (uint32_t)pn;
+    a.portion_parity = (int)(q & 1);
+    a.has_next_portion = q + 1 < nportions;
+    a.status = reinterpret_cast<uint32_t*>(status + (size_t)q * status_per);
+    a.tile_counter = counters + q;
+    const int64_t ntiles = (pn + TILE - 1) / TILE;
+    prof_scope ps("range_scatter", stream);
+    const size_t smem_bytes = onesweep_smem<UK, T, I, VT>(true);
+    B2_LAUNCH((onesweep_kernel<UK, T, I, 2, VT, CARRY, false, false, false, false, true>), (unsigned)ntiles, T + 32 * LBW, smem_bytes, stream, a);
+  }
+}
+
+void range_partition_scatter(const b2_column_view& keys, const b2_column_view* values, const void* splitters, int P, void* const* key_dst,
+                             void* const* val_dst, cudaStream_t stream)
+{
+  if (keys.size == 0) return;
+  if (values == nullptr) return range_scatter_impl<uint32_t, false>(keys, nullptr, splitters, P, key_dst, nullptr, stream);
+  const int vw = type_width(values->type_id);
+  const void* vin = static_cast<const char*>(values->data) + (size_t)values->offset * vw;
+  if (vw == 8) range_scatter_impl<uint64_t, true>(keys, vin, splitters, P, key_dst, val_dst, stream);
+  else range_scatter_impl<uint32_t, true>(keys, vin, splitters, P, key_dst, val_dst, stream);
 }
 
 namespace {

@@ -146,6 +146,38 @@ class CudaOps:
         finally:
             lib.lib.b2_partition_plan_free(plan)
 
+    def range_exchange(self, keys: torch.Tensor, values, splitters, group=None, slot_base: int = 0):
+        """Range partition fused into ONE one-sweep pass that writes every bucket straight into its destination GPU's receive
+        buffer (b2_range_partition_counts / _scatter; int64 / uint64 keys, optionally one 4- / 8-byte payload column).
+        Returns (received keys, received values or None): views of the exchange buffers."""
+        plc, lib = self.plc, self._lib
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        kcol = plc.Column.from_torch(keys)
+        kv = kcol._view()
+        sp = C.c_void_p(splitters.data_ptr()) if splitters is not None and splitters.numel() else None
+        counts = (C.c_int64 * world)()
+        lib.check(lib.lib.b2_range_partition_counts(C.byref(kv), sp, world, lib.stream_arg(None), counts))
+        mine = torch.tensor(list(counts), dtype=torch.int64, device=keys.device)
+        allc = torch.empty(world * world, dtype=torch.int64, device=keys.device)
+        dist.all_gather_into_tensor(allc, mine, group=group)
+        cm = allc.view(world, world).cpu()                          # cm[r][d] = rows rank r sends to rank d
+        recv_total = int(cm[:, rank].sum())
+        cap_rows = max(int(cm.sum(dim=0).max()), int(cm.sum(dim=1).max()))   # from the shared matrix: every rank agrees
+        cols = [keys] + ([values] if values is not None else [])
+        exs = [PeerExchange.get(lib, int(cap_rows * c.element_size() * 1.05) + (1 << 20), group, slot=slot_base + j) for j, c in enumerate(cols)]
+        my_off = cm[:rank, :].sum(dim=0)                              # rows written before mine in each destination
+        kd = (C.c_void_p * world)(*[exs[0].peer_ptrs[d] + int(my_off[d]) * keys.element_size() for d in range(world)])
+        vd, vv = None, None
+        if values is not None:
+            vd = (C.c_void_p * world)(*[exs[1].peer_ptrs[d] + int(my_off[d]) * values.element_size() for d in range(world)])
+            vcol = plc.Column.from_torch(values)
+            vv = vcol._view()
+        dist.barrier(group=group)                                     # peers are done reading the previous contents
+        lib.check(lib.lib.b2_range_partition_scatter(C.byref(kv), C.byref(vv) if vv is not None else None, sp, world, kd, vd, lib.stream_arg(None)))
+        dist.barrier(group=group)                                     # stream-ordered after the pass: all buckets landed
+        rk = exs[0].view(recv_total, keys.dtype)
+        return rk, (exs[1].view(recv_total, values.dtype) if values is not None else None)
+
     def sort_by_key(self, values: torch.Tensor, keys: torch.Tensor) -> torch.Tensor:
         plc = self.plc
         out = plc.sorting.sort_by_key(plc.Table([plc.Column.from_torch(values)]), plc.Table([plc.Column.from_torch(keys)]),
@@ -293,8 +325,10 @@ def _exchange_cols(cols, offsets, ops, group=None, slot_base: int = 0):
 
 def _exchange_variant(t: torch.Tensor, ops) -> str:
     """Bucket exchange on GPUs (B2_SHARD_P2P forces one; measurements in profiles/r2_multi_gpu.md):
-      "staged" (default): fused partition + exchange, per-peer runs of a 4096-row tile staged in shared memory before the
-          remote stores (2 GPUs: 14.0 ms per 1e9 rows)
+      "fused" (default for the sort on int64 keys): the range partition is ONE one-sweep pass whose digit is the destination
+          rank and whose per-(tile, bucket) runs are written straight into the peers' receive buffers (b2_range_partition_*)
+      "staged": plan (bucket + stable rank per row) + scatter kernel, per-peer runs of a 4096-row tile staged in shared memory
+          before the remote stores (2 GPUs: 14.0 ms per 1e9 rows, 8 GPUs: 22.1 ms); the join's hash partition uses it
       "1" / "plain": fused, row-by-row remote stores (2 GPUs: 16.9 ms; at 8 GPUs a warp's rows split into 32-byte writes)
       "0" / "copy": b2_partition, then one contiguous b2_peer_copy per destination (B2_SHARD_XCHG=nccl: all_to_all_single)
     CPU tensors (gloo tests) always take the partition + process-group all-to-all path."""
@@ -305,7 +339,9 @@ def _exchange_variant(t: torch.Tensor, ops) -> str:
         return "copy"
     if env in ("1", "plain"):
         return "plain"
-    return "staged"
+    if env == "staged":
+        return "staged"
+    return "fused"
 
 
 def choose_splitters(samples_sorted: torch.Tensor, world: int) -> torch.Tensor:
@@ -336,7 +372,15 @@ def sort_by_key_sharded(values: torch.Tensor, keys: torch.Tensor, ops=None, grou
     splitters = choose_splitters(ops.sort_keys(gathered), world)
     same = values.data_ptr() == keys.data_ptr() and values.numel() == keys.numel()
     variant = _exchange_variant(keys, ops)
-    if variant in ("staged", "plain"):
+    fusable = keys.dtype == torch.int64 and (same or values.element_size() in (4, 8)) and hasattr(ops, "range_exchange")
+    if variant == "fused" and fusable:
+        ph.mark("partition+exchange(fused pass)")
+        rk, rv = ops.range_exchange(keys, None if same else values, splitters, group)
+        if same:
+            rv = rk
+    elif variant in ("fused", "staged", "plain"):
+        if variant == "fused":
+            variant = "staged"
         ph.mark("partition+exchange(p2p)")
         if same:
             rk = ops.partition_exchange(keys, keys, 0, splitters, group, variant=variant)
@@ -374,6 +418,8 @@ def inner_join_sharded(left_keys: torch.Tensor, right_keys: torch.Tensor, ops=No
         if world == 1:
             return keys, gid
         variant = _exchange_variant(keys, ops)
+        if variant == "fused":
+            variant = "staged"   # the fused pass is a range partition; the join's hash partition takes the plan + staged scatter
         if variant in ("staged", "plain"):
             ph.mark("partition+exchange(p2p)")
             got = ops.partition_exchange([keys, gid], keys, 1, None, group, slot_base=slot_base, variant=variant)

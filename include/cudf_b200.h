@@ -322,6 +322,15 @@ B2_API b2_status b2_partition_scatter(const b2_partition_plan* plan, const b2_co
 B2_API b2_status b2_partition_scatter_staged(const b2_partition_plan* plan, const b2_column_view* column,
                                              void* const* dest_ptrs, b2_stream stream);
 B2_API void      b2_partition_plan_free(b2_partition_plan* plan);
+/* Range partition fused into ONE one-sweep pass whose digit is the bucket (number of splitters <= key): first the bucket counts of
+ * this rank's rows, then — after the ranks exchanged their counts — a stable pass that writes bucket b's keys (and optionally one
+ * 4- / 8-byte payload column) to key_dst[b] / val_dst[b], local or peer memory (host arrays of num_partitions device pointers: the
+ * address of THIS rank's first row of bucket b). One null-free 8-byte integer-like key column; splitters = device array of P - 1
+ * ascending keys of the column's type. The sharded sort's partition + exchange ("fuse with the first radix pass"). */
+B2_API b2_status b2_range_partition_counts(const b2_column_view* keys, const void* splitters, int32_t num_partitions, b2_stream stream,
+                                           int64_t* out_counts);
+B2_API b2_status b2_range_partition_scatter(const b2_column_view* keys, const b2_column_view* values, const void* splitters,
+                                            int32_t num_partitions, void* const* key_dst, void* const* val_dst, b2_stream stream);
 /* CUDA-IPC exchange buffers (cudaMalloc + cudaIpcGetMemHandle / cudaIpcOpenMemHandle); handle = 64 bytes */
 B2_API b2_status b2_ipc_alloc(size_t bytes, void** out_ptr, uint8_t* out_handle64);
 B2_API b2_status b2_ipc_open(const uint8_t* handle64, void** out_ptr);

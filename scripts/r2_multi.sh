@@ -23,6 +23,7 @@ for v in $VARIANTS; do
   case $v in
     peer)   E="B2_SHARD_P2P=copy B2_SHARD_XCHG=peer" ;;
     staged) E="B2_SHARD_P2P=staged" ;;
+    fused)  E="X=1" ;;
     copy)   E="B2_SHARD_P2P=copy" ;;
     p2p)    E="B2_SHARD_P2P=1" ;;
     nccl)   E="B2_SHARD_P2P=copy B2_SHARD_XCHG=nccl" ;;
