@@ -35,6 +35,15 @@ stats_out = torch.stack([out.sum(), torch.tensor(out.numel(), device="cuda"), (o
 dist.all_reduce(stats_in); dist.all_reduce(stats_out)
 assert torch.equal(stats_in, stats_out), (stats_in, stats_out)
 cnt = torch.tensor([out.numel()], device="cuda"); cnts = [torch.empty_like(cnt) for _ in range(world)]; dist.all_gather(cnts, cnt)
+# payload column distinct from the keys: values = 3 * key + 1 (wrapping) must arrive in key order
+vals = keys * 3 + 1
+outv = sharded.sort_by_key_sharded(vals, keys)
+torch.cuda.synchronize()
+assert outv.numel() == out.numel() and bool((outv == out * 3 + 1).all())
+v32 = (keys & 0x7FFFFFFF).to(torch.int32)
+outv32 = sharded.sort_by_key_sharded(v32, keys)
+torch.cuda.synchronize()
+assert bool((outv32 == (out & 0x7FFFFFFF).to(torch.int32)).all())
 # join: right = fresh keys, left = 10 % copies of right rows of ANY rank via the shared generator
 m = max(1000, n // 10)
 rk = torch.empty(m, dtype=torch.int64, device="cuda")
