@@ -171,8 +171,9 @@ check([(p[:3000], None)], [(b, None)], 'dup x chunks', ("inner_join", "left_join
 print('RADIX_JOIN_OK')
 """
     run(code, "RADIX_JOIN_OK", env={"B2_JOIN_RADIX_ROWS": "1"})
-    # output-size guess too small: the walk is repeated with the exact size
-    run(code, "RADIX_JOIN_OK", env={"B2_JOIN_RADIX_ROWS": "1", "B2_JOIN_RADIX_CAPACITY": "100"})
+    # output-size guess too small: the walk is repeated with the exact size (first cases only: the emulator is slow)
+    short = code[:code.index("b = rng.integers(0, 1000, 60_000)")] + "print('RADIX_JOIN_OK')\n"
+    run(short, "RADIX_JOIN_OK", env={"B2_JOIN_RADIX_ROWS": "1", "B2_JOIN_RADIX_CAPACITY": "100"})
 
 
 def test_emu_wide_keys(emu_lib):
