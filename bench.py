@@ -196,6 +196,31 @@ def measured_traffic(kernel_key: str):
         return None, "no ncu capture of this kernel under profiles/ yet"
 
 
+def pin_to_gpu_numa_node(gpu_index: int):
+    """Bind this process to the CPUs of the NUMA node its GPU hangs off, before the pinned host buffers are allocated (they are then
+    placed on that node): the e2e copies of 8 ranks otherwise cross the host's socket interconnect. Returns a short note."""
+    try:
+        out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(gpu_index)], capture_output=True, text=True,
+                             timeout=20).stdout.strip()
+        bdf = out.lower()
+        if bdf.count(":") == 2 and len(bdf.split(":")[0]) == 8:   # 00000000:1B:00.0 -> 0000:1b:00.0
+            bdf = bdf[4:]
+        node = int(Path(f"/sys/bus/pci/devices/{bdf}/numa_node").read_text().strip())
+        if node < 0:
+            return "numa: single node"
+        cpus = set()
+        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return f"numa: node {node}, {len(allowed)} cpus"
+        return "numa: no allowed cpu on the GPU's node"
+    except Exception as ex:  # best effort
+        return f"numa: not pinned ({type(ex).__name__})"
+
+
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
@@ -210,6 +235,7 @@ def run_ours(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
     torch.cuda.set_device(local_rank)
+    numa_note = pin_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -424,7 +450,7 @@ def run_ours(args):
             del keep
             assert bool((h_out[0][1:1000001] >= h_out[0][:1000000]).all()) and bool((h_out[1][1:1000001] >= h_out[1][:1000000]).all())
             e2e = {"value": world * n / (ems / 1e3), "unit": UNIT, "h2d_bytes_per_step": 8 * n * world,
-                   "d2h_bytes_per_step": 8 * n * world, "ms_per_step": ems, "steps": k,
+                   "d2h_bytes_per_step": 8 * n * world, "ms_per_step": ems, "steps": k, "host_placement": numa_note,
                    "pipeline": "three streams, double-buffered: H2D(i+1) | sort(i) | D2H(i-1); every step copies its 8 GB/GPU input from "
                                "pinned host memory and its sorted 8 GB/GPU output back to pinned host memory inside the timed region"}
             del h_in, h_out, d_in
