@@ -370,6 +370,18 @@ struct pass_args {
   int32_t range_parts;
 };
 
+// Block-wide barrier of a warp-specialised kernel: the ranking warps and the look-back warps reach it from different branches, which
+// `__syncthreads()` only tolerates in practice; `bar.sync 0, n` with the explicit thread count is the PTX-conformant form (what
+// compute-sanitizer synccheck expects).
+__device__ __forceinline__ void cta_barrier(int nthreads)
+{
+#ifdef B2_EMU
+  (void)nthreads;
+  __syncthreads();
+#else
+  asm volatile("bar.sync 0, %0;" ::"r"(nthreads) : "memory");
+#endif
+}
 __device__ __forceinline__ void ranker_barrier(int nthreads)
 {
 #ifdef B2_EMU
@@ -411,20 +423,20 @@ constexpr int LBT = 8;   // predecessor tiles fetched per round
 // (EXPERIMENTAL in round 1: opt-in with B2_SORT_CARRY=1, not yet run on hardware).
 // MIX: raw 64-bit keys are replaced by mix64(key) on load (hash-join partitioning: the first executed pass reads the
 // packed key column itself, so the mixed keys are never materialised unsorted).
-// SAFE: one more __syncwarp in the bitmap ranking loop (formally race-free under independent thread scheduling; the
-// shipped form relies on the warp staying converged, which hardware validation confirms) — B2_SORT_CFG=10 measures it.
+// SAFE (default): a __syncwarp between the followers' read of the peer bitmap and the leader's clear — race-free under
+// independent thread scheduling (compute-sanitizer racecheck flags the form without it); measured cost: none (7.86 vs 7.85 ms).
 #ifdef B2_EMU
 constexpr bool EMU_BUILD = true;
 #else
 constexpr bool EMU_BUILD = false;
 #endif
-// RMW: the leader advances the warp's running digit offset with one ATOMS.ADD (returning the old value) instead of
-// LDS + STS — one shared-memory operation less per key in a kernel bound by shared-memory wavefronts (B2_SORT_CFG=11).
+// RMW (default): the leader advances the warp's running digit offset with one ATOMS.ADD (returning the old value) instead of
+// LDS + STS — one shared-memory operation less per key in a kernel bound by shared-memory wavefronts (7.49 vs 7.85 ms per pass).
 // BULK: full, 16-byte aligned key tiles arrive in shared memory through ONE bulk async copy (cp.async.bulk, the 1-D TMA
 // path: UBLKCP in SASS) signalled by an mbarrier, and the ranking warps pick their keys up from there instead of issuing
 // IPT global loads each (B2_SORT_CFG=12; other tiles take the ordinary loads).
-template <typename UK, int THREADS, int IPT, int MINB, typename VT = uint32_t, bool CARRY = false, bool MIX = false, bool SAFE = false,
-          bool RMW = false, bool BULK = false, bool RANGE = false>
+template <typename UK, int THREADS, int IPT, int MINB, typename VT = uint32_t, bool CARRY = false, bool MIX = false, bool SAFE = true,
+          bool RMW = true, bool BULK = false, bool RANGE = false>
 __global__ void __launch_bounds__(THREADS + 32 * LBW, MINB) onesweep_kernel(pass_args a)
 {
   constexpr int TILE   = THREADS * IPT;
@@ -488,7 +500,7 @@ __global__ void __launch_bounds__(THREADS + 32 * LBW, MINB) onesweep_kernel(pass
 
   if (!ranker) {
     // ================================ look-back warp ==============================================
-    __syncthreads();  // (S2) agg[tile][*] written by the rankers; s_cnt = {count, tile-local start}
+    cta_barrier(THREADS + 32 * LBW);  // (S2) agg[tile][*] written by the rankers; s_cnt = {count, tile-local start}
     const int d0 = ((warp - NWARPS) * 32 + lane) * DPL;
     uint32_t cnt[DPL], loc[DPL], excl[DPL];
 #pragma unroll
@@ -550,7 +562,7 @@ __global__ void __launch_bounds__(THREADS + 32 * LBW, MINB) onesweep_kernel(pass
       s_off[d0 + j] = g + excl[j] - loc[j];
       if (last_of_portion) a.ctl->base[a.portion_parity ^ 1][a.pass][d0 + j] = g + excl[j] + cnt[j];
     }
-    __syncthreads();  // (S4) offsets ready
+    cta_barrier(THREADS + 32 * LBW);  // (S4) offsets ready
     return;
   }
 
@@ -673,7 +685,7 @@ __global__ void __launch_bounds__(THREADS + 32 * LBW, MINB) onesweep_kernel(pass
 #pragma unroll
     for (int w = 0; w < NWARPS; ++w) s_whist[w * RADIX + tid] += tstart;
   }
-  __syncthreads();  // (S2) releases the look-back warps; warp offsets final
+  cta_barrier(THREADS + 32 * LBW);  // (S2) releases the look-back warps; warp offsets final
 
   // ---- rank within warp (stable): MATCH.ANY peers + running per-warp digit offsets --------------
   // All MATCH ops are issued first (independent, pipelined); only the counter chain is serial.
@@ -763,7 +775,7 @@ __global__ void __launch_bounds__(THREADS + 32 * LBW, MINB) onesweep_kernel(pass
       }
     }
   }
-  __syncthreads();  // (S4) keys staged, scatter offsets ready
+  cta_barrier(THREADS + 32 * LBW);  // (S4) keys staged, scatter offsets ready
 
   const bool write_keys = !(a.pairs && pl.last) || a.keep_keys || pl.hybrid;
   UK* kdst = static_cast<UK*>(const_cast<void*>(pl.key_dst == 1 ? a.key_bufs[1] : a.key_bufs[2]));
@@ -1075,8 +1087,8 @@ int64_t hybrid_min_rows()
 //  raw_keys != nullptr : keys are the user's raw column (twiddled on load, implicit row ids)
 //  raw_keys == nullptr : keys are pre-twiddled in bufA with explicit row ids in idx buffer pre_idx_buf
 //  pairs: idx_out receives the permutation ; keys-only: bufA is the OUTPUT, bufB the temp.
-template <typename UK, int T, int I, int MINB, typename VT = uint32_t, bool CARRY = false, bool MIX = false, bool SAFE = false,
-          bool RMW = false, bool BULK = false>
+template <typename UK, int T, int I, int MINB, typename VT = uint32_t, bool CARRY = false, bool MIX = false, bool SAFE = true,
+          bool RMW = true, bool BULK = false>
 void run_radix_cfg(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int32_t* idx_tmp, int32_t* idx_tmp2, int pre_idx_buf, int64_t n,
                    int kind, bool descending, bool pairs, cudaStream_t stream, int first_pass = 0, int last_pass = 7,
                    bool keep_keys = false, const void* val_in = nullptr, uint32_t* top_digit_base_out = nullptr)
@@ -1247,17 +1259,17 @@ void run_radix(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int32_t
       case 7: B2_RUN(256, 20, 2); break;
       case 8: B2_RUN(320, 16, 2); break;
       case 9: B2_RUN(320, 12, 2); break;
-      case 10:  // default shape, formally race-free bitmap ranking
-        run_radix_cfg<UK, 384, 16, 2, uint32_t, false, false, true>(raw_keys, bufA, bufB, idx_out, idx_tmp, idx_tmp2, pre_idx_buf, n, kind,
-                                                                    descending, pairs, stream);
+      case 10:  // default shape, round-1 ranking: no extra __syncwarp (relies on warp convergence), offsets by LDS + STS
+        run_radix_cfg<UK, 384, 16, 2, uint32_t, false, false, false, false>(raw_keys, bufA, bufB, idx_out, idx_tmp, idx_tmp2, pre_idx_buf, n,
+                                                                            kind, descending, pairs, stream);
         break;
-      case 12:  // default shape, key tiles by one bulk async copy (TMA 1-D) + mbarrier
-        run_radix_cfg<UK, 384, 16, 2, uint32_t, false, false, false, false, true>(raw_keys, bufA, bufB, idx_out, idx_tmp, idx_tmp2, pre_idx_buf,
-                                                                                  n, kind, descending, pairs, stream);
-        break;
-      case 11:  // default shape, running digit offsets advanced by one ATOMS.ADD
-        run_radix_cfg<UK, 384, 16, 2, uint32_t, false, false, false, true>(raw_keys, bufA, bufB, idx_out, idx_tmp, idx_tmp2, pre_idx_buf, n,
+      case 11:  // default shape, race-free ranking, offsets by LDS + STS
+        run_radix_cfg<UK, 384, 16, 2, uint32_t, false, false, true, false>(raw_keys, bufA, bufB, idx_out, idx_tmp, idx_tmp2, pre_idx_buf, n,
                                                                            kind, descending, pairs, stream);
+        break;
+      case 12:  // default shape and ranking, key tiles by one bulk async copy (TMA 1-D) + mbarrier
+        run_radix_cfg<UK, 384, 16, 2, uint32_t, false, false, true, true, true>(raw_keys, bufA, bufB, idx_out, idx_tmp, idx_tmp2, pre_idx_buf,
+                                                                                n, kind, descending, pairs, stream);
         break;
       default: B2_RUN(384, 16, 2); break;
     }
@@ -1402,7 +1414,7 @@ static void range_scatter_impl(const b2_column_view& keys, const void* vals, con
 
   static std::atomic<uint64_t> attr_done{0};
   once_per_device(attr_done, [] {
-    B2_CUDA_TRY(cudaFuncSetAttribute(onesweep_kernel<UK, T, I, 2, VT, CARRY, false, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B2_CUDA_TRY(cudaFuncSetAttribute(onesweep_kernel<UK, T, I, 2, VT, CARRY, false, true, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)onesweep_smem<UK, T, I, VT>(true)));
   });
   pass_args a{};
@@ -1429,7 +1441,7 @@ static void range_scatter_impl(const b2_column_view& keys, const void* vals, con
     const int64_t ntiles = (pn + TILE - 1) / TILE;
     prof_scope ps("range_scatter", stream);
     const size_t smem_bytes = onesweep_smem<UK, T, I, VT>(true);
-    B2_LAUNCH((onesweep_kernel<UK, T, I, 2, VT, CARRY, false, false, false, false, true>), (unsigned)ntiles, T + 32 * LBW, smem_bytes, stream, a);
+    B2_LAUNCH((onesweep_kernel<UK, T, I, 2, VT, CARRY, false, true, true, false, true>), (unsigned)ntiles, T + 32 * LBW, smem_bytes, stream, a);
   }
 }
 
@@ -1684,23 +1696,18 @@ column_ptr sort_by_key_carry(const b2_column_view& keys, const b2_column_view& v
     using VT = decltype(vtag);
     dbuf a(sizeof(UK) * n, stream), b(sizeof(UK) > 1 ? sizeof(UK) * n : 0, stream);
     if constexpr (sizeof(UK) == 8) {
-      // B2_SORT_CFG on the payload-carrying kernel: 10 = formally race-free ranking (one more __syncwarp), 11 = running
-      // offsets by one ATOMS.ADD, 13 = both
+      // B2_SORT_CFG on the payload-carrying kernel: 10 = round-1 ranking (no extra __syncwarp, offsets by LDS + STS), 11 = race-free
+      // ranking with LDS + STS offsets; the default is race-free + one ATOMS.ADD per digit run (measured: 7.49 vs 7.85 ms per pass)
       switch (sort_cfg_env()) {
         case 10:
-          run_radix_cfg<UK, 384, 16, 2, VT, true, false, true>(static_cast<const UK*>(keys.data) + keys.offset, a.as<UK>(), b.as<UK>(),
-                                                               out->data.as<int32_t>(), vtmp.as<int32_t>(), nullptr, 0, n, kind, !ascending,
-                                                               true, stream, 0, 7, false, vin);
+          run_radix_cfg<UK, 384, 16, 2, VT, true, false, false, false>(static_cast<const UK*>(keys.data) + keys.offset, a.as<UK>(), b.as<UK>(),
+                                                                       out->data.as<int32_t>(), vtmp.as<int32_t>(), nullptr, 0, n, kind,
+                                                                       !ascending, true, stream, 0, 7, false, vin);
           break;
         case 11:
-          run_radix_cfg<UK, 384, 16, 2, VT, true, false, false, true>(static_cast<const UK*>(keys.data) + keys.offset, a.as<UK>(), b.as<UK>(),
+          run_radix_cfg<UK, 384, 16, 2, VT, true, false, true, false>(static_cast<const UK*>(keys.data) + keys.offset, a.as<UK>(), b.as<UK>(),
                                                                       out->data.as<int32_t>(), vtmp.as<int32_t>(), nullptr, 0, n, kind,
                                                                       !ascending, true, stream, 0, 7, false, vin);
-          break;
-        case 13:
-          run_radix_cfg<UK, 384, 16, 2, VT, true, false, true, true>(static_cast<const UK*>(keys.data) + keys.offset, a.as<UK>(), b.as<UK>(),
-                                                                     out->data.as<int32_t>(), vtmp.as<int32_t>(), nullptr, 0, n, kind,
-                                                                     !ascending, true, stream, 0, 7, false, vin);
           break;
         default:
           run_radix_cfg<UK, 384, 16, 2, VT, true>(static_cast<const UK*>(keys.data) + keys.offset, a.as<UK>(), b.as<UK>(),

@@ -337,8 +337,8 @@ std::unique_ptr<b2_scalar> reduce(const b2_column_view& col, int32_t kind, int32
 // ------------------------------------------------------------------------------------------------
 namespace {
 
-constexpr int SC_THREADS = 256;  // 4 CTAs per SM: while one CTA's warps wait at the barrier for its look-back warp, three others run (ncu: barrier was the top stall at 512 x 2)
-// 16-byte vectors per lane per tile: 32 KB tiles for 8-byte types (4096 elements), 16 KB otherwise. The look-back consumes
+constexpr int SC_THREADS = 512;  // two CTAs per SM (256 x 4 measured the same for int64 and 5 % slower for float64)
+// 16-byte vectors per lane per tile: 64 KB tiles for 8-byte types (8192 elements), 32 KB otherwise. The look-back consumes
 // SC_LB * 32 predecessor records per global-memory round trip, so tiles/us <= SC_LB * 32 / latency: larger tiles and a
 // wider window lift that ceiling above the HBM rate (round 1: 32 KB tiles, 32 records per round = 0.26 of peak).
 template <typename T> constexpr int sc_k() { return sizeof(T) == 8 ? 8 : 4; }
@@ -403,7 +403,7 @@ __device__ __forceinline__ uint32_t valid_bits_at(const uint32_t* mask, int64_t 
 }
 
 template <typename T, int OP, bool COUNT>
-__global__ void __launch_bounds__(SC_THREADS, 4) scan_kernel(const T* __restrict__ in, const uint32_t* __restrict__ mask,
+__global__ void __launch_bounds__(SC_THREADS, 2) scan_kernel(const T* __restrict__ in, const uint32_t* __restrict__ mask,
                                                           int64_t bit_offset, int64_t n, bool exclusive, bool in_aligned,
                                                           T* __restrict__ out, scan_state st)
 {
