@@ -898,22 +898,43 @@ __global__ void __launch_bounds__(FIX_THREADS) segment_fix_kernel(pass_args a, i
       const int rmax = (int)(n - 1 - gi < FIX_HALO ? n - 1 - gi : (int64_t)FIX_HALO);
       int left = 0, before = 0;
       bool all_equal = true, cut = false;
-      for (;;) {
-        if (left == lmax) { cut = lmax == FIX_HALO; break; }
-        const UK o = sk[FIX_HALO + i - left - 1];
-        if ((UK)(o >> shift) != pf) break;
-        ++left;
-        before += o <= k ? 1 : 0;   // earlier rows win ties
-        all_equal = all_equal && o == k;
+      // The first FIX_FAST neighbours on each side are examined without branches (every lane of the warp does the same
+      // work: a divergent walk costs the warp its LONGEST segment, which tripled the kernel's time at ~2 rows per segment);
+      // only rows whose segment reaches further continue with the loops below.
+      constexpr int FIX_FAST = 3;
+      bool in_l = true, in_r = true;
+#pragma unroll
+      for (int s = 1; s <= FIX_FAST; ++s) {
+        const UK ol = sk[FIX_HALO + i - s];   // inside the halo: FIX_HALO >= FIX_FAST
+        const UK orr = sk[FIX_HALO + i + s];
+        in_l = in_l && s <= lmax && (UK)(ol >> shift) == pf;
+        in_r = in_r && s <= rmax && (UK)(orr >> shift) == pf;
+        left += in_l ? 1 : 0;
+        before += (in_l && ol <= k) ? 1 : 0;   // earlier rows win ties
+        before += (in_r && orr < k) ? 1 : 0;
+        all_equal = all_equal && (!in_l || ol == k) && (!in_r || orr == k);
       }
       int right = 0;
-      for (;;) {
-        if (right == rmax) { cut = cut || rmax == FIX_HALO; break; }
-        const UK o = sk[FIX_HALO + i + right + 1];
-        if ((UK)(o >> shift) != pf) break;
-        ++right;
-        before += o < k ? 1 : 0;
-        all_equal = all_equal && o == k;
+      if (in_l) {  // the segment extends further to the left
+        for (;;) {
+          if (left == lmax) { cut = lmax == FIX_HALO; break; }
+          const UK o = sk[FIX_HALO + i - left - 1];
+          if ((UK)(o >> shift) != pf) break;
+          ++left;
+          before += o <= k ? 1 : 0;
+          all_equal = all_equal && o == k;
+        }
+      }
+      if (in_r) {
+        right = FIX_FAST;
+        for (;;) {
+          if (right == rmax) { cut = cut || rmax == FIX_HALO; break; }
+          const UK o = sk[FIX_HALO + i + right + 1];
+          if ((UK)(o >> shift) != pf) break;
+          ++right;
+          before += o < k ? 1 : 0;
+          all_equal = all_equal && o == k;
+        }
       }
       int64_t dst = gi - left + before;
       if (cut) {
