@@ -371,15 +371,16 @@ struct pass_args {
 };
 
 // Block-wide barrier of a warp-specialised kernel: the ranking warps and the look-back warps reach it from different branches, which
-// `__syncthreads()` only tolerates in practice; `bar.sync 0, n` with the explicit thread count is the PTX-conformant form (what
-// compute-sanitizer synccheck expects).
+// `__syncthreads()` only tolerates in practice; a named barrier with the explicit thread count (`bar.sync 2, n`) is the
+// PTX-conformant form for sm_70+ (barrier 0 is what `__syncthreads()` lowers to, and compute-sanitizer synccheck holds it to the
+// C++ rule that every thread reaches the same call site).
 __device__ __forceinline__ void cta_barrier(int nthreads)
 {
 #ifdef B2_EMU
   (void)nthreads;
   __syncthreads();
 #else
-  asm volatile("bar.sync 0, %0;" ::"r"(nthreads) : "memory");
+  asm volatile("bar.sync 2, %0;" ::"r"(nthreads) : "memory");
 #endif
 }
 __device__ __forceinline__ void ranker_barrier(int nthreads)
