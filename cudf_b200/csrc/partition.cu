@@ -657,7 +657,6 @@ extern "C" b2_status b2_range_partition_counts(const b2_column_view* keys, const
     B2_EXPECTS(keys && out_counts, B2_ERR_INVALID_ARGUMENT, "null argument");
     b2::validate_column(*keys);
     B2_EXPECTS(num_partitions >= 1 && num_partitions <= 256, B2_ERR_INVALID_ARGUMENT, "num_partitions must be in [1, 256]");
-    B2_EXPECTS(num_partitions == 1 || splitters != nullptr, B2_ERR_INVALID_ARGUMENT, "range partition needs splitters");
     B2_EXPECTS(b2::type_width(keys->type_id) == 8 && !b2::is_float_id(b2::storage_type(keys->type_id)) && !b2::has_nulls(*keys), B2_ERR_DATA_TYPE,
                "b2_range_partition_*: one null-free 8-byte integer-like key column");
     b2::range_partition_counts(*keys, splitters, num_partitions, out_counts, static_cast<cudaStream_t>(stream));
@@ -670,7 +669,6 @@ extern "C" b2_status b2_range_partition_scatter(const b2_column_view* keys, cons
     B2_EXPECTS(keys && key_dst, B2_ERR_INVALID_ARGUMENT, "null argument");
     b2::validate_column(*keys);
     B2_EXPECTS(num_partitions >= 1 && num_partitions <= 256, B2_ERR_INVALID_ARGUMENT, "num_partitions must be in [1, 256]");
-    B2_EXPECTS(num_partitions == 1 || splitters != nullptr, B2_ERR_INVALID_ARGUMENT, "range partition needs splitters");
     B2_EXPECTS(b2::type_width(keys->type_id) == 8 && !b2::is_float_id(b2::storage_type(keys->type_id)) && !b2::has_nulls(*keys), B2_ERR_DATA_TYPE,
                "b2_range_partition_*: one null-free 8-byte integer-like key column");
     if (values) {

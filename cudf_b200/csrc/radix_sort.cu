@@ -368,7 +368,16 @@ struct pass_args {
   void* const* range_key_dst;        // device array of range_parts pointers
   void* const* range_val_dst;        // same for the carried payload (CARRY) or null
   int32_t range_parts;
+  int32_t range_hash;                // 1: no splitters, bucket = range_hash_bucket(key) (hash partition: the sharded join's shuffle)
 };
+
+// Hash bucket of the fused partition pass. The additive constant decorrelates it from the local radix join, which partitions
+// by the top bits of mix64(key) itself: rows that share an exchange bucket still spread over all of the join's partitions.
+__host__ __device__ __forceinline__ unsigned range_hash_bucket(uint64_t twiddled_key, int parts)
+{
+  const uint64_t h = mix64(twiddled_key + 0x9E3779B97F4A7C15ull);
+  return (unsigned)(((h >> 32) * (uint64_t)parts) >> 32);
+}
 
 // Block-wide barrier of a warp-specialised kernel: the ranking warps and the look-back warps reach it from different branches, which
 // `__syncthreads()` only tolerates in practice; a named barrier with the explicit thread count (`bar.sync 2, n`) is the
@@ -485,7 +494,7 @@ __global__ void __launch_bounds__(THREADS + 32 * LBW, MINB) onesweep_kernel(pass
   }
   if constexpr (RANGE) {
     for (int i = tid; i < RADIX; i += THREADS + 32 * LBW) {
-      s_split[i] = i < a.range_parts - 1 ? static_cast<const UK*>(a.range_splitters)[i] : ~UK(0);
+      s_split[i] = (!a.range_hash && i < a.range_parts - 1) ? static_cast<const UK*>(a.range_splitters)[i] : ~UK(0);
       s_kdst[i]  = i < a.range_parts ? a.range_key_dst[i] : nullptr;
       s_vdst[i]  = (CARRY && i < a.range_parts) ? a.range_val_dst[i] : nullptr;
     }
@@ -626,6 +635,7 @@ __global__ void __launch_bounds__(THREADS + 32 * LBW, MINB) onesweep_kernel(pass
   // digit of a key: a byte of it, or (RANGE) the number of splitters <= key — padding items (all-ones key) land in the last bucket
   auto digit_of = [&](UK k) -> unsigned {
     if constexpr (RANGE) {
+      if (a.range_hash) return range_hash_bucket((uint64_t)k, a.range_parts);
       int lo = 0, hi = a.range_parts - 1;
       while (lo < hi) {
         const int mid = (lo + hi) >> 1;
@@ -887,36 +897,49 @@ __global__ void __launch_bounds__(FIX_THREADS) segment_fix_kernel(pass_args a, i
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < FIX_IPT; ++j) {
+      // a warp holds 32 consecutive rows: segment boundaries inside them come from one ballot, and a segment that lies wholly
+      // inside the warp's rows ("closed", the common case) is ranked by a loop whose trip count is the longest such segment
+      // of the warp — no per-lane walks, which cost a warp its longest walk in BOTH directions
       const int i = j * FIX_THREADS + threadIdx.x;
       const int64_t gi = base + i;
-      if (gi >= n) continue;
+      const bool active = gi < n;
+      const int lane = threadIdx.x & 31;
       VT v{};
-      if (a.pairs) v = ld_stream(vin + gi);
+      if (a.pairs && active) v = ld_stream(vin + gi);
       const UK k  = sk[FIX_HALO + i];
       const UK pf = k >> shift;
-      // rows to the left / right that exist (array ends are segment ends)
-      const int lmax = (int)(gi < FIX_HALO ? gi : (int64_t)FIX_HALO);
-      const int rmax = (int)(n - 1 - gi < FIX_HALO ? n - 1 - gi : (int64_t)FIX_HALO);
-      int left = 0, before = 0;
-      bool all_equal = true, cut = false;
-      // The first FIX_FAST neighbours on each side are examined without branches (every lane of the warp does the same
-      // work: a divergent walk costs the warp its LONGEST segment, which tripled the kernel's time at ~2 rows per segment);
-      // only rows whose segment reaches further continue with the loops below.
-      constexpr int FIX_FAST = 3;
-      bool in_l = true, in_r = true;
+      const bool head = !active || gi == 0 || (UK)(sk[FIX_HALO + i - 1] >> shift) != pf;       // first row of its segment
+      const bool next_head = gi + 1 >= n || (UK)(sk[FIX_HALO + i + 1] >> shift) != pf;        // the row after this one starts a segment
+      const uint32_t hm = __ballot_sync(0xffffffffu, head);
+      const bool tail_closed = __shfl_sync(0xffffffffu, (int)next_head, 31) != 0;
+      const uint32_t le = 0xffffffffu >> (31 - lane);          // lanes <= this one
+      const uint32_t lo = hm & le, hi = hm & ~le;
+      const bool closed = lo != 0u && (hi != 0u || tail_closed);
+      const int s0 = lo ? 31 - __clz((int)lo) : 0;             // lane of the segment's first row
+      const int s1 = hi ? __ffs((int)hi) - 1 : 32;              // lane after its last row
+      const int len = (active && closed) ? s1 - s0 : 0;
+      int maxlen = len;
 #pragma unroll
-      for (int s = 1; s <= FIX_FAST; ++s) {
-        const UK ol = sk[FIX_HALO + i - s];   // inside the halo: FIX_HALO >= FIX_FAST
-        const UK orr = sk[FIX_HALO + i + s];
-        in_l = in_l && s <= lmax && (UK)(ol >> shift) == pf;
-        in_r = in_r && s <= rmax && (UK)(orr >> shift) == pf;
-        left += in_l ? 1 : 0;
-        before += (in_l && ol <= k) ? 1 : 0;   // earlier rows win ties
-        before += (in_r && orr < k) ? 1 : 0;
-        all_equal = all_equal && (!in_l || ol == k) && (!in_r || orr == k);
+      for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
+      int64_t dst = gi;
+      if (maxlen > 1) {
+        int before = 0;
+        const int row0 = FIX_HALO + i - lane + s0;             // shared-memory index of the segment's first row
+        for (int t = 0; t < maxlen; ++t) {
+          if (t < len) {
+            const UK o = sk[row0 + t];
+            const int s = s0 + t;
+            before += (s < lane) ? (o <= k ? 1 : 0) : ((s > lane && o < k) ? 1 : 0);   // earlier rows win ties
+          }
+        }
+        if (len > 1) dst = gi - (lane - s0) + before;
       }
-      int right = 0;
-      if (in_l) {  // the segment extends further to the left
+      if (active && !closed) {
+        // the segment crosses the warp's rows: walk outwards (at most FIX_HALO rows each way; array ends are segment ends)
+        const int lmax = (int)(gi < FIX_HALO ? gi : (int64_t)FIX_HALO);
+        const int rmax = (int)(n - 1 - gi < FIX_HALO ? n - 1 - gi : (int64_t)FIX_HALO);
+        int left = 0, right = 0, before = 0;
+        bool all_equal = true, cut = false;
         for (;;) {
           if (left == lmax) { cut = lmax == FIX_HALO; break; }
           const UK o = sk[FIX_HALO + i - left - 1];
@@ -925,9 +948,6 @@ __global__ void __launch_bounds__(FIX_THREADS) segment_fix_kernel(pass_args a, i
           before += o <= k ? 1 : 0;
           all_equal = all_equal && o == k;
         }
-      }
-      if (in_r) {
-        right = FIX_FAST;
         for (;;) {
           if (right == rmax) { cut = cut || rmax == FIX_HALO; break; }
           const UK o = sk[FIX_HALO + i + right + 1];
@@ -936,14 +956,16 @@ __global__ void __launch_bounds__(FIX_THREADS) segment_fix_kernel(pass_args a, i
           before += o < k ? 1 : 0;
           all_equal = all_equal && o == k;
         }
+        dst = gi - left + before;
+        if (cut) {
+          dst = gi;
+          if (!all_equal) atomicOr(&a.ctl->overflow, 1u);
+        }
       }
-      int64_t dst = gi - left + before;
-      if (cut) {
-        dst = gi;
-        if (!all_equal) atomicOr(&a.ctl->overflow, 1u);
+      if (active) {
+        if (a.pairs) vout[dst] = v;
+        else kout[dst] = untwiddle_rt<UK>(k, a.kind, desc);
       }
-      if (a.pairs) vout[dst] = v;
-      else kout[dst] = untwiddle_rt<UK>(k, a.kind, desc);
     }
   }
 }
@@ -1348,7 +1370,7 @@ __global__ void __launch_bounds__(512) range_count_kernel(const UK* __restrict__
   __shared__ UK sp[RADIX];
   __shared__ unsigned int cnt[RADIX];
   for (int i = threadIdx.x; i < RADIX; i += blockDim.x) {
-    sp[i]  = i < P - 1 ? splitters[i] : ~UK(0);
+    sp[i]  = (splitters != nullptr && i < P - 1) ? splitters[i] : ~UK(0);
     cnt[i] = 0;
   }
   __syncthreads();
@@ -1356,6 +1378,7 @@ __global__ void __launch_bounds__(512) range_count_kernel(const UK* __restrict__
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const UK k = twiddle_rt<UK>(ld_stream(keys + i), kind, UK(0));
     int lo = 0, hi = P - 1;
+    if (splitters == nullptr) lo = hi = (int)range_hash_bucket((uint64_t)k, P);
     while (lo < hi) {
       const int mid = (lo + hi) >> 1;
       if (sp[mid] <= k) lo = mid + 1;
@@ -1389,12 +1412,13 @@ void range_partition_counts(const b2_column_view& keys, const void* splitters, i
   if (n == 0) return;
   dbuf cnt(sizeof(unsigned long long) * RADIX, stream), sp(sizeof(UK) * RADIX, stream);
   B2_CUDA_TRY(cudaMemsetAsync(cnt.ptr, 0, cnt.bytes, stream));
-  if (P > 1) B2_LAUNCH((twiddle_splitters_kernel<UK>), 1, RADIX, 0, stream, static_cast<const UK*>(splitters), P - 1, kind, sp.as<UK>());
+  const bool hashed = splitters == nullptr;  // no splitters: hash partition (range_hash_bucket)
+  if (P > 1 && !hashed) B2_LAUNCH((twiddle_splitters_kernel<UK>), 1, RADIX, 0, stream, static_cast<const UK*>(splitters), P - 1, kind, sp.as<UK>());
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 511) / 512, NUM_SMS_B200 * 4));
   {
     prof_scope ps("range_count", stream);
-    B2_LAUNCH((range_count_kernel<UK>), grid, 512, 0, stream, static_cast<const UK*>(keys.data) + keys.offset, n, kind, sp.as<UK>(), P,
-              cnt.as<unsigned long long>());
+    B2_LAUNCH((range_count_kernel<UK>), grid, 512, 0, stream, static_cast<const UK*>(keys.data) + keys.offset, n, kind,
+              hashed ? static_cast<const UK*>(nullptr) : sp.as<UK>(), P, cnt.as<unsigned long long>());
   }
   unsigned long long h[RADIX];
   B2_CUDA_TRY(cudaMemcpyAsync(h, cnt.ptr, sizeof(h), cudaMemcpyDeviceToHost, stream));
@@ -1425,7 +1449,7 @@ static void range_scatter_impl(const b2_column_view& keys, const void* vals, con
   auto* d_split  = reinterpret_cast<UK*>(status + status_per * nportions);
   auto* d_kdst   = reinterpret_cast<void**>(d_split + RADIX);
   auto* d_vdst   = d_kdst + RADIX;
-  if (P > 1) B2_LAUNCH((twiddle_splitters_kernel<UK>), 1, RADIX, 0, stream, static_cast<const UK*>(splitters), P - 1, kind, d_split);
+  if (P > 1 && splitters != nullptr) B2_LAUNCH((twiddle_splitters_kernel<UK>), 1, RADIX, 0, stream, static_cast<const UK*>(splitters), P - 1, kind, d_split);
   B2_CUDA_TRY(cudaMemcpyAsync(d_kdst, key_dst, sizeof(void*) * P, cudaMemcpyHostToDevice, stream));
   if (CARRY) B2_CUDA_TRY(cudaMemcpyAsync(d_vdst, val_dst, sizeof(void*) * P, cudaMemcpyHostToDevice, stream));
   // the plan of the single pass 0: executed, raw keys, last pass (keys-only mode untwiddles what it writes); base = 0: positions
@@ -1450,6 +1474,7 @@ static void range_scatter_impl(const b2_column_view& keys, const void* vals, con
   a.range_key_dst = d_kdst;
   a.range_val_dst = d_vdst;
   a.range_parts = P;
+  a.range_hash = (P > 1 && splitters == nullptr) ? 1 : 0;
   a.pass = 0;
   for (int64_t q = 0; q < nportions; ++q) {
     const int64_t start = q * plim;

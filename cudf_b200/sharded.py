@@ -325,10 +325,11 @@ def _exchange_cols(cols, offsets, ops, group=None, slot_base: int = 0):
 
 def _exchange_variant(t: torch.Tensor, ops) -> str:
     """Bucket exchange on GPUs (B2_SHARD_P2P forces one; measurements in profiles/r2_multi_gpu.md):
-      "fused" (default for the sort on int64 keys): the range partition is ONE one-sweep pass whose digit is the destination
-          rank and whose per-(tile, bucket) runs are written straight into the peers' receive buffers (b2_range_partition_*)
+      "fused" (default on int64 keys): the partition is ONE one-sweep pass whose digit is the destination rank (sort: number of
+          splitters <= key; join: a hash of the key) and whose per-(tile, bucket) runs are written straight into the peers'
+          receive buffers (b2_range_partition_*; 2 GPUs: 9.2 ms per 1e9 keys)
       "staged": plan (bucket + stable rank per row) + scatter kernel, per-peer runs of a 4096-row tile staged in shared memory
-          before the remote stores (2 GPUs: 14.0 ms per 1e9 rows, 8 GPUs: 22.1 ms); the join's hash partition uses it
+          before the remote stores (2 GPUs: 14.0 ms per 1e9 rows, 8 GPUs: 22.1 ms)
       "1" / "plain": fused, row-by-row remote stores (2 GPUs: 16.9 ms; at 8 GPUs a warp's rows split into 32-byte writes)
       "0" / "copy": b2_partition, then one contiguous b2_peer_copy per destination (B2_SHARD_XCHG=nccl: all_to_all_single)
     CPU tensors (gloo tests) always take the partition + process-group all-to-all path."""
@@ -418,8 +419,13 @@ def inner_join_sharded(left_keys: torch.Tensor, right_keys: torch.Tensor, ops=No
         if world == 1:
             return keys, gid
         variant = _exchange_variant(keys, ops)
+        if variant == "fused" and keys.dtype == torch.int64 and hasattr(ops, "range_exchange"):
+            # hash partition fused into ONE one-sweep pass (no splitters: bucket = hash of the key) carrying the global row id
+            ph.mark("partition+exchange(fused pass)")
+            got = ops.range_exchange(keys, gid, None, group, slot_base=slot_base)
+            return got[0], got[1]
         if variant == "fused":
-            variant = "staged"   # the fused pass is a range partition; the join's hash partition takes the plan + staged scatter
+            variant = "staged"
         if variant in ("staged", "plain"):
             ph.mark("partition+exchange(p2p)")
             got = ops.partition_exchange([keys, gid], keys, 1, None, group, slot_base=slot_base, variant=variant)

@@ -326,7 +326,9 @@ B2_API void      b2_partition_plan_free(b2_partition_plan* plan);
  * this rank's rows, then — after the ranks exchanged their counts — a stable pass that writes bucket b's keys (and optionally one
  * 4- / 8-byte payload column) to key_dst[b] / val_dst[b], local or peer memory (host arrays of num_partitions device pointers: the
  * address of THIS rank's first row of bucket b). One null-free 8-byte integer-like key column; splitters = device array of P - 1
- * ascending keys of the column's type. The sharded sort's partition + exchange ("fuse with the first radix pass"). */
+ * ascending keys of the column's type. The sharded sort's partition + exchange ("fuse with the first radix pass").
+ * splitters == NULL selects a HASH partition instead (bucket = high-multiply of a 64-bit mix of the key by num_partitions; the
+ * same function in both calls and on every rank): the sharded join's shuffle. */
 B2_API b2_status b2_range_partition_counts(const b2_column_view* keys, const void* splitters, int32_t num_partitions, b2_stream stream,
                                            int64_t* out_counts);
 B2_API b2_status b2_range_partition_scatter(const b2_column_view* keys, const b2_column_view* values, const void* splitters,

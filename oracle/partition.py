@@ -99,3 +99,31 @@ def hash_partition(table_cols, key_cols, num_partitions: int, seed: int = 0, ide
     counts = np.bincount(ids, minlength=num_partitions)
     offs = np.concatenate([[0], np.cumsum(counts)]).astype(int).tolist()
     return [(v[order], None if m is None else np.asarray(m)[order]) for v, m in table_cols], offs
+
+
+def mix64(k: np.ndarray) -> np.ndarray:
+    """murmur3's 64-bit finalizer (fmix64, public domain, Appleby): the framework's own table / shuffle hash — not a libcudf
+    function, so the oracle restates cudf_b200/csrc/device_utils.cuh::mix64 and is pinned on fmix64's fixed point 0 -> 0 and
+    its bijectivity in tests/test_oracle_golden.py."""
+    k = np.asarray(k, dtype=np.uint64).copy()
+    with np.errstate(over="ignore"):
+        k ^= k >> np.uint64(33)
+        k *= np.uint64(0xFF51AFD7ED558CCD)
+        k ^= k >> np.uint64(33)
+        k *= np.uint64(0xC4CEB9FE1A85EC53)
+        k ^= k >> np.uint64(33)
+    return k
+
+
+def shuffle_bucket(keys: np.ndarray, num_partitions: int) -> np.ndarray:
+    """Destination rank of a row in the sharded join's fused shuffle (b2_range_partition_* with splitters == NULL): the keys in
+    radix order (signed: sign bit flipped), plus the golden-ratio constant, through mix64; bucket = high 32 bits * P >> 32.
+    The reference shuffles with its row hash modulo P (cpp/src/partitioning/partitioning.cu:hash_partition); any function both
+    sides agree on gives the same join result, so this one is framework-defined."""
+    k = np.asarray(keys)
+    u = k.view(np.uint64).copy() if k.dtype.kind in "iu" and k.dtype.itemsize == 8 else k.astype(np.uint64)
+    if k.dtype.kind == "i":
+        u ^= np.uint64(1 << 63)
+    with np.errstate(over="ignore"):
+        h = mix64(u + np.uint64(0x9E3779B97F4A7C15))
+    return (((h >> np.uint64(32)) * np.uint64(num_partitions)) >> np.uint64(32)).astype(np.int64)

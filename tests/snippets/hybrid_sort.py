@@ -26,6 +26,8 @@ for n in SIZES:
         check(rng.integers(-2**63, 2**63 - 1, n, dtype=np.int64), rng.integers(0, 1 << 40, n).astype(np.int64), order)
         # 50 prefixes x 2^20 low values: segments of several rows
         check((rng.integers(0, 50, n).astype(np.int64) << 40) | rng.integers(0, 1 << 20, n).astype(np.int64), rng.standard_normal(n), order)
+        # ~n/2 prefixes above bit 40: segments of about two rows, many of them straddling a warp's 32 rows
+        check((rng.integers(0, max(1, n // 2), n).astype(np.int64) << 40) | rng.integers(0, 1 << 40, n).astype(np.int64), rng.integers(0, 1 << 40, n).astype(np.int64), order)
         # long runs of one value (duplicates longer than the fix-up window)
         check(rng.integers(0, 3, n).astype(np.int64) * (1 << 50) + 7, rng.integers(0, 100, n).astype(np.int32), order)
         # mostly one hot key + uniform rest

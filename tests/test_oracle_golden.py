@@ -109,3 +109,30 @@ def test_murmur3_row_hash_pinned():
     h0, h1 = op.murmur3_32_fixed(a), op.murmur3_32_fixed(a.astype(np.int64))
     comb = h0 ^ ((h1 + np.uint32(0x9E3779B9) + (h0 << np.uint32(6)) + (h0 >> np.uint32(2))).astype(np.uint32))
     assert np.array_equal(op.row_hash([(a, None), (a.astype(np.int64), None)]), comb)
+
+
+def test_mix64_shuffle_bucket_pinned():
+    """oracle/partition.py::mix64 is MurmurHash3's fmix64: fixed point 0, the widely quoted fmix64(1) = 0xB456BCFC34C2CB2C, and
+    agreement with an independent big-integer restatement; shuffle_bucket stays inside [0, P) and is balanced."""
+    import numpy as np
+
+    from oracle import partition as op
+
+    M = (1 << 64) - 1
+
+    def fmix(k):
+        k ^= k >> 33; k = k * 0xFF51AFD7ED558CCD & M
+        k ^= k >> 33; k = k * 0xC4CEB9FE1A85EC53 & M
+        return k ^ (k >> 33)
+
+    assert int(op.mix64(np.array([0], np.uint64))[0]) == 0
+    assert int(op.mix64(np.array([1], np.uint64))[0]) == 0xB456BCFC34C2CB2C
+    rng = np.random.default_rng(3)
+    v = rng.integers(0, 2**64 - 1, 500, dtype=np.uint64)
+    assert [int(x) for x in op.mix64(v)] == [fmix(int(x)) for x in v]
+    k = rng.integers(-2**63, 2**63 - 1, 200_000, dtype=np.int64)
+    for P in (2, 3, 8):
+        b = op.shuffle_bucket(k, P)
+        assert b.min() >= 0 and b.max() < P
+        assert np.abs(np.bincount(b, minlength=P) / len(k) - 1 / P).max() < 0.01
+        assert b[0] == (((fmix(((int(k[0]) & M) ^ (1 << 63)) + 0x9E3779B97F4A7C15 & M) >> 32) * P) >> 32)

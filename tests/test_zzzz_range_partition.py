@@ -13,7 +13,7 @@ def _run(plc, keys, vals, splitters, P):
 
     lib = _lib.lib
     kc = plc.Column.from_numpy(keys)
-    sc = plc.Column.from_numpy(splitters) if P > 1 else None
+    sc = plc.Column.from_numpy(splitters) if P > 1 and splitters is not None else None
     sp = C.c_void_p(sc._data) if sc is not None else None
     counts = (C.c_int64 * P)()
     kv = kc._view()
@@ -57,3 +57,22 @@ def test_range_partition_matches_stable_numpy(plc, kdt):
                 assert np.array_equal(gk, keys[order]), (n, P, vdt)
                 if vals is not None:
                     assert np.array_equal(gv, vals[order]), (n, P, vdt)
+
+
+@pytest.mark.parametrize("kdt", [np.int64, np.uint64])
+def test_hash_mode_matches_oracle_bucket(plc, kdt):
+    """splitters == NULL: the sharded join's shuffle — stable partition by oracle.partition.shuffle_bucket."""
+    from oracle.partition import shuffle_bucket
+
+    rng = np.random.default_rng(77)
+    for n in (1, 6143, 30_001):
+        for P in (2, 3, 8):
+            info = np.iinfo(kdt)
+            keys = rng.integers(info.min, info.max, n, dtype=kdt, endpoint=True)
+            keys[::5] = keys[0]
+            bucket = shuffle_bucket(keys, P)
+            order = np.argsort(bucket, kind="stable")
+            vals = np.arange(n, dtype=np.int64)
+            counts, gk, gv = _run(plc, keys, vals, None, P)
+            assert counts == np.bincount(bucket, minlength=P).tolist(), (n, P)
+            assert np.array_equal(gk, keys[order]) and np.array_equal(gv, order), (n, P)
