@@ -268,6 +268,10 @@ void radix_partition_top16_mix(const uint64_t* packed_keys, int64_t n, uint64_t*
 
 void radix_partition_mix_carry(const uint64_t* keys, const void* vals, int val_bytes, int64_t n, uint64_t* mixed_keys_out, void* vals_out,
                                uint32_t* part_base, cudaStream_t stream);
+// histogram-free variant (estimated partition bases; radix_sort.cu)
+uint32_t radix_partition_est_capacity(const uint64_t* keys, int64_t n, cudaStream_t stream);
+bool radix_partition_mix_carry_est(const uint64_t* keys, const void* vals, int val_bytes, int64_t n, uint32_t cap, uint64_t* mixed_keys_out,
+                                   void* vals_out, uint32_t* part_base, uint32_t* part_end, cudaStream_t stream);
 
 void range_partition_counts(const b2_column_view& keys, const void* splitters, int P, int64_t* out_counts, cudaStream_t stream);
 void range_partition_scatter(const b2_column_view& keys, const b2_column_view* values, const void* splitters, int P, void* const* key_dst,

@@ -260,6 +260,7 @@ __global__ void __launch_bounds__(256) groupby_kernel(key_cols kc, int64_t n, bo
 // Groups that do not fit in the shared table (more than ~4.9 K groups in a partition) go to the global table row by row.
 constexpr int PGB_THREADS = 1024;
 constexpr int PGB_MAX_OPS = 3;
+constexpr bool PGB_EST_DEFAULT = false;  // histogram-free partition pass (radix_partition_mix_carry_est): opt-in until measured
 constexpr uint64_t PGB_EMPTY = ~0ull;
 
 struct pgb_args {
@@ -268,6 +269,7 @@ struct pgb_args {
   int32_t val_bytes;
   int32_t src_type;          // storage type id of the value column
   const uint32_t* part_base; // [256] first row of each partition
+  const uint32_t* part_end;  // [256] one past its last row (partitions need not be adjacent: estimated bases leave gaps)
   uint32_t n;
   const uint32_t* item_start;  // [257] first work item of each partition (exclusive scan of chunk counts)
   uint32_t* item_counter;
@@ -339,12 +341,14 @@ __device__ __forceinline__ void pgb_combine(unsigned long long* a, int8_t op, in
   }
 }
 
-__global__ void pgb_items_kernel(const uint32_t* __restrict__ part_base, uint32_t n, uint32_t chunk, uint32_t* __restrict__ item_start)
+__global__ void pgb_items_kernel(const uint32_t* __restrict__ part_base, uint32_t* __restrict__ part_end, bool ends_given, uint32_t n, uint32_t chunk,
+                                 uint32_t* __restrict__ item_start)
 {
-  // 256 threads: chunks per partition, exclusive scan
+  // 256 threads: chunks per partition, exclusive scan; adjacent partitions (exact bases): part_end is derived here
   __shared__ uint32_t wt[8];
   const int d = threadIdx.x;
-  const uint32_t b = part_base[d], e = d == 255 ? n : part_base[d + 1];
+  const uint32_t b = part_base[d], e = ends_given ? part_end[d] : (d == 255 ? n : part_base[d + 1]);
+  if (!ends_given) part_end[d] = e;
   const uint32_t c = (e - b + chunk - 1) / chunk;
   const uint32_t inc = warp_inclusive_sum(c);
   if ((d & 31) == 31) wt[d >> 5] = inc;
@@ -407,7 +411,7 @@ __global__ void __launch_bounds__(PGB_THREADS, 1) pgb_agg_kernel(pgb_args a, slo
       const int mid = (lo + hi + 1) >> 1;
       if (s_start[mid] <= item) lo = mid; else hi = mid - 1;
     }
-    const uint32_t pb = a.part_base[lo], pe = lo == 255 ? a.n : a.part_base[lo + 1];
+    const uint32_t pb = a.part_base[lo], pe = a.part_end[lo];
     const uint32_t r0 = pb + (item - s_start[lo]) * a.chunk;
     const uint32_t r1 = min(pe, r0 + a.chunk);
     constexpr int U = 4;  // rows in flight per thread
@@ -695,18 +699,41 @@ void groupby_aggregate(const b2_groupby& gb, const std::vector<request_view>& re
     use_pgb = ok && data_ops <= PGB_MAX_OPS;
   }
   dbuf pgb_keys, pgb_vals, pgb_base, pgb_items;
+  bool pgb_ends_given = false;
   if (use_pgb) {
     prof_scope ps("groupby_partition", stream);
     const int vb = pgb_val ? type_width(pgb_val->type_id) : 0;
-    pgb_keys  = dbuf(sizeof(uint64_t) * n, stream);
-    pgb_base  = dbuf(sizeof(uint32_t) * 256, stream);
+    pgb_base  = dbuf(sizeof(uint32_t) * 512, stream);  // [256] first row, [256] end of each partition
     pgb_items = dbuf(sizeof(uint32_t) * 258, stream);
     const uint64_t* kin = static_cast<const uint64_t*>(gb.keys[0].data) + gb.keys[0].offset;
-    if (vb) {
+    // Histogram-free partition pass when a sample of the keys says the partitions are even enough (B2_GROUPBY_EST=0: never):
+    // partition d gets a fixed range of `cap` rows, the pass reports where each one ended.
+    static const bool est_enabled = [] {
+      const char* e = std::getenv("B2_GROUPBY_EST");
+      return e ? std::atoi(e) != 0 : PGB_EST_DEFAULT;
+    }();
+    const uint32_t est_cap = est_enabled ? radix_partition_est_capacity(kin, n, stream) : 0u;
+    if (est_cap) {
+      const int cb = vb ? vb : 8;
+      pgb_keys = dbuf(sizeof(uint64_t) * 256 * (size_t)est_cap, stream);
+      pgb_vals = dbuf((size_t)cb * 256 * (size_t)est_cap, stream);
+      const void* vin = vb ? static_cast<const void*>(static_cast<const char*>(pgb_val->data) + (size_t)pgb_val->offset * vb) : static_cast<const void*>(kin);
+      pgb_ends_given = radix_partition_mix_carry_est(kin, vin, cb, n, est_cap, pgb_keys.as<uint64_t>(), pgb_vals.ptr, pgb_base.as<uint32_t>(),
+                                                     pgb_base.as<uint32_t>() + 256, stream);
+      if (!pgb_ends_given) {  // a partition overflowed its range (the sample missed a hot spot): exact bases below
+        pgb_keys = dbuf();
+        pgb_vals = dbuf();
+      }
+    }
+    if (pgb_ends_given) {
+      // partitioned by the estimated bases
+    } else if (vb) {
+      pgb_keys  = dbuf(sizeof(uint64_t) * n, stream);
       pgb_vals = dbuf((size_t)vb * n, stream);
       radix_partition_mix_carry(kin, static_cast<const char*>(pgb_val->data) + (size_t)pgb_val->offset * vb, vb, n, pgb_keys.as<uint64_t>(),
                                 pgb_vals.ptr, pgb_base.as<uint32_t>(), stream);
     } else {  // counts only: the key column doubles as the carried payload
+      pgb_keys = dbuf(sizeof(uint64_t) * n, stream);
       pgb_vals = dbuf(sizeof(uint64_t) * n, stream);
       radix_partition_mix_carry(kin, kin, 8, n, pgb_keys.as<uint64_t>(), pgb_vals.ptr, pgb_base.as<uint32_t>(), stream);
     }
@@ -817,6 +844,7 @@ void groupby_aggregate(const b2_groupby& gb, const std::vector<request_view>& re
       pa.val_bytes = pgb_val ? type_width(pgb_val->type_id) : 0;
       pa.src_type  = pgb_val ? storage_type(pgb_val->type_id) : B2_INT64;
       pa.part_base = pgb_base.as<uint32_t>();
+      pa.part_end  = pgb_base.as<uint32_t>() + 256;
       pa.n = (uint32_t)n;
       pa.item_start = pgb_items.as<uint32_t>();
       pa.item_counter = pgb_items.as<uint32_t>() + 257;
@@ -845,7 +873,8 @@ void groupby_aggregate(const b2_groupby& gb, const std::vector<request_view>& re
         B2_CUDA_TRY(cudaFuncSetAttribute(pgb_agg_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 20));
       });
       B2_CUDA_TRY(cudaMemsetAsync(pa.item_counter, 0, sizeof(uint32_t), stream));
-      B2_LAUNCH(pgb_items_kernel, 1, 256, 0, stream, pa.part_base, pa.n, pa.chunk, pgb_items.as<uint32_t>());
+      B2_LAUNCH(pgb_items_kernel, 1, 256, 0, stream, pa.part_base, pgb_base.as<uint32_t>() + 256, pgb_ends_given, pa.n, pa.chunk,
+                pgb_items.as<uint32_t>());
       int mode = 0;
       if (ops.n == 0) mode = 3;
       else if (ops.n == 1 && pa.op[0] == OPK_SUM && pa.val_bytes == 8) mode = pa.acc[0] == ACC_F64 ? 1 : 2;

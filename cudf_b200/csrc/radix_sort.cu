@@ -24,6 +24,7 @@
 #include "device_utils.cuh"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 
 namespace b2 {
@@ -369,6 +370,10 @@ struct pass_args {
   void* const* range_val_dst;        // same for the carried payload (CARRY) or null
   int32_t range_parts;
   int32_t range_hash;                // 1: no splitters, bucket = range_hash_bucket(key) (hash partition: the sharded join's shuffle)
+  // MIX kernels, estimated bases (radix_partition_mix_carry_est): no histogram ran; digit d owns rows [d * est_cap, (d + 1) * est_cap) of the
+  // output, rows beyond that range are dropped and ctl->overflow is raised; the last tile leaves every digit's end offset in
+  // ctl->base[portion_parity ^ 1][pass]
+  uint32_t est_cap;
 };
 
 // Hash bucket of the fused partition pass. The additive constant decorrelates it from the local radix join, which partitions
@@ -565,7 +570,9 @@ __global__ void __launch_bounds__(THREADS + 32 * LBW, MINB) onesweep_kernel(pass
       publish(FLAG_INCL, excl[0] + cnt[0], excl[1] + cnt[1], excl[2] + cnt[2], excl[3] + cnt[3]);
     }
     const uint32_t* gb = &a.ctl->base[a.portion_parity][a.pass][d0];
-    const bool last_of_portion = a.has_next_portion && tile_base + tile_n == a.portion_n;
+    bool wants_end = a.has_next_portion != 0;
+    if constexpr (MIX) wants_end = wants_end || a.est_cap != 0u;
+    const bool last_of_portion = wants_end && tile_base + tile_n == a.portion_n;
 #pragma unroll
     for (int j = 0; j < DPL; ++j) {
       const uint32_t g = gb[j];
@@ -800,10 +807,16 @@ __global__ void __launch_bounds__(THREADS + 32 * LBW, MINB) onesweep_kernel(pass
     if constexpr (RANGE) d = s_dig[q];
     else d = (unsigned)(k >> shift) & 255u;
     dst[j] = s_off[d] + q;
+    if constexpr (MIX) {
+      if (a.est_cap != 0u && dst[j] >= (d + 1u) * a.est_cap) {  // digit d's reserved range is full: the caller falls back to exact bases
+        if (q < tile_n) a.ctl->overflow = 1u;
+        dst[j] = 0xFFFFFFFFu;
+      }
+    }
     if constexpr (RANGE) {
       dstd[j] = (uint8_t)d;
       if (q < tile_n) static_cast<UK*>(s_kdst[d])[dst[j]] = untwiddle_rt<UK>(k, a.kind, desc);  // the receiver sorts raw column values
-    } else if (write_keys && q < tile_n) {
+    } else if (write_keys && q < tile_n && (!MIX || dst[j] != 0xFFFFFFFFu)) {
       if (!a.pairs && pl.last && !pl.hybrid) k = untwiddle_rt<UK>(k, a.kind, desc);
       kdst[dst[j]] = k;
     }
@@ -820,7 +833,7 @@ __global__ void __launch_bounds__(THREADS + 32 * LBW, MINB) onesweep_kernel(pass
       if constexpr (RANGE) {
         if (q < tile_n) static_cast<VT*>(s_vdst[dstd[j]])[dst[j]] = s_vals[q];
       } else {
-        if (q < tile_n) idst[dst[j]] = s_vals[q];
+        if (q < tile_n && (!MIX || dst[j] != 0xFFFFFFFFu)) idst[dst[j]] = s_vals[q];
       }
     }
   }
@@ -897,49 +910,36 @@ __global__ void __launch_bounds__(FIX_THREADS) segment_fix_kernel(pass_args a, i
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < FIX_IPT; ++j) {
-      // a warp holds 32 consecutive rows: segment boundaries inside them come from one ballot, and a segment that lies wholly
-      // inside the warp's rows ("closed", the common case) is ranked by a loop whose trip count is the longest such segment
-      // of the warp — no per-lane walks, which cost a warp its longest walk in BOTH directions
       const int i = j * FIX_THREADS + threadIdx.x;
       const int64_t gi = base + i;
-      const bool active = gi < n;
-      const int lane = threadIdx.x & 31;
+      if (gi >= n) continue;
       VT v{};
-      if (a.pairs && active) v = ld_stream(vin + gi);
+      if (a.pairs) v = ld_stream(vin + gi);
       const UK k  = sk[FIX_HALO + i];
       const UK pf = k >> shift;
-      const bool head = !active || gi == 0 || (UK)(sk[FIX_HALO + i - 1] >> shift) != pf;       // first row of its segment
-      const bool next_head = gi + 1 >= n || (UK)(sk[FIX_HALO + i + 1] >> shift) != pf;        // the row after this one starts a segment
-      const uint32_t hm = __ballot_sync(0xffffffffu, head);
-      const bool tail_closed = __shfl_sync(0xffffffffu, (int)next_head, 31) != 0;
-      const uint32_t le = 0xffffffffu >> (31 - lane);          // lanes <= this one
-      const uint32_t lo = hm & le, hi = hm & ~le;
-      const bool closed = lo != 0u && (hi != 0u || tail_closed);
-      const int s0 = lo ? 31 - __clz((int)lo) : 0;             // lane of the segment's first row
-      const int s1 = hi ? __ffs((int)hi) - 1 : 32;              // lane after its last row
-      const int len = (active && closed) ? s1 - s0 : 0;
-      int maxlen = len;
+      // rows to the left / right that exist (array ends are segment ends)
+      const int lmax = (int)(gi < FIX_HALO ? gi : (int64_t)FIX_HALO);
+      const int rmax = (int)(n - 1 - gi < FIX_HALO ? n - 1 - gi : (int64_t)FIX_HALO);
+      int left = 0, before = 0;
+      bool all_equal = true, cut = false;
+      // The first FIX_FAST neighbours on each side are examined without branches (every lane of the warp does the same
+      // work: a divergent walk costs the warp its LONGEST segment, which tripled the kernel's time at ~2 rows per segment);
+      // only rows whose segment reaches further continue with the loops below.
+      constexpr int FIX_FAST = 3;
+      bool in_l = true, in_r = true;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
-      int64_t dst = gi;
-      if (maxlen > 1) {
-        int before = 0;
-        const int row0 = FIX_HALO + i - lane + s0;             // shared-memory index of the segment's first row
-        for (int t = 0; t < maxlen; ++t) {
-          if (t < len) {
-            const UK o = sk[row0 + t];
-            const int s = s0 + t;
-            before += (s < lane) ? (o <= k ? 1 : 0) : ((s > lane && o < k) ? 1 : 0);   // earlier rows win ties
-          }
-        }
-        if (len > 1) dst = gi - (lane - s0) + before;
+      for (int s = 1; s <= FIX_FAST; ++s) {
+        const UK ol = sk[FIX_HALO + i - s];   // inside the halo: FIX_HALO >= FIX_FAST
+        const UK orr = sk[FIX_HALO + i + s];
+        in_l = in_l && s <= lmax && (UK)(ol >> shift) == pf;
+        in_r = in_r && s <= rmax && (UK)(orr >> shift) == pf;
+        left += in_l ? 1 : 0;
+        before += (in_l && ol <= k) ? 1 : 0;   // earlier rows win ties
+        before += (in_r && orr < k) ? 1 : 0;
+        all_equal = all_equal && (!in_l || ol == k) && (!in_r || orr == k);
       }
-      if (active && !closed) {
-        // the segment crosses the warp's rows: walk outwards (at most FIX_HALO rows each way; array ends are segment ends)
-        const int lmax = (int)(gi < FIX_HALO ? gi : (int64_t)FIX_HALO);
-        const int rmax = (int)(n - 1 - gi < FIX_HALO ? n - 1 - gi : (int64_t)FIX_HALO);
-        int left = 0, right = 0, before = 0;
-        bool all_equal = true, cut = false;
+      int right = 0;
+      if (in_l) {  // the segment extends further to the left
         for (;;) {
           if (left == lmax) { cut = lmax == FIX_HALO; break; }
           const UK o = sk[FIX_HALO + i - left - 1];
@@ -948,6 +948,9 @@ __global__ void __launch_bounds__(FIX_THREADS) segment_fix_kernel(pass_args a, i
           before += o <= k ? 1 : 0;
           all_equal = all_equal && o == k;
         }
+      }
+      if (in_r) {
+        right = FIX_FAST;
         for (;;) {
           if (right == rmax) { cut = cut || rmax == FIX_HALO; break; }
           const UK o = sk[FIX_HALO + i + right + 1];
@@ -956,16 +959,14 @@ __global__ void __launch_bounds__(FIX_THREADS) segment_fix_kernel(pass_args a, i
           before += o < k ? 1 : 0;
           all_equal = all_equal && o == k;
         }
-        dst = gi - left + before;
-        if (cut) {
-          dst = gi;
-          if (!all_equal) atomicOr(&a.ctl->overflow, 1u);
-        }
       }
-      if (active) {
-        if (a.pairs) vout[dst] = v;
-        else kout[dst] = untwiddle_rt<UK>(k, a.kind, desc);
+      int64_t dst = gi - left + before;
+      if (cut) {
+        dst = gi;
+        if (!all_equal) atomicOr(&a.ctl->overflow, 1u);
       }
+      if (a.pairs) vout[dst] = v;
+      else kout[dst] = untwiddle_rt<UK>(k, a.kind, desc);
     }
   }
 }
@@ -1359,6 +1360,136 @@ void radix_partition_mix_carry(const uint64_t* keys, const void* vals, int val_b
     run_radix_cfg<uint64_t, 384, 16, 2, uint32_t, true, true>(keys, mixed_keys_out, b.as<uint64_t>(), static_cast<int32_t*>(vals_out),
                                                                vt.as<int32_t>(), nullptr, 0, n, (int)key_kind::UNSIGNED, false, true, stream,
                                                                7, 7, true, vals, part_base);
+}
+
+namespace {
+// plan of the single executed pass `pass` with estimated bases: digit d starts at d * cap
+__global__ void est_plan_kernel(sort_ctl* ctl, int pass, uint32_t cap)
+{
+  const int d = threadIdx.x;  // 256 threads
+  ctl->base[0][pass][d] = (uint32_t)d * cap;
+  if (d < 8) {
+    pass_plan pl{};
+    pl.trivial = d != pass;
+    if (d == pass) {
+      pl.key_src = 0;
+      pl.idx_src = -1;
+      pl.key_dst = 1;
+      pl.idx_dst = 0;
+      pl.last    = 1;
+      pl.hybrid  = 0;
+    }
+    ctl->plan[d] = pl;
+  }
+  if (d == 0) {
+    ctl->any_pass = 1;
+    ctl->hybrid   = 0;
+    ctl->overflow = 0;
+  }
+}
+
+// counts[b] = sampled rows (every `stride`-th) whose mix64(key) has top byte b
+__global__ void __launch_bounds__(256) est_sample_kernel(const uint64_t* __restrict__ keys, int64_t n, int64_t stride, unsigned int* __restrict__ counts)
+{
+  __shared__ unsigned int sh[RADIX];
+  sh[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t m = (n + stride - 1) / stride;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x)
+    atomicAdd(&sh[(unsigned)(mix64(keys[i * stride]) >> 56)], 1u);
+  __syncthreads();
+  if (sh[threadIdx.x]) atomicAdd(&counts[threadIdx.x], sh[threadIdx.x]);
+}
+
+template <typename VT>
+bool est_pass_impl(const uint64_t* keys, const void* vals, int64_t n, uint32_t cap, uint64_t* mixed_keys_out, void* vals_out, uint32_t* part_base,
+                   uint32_t* part_end, cudaStream_t stream)
+{
+  constexpr int T = 384, I = 16, TILE = T * I, PASS = 7;
+  using UK = uint64_t;
+  const int64_t ntiles = (n + TILE - 1) / TILE;
+  const size_t ctl_bytes = (sizeof(sort_ctl) + 255) / 256 * 256;
+  const size_t status_bytes = sizeof(uint32_t) * RADIX * (size_t)ntiles;
+  dbuf work(ctl_bytes + 256 + status_bytes, stream);
+  auto* ctl = reinterpret_cast<sort_ctl*>(work.ptr);
+  auto* counter = reinterpret_cast<uint32_t*>(static_cast<char*>(work.ptr) + ctl_bytes);
+  auto* status = reinterpret_cast<uint32_t*>(static_cast<char*>(work.ptr) + ctl_bytes + 256);
+  static std::atomic<uint64_t> attr_done{0};
+  once_per_device(attr_done, [] {
+    B2_CUDA_TRY(cudaFuncSetAttribute(onesweep_kernel<UK, T, I, 2, VT, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)onesweep_smem<UK, T, I, VT>()));
+  });
+  B2_CUDA_TRY(cudaMemsetAsync(work.ptr, 0, work.bytes, stream));
+  B2_LAUNCH(est_plan_kernel, 1, RADIX, 0, stream, ctl, PASS, cap);
+  pass_args a{};
+  a.key_bufs[0] = keys;
+  a.key_bufs[1] = mixed_keys_out;
+  a.key_bufs[2] = mixed_keys_out;
+  a.idx_bufs[0] = static_cast<int32_t*>(vals_out);
+  a.idx_bufs[1] = static_cast<int32_t*>(vals_out);
+  a.idx_bufs[2] = static_cast<int32_t*>(vals_out);
+  a.ctl = ctl;
+  a.kind = (int)key_kind::UNSIGNED;
+  a.pairs = 1;
+  a.keep_keys = 1;
+  a.val_in = vals;
+  a.desc_mask = 0;
+  a.pass = PASS;
+  a.portion_start = 0;
+  a.portion_n = (uint32_t)n;
+  a.portion_parity = 0;
+  a.has_next_portion = 0;
+  a.status = status;
+  a.tile_counter = counter;
+  a.est_cap = cap;
+  {
+    prof_scope ps("onesweep", stream);
+    B2_LAUNCH((onesweep_kernel<UK, T, I, 2, VT, true, true>), (unsigned)ntiles, T + 32 * LBW, (onesweep_smem<UK, T, I, VT>()), stream, a);
+  }
+  B2_CUDA_TRY(cudaMemcpyAsync(part_base, &ctl->base[0][PASS][0], sizeof(uint32_t) * RADIX, cudaMemcpyDeviceToDevice, stream));
+  B2_CUDA_TRY(cudaMemcpyAsync(part_end, &ctl->base[1][PASS][0], sizeof(uint32_t) * RADIX, cudaMemcpyDeviceToDevice, stream));
+  uint32_t overflow = 0;
+  B2_CUDA_TRY(cudaMemcpyAsync(&overflow, &ctl->overflow, sizeof(overflow), cudaMemcpyDeviceToHost, stream));
+  B2_CUDA_TRY(cudaStreamSynchronize(stream));
+  return overflow == 0;
+}
+}  // namespace
+
+// Rows per partition to reserve for the histogram-free partition pass below, or 0 when a strided sample of the keys says the
+// partitions are too uneven for it (few distinct keys, hot keys): max sampled share + 5 sigma of the sampling noise must fit.
+uint32_t radix_partition_est_capacity(const uint64_t* keys, int64_t n, cudaStream_t stream)
+{
+  static const int64_t min_rows = [] {
+    const char* e = std::getenv("B2_GROUPBY_EST_MIN");  // test hook
+    return e ? (int64_t)std::atoll(e) : (int64_t(1) << 22);
+  }();
+  if (n < min_rows || n > portion_limit()) return 0;
+  if (const char* e = std::getenv("B2_GROUPBY_EST_CAP")) return (uint32_t)std::max(1, std::atoi(e));  // test hook: forces the overflow fallback
+  const int64_t want = int64_t(1) << 20;
+  const int64_t stride = std::max<int64_t>(1, n / want);
+  const int64_t m = (n + stride - 1) / stride;
+  dbuf cnt(sizeof(unsigned int) * RADIX, stream);
+  B2_CUDA_TRY(cudaMemsetAsync(cnt.ptr, 0, cnt.bytes, stream));
+  B2_LAUNCH(est_sample_kernel, NUM_SMS_B200 * 4, 256, 0, stream, keys, n, stride, cnt.as<unsigned int>());
+  unsigned int h[RADIX];
+  B2_CUDA_TRY(cudaMemcpyAsync(h, cnt.ptr, sizeof(h), cudaMemcpyDeviceToHost, stream));
+  B2_CUDA_TRY(cudaStreamSynchronize(stream));
+  unsigned int mx = 0;
+  for (int d = 0; d < RADIX; ++d) mx = std::max(mx, h[d]);
+  const double cap = (double)(n / RADIX) * 1.25 + 4096.0;
+  const double worst = ((double)mx + 5.0 * std::sqrt((double)mx) + 1.0) * ((double)n / (double)m);
+  if (worst > cap || cap * RADIX >= 4.0e9) return 0;
+  return (uint32_t)cap;
+}
+
+// radix_partition_mix_carry without the histogram: the pass runs with estimated bases (partition d owns rows [d * cap, (d + 1) * cap) of
+// the outputs, which hold 256 * cap rows) and reports the exact end of every partition in part_end[d]. Returns false when a partition
+// overflowed its range (the outputs are then incomplete: run radix_partition_mix_carry).
+bool radix_partition_mix_carry_est(const uint64_t* keys, const void* vals, int val_bytes, int64_t n, uint32_t cap, uint64_t* mixed_keys_out,
+                                   void* vals_out, uint32_t* part_base, uint32_t* part_end, cudaStream_t stream)
+{
+  if (val_bytes == 8) return est_pass_impl<uint64_t>(keys, vals, n, cap, mixed_keys_out, vals_out, part_base, part_end, stream);
+  return est_pass_impl<uint32_t>(keys, vals, n, cap, mixed_keys_out, vals_out, part_base, part_end, stream);
 }
 
 namespace {

@@ -42,7 +42,7 @@ def emu_lib():
 
 def run(code: str, marker: str, env=None, timeout=900):
     e = dict(os.environ)
-    for k in ("B2_JOIN_RADIX_CAPACITY", "B2_SORT_PLAN_READBACK_MIN", "B2_GROUPBY_PARTITION_ROWS", "B2_GROUPBY_SMEM_SLOTS", "B2_SORT_HYBRID", "B2_SORT_HYBRID_MIN", "B2_SORT_CARRY", "B2_SORT_ALIAS", "B2_JOIN_RADIX_ROWS", "B2_JOIN_PARTITION_ROWS", "B2_SORT_CFG", "B2_SORT_PORTION"):
+    for k in ("B2_JOIN_RADIX_CAPACITY", "B2_SORT_PLAN_READBACK_MIN", "B2_GROUPBY_PARTITION_ROWS", "B2_GROUPBY_SMEM_SLOTS", "B2_SORT_HYBRID", "B2_SORT_HYBRID_MIN", "B2_SORT_CARRY", "B2_SORT_ALIAS", "B2_JOIN_RADIX_ROWS", "B2_JOIN_KERNEL", "B2_GROUPBY_EST", "B2_GROUPBY_EST_MIN", "B2_GROUPBY_EST_CAP", "B2_JOIN_PARTITION_ROWS", "B2_SORT_CFG", "B2_SORT_PORTION"):
         e.pop(k, None)
     e.update(env or {})
     r = subprocess.run([sys.executable, "-c", PRELUDE + code], capture_output=True, text=True, env=e, cwd=ROOT, timeout=timeout)
@@ -124,7 +124,9 @@ def test_emu_groupby_partitioned(emu_lib):
     from tests.snippets.partitioned_groupby import CODE
 
     cases = "CASES = [(1, 1), (100, 7), (5000, 300), (40_000, 20_000), (60_000, 3)]\n"
-    for env in ({}, {"B2_GROUPBY_SMEM_SLOTS": "64"}):
+    # B2_GROUPBY_EST: histogram-free partition pass (estimated bases); a forced tiny capacity exercises its overflow fallback
+    for env in ({"B2_GROUPBY_EST": "0"}, {"B2_GROUPBY_EST": "0", "B2_GROUPBY_SMEM_SLOTS": "64"}, {"B2_GROUPBY_EST": "1", "B2_GROUPBY_EST_MIN": "1"},
+                {"B2_GROUPBY_EST": "1", "B2_GROUPBY_EST_MIN": "1", "B2_GROUPBY_EST_CAP": "40"}):
         run(cases + CODE, "PGB_OK", env=dict(env, B2_GROUPBY_PARTITION_ROWS="1"))
 
 
@@ -170,10 +172,12 @@ b = rng.integers(0, 100_000, 40_000); b[:20_000] = 555
 check([(p[:3000], None)], [(b, None)], 'dup x chunks', ("inner_join", "left_join"))
 print('RADIX_JOIN_OK')
 """
-    run(code, "RADIX_JOIN_OK", env={"B2_JOIN_RADIX_ROWS": "1"})
+    run(code, "RADIX_JOIN_OK", env={"B2_JOIN_RADIX_ROWS": "1", "B2_JOIN_KERNEL": "1"})
+    run(code, "RADIX_JOIN_OK", env={"B2_JOIN_RADIX_ROWS": "1", "B2_JOIN_KERNEL": "2"})  # tag table, two CTAs per SM
     # output-size guess too small: the walk is repeated with the exact size (first cases only: the emulator is slow)
     short = code[:code.index("b = rng.integers(0, 1000, 60_000)")] + "print('RADIX_JOIN_OK')\n"
-    run(short, "RADIX_JOIN_OK", env={"B2_JOIN_RADIX_ROWS": "1", "B2_JOIN_RADIX_CAPACITY": "100"})
+    run(short, "RADIX_JOIN_OK", env={"B2_JOIN_RADIX_ROWS": "1", "B2_JOIN_RADIX_CAPACITY": "100", "B2_JOIN_KERNEL": "1"})
+    run(short, "RADIX_JOIN_OK", env={"B2_JOIN_RADIX_ROWS": "1", "B2_JOIN_RADIX_CAPACITY": "100", "B2_JOIN_KERNEL": "2"})
 
 
 def test_emu_wide_keys(emu_lib):

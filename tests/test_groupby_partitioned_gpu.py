@@ -21,11 +21,15 @@ cu, o = PlcImpl(plc), OracleImpl()
 """
 
 
-@pytest.mark.parametrize("smem_slots", ["0", "64"])
-def test_partitioned_groupby_forced(smem_slots):
+@pytest.mark.parametrize("smem_slots,est", [("0", "0"), ("64", "0"), ("0", "1"), ("0", "cap")])
+def test_partitioned_groupby_forced(smem_slots, est):
+    """est: the histogram-free partition pass (estimated bases, B2_GROUPBY_EST=1); "cap" forces a tiny capacity = its overflow fallback."""
     from tests.snippets.partitioned_groupby import CODE
 
-    env = dict(os.environ, B2_GROUPBY_PARTITION_ROWS="1", B2_GROUPBY_SMEM_SLOTS=smem_slots)
+    env = dict(os.environ, B2_GROUPBY_PARTITION_ROWS="1", B2_GROUPBY_SMEM_SLOTS=smem_slots, B2_GROUPBY_EST="0" if est == "0" else "1",
+               B2_GROUPBY_EST_MIN="1")
+    if est == "cap":
+        env["B2_GROUPBY_EST_CAP"] = "40"
     cases = "CASES = [(1, 1), (100, 7), (5000, 300), (40_000, 20_000), (60_000, 3), (3_000_000, 1_500_000)]\n"
     r = subprocess.run([sys.executable, "-c", PRELUDE + cases + CODE], capture_output=True, text=True, env=env, cwd=ROOT, timeout=900)
     assert "PGB_OK" in r.stdout, r.stdout[-1500:] + r.stderr[-2500:]
