@@ -472,6 +472,8 @@ def run_ours(args):
         import bench_extra
 
         del keys, col, tbl
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
         _lib.check(_lib.lib.b2_trim_pool())
         try:
             ops = bench_extra.run(plc, _lib, n, peak, cpu_rows=args.cpu_rows)

@@ -109,6 +109,14 @@ def run(plc, _lib, n, peak_gbs, cpu_rows=10_000_000, with_cpu=True):
             e["cpu_baseline"] = cpu[cpu_key]
         return e
 
+    def release():
+        """Hand every cached block back to the driver (torch's caching allocator and the library's pool): the next operation
+        starts from the same memory state whatever ran before it (call 8: a join measured 117 ms instead of 57 ms, all of the
+        difference inside the allocations of its partition temporaries, with ~100 GB of deleted tensors still cached by torch)."""
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+        _lib.check(_lib.lib.b2_trim_pool())
+
     def profiled(fn, steps=3, warmup=2):
         for _ in range(warmup):
             o = fn()
@@ -120,6 +128,7 @@ def run(plc, _lib, n, peak_gbs, cpu_rows=10_000_000, with_cpu=True):
         return ms
 
     # ---- scan / reduce / segmented reduce (int64 and float64) ----
+    release()
     x = _fill(_lib, torch.empty(n, dtype=torch.int64, device=dev), n, 7)
     f = _fill(_lib, torch.empty(n, dtype=torch.float64, device=dev), n, 8, kind=1)
     ci, cf = plc.Column.from_torch(x), plc.Column.from_torch(f)
@@ -142,6 +151,7 @@ def run(plc, _lib, n, peak_gbs, cpu_rows=10_000_000, with_cpu=True):
     res["segmented_reduce_sum_float64_1e6_segments"] = entry(
         _time(torch, lambda: plc.reduce.segmented_reduce(cf, co, agg.sum(), plc.DataType(plc.TypeId.FLOAT64))), n, 8 * n + 4 * (S + 1) + 8 * S)
     del x, ci, offs, co
+    release()
 
     # ---- groupby (BASELINE configs[3]): int64 key with 1e6 groups, sum(float64) + count(int32) ----
     G = 1_000_000
@@ -155,6 +165,7 @@ def run(plc, _lib, n, peak_gbs, cpu_rows=10_000_000, with_cpu=True):
                                                 phases_ms=phases("groupby_partition", "groupby_aggregate"),
                                                 note="partition pass (one-sweep, mix64 top byte, value carried) + shared-memory aggregation per partition chunk")
     del k, v2, gb, reqs, keys_out
+    release()
 
     # ---- inner join (BASELINE configs[2]): |R| = |L| = n, 10 % of probe rows match exactly once; payload gather with 50 % nulls ----
     try:
@@ -166,10 +177,10 @@ def run(plc, _lib, n, peak_gbs, cpu_rows=10_000_000, with_cpu=True):
         del u
         lk[hit] = rk[sel[hit]]
         del sel, hit
+        release()
         L, R = plc.Table([plc.Column.from_torch(lk)]), plc.Table([plc.Column.from_torch(rk)])
         slots = 1 << (2 * n - 1).bit_length()
-        _lib.check(_lib.lib.b2_trim_pool())
-        ms = profiled(lambda: plc.join.inner_join(L, R, plc.NullEquality.EQUAL), steps=2, warmup=1)
+        ms = profiled(lambda: plc.join.inner_join(L, R, plc.NullEquality.EQUAL), steps=3, warmup=2)
         li, ri = plc.join.inner_join(L, R, plc.NullEquality.EQUAL)
         M = li.size()
         alg = 16 * slots + 24 * n + 24 * n + 8 * M
@@ -182,7 +193,7 @@ def run(plc, _lib, n, peak_gbs, cpu_rows=10_000_000, with_cpu=True):
         for label, val in (("inner_join_10pct_hash_table_path", "0"), ("inner_join_10pct_partitioned_path", "1000000")):
             os.environ["B2_JOIN_RADIX_ROWS"] = val
             try:
-                _lib.check(_lib.lib.b2_trim_pool())
+                release()
                 rms = profiled(lambda: plc.join.inner_join(L, R, plc.NullEquality.EQUAL), steps=2, warmup=1)
                 li2, _ri2 = plc.join.inner_join(L, R, plc.NullEquality.EQUAL)
                 res[label] = entry(rms, n, alg, unit="probe rows/s", matches=li2.size(), same_match_count=bool(li2.size() == M),
@@ -195,7 +206,7 @@ def run(plc, _lib, n, peak_gbs, cpu_rows=10_000_000, with_cpu=True):
         else:
             os.environ["B2_JOIN_RADIX_ROWS"] = prev
         # materialisation: gather both payload columns (float64, 50 % nulls) through the index columns
-        _lib.check(_lib.lib.b2_trim_pool())
+        release()
         pay = f
         nwords = (n + 31) // 32
         mask = _fill(_lib, torch.empty(nwords, dtype=torch.int32, device=dev), n, 3, kind=4)

@@ -260,6 +260,7 @@ __global__ void __launch_bounds__(256) groupby_kernel(key_cols kc, int64_t n, bo
 // Groups that do not fit in the shared table (more than ~4.9 K groups in a partition) go to the global table row by row.
 constexpr int PGB_THREADS = 1024;
 constexpr int PGB_MAX_OPS = 3;
+constexpr uint32_t PGB_CHUNK_DEFAULT = 1u << 18;
 constexpr bool PGB_EST_DEFAULT = false;  // histogram-free partition pass (radix_partition_mix_carry_est): opt-in until measured
 constexpr uint64_t PGB_EMPTY = ~0ull;
 
@@ -848,7 +849,12 @@ void groupby_aggregate(const b2_groupby& gb, const std::vector<request_view>& re
       pa.n = (uint32_t)n;
       pa.item_start = pgb_items.as<uint32_t>();
       pa.item_counter = pgb_items.as<uint32_t>() + 257;
-      pa.chunk = 1u << 18;
+      static const uint32_t chunk_rows = [] {  // tuning knob: rows per work item (each item merges its groups into the global table once)
+        const char* e = std::getenv("B2_GROUPBY_CHUNK");
+        const long long v = e ? std::atoll(e) : 0;
+        return (v >= 1024 && v <= (1ll << 24)) ? (uint32_t)v : PGB_CHUNK_DEFAULT;
+      }();
+      pa.chunk = chunk_rows;
       pa.nops = ops.n;
       for (int k = 0; k < ops.n; ++k) {
         pa.op[k] = ops.op[k].op; pa.acc[k] = ops.op[k].acc; pa.accum[k] = ops.op[k].accum; pa.init[k] = acc_init(ops.op[k].acc, ops.op[k].op);
