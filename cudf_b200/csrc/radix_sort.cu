@@ -62,7 +62,7 @@ struct sort_ctl {
   // two-phase histogram of the hybrid plan: phase 1 counts the top four digits only; the low digits are counted (phase 2) only
   // when the plan cannot stop above them
   int32_t need_low;            // 1: phase 1 could not decide, the low digits' histograms are required
-  int32_t pad2;
+  int32_t fix_fast;            // hybrid plan: which segment_fix_kernel instantiation runs (0: plain walks, 1: branch-free first neighbours)
   unsigned long long vary;     // OR of (key ^ first key) over the input
 };
 
@@ -275,6 +275,7 @@ __global__ void plan_kernel(const uint32_t* __restrict__ ghist, int npass, uint3
     int nexec = 0;
     for (int p = 0; p < npass; ++p) nexec += triv[p] ? 0 : 1;
     int hybrid = 0, low = 0;
+    double seg_est = 0.0;    // hybrid plan: expected rows per segment
     bool undecided = false;  // phase 1: the decision would need an uncounted digit
     if (hyb_allowed && nexec > HYB_MIN_SAVED_PASSES) {
       double e = (double)n;
@@ -289,6 +290,7 @@ __global__ void plan_kernel(const uint32_t* __restrict__ ghist, int npass, uint3
       }
       if (!undecided && e <= HYB_MAX_EXPECTED_SEGMENT && nexec - k >= HYB_MIN_SAVED_PASSES) {
         hybrid = 1;
+        seg_est = e;
         for (int p = 0; p < low; ++p) triv[p] = 1;
         nexec = k;
       }
@@ -304,6 +306,9 @@ __global__ void plan_kernel(const uint32_t* __restrict__ ghist, int npass, uint3
       ctl->need_low = 0;
     }
     ctl->hybrid    = hybrid;
+    // expected rows per segment decides the fix-up flavour: mostly single-row segments (1e9 uniform keys: 0.23) are fastest with the
+    // plain walks (5.6 vs 6.9 ms), ~2-row segments (a rank's shard of the sharded sort: 1.9) with the branch-free form (8.8 vs 9.5 ms)
+    ctl->fix_fast  = (hybrid && seg_est > 0.75) ? 1 : 0;
     ctl->fix_shift = low * RADIX_BITS;
     ctl->overflow  = 0;
     // idx buffers: 0 = output, 1 = temp. the last executed pass must write 0.
@@ -343,6 +348,8 @@ __global__ void plan_kernel(const uint32_t* __restrict__ ghist, int npass, uint3
     ctl->any_pass = nexec;
   }
 }
+
+__global__ void set_fix_fast_kernel(sort_ctl* ctl, int v) { ctl->fix_fast = v; }
 
 // ------------------------------------------------------------------------------------------------
 // 3. one-sweep pass
@@ -888,10 +895,10 @@ constexpr int FIX_IPT     = 8;
 constexpr int FIX_TILE    = FIX_THREADS * FIX_IPT;
 constexpr int FIX_HALO    = 64;
 
-template <typename UK, typename VT>
+template <typename UK, typename VT, int FIX_FAST>
 __global__ void __launch_bounds__(FIX_THREADS) segment_fix_kernel(pass_args a, int64_t n)
 {
-  if (!a.ctl->hybrid) return;
+  if (!a.ctl->hybrid || a.ctl->fix_fast != (FIX_FAST ? 1 : 0)) return;
   __shared__ UK sk[FIX_TILE + 2 * FIX_HALO];
   const int shift = a.ctl->fix_shift;
   const UK* __restrict__ keys = static_cast<const UK*>(a.ctl->fix_key_buf == 1 ? a.key_bufs[1] : a.key_bufs[2]);
@@ -925,8 +932,7 @@ __global__ void __launch_bounds__(FIX_THREADS) segment_fix_kernel(pass_args a, i
       // The first FIX_FAST neighbours on each side are examined without branches (every lane of the warp does the same
       // work: a divergent walk costs the warp its LONGEST segment, which tripled the kernel's time at ~2 rows per segment);
       // only rows whose segment reaches further continue with the loops below.
-      constexpr int FIX_FAST = 3;
-      bool in_l = true, in_r = true;
+      bool in_l = true, in_r = true;  // FIX_FAST = 0: no unrolled part, both walks start at the row itself
 #pragma unroll
       for (int s = 1; s <= FIX_FAST; ++s) {
         const UK ol = sk[FIX_HALO + i - s];   // inside the halo: FIX_HALO >= FIX_FAST
@@ -1202,6 +1208,13 @@ void run_radix_cfg(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int
       }
     }
 
+    {
+      static const int force_fix = [] {  // test hook: B2_SORT_FIX_FAST=0/1 overrides the plan's choice of the fix-up flavour
+        const char* e = std::getenv("B2_SORT_FIX_FAST");
+        return e ? (std::atoi(e) != 0 ? 1 : 0) : -1;
+      }();
+      if (force_fix >= 0 && try_hybrid) B2_LAUNCH(set_fix_fast_kernel, 1, 1, 0, stream, ctl, force_fix);
+    }
     pass_args a{};
     a.key_bufs[0] = raw_keys;
     a.key_bufs[1] = bufA;
@@ -1257,7 +1270,8 @@ void run_radix_cfg(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int
         const int64_t ntiles = (n + FIX_TILE - 1) / FIX_TILE;
         const int grid = (int)std::min<int64_t>(ntiles, NUM_SMS_B200 * 8);
         prof_scope ps("segment_fix", stream);
-        B2_LAUNCH((segment_fix_kernel<UK, VT>), grid, FIX_THREADS, 0, stream, a, n);
+        B2_LAUNCH((segment_fix_kernel<UK, VT, 0>), grid, FIX_THREADS, 0, stream, a, n);  // the plan's ctl->fix_fast picks one of the two
+        B2_LAUNCH((segment_fix_kernel<UK, VT, 3>), grid, FIX_THREADS, 0, stream, a, n);
       }
     }
     {

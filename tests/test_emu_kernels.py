@@ -42,7 +42,7 @@ def emu_lib():
 
 def run(code: str, marker: str, env=None, timeout=900):
     e = dict(os.environ)
-    for k in ("B2_JOIN_RADIX_CAPACITY", "B2_SORT_PLAN_READBACK_MIN", "B2_GROUPBY_PARTITION_ROWS", "B2_GROUPBY_SMEM_SLOTS", "B2_SORT_HYBRID", "B2_SORT_HYBRID_MIN", "B2_SORT_CARRY", "B2_SORT_ALIAS", "B2_JOIN_RADIX_ROWS", "B2_JOIN_KERNEL", "B2_GROUPBY_EST", "B2_GROUPBY_EST_MIN", "B2_GROUPBY_EST_CAP", "B2_JOIN_PARTITION_ROWS", "B2_SORT_CFG", "B2_SORT_PORTION"):
+    for k in ("B2_JOIN_RADIX_CAPACITY", "B2_SORT_PLAN_READBACK_MIN", "B2_GROUPBY_PARTITION_ROWS", "B2_GROUPBY_SMEM_SLOTS", "B2_SORT_HYBRID", "B2_SORT_HYBRID_MIN", "B2_SORT_FIX_FAST", "B2_SORT_CARRY", "B2_SORT_ALIAS", "B2_JOIN_RADIX_ROWS", "B2_JOIN_KERNEL", "B2_GROUPBY_EST", "B2_GROUPBY_EST_MIN", "B2_GROUPBY_EST_CAP", "B2_JOIN_PARTITION_ROWS", "B2_SORT_CFG", "B2_SORT_PORTION"):
         e.pop(k, None)
     e.update(env or {})
     r = subprocess.run([sys.executable, "-c", PRELUDE + code], capture_output=True, text=True, env=e, cwd=ROOT, timeout=timeout)
@@ -112,7 +112,7 @@ def test_emu_sort_hybrid(emu_lib):
     """Partial LSD passes + segment fix-up (the default plan for large 64-bit key columns), including the overflow rerun."""
     from tests.snippets.hybrid_sort import CODE
 
-    for env in ({}, {"B2_SORT_CARRY": "0"}, {"B2_SORT_PLAN_READBACK_MIN": "0"}):
+    for env in ({"B2_SORT_FIX_FAST": "0"}, {"B2_SORT_CARRY": "0", "B2_SORT_FIX_FAST": "1"}, {"B2_SORT_PLAN_READBACK_MIN": "0"}):
         code = "SIZES = (3, 100, 2047, 2049, 6145, 20011)\n" + CODE
         if "B2_SORT_PLAN_READBACK_MIN" in env:  # skipped passes are not launched at all: the launch-count check does not apply
             code = code.replace("assert b > a + 8, (a, b)", "assert b > a, (a, b)")
@@ -169,11 +169,11 @@ check([(p, None)], [(b, None)], 'probe pieces')
 # a left join whose hot probe key spans several pieces AND several build chunks
 p = rng.integers(0, 100_000, 90_000); p[:70_000] = 555
 b = rng.integers(0, 100_000, 40_000); b[:20_000] = 555
-check([(p[:3000], None)], [(b, None)], 'dup x chunks', ("inner_join", "left_join"))
+check([(p[:DUPN], None)], [(b, None)], 'dup x chunks', ("inner_join", "left_join"))
 print('RADIX_JOIN_OK')
 """
-    run(code, "RADIX_JOIN_OK", env={"B2_JOIN_RADIX_ROWS": "1", "B2_JOIN_KERNEL": "1"})
-    run(code, "RADIX_JOIN_OK", env={"B2_JOIN_RADIX_ROWS": "1", "B2_JOIN_KERNEL": "2"})  # tag table, two CTAs per SM
+    run("DUPN = 3000\n" + code, "RADIX_JOIN_OK", env={"B2_JOIN_RADIX_ROWS": "1", "B2_JOIN_KERNEL": "1"})
+    run("DUPN = 500\n" + code, "RADIX_JOIN_OK", env={"B2_JOIN_RADIX_ROWS": "1", "B2_JOIN_KERNEL": "2"})  # tag table, two CTAs per SM
     # output-size guess too small: the walk is repeated with the exact size (first cases only: the emulator is slow)
     short = code[:code.index("b = rng.integers(0, 1000, 60_000)")] + "print('RADIX_JOIN_OK')\n"
     run(short, "RADIX_JOIN_OK", env={"B2_JOIN_RADIX_ROWS": "1", "B2_JOIN_RADIX_CAPACITY": "100", "B2_JOIN_KERNEL": "1"})

@@ -20,11 +20,12 @@ from oracle import sort as osort
 """
 
 
-@pytest.mark.parametrize("carry", ["1", "0"])
-def test_hybrid_small_inputs(carry):
+@pytest.mark.parametrize("carry,fix_fast", [("1", "0"), ("1", "1"), ("0", "0"), ("0", "1")])
+def test_hybrid_small_inputs(carry, fix_fast):
+    """fix_fast: both flavours of the segment fix-up (the plan picks one from its expected segment length; B2_SORT_FIX_FAST forces it)."""
     from tests.snippets.hybrid_sort import CODE
 
-    env = dict(os.environ, B2_SORT_HYBRID_MIN="0", B2_SORT_CARRY=carry)
+    env = dict(os.environ, B2_SORT_HYBRID_MIN="0", B2_SORT_CARRY=carry, B2_SORT_FIX_FAST=fix_fast)
     r = subprocess.run([sys.executable, "-c", PRELUDE + "SIZES = (3, 100, 2047, 2049, 6145, 20011, 300_007)\n" + CODE], capture_output=True,
                        text=True, env=env, cwd=ROOT, timeout=600)
     assert "HYBRID_OK" in r.stdout, r.stdout[-1500:] + r.stderr[-2500:]
