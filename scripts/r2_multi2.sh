@@ -11,8 +11,8 @@ TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr
 run() { local name=$1 to=$2; shift 2; local t0=$SECONDS; timeout "$to" "$@" > "$O/$name.log" 2>&1; echo "$name exit=$? secs=$((SECONDS - t0))" | tee -a "$O/summary.txt"; }
 run check 150 $TR scripts/sharded_check.py --rows 20000000
 grep -h SHARDED_OK "$O/check.log" | tee -a "$O/summary.txt"
-run bench_default 300 $TR bench.py --gpus $N --steps 5 --warmup 3 --no-e2e --cpu-rows 100000
-B2_SHARD_P2P=staged run bench_staged 300 $TR bench.py --gpus $N --steps 5 --warmup 3 --no-e2e --no-join --cpu-rows 100000
+run bench_default 300 $TR bench.py --gpus $N --steps 4 --warmup 3 --no-e2e --cpu-rows 100000
+B2_SHARD_P2P=staged run bench_staged 300 $TR bench.py --gpus $N --steps 4 --warmup 3 --no-e2e --no-join --cpu-rows 100000
 for f in bench_default bench_staged; do
 grep -h '"metric"' "$O/$f.log" | python -c "
 import sys, json
