@@ -1,0 +1,4 @@
+"""pylibcudf.sorting (python/pylibcudf/pylibcudf/sorting.pyx:37-79,333-520): compiled in _core.pyx."""
+from ._core import sort, sort_by_key, sorted_order, stable_sort, stable_sort_by_key, stable_sorted_order
+
+__all__ = ["sorted_order", "stable_sorted_order", "sort", "stable_sort", "sort_by_key", "stable_sort_by_key"]

@@ -86,3 +86,38 @@ def install():
     Column.from_numpy = classmethod(from_numpy)
     Column.to_numpy = to_numpy
     return emu
+
+
+def install_cy():
+    """`install()` + the Cython binding (cudf_b200.pylibcudf_cy) built against the emulator's library: the same _core.pyx, linked
+    with tests/emu/_build/libcudf_b200_emu.so and loaded RTLD_DEEPBIND so that its b2_* calls bind to that library although the
+    real one sits in the global scope. Returns the package."""
+    import importlib.util
+    import os
+
+    install()
+    from tests.emu.build_emu import LIB, OUT
+
+    # build_cy.py is loaded by path: importing the package would load the product extension first
+    bspec = importlib.util.spec_from_file_location("_b2_build_cy", str(ROOT / "cudf_b200" / "pylibcudf_cy" / "build_cy.py"))
+    bmod = importlib.util.module_from_spec(bspec)
+    bspec.loader.exec_module(bmod)
+    build_cy = bmod.build
+
+    so = build_cy(lib=LIB, out_dir=OUT / "cy")
+    name = "cudf_b200.pylibcudf_cy._core"
+    for m in [m for m in sys.modules if m == "cudf_b200.pylibcudf_cy" or m.startswith("cudf_b200.pylibcudf_cy.")]:
+        del sys.modules[m]  # the product extension may have been imported already (e.g. by __graft_entry__.build())
+    old = sys.getdlopenflags()
+    sys.setdlopenflags(os.RTLD_NOW | os.RTLD_DEEPBIND)
+    try:
+        spec = importlib.util.spec_from_file_location(name, str(so))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[name] = mod
+        spec.loader.exec_module(mod)
+    finally:
+        sys.setdlopenflags(old)
+    import cudf_b200.pylibcudf_cy as cy
+
+    assert cy._core is mod
+    return cy
