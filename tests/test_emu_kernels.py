@@ -172,8 +172,8 @@ b = rng.integers(0, 100_000, 40_000); b[:20_000] = 555
 check([(p[:DUPN], None)], [(b, None)], 'dup x chunks', ("inner_join", "left_join"))
 print('RADIX_JOIN_OK')
 """
-    run("DUPN = 3000\n" + code, "RADIX_JOIN_OK", env={"B2_JOIN_RADIX_ROWS": "1", "B2_JOIN_KERNEL": "1"})
-    run("DUPN = 500\n" + code, "RADIX_JOIN_OK", env={"B2_JOIN_RADIX_ROWS": "1", "B2_JOIN_KERNEL": "2"})  # tag table, two CTAs per SM
+    run("DUPN = 1000\n" + code, "RADIX_JOIN_OK", env={"B2_JOIN_RADIX_ROWS": "1", "B2_JOIN_KERNEL": "1"})
+    run("DUPN = 400\n" + code, "RADIX_JOIN_OK", env={"B2_JOIN_RADIX_ROWS": "1", "B2_JOIN_KERNEL": "2"})  # tag table, two CTAs per SM
     # output-size guess too small: the walk is repeated with the exact size (first cases only: the emulator is slow)
     short = code[:code.index("b = rng.integers(0, 1000, 60_000)")] + "print('RADIX_JOIN_OK')\n"
     run(short, "RADIX_JOIN_OK", env={"B2_JOIN_RADIX_ROWS": "1", "B2_JOIN_RADIX_CAPACITY": "100", "B2_JOIN_KERNEL": "1"})
