@@ -1176,7 +1176,9 @@ void run_radix_cfg(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int
   bool try_hybrid = sizeof(UK) == 8 && !MIX && raw && first_pass == 0 && last_pass >= NP - 1 && !keep_keys && n >= hybrid_min_rows();
 
   for (;;) {
-    B2_CUDA_TRY(cudaMemsetAsync(work.ptr, 0, work.bytes, stream));
+    // control block, histograms and tile counters are zeroed here; the look-back rows of a (pass, portion) right before its launch, so
+    // that passes the plan skips cost nothing (1e9 rows: 163 MB per executed pass instead of 1.3 GB per sort)
+    B2_CUDA_TRY(cudaMemsetAsync(work.ptr, 0, ctl_bytes + hist_bytes + cnt_bytes, stream));
     {
       int grid = (int)std::min<int64_t>((n + 512 * 16 - 1) / (512 * 16), NUM_SMS_B200 * 4);
       grid = std::max(grid, 1);
@@ -1261,6 +1263,7 @@ void run_radix_cfg(const UK* raw_keys, UK* bufA, UK* bufB, int32_t* idx_out, int
         a.tile_counter = counters + p * nportions + q;
         const int64_t ntiles = (pn + TILE - 1) / TILE;
         const size_t smem_bytes = onesweep_smem<UK, T, I, VT>();
+        B2_CUDA_TRY(cudaMemsetAsync(a.status, 0, sizeof(uint32_t) * RADIX * (size_t)ntiles, stream));
         prof_scope ps("onesweep", stream);
         B2_LAUNCH((onesweep_kernel<UK, T, I, MINB, VT, CARRY, MIX, SAFE, RMW, BULK>), (unsigned)ntiles, T + 32 * LBW, smem_bytes, stream, a);
       }
