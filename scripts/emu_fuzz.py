@@ -16,7 +16,12 @@ os.chdir(ROOT)
 
 # --mode selects an opt-in path for the whole run (the switches are read by the library, some of them only once)
 _MODES = {"default": {}, "carry": {"B2_SORT_CARRY": "1"}, "alias": {"B2_SORT_ALIAS": "1"}, "radix": {"B2_JOIN_RADIX_ROWS": "1"},
-          "rmw": {"B2_SORT_CFG": "11"}, "portion": {"B2_SORT_PORTION": "6144"}, "mixed": {"B2_JOIN_PARTITION_ROWS": "64"}}
+          "rmw": {"B2_SORT_CFG": "11"}, "portion": {"B2_SORT_PORTION": "6144"}, "mixed": {"B2_JOIN_PARTITION_ROWS": "64"},
+          "radix2": {"B2_JOIN_RADIX_ROWS": "1", "B2_JOIN_KERNEL": "2"},
+          "pgb": {"B2_GROUPBY_PARTITION_ROWS": "1", "B2_GROUPBY_EST": "1", "B2_GROUPBY_EST_MIN": "1"},
+          "pgbcap": {"B2_GROUPBY_PARTITION_ROWS": "1", "B2_GROUPBY_EST": "1", "B2_GROUPBY_EST_MIN": "1", "B2_GROUPBY_EST_CAP": "48"},
+          "pgbhist": {"B2_GROUPBY_PARTITION_ROWS": "1", "B2_GROUPBY_EST": "0"},
+          "fix0": {"B2_SORT_HYBRID_MIN": "0", "B2_SORT_FIX_FAST": "0"}, "fix1": {"B2_SORT_HYBRID_MIN": "0", "B2_SORT_FIX_FAST": "1"}}
 for _i, _a in enumerate(sys.argv):
     if _a == "--mode" and _i + 1 < len(sys.argv):
         os.environ.update(_MODES[sys.argv[_i + 1]])
@@ -197,7 +202,7 @@ def fuzz_seg_rank(rng):
         pmap = rng.integers(0, P, n).astype(np.int32)
         out, poffs = plc.partitioning.partition(plc.Table([plc.Column.from_numpy(np.arange(n, dtype=np.int64))]), plc.Column.from_numpy(pmap), P)
         assert np.array_equal(out.columns()[0].to_numpy()[0], np.argsort(pmap, kind="stable")), ("partition", n, P)
-        assert poffs == np.concatenate([[0], np.cumsum(np.bincount(pmap, minlength=P))[:-1]]).tolist()
+        assert poffs == np.concatenate([[0], np.cumsum(np.bincount(pmap, minlength=P))]).tolist()  # P + 1 offsets (partitioning.hpp:58-101)
     for method in range(5):
         order, policy, nprec = int(rng.integers(2)), int(rng.integers(2)), int(rng.integers(2))
         pct = bool(rng.integers(2))
