@@ -34,6 +34,17 @@ GROUPBY_CASES = [
     dict(name="mean_basic", cite="mean_tests.cpp:37-55", keys=GB_KEYS, vals=GB_VALS, kind="mean", ekeys=[1, 2, 3],
          evals=[3.0, 19.0 / 4, 17.0 / 3]),
     dict(name="empty", cite="sum_tests.cpp:82-93", keys=[], vals=[], kind="sum", ekeys=[], evals=[]),
+    # min_tests.cpp / max_tests.cpp (every case there runs the hash and the sort implementation)
+    dict(name="min_basic", cite="min_tests.cpp:25-41", keys=GB_KEYS, vals=GB_VALS, kind="min", ekeys=[1, 2, 3], evals=[0, 1, 2]),
+    dict(name="min_zero_valid_keys", cite="min_tests.cpp:61-77", keys=[N, N, N], vals=[3, 4, 5], kind="min", ekeys=[], evals=[]),
+    dict(name="min_zero_valid_values", cite="min_tests.cpp:79-95", keys=[1, 1, 1], vals=[N, N, N], kind="min", ekeys=[1], evals=[N]),
+    dict(name="min_null_keys_and_values", cite="min_tests.cpp:97-119",
+         keys=[1, 2, 3, 1, 2, 2, 1, N, 3, 2, 4], vals=[N, 1, 2, 3, 4, N, 6, 7, 8, 9, N], kind="min",
+         ekeys=[1, 2, 3, 4], evals=[3, 1, 2, N]),
+    dict(name="max_basic", cite="max_tests.cpp:27-46", keys=GB_KEYS, vals=GB_VALS, kind="max", ekeys=[1, 2, 3], evals=[6, 9, 8]),
+    dict(name="max_null_keys_and_values", cite="max_tests.cpp:102-124",
+         keys=[1, 2, 3, 1, 2, 2, 1, N, 3, 2, 4], vals=[0, 1, 2, 3, 4, 5, N, 7, 8, N, N], kind="max",
+         ekeys=[1, 2, 3, 4], evals=[3, 5, 8, N]),
 ]
 GROUPBY_SCAN_CASES = [
     dict(name="sum_scan_basic", cite="sum_scan_tests.cpp:33-49", keys=GB_KEYS, vals=GB_VALS, kind="sum",
@@ -45,6 +56,16 @@ GROUPBY_SCAN_CASES = [
          ekeys=[1, 1, 1, 2, 2, 2, 2, 3, 3, 4], evals=[N, 3, 9, 1, 5, N, 14, 2, 10, N]),
     dict(name="count_scan_basic", cite="count_scan_tests.cpp:27-46", keys=GB_KEYS, vals=GB_VALS, kind="count",
          ekeys=[1, 1, 1, 2, 2, 2, 2, 3, 3, 3], evals=[1, 2, 3, 1, 2, 3, 4, 1, 2, 3]),
+    dict(name="min_scan_basic", cite="min_scan_tests.cpp:27-42", keys=GB_KEYS, vals=[5, 6, 7, 8, 9, 0, 1, 2, 3, 4], kind="min",
+         ekeys=[1, 1, 1, 2, 2, 2, 2, 3, 3, 3], evals=[5, 5, 1, 6, 6, 0, 0, 7, 2, 2]),
+    dict(name="min_scan_null_keys_and_values", cite="min_scan_tests.cpp:109-127",
+         keys=[1, 2, 3, 1, 2, 2, 1, N, 3, 2, 4], vals=[N, 6, 7, 8, 9, N, 1, 2, 3, 4, N], kind="min",
+         ekeys=[1, 1, 1, 2, 2, 2, 2, 3, 3, 4], evals=[N, 8, 1, 6, 6, N, 4, 7, 3, N]),
+    dict(name="max_scan_basic", cite="max_scan_tests.cpp:29-45", keys=GB_KEYS, vals=[5, 6, 7, 8, 9, 0, 1, 2, 3, 4], kind="max",
+         ekeys=[1, 1, 1, 2, 2, 2, 2, 3, 3, 3], evals=[5, 8, 8, 6, 9, 9, 9, 7, 7, 7]),
+    dict(name="max_scan_null_keys_and_values", cite="max_scan_tests.cpp:112-130",
+         keys=[1, 2, 3, 1, 2, 2, 1, N, 3, 2, 4], vals=[N, 6, 7, 8, 9, N, 1, 2, 3, 4, N], kind="max",
+         ekeys=[1, 1, 1, 2, 2, 2, 2, 3, 3, 4], evals=[N, 8, 8, 6, 9, N, 9, 7, 7, N]),
 ]
 
 # ---- scan (cpp/tests/reductions/scan_tests.cpp:160-216) ----------------------------------------------

@@ -85,7 +85,8 @@ def test_groupby_golden(impl, case, vdtype):
     got = res[0][0]
     exp_valid = np.array([v is not None for v in case["evals"]], dtype=bool)
     exp_vals = np.array([0 if v is None else v for v in case["evals"]])
-    rdt = {"sum": np.int64 if np.dtype(vdtype).kind in "iu" else vdtype, "count": np.int32, "count_all": np.int32, "mean": np.float64}[case["kind"]]
+    rdt = {"sum": np.int64 if np.dtype(vdtype).kind in "iu" else vdtype, "count": np.int32, "count_all": np.int32, "mean": np.float64,
+           "min": vdtype, "max": vdtype}[case["kind"]]
     assert np.asarray(got[0]).dtype == np.dtype(rdt), f"{case['name']}: result dtype {np.asarray(got[0]).dtype}"
     gm = np.ones(len(exp_vals), bool) if got[1] is None else np.asarray(got[1])
     assert gm.tolist() == exp_valid.tolist()
