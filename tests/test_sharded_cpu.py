@@ -1,4 +1,4 @@
-"""world_size-2 gloo tests (CPU) of the host logic of the sharded sort / join: splitters, all-to-all-v sizes,
+"""world_size-2 and -4 gloo tests (CPU) of the host logic of the sharded sort / join: splitters, all-to-all-v sizes,
 rank-ordered result.  The device primitives are replaced by a numpy twin (tests may use the oracle)."""
 import os
 import socket
@@ -86,7 +86,8 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_sharded_sort_and_join_gloo(tmp_path, monkeypatch):
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_sort_and_join_gloo(tmp_path, monkeypatch, world):
     # load cudf_b200/sharded.py as a standalone module: the package __init__ needs the CUDA library
     import importlib.util
     import sys
@@ -100,7 +101,6 @@ def test_sharded_sort_and_join_gloo(tmp_path, monkeypatch):
     (shim_dir / "sharded.py").write_text(src)
     monkeypatch.setenv("PYTHONPATH", f"{tmp_path}{os.pathsep}{Path(__file__).resolve().parent.parent}{os.pathsep}" + os.environ.get("PYTHONPATH", ""))
     sys.path.insert(0, str(tmp_path))
-    world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
