@@ -470,6 +470,30 @@ cdef class HashJoin:
     def full_join_size(self, Table probe, stream=None):
         return self._size(b2_hash_join_full_join_size, probe, stream)
 
+    # ---- match context / partitioned probes (hash_join.hpp:254-440); implemented below the class ----
+    def inner_join_match_context(self, Table probe, stream=None):
+        return hash_join_match_context(self, 0, probe, stream)
+
+    def left_join_match_context(self, Table probe, stream=None):
+        return hash_join_match_context(self, 1, probe, stream)
+
+    def full_join_match_context(self, Table probe, stream=None):
+        return hash_join_match_context(self, 2, probe, stream)
+
+    def partitioned_inner_join(self, context, stream=None):
+        return hash_join_partitioned(self, 0, context, stream)
+
+    def partitioned_left_join(self, context, stream=None):
+        return hash_join_partitioned(self, 1, context, stream)
+
+    def partitioned_full_join(self, context, stream=None):
+        """Probe side only; finalize_partitioned_full_join appends the unmatched build rows."""
+        return hash_join_partitioned(self, 2, context, stream)
+
+    @staticmethod
+    def finalize_partitioned_full_join(left_partials, right_partials, left_table_num_rows, right_table_num_rows, stream=None):
+        return finalize_partitioned_full_join(left_partials, right_partials, left_table_num_rows, right_table_num_rows, stream)
+
 
 # ---------------------------------------------------------------------------------------------------------------------
 # groupby (python/pylibcudf/pylibcudf/groupby.pyx:36-243)
@@ -602,3 +626,296 @@ def segmented_reduce(Column segmented_values, Column offsets, agg, data_type, nu
         st = b2_segmented_reduce(&segmented_values.v, optr, nof, kind, tid, nh, ini, s, &out)
     check(st)
     return Column.from_handle(out)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# sorting: segmented sort / top-k / rank (python/pylibcudf/pylibcudf/sorting.pyx; cpp/include/cudf/sorting.hpp:165-416)
+# ---------------------------------------------------------------------------------------------------------------------
+cdef Column _segmented_sorted_order(Table keys, Column segment_offsets, object column_order, object null_precedence, int stable, object stream):
+    cdef _TableView kv = _TableView.of(keys)
+    cdef _Flags o = _Flags.of(column_order), p = _Flags.of(null_precedence)
+    cdef b2_stream s = _stream(stream)
+    cdef b2_column* out = NULL
+    cdef b2_status st
+    with nogil:
+        st = b2_segmented_sorted_order(&kv.tv, &segment_offsets.v, o.p, o.n, p.p, p.n, stable, s, &out)
+    check(st)
+    return Column.from_handle(out)
+
+
+cdef Table _segmented_sort_by_key(Table values, Table keys, Column segment_offsets, object column_order, object null_precedence, int stable,
+                                  object stream):
+    cdef _TableView vv = _TableView.of(values), kv = _TableView.of(keys)
+    cdef _Flags o = _Flags.of(column_order), p = _Flags.of(null_precedence)
+    cdef b2_stream s = _stream(stream)
+    cdef b2_table* out = NULL
+    cdef b2_status st
+    with nogil:
+        st = b2_segmented_sort_by_key(&vv.tv, &kv.tv, &segment_offsets.v, o.p, o.n, p.p, p.n, stable, s, &out)
+    check(st)
+    return Table.from_handle(out)
+
+
+def segmented_sorted_order(Table keys, Column segment_offsets, column_order, null_precedence, stream=None, mr=None):
+    return _segmented_sorted_order(keys, segment_offsets, column_order, null_precedence, 0, stream)
+
+
+def stable_segmented_sorted_order(Table keys, Column segment_offsets, column_order, null_precedence, stream=None, mr=None):
+    return _segmented_sorted_order(keys, segment_offsets, column_order, null_precedence, 1, stream)
+
+
+def segmented_sort_by_key(Table values, Table keys, Column segment_offsets, column_order, null_precedence, stream=None, mr=None):
+    return _segmented_sort_by_key(values, keys, segment_offsets, column_order, null_precedence, 0, stream)
+
+
+def stable_segmented_sort_by_key(Table values, Table keys, Column segment_offsets, column_order, null_precedence, stream=None, mr=None):
+    return _segmented_sort_by_key(values, keys, segment_offsets, column_order, null_precedence, 1, stream)
+
+
+ctypedef b2_status (*topk_fn)(const b2_column_view*, int32_t, int32_t, b2_stream, b2_column**) noexcept nogil
+
+
+cdef Column _top_k(topk_fn fn, Column col, int32_t k, int32_t sort_order, object stream):
+    cdef b2_stream s = _stream(stream)
+    cdef b2_column* out = NULL
+    cdef b2_status st
+    with nogil:
+        st = fn(&col.v, k, sort_order, s, &out)
+    check(st)
+    return Column.from_handle(out)
+
+
+def top_k(Column col, int k, sort_order=1, stream=None, mr=None):
+    """cudf::top_k (sorting.hpp:370-391); sort_order defaults to DESCENDING (high to low)."""
+    return _top_k(b2_top_k, col, k, int(sort_order), stream)
+
+
+def top_k_order(Column col, int k, sort_order=1, stream=None, mr=None):
+    return _top_k(b2_top_k_order, col, k, int(sort_order), stream)
+
+
+def rank(Column input_view, method, column_order, null_handling, null_precedence, percentage, stream=None, mr=None):
+    """cudf::rank (sorting.hpp:165-230); method: RankMethod (0 FIRST, 1 AVERAGE, 2 MIN, 3 MAX, 4 DENSE)."""
+    cdef int32_t m = int(method), co = int(column_order), nh = int(null_handling), npr = int(null_precedence), pct = 1 if percentage else 0
+    cdef b2_stream s = _stream(stream)
+    cdef b2_column* out = NULL
+    cdef b2_status st
+    with nogil:
+        st = b2_rank(&input_view.v, m, co, nh, npr, pct, s, &out)
+    check(st)
+    return Column.from_handle(out)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# hash_join match contexts / partitioned probes (cpp/include/cudf/join/hash_join.hpp:254-440, join.hpp:81-125)
+# ---------------------------------------------------------------------------------------------------------------------
+cdef class JoinMatchContext:
+    """cudf::join_match_context: the left table and its per-row match counts (INT32 column)."""
+    cdef public Table _left_table
+    cdef public Column _match_counts
+    cdef public int _kind
+
+    def __init__(self, Table left_table, Column match_counts, int kind=0):
+        self._left_table = left_table
+        self._match_counts = match_counts
+        self._kind = kind
+
+
+cdef class JoinPartitionContext:
+    """cudf::join_partition_context (join.hpp:120-125)."""
+    cdef public JoinMatchContext left_table_context
+    cdef public int left_start_idx
+    cdef public int left_end_idx
+
+    def __init__(self, JoinMatchContext left_table_context, int left_start_idx, int left_end_idx):
+        self.left_table_context = left_table_context
+        self.left_start_idx = left_start_idx
+        self.left_end_idx = left_end_idx
+
+
+def hash_join_match_context(HashJoin hj, int kind, Table probe, stream=None):
+    cdef _TableView pv = _TableView.of(probe)
+    cdef b2_stream s = _stream(stream)
+    cdef b2_column* out = NULL
+    cdef b2_status st
+    with nogil:
+        st = b2_hash_join_match_counts(hj.hj, &pv.tv, kind, s, &out)
+    check(st)
+    return JoinMatchContext(probe, Column.from_handle(out), kind)
+
+
+def hash_join_partitioned(HashJoin hj, int kind, JoinPartitionContext context, stream=None):
+    cdef JoinMatchContext ctx = context.left_table_context
+    if ctx is None or ctx._match_counts is None:
+        raise ValueError("join_partition_context without a match context")
+    cdef _TableView pv = _TableView.of(ctx._left_table)
+    cdef Column counts = ctx._match_counts
+    cdef int32_t a = context.left_start_idx, b = context.left_end_idx
+    cdef b2_stream s = _stream(stream)
+    cdef b2_column* lo = NULL
+    cdef b2_column* ro = NULL
+    cdef b2_status st
+    with nogil:
+        st = b2_hash_join_partitioned_join(hj.hj, &pv.tv, &counts.v, a, b, kind, s, &lo, &ro)
+    check(st)
+    cdef Column l = Column.from_handle(lo)
+    return l, Column.from_handle(ro)
+
+
+def finalize_partitioned_full_join(left_partials, right_partials, int left_table_num_rows, int right_table_num_rows, stream=None):
+    cdef list lp = list(left_partials), rp = list(right_partials)
+    cdef Py_ssize_t n = len(lp), i
+    if len(rp) != n:
+        raise ValueError("left and right partials differ in number")
+    cdef b2_column_view* lv = <b2_column_view*>calloc(n if n > 0 else 1, sizeof(b2_column_view))
+    cdef b2_column_view* rv = <b2_column_view*>calloc(n if n > 0 else 1, sizeof(b2_column_view))
+    cdef b2_stream s = _stream(stream)
+    cdef b2_column* lo = NULL
+    cdef b2_column* ro = NULL
+    cdef b2_status st
+    if lv == NULL or rv == NULL:
+        free(lv)
+        free(rv)
+        raise MemoryError()
+    try:
+        for i in range(n):
+            lv[i] = (<Column?>lp[i]).v
+            rv[i] = (<Column?>rp[i]).v
+        with nogil:
+            st = b2_hash_join_finalize_full_join(lv, rv, <int32_t>n, left_table_num_rows, right_table_num_rows, s, &lo, &ro)
+        check(st)
+    finally:
+        free(lv)
+        free(rv)
+    cdef Column l = Column.from_handle(lo)
+    return l, Column.from_handle(ro)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# partitioning (python/pylibcudf/pylibcudf/partitioning.pyx; cpp/include/cudf/partitioning.hpp:58-175)
+# ---------------------------------------------------------------------------------------------------------------------
+def hash_partition(Table input, keys, int num_partitions, hash_function=1, seed=0, stream=None, mr=None):  # noqa: A002
+    """cudf::hash_partition: `keys` is a Table of key columns or a list of column indices of `input`; libcudf's row hash
+    (MurmurHash3_x86_32 per column, hash_combine), partition = hash % num_partitions. -> (table, num_partitions + 1 offsets)."""
+    cdef Table ktab
+    if isinstance(keys, Table):
+        ktab = keys
+    else:
+        cols = input.cols
+        for i in keys:
+            if not 0 <= int(i) < len(cols):
+                raise IndexError("columns_to_hash: invalid column index")  # std::out_of_range
+        ktab = Table([cols[int(i)] for i in keys])
+    if ktab.num_columns() and ktab.num_rows() != input.num_rows():
+        raise ValueError("Input table and key table must have same number of rows, or key table should have no columns.")
+    cdef _TableView tv = _TableView.of(input), kv = _TableView.of(ktab)
+    cdef Py_ssize_t noff = (num_partitions if num_partitions > 0 else 0) + 1
+    cdef int32_t* offs = <int32_t*>calloc(noff, sizeof(int32_t))
+    cdef int32_t hf = int(hash_function)
+    cdef uint32_t sd = int(seed) & 0xFFFFFFFF
+    cdef b2_stream s = _stream(stream)
+    cdef b2_table* out = NULL
+    cdef b2_status st
+    if offs == NULL:
+        raise MemoryError()
+    try:
+        with nogil:
+            st = b2_hash_partition(&tv.tv, &kv.tv, num_partitions, hf, sd, s, &out, offs)
+        check(st)
+        res = [offs[j] for j in range(noff)]
+    finally:
+        free(offs)
+    return Table.from_handle(out), res
+
+
+def partition(Table t, Column partition_map, int num_partitions, stream=None, mr=None):
+    """cudf::partition (partitioning.hpp:58-101): rows go to the partition their map entry names (stable).
+    -> (partitioned table, num_partitions + 1 offsets)."""
+    if partition_map.v.null_count > 0:
+        raise RuntimeError("Unexpected null values in partition_map.")  # cudf::logic_error
+    if num_partitions < 0:
+        raise ValueError("num_partitions must not be negative")
+    if partition_map.v.size != (t.num_rows() if t.num_columns() else 0):
+        raise RuntimeError("Size mismatch between table and partition map.")
+    cdef _TableView tv = _TableView.of(t)
+    cdef Py_ssize_t noff = num_partitions + 1
+    cdef int32_t* offs = <int32_t*>calloc(noff, sizeof(int32_t))
+    cdef b2_stream s = _stream(stream)
+    cdef b2_table* out = NULL
+    cdef b2_status st
+    if offs == NULL:
+        raise MemoryError()
+    try:
+        with nogil:
+            st = b2_partition_by_map(&tv.tv, &partition_map.v, num_partitions, s, &out, offs)
+        check(st)
+        res = [offs[j] for j in range(noff)]
+    finally:
+        free(offs)
+    return Table.from_handle(out), res
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# null masks (python/pylibcudf/pylibcudf/null_mask.pyx; cpp/include/cudf/null_mask.hpp)
+# ---------------------------------------------------------------------------------------------------------------------
+def _device_buffer(uintptr_t handle):
+    from cudf_b200.pylibcudf.null_mask import DeviceBuffer  # owning rmm::device_buffer stand-in of the ctypes twin
+
+    return DeviceBuffer(handle)
+
+
+def bitmask_allocation_size_bytes(int number_of_bits):
+    return int(b2_bitmask_allocation_size_bytes(number_of_bits))
+
+
+def create_null_mask(int size, state=0, stream=None, mr=None):
+    cdef int32_t stt = int(state)
+    cdef b2_stream s = _stream(stream)
+    cdef b2_buffer* out = NULL
+    cdef b2_status st
+    with nogil:
+        st = b2_create_null_mask(size, stt, s, &out)
+    check(st)
+    return _device_buffer(<uintptr_t>out)
+
+
+def copy_bitmask(Column col, stream=None, mr=None):
+    cdef b2_stream s = _stream(stream)
+    cdef b2_buffer* out = NULL
+    cdef b2_status st
+    with nogil:
+        st = b2_copy_bitmask(col.v.null_mask, col.v.offset, col.v.offset + col.v.size, s, &out)
+    check(st)
+    return _device_buffer(<uintptr_t>out)
+
+
+def bitmask_and(columns, stream=None, mr=None):
+    cdef Table tbl = columns if isinstance(columns, Table) else Table(columns)
+    cdef _TableView tv = _TableView.of(tbl)
+    cdef b2_stream s = _stream(stream)
+    cdef b2_buffer* out = NULL
+    cdef int32_t nc = 0
+    cdef b2_status st
+    with nogil:
+        st = b2_bitmask_and(&tv.tv, s, &out, &nc)
+    check(st)
+    return _device_buffer(<uintptr_t>out), nc
+
+
+def null_count(uintptr_t bitmask_ptr, int start, int stop, stream=None):
+    cdef b2_stream s = _stream(stream)
+    cdef int32_t out = 0
+    check(b2_null_count(<const uint32_t*>bitmask_ptr, start, stop, s, &out))
+    return out
+
+
+def count_set_bits(uintptr_t bitmask_ptr, int start, int stop, stream=None):
+    cdef b2_stream s = _stream(stream)
+    cdef int32_t out = 0
+    check(b2_count_set_bits(<const uint32_t*>bitmask_ptr, start, stop, s, &out))
+    return out
+
+
+def set_null_mask(uintptr_t bitmask_ptr, int begin_bit, int end_bit, valid, stream=None):
+    cdef b2_stream s = _stream(stream)
+    check(b2_set_null_mask(<uint32_t*>bitmask_ptr, begin_bit, end_bit, 1 if valid else 0, s))

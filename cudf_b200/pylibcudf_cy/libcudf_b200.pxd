@@ -99,3 +99,37 @@ cdef extern from "cudf_b200.h" nogil:
                                   b2_column** out)
     b2_status b2_scan(const b2_column_view* col, int32_t agg_kind, int32_t scan_type, int32_t null_handling, b2_stream stream,
                       b2_column** out)
+
+    # ---- the rest of the path's modules ----
+    ctypedef struct b2_buffer
+    size_t b2_bitmask_allocation_size_bytes(int32_t number_of_bits)
+    b2_status b2_create_null_mask(int32_t size, int32_t mask_state, b2_stream stream, b2_buffer** out)
+    b2_status b2_set_null_mask(uint32_t* bitmask, int32_t begin_bit, int32_t end_bit, int32_t valid, b2_stream stream)
+    b2_status b2_copy_bitmask(const uint32_t* mask, int32_t begin_bit, int32_t end_bit, b2_stream stream, b2_buffer** out)
+    b2_status b2_count_set_bits(const uint32_t* bitmask, int32_t start, int32_t stop, b2_stream stream, int32_t* out)
+    b2_status b2_bitmask_and(const b2_table_view* view, b2_stream stream, b2_buffer** out_mask, int32_t* out_null_count)
+
+    b2_status b2_segmented_sorted_order(const b2_table_view* keys, const b2_column_view* segment_offsets, const uint8_t* column_order,
+                                        int32_t n_order, const uint8_t* null_precedence, int32_t n_null_prec, int32_t stable,
+                                        b2_stream stream, b2_column** out)
+    b2_status b2_segmented_sort_by_key(const b2_table_view* values, const b2_table_view* keys, const b2_column_view* segment_offsets,
+                                       const uint8_t* column_order, int32_t n_order, const uint8_t* null_precedence, int32_t n_null_prec,
+                                       int32_t stable, b2_stream stream, b2_table** out)
+    b2_status b2_top_k(const b2_column_view* col, int32_t k, int32_t topk_order, b2_stream stream, b2_column** out)
+    b2_status b2_top_k_order(const b2_column_view* col, int32_t k, int32_t topk_order, b2_stream stream, b2_column** out)
+    b2_status b2_rank(const b2_column_view* input, int32_t method, int32_t column_order, int32_t null_handling, int32_t null_precedence,
+                      int32_t percentage, b2_stream stream, b2_column** out)
+
+    b2_status b2_hash_join_match_counts(const b2_hash_join* hj, const b2_table_view* probe, int32_t join_kind, b2_stream stream,
+                                        b2_column** out_counts)
+    b2_status b2_hash_join_partitioned_join(const b2_hash_join* hj, const b2_table_view* probe, const b2_column_view* match_counts,
+                                            int32_t left_start, int32_t left_end, int32_t join_kind, b2_stream stream,
+                                            b2_column** out_left, b2_column** out_right)
+    b2_status b2_hash_join_finalize_full_join(const b2_column_view* left_partials, const b2_column_view* right_partials,
+                                              int32_t num_partials, int32_t left_table_num_rows, int32_t right_table_num_rows,
+                                              b2_stream stream, b2_column** out_left, b2_column** out_right)
+
+    b2_status b2_hash_partition(const b2_table_view* input, const b2_table_view* keys, int32_t num_partitions, int32_t hash_function,
+                                uint32_t seed, b2_stream stream, b2_table** out, int32_t* out_offsets)
+    b2_status b2_partition_by_map(const b2_table_view* input, const b2_column_view* partition_map, int32_t num_partitions,
+                                  b2_stream stream, b2_table** out, int32_t* out_offsets)

@@ -21,7 +21,9 @@ def test_extension_builds_and_links():
     assert "libcudf_b200.so" in dyn and "$ORIGIN/.." in dyn, dyn
     for mod, names in ((cy.sorting, ["sorted_order", "stable_sorted_order", "sort", "stable_sort", "sort_by_key", "stable_sort_by_key"]),
                        (cy.join, ["inner_join", "left_join", "full_join", "HashJoin"]), (cy.groupby, ["GroupBy", "GroupByRequest"]),
-                       (cy.reduce, ["reduce", "scan", "segmented_reduce", "ScanType"]), (cy.copying, ["gather"])):
+                       (cy.reduce, ["reduce", "scan", "segmented_reduce", "ScanType"]), (cy.copying, ["gather"]),
+                       (cy.partitioning, ["hash_partition", "partition", "HashId"]),
+                       (cy.null_mask, ["create_null_mask", "copy_bitmask", "bitmask_and", "null_count", "count_set_bits", "set_null_mask"])):
         for n in names:
             assert hasattr(mod, n), (mod.__name__, n)
     assert type(cy.Column).__module__ != "ctypes" and cy.Column.__module__.endswith("_core")
@@ -105,6 +107,54 @@ for fn, exc in ((lambda: cy.sorting.sort_by_key(cy.Table([cy.Column.from_numpy(v
         raise SystemExit("no error")
     except exc:
         pass
+# ---- the other modules of the path: segmented sort / top-k / rank, match contexts, partitioning, null masks ----
+from oracle import partition as opart
+kcol = (rng.integers(0, 50, 3000).astype(np.int32), rng.random(3000) < 0.9)
+soffs = np.array([0, 10, 10, 700, 2999], dtype=np.int32)
+for order in (0, 1):
+    got = cy.sorting.stable_segmented_sorted_order(cy.Table([cy.Column.from_numpy(*kcol)]), cy.Column.from_numpy(soffs), [order], [order]).to_numpy()[0]
+    assert np.array_equal(got, osort.segmented_sorted_order([kcol], soffs, [order], [order])), order
+    tk = cy.sorting.top_k_order(cy.Column.from_numpy(*kcol), 17, order).to_numpy()[0]
+    assert np.array_equal(tk, osort.top_k_order(kcol, 17, order)), order
+sv = cy.sorting.segmented_sort_by_key(cy.Table([cy.Column.from_numpy(np.arange(3000, dtype=np.int64))]), cy.Table([cy.Column.from_numpy(*kcol)]),
+                                      cy.Column.from_numpy(soffs), [0], [1]).columns()[0].to_numpy()[0]
+assert sorted(sv.tolist()) == list(range(3000))
+tv = cy.sorting.top_k(cy.Column.from_numpy(kcol[0]), 5, 1).to_numpy()[0]
+assert sorted(tv.tolist()) == sorted(np.sort(kcol[0])[-5:].tolist())
+for method in range(5):
+    g = cy.sorting.rank(cy.Column.from_numpy(*kcol), method, 0, 0, 1, False).to_numpy()
+    assert_columns_equal(g, osort.rank(kcol, method, 0, 0, 1, False), what=f"rank {method}")
+for kind in ("inner", "left", "full"):
+    assert np.array_equal(cu.match_counts(l, r, 0, kind), o.match_counts(l, r, 0, kind)), kind
+    g, e = cu.partitioned_join(l, r, 0, kind, (0, 1000, 2500)), o.partitioned_join(l, r, 0, kind)
+    assert np.array_equal(g[0], e[0]) and np.array_equal(g[1], e[1]), kind
+tcols = [(rng.integers(-5, 5, 2000).astype(np.int64), rng.random(2000) < 0.9), (rng.random(2000).astype(np.float32), None)]
+for P in (1, 7, 300):
+    out, offs = cy.partitioning.hash_partition(cy.Table([cy.Column.from_numpy(*c) for c in tcols]), [0, 1], P)
+    ecols, eoffs = opart.hash_partition(tcols, tcols, P, 0, False)
+    assert offs == list(eoffs), P
+    for gc, ec in zip(out.columns(), ecols):
+        assert_columns_equal(gc.to_numpy(), ec, what=f"hash_partition {P}")
+pmap = rng.integers(0, 9, 2000).astype(np.int32)
+pout, poffs = cy.partitioning.partition(cy.Table([cy.Column.from_numpy(np.arange(2000, dtype=np.int64))]), cy.Column.from_numpy(pmap), 9)
+assert np.array_equal(pout.columns()[0].to_numpy()[0], np.argsort(pmap, kind="stable")) and poffs == np.concatenate([[0], np.cumsum(np.bincount(pmap, minlength=9))]).tolist()
+try:
+    cy.partitioning.hash_partition(cy.Table([cy.Column.from_numpy(pmap)]), [3], 4)
+    raise SystemExit("no error")
+except IndexError:
+    pass
+nm = cy.null_mask
+assert nm.bitmask_allocation_size_bytes(100) == 64
+mcol = cy.Column.from_numpy(*kcol)
+mptr = mcol.null_mask().ptr
+assert nm.null_count(mptr, 0, 3000) == int((~kcol[1]).sum()) and nm.count_set_bits(mptr, 5, 2000) == int(kcol[1][5:2000].sum())
+buf, nc = nm.bitmask_and([mcol, cy.Column.from_numpy(kcol[0], ~kcol[1] | (rng.random(3000) < 0.5))])
+assert nc >= int((~kcol[1]).sum()) and buf.size >= 3000 // 8
+cp = nm.copy_bitmask(mcol.slice(3, 2000))
+assert nm.count_set_bits(cp.ptr, 0, 1997) == int(kcol[1][3:2000].sum())
+all_valid = nm.create_null_mask(200, nm.MaskState.ALL_VALID)
+nm.set_null_mask(all_valid.ptr, 10, 20, False)
+assert nm.null_count(all_valid.ptr, 0, 200) == 10
 # ctypes twin <-> compiled twin share memory
 import cudf_b200.pylibcudf as plc
 pc = plc.Column.from_numpy(keys)
