@@ -1,5 +1,5 @@
 """Compiled (Cython) binding of the hot path: `cudf_b200.pylibcudf_cy` has the module layout of pylibcudf
-(`Column`, `Table`, `sorting`, `join`, `groupby`, `reduce`, `copying`, `partitioning`, `null_mask`, `aggregation`, `types`) with the operations implemented in
+(`Column`, `Table`, `sorting`, `join`, `groupby`, `reduce`, `copying`, `partitioning`, `null_mask`, `contiguous_split`, `aggregation`, `types`) with the operations implemented in
 `_core.pyx` as typed, GIL-releasing calls into libcudf_b200.so (declared in libcudf_b200.pxd). Enumerations, DataType,
 Aggregation and Scalar are the pure-Python classes of the ctypes twin `cudf_b200.pylibcudf`.
 
@@ -11,7 +11,7 @@ from ..pylibcudf.column import Scalar
 from ..pylibcudf.types import (DataType, NullEquality, NullOrder, NullPolicy, Order, OutOfBoundsPolicy, Sorted, TypeId)
 from . import _core
 from ._core import Column, Table
-from . import copying, groupby, join, null_mask, partitioning, reduce, sorting
+from . import contiguous_split, copying, groupby, join, null_mask, partitioning, reduce, sorting
 
 __all__ = ["Column", "Table", "Scalar", "DataType", "TypeId", "Order", "NullOrder", "NullPolicy", "NullEquality", "Sorted",
-           "OutOfBoundsPolicy", "aggregation", "types", "sorting", "join", "groupby", "reduce", "copying", "null_mask", "partitioning"]
+           "OutOfBoundsPolicy", "aggregation", "types", "sorting", "join", "groupby", "reduce", "copying", "null_mask", "partitioning", "contiguous_split"]

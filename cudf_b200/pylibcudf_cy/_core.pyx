@@ -919,3 +919,74 @@ def count_set_bits(uintptr_t bitmask_ptr, int start, int stop, stream=None):
 def set_null_mask(uintptr_t bitmask_ptr, int begin_bit, int end_bit, valid, stream=None):
     cdef b2_stream s = _stream(stream)
     check(b2_set_null_mask(<uint32_t*>bitmask_ptr, begin_bit, end_bit, 1 if valid else 0, s))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# contiguous_split: pack / unpack in libcudf's wire format (python/pylibcudf/pylibcudf/contiguous_split.pyx;
+# cpp/include/cudf/contiguous_split.hpp:233-317). PackedColumns is the ctypes twin's class.
+# ---------------------------------------------------------------------------------------------------------------------
+def packed_size(Table input, stream=None):  # noqa: A002
+    cdef _TableView tv = _TableView.of(input)
+    cdef size_t out = 0
+    check(b2_packed_size(&tv.tv, &out))
+    return out
+
+
+def pack(Table input, stream=None, mr=None):  # noqa: A002
+    from cudf_b200.pylibcudf.contiguous_split import PackedColumns, _Buffer
+
+    cdef _TableView tv = _TableView.of(input)
+    cdef size_t cap = 16 + 40 * len(input.cols), mdsz = 0
+    cdef uint8_t* md = <uint8_t*>calloc(cap, 1)
+    cdef b2_stream s = _stream(stream)
+    cdef b2_buffer* buf = NULL
+    cdef b2_status st
+    if md == NULL:
+        raise MemoryError()
+    try:
+        with nogil:
+            st = b2_pack(&tv.tv, s, md, cap, &mdsz, &buf)
+        check(st)
+        meta = bytes(md[:mdsz])
+    finally:
+        free(md)
+    owner = _Buffer(<uintptr_t>buf)
+    return PackedColumns(meta, <uintptr_t>b2_buffer_data(buf), b2_buffer_size(buf), owner)
+
+
+def pack_metadata(Table table, uintptr_t contiguous_buffer_ptr, size_t buffer_size):
+    cdef _TableView tv = _TableView.of(table)
+    cdef size_t cap = 16 + 40 * len(table.cols), mdsz = 0
+    cdef uint8_t* md = <uint8_t*>calloc(cap, 1)
+    if md == NULL:
+        raise MemoryError()
+    try:
+        check(b2_pack_metadata(&tv.tv, <const uint8_t*>contiguous_buffer_ptr, buffer_size, md, cap, &mdsz))
+        return bytes(md[:mdsz])
+    finally:
+        free(md)
+
+
+def unpack_from_memoryviews(metadata, uintptr_t gpu_data_ptr, owner=None):
+    """cudf::unpack(metadata, gpu_data): the columns of the result point into gpu_data (kept alive through `owner`)."""
+    cdef bytes md = bytes(metadata)
+    cdef Py_ssize_t n = len(md)
+    cdef int32_t ncap = <int32_t>(max(0, (n - 16) // 40) + 1)
+    cdef b2_column_view* views = <b2_column_view*>calloc(ncap, sizeof(b2_column_view))
+    cdef int32_t ncols = 0, nrows = 0, i
+    cdef const uint8_t* mp = <const uint8_t*>md
+    cdef list cols = []
+    if views == NULL:
+        raise MemoryError()
+    try:
+        check(b2_unpack(mp, <size_t>n, <const void*>gpu_data_ptr, views, ncap, &ncols, &nrows))
+        for i in range(ncols):
+            cols.append(Column.from_pointers(DataType(TypeId(views[i].type_id)), views[i].size, <uintptr_t>views[i].data,
+                                             <uintptr_t>views[i].null_mask, views[i].null_count, 0, [owner]))
+    finally:
+        free(views)
+    return Table(cols)
+
+
+def unpack(input):  # noqa: A002
+    return unpack_from_memoryviews(input.metadata, input.gpu_data_ptr, input)

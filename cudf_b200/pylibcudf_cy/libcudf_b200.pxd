@@ -133,3 +133,14 @@ cdef extern from "cudf_b200.h" nogil:
                                 uint32_t seed, b2_stream stream, b2_table** out, int32_t* out_offsets)
     b2_status b2_partition_by_map(const b2_table_view* input, const b2_column_view* partition_map, int32_t num_partitions,
                                   b2_stream stream, b2_table** out, int32_t* out_offsets)
+
+    # cudf::pack / unpack (cpp/include/cudf/contiguous_split.hpp:233-317)
+    void* b2_buffer_data(const b2_buffer* buf)
+    size_t b2_buffer_size(const b2_buffer* buf)
+    b2_status b2_packed_size(const b2_table_view* input, size_t* out_bytes)
+    b2_status b2_pack(const b2_table_view* input, b2_stream stream, uint8_t* metadata, size_t metadata_capacity, size_t* metadata_size,
+                      b2_buffer** gpu_data)
+    b2_status b2_pack_metadata(const b2_table_view* input, const uint8_t* contiguous_buffer, size_t buffer_size, uint8_t* metadata,
+                               size_t metadata_capacity, size_t* metadata_size)
+    b2_status b2_unpack(const uint8_t* metadata, size_t metadata_size, const void* gpu_data, b2_column_view* out_columns, int32_t capacity,
+                        int32_t* num_columns, int32_t* num_rows)

@@ -23,6 +23,7 @@ def test_extension_builds_and_links():
                        (cy.join, ["inner_join", "left_join", "full_join", "HashJoin"]), (cy.groupby, ["GroupBy", "GroupByRequest"]),
                        (cy.reduce, ["reduce", "scan", "segmented_reduce", "ScanType"]), (cy.copying, ["gather"]),
                        (cy.partitioning, ["hash_partition", "partition", "HashId"]),
+                       (cy.contiguous_split, ["pack", "unpack", "packed_size", "pack_metadata", "PackedColumns"]),
                        (cy.null_mask, ["create_null_mask", "copy_bitmask", "bitmask_and", "null_count", "count_set_bits", "set_null_mask"])):
         for n in names:
             assert hasattr(mod, n), (mod.__name__, n)
@@ -155,6 +156,18 @@ assert nm.count_set_bits(cp.ptr, 0, 1997) == int(kcol[1][3:2000].sum())
 all_valid = nm.create_null_mask(200, nm.MaskState.ALL_VALID)
 nm.set_null_mask(all_valid.ptr, 10, 20, False)
 assert nm.null_count(all_valid.ptr, 0, 200) == 10
+# pack / unpack round trip and metadata bytes against the oracle's wire format
+from oracle import pack as opack
+pcols = [(rng.integers(-9, 9, 777).astype(np.int64), rng.random(777) < 0.8), (rng.random(777).astype(np.float32), None)]
+pt = cy.Table([cy.Column.from_numpy(*c) for c in pcols])
+packed = cy.contiguous_split.pack(pt)
+assert cy.contiguous_split.packed_size(pt) == packed.gpu_data_size == opack.packed_size(pcols)
+md, _data = opack.pack(pcols, [int(c.type().id()) for c in pt.columns()])
+assert packed.metadata == md
+up = cy.contiguous_split.unpack(packed)
+for gc, ec in zip(up.columns(), pcols):
+    assert_columns_equal(gc.to_numpy(), ec, what="unpack")
+assert cy.contiguous_split.pack_metadata(up, packed.gpu_data_ptr, packed.gpu_data_size) == md
 # ctypes twin <-> compiled twin share memory
 import cudf_b200.pylibcudf as plc
 pc = plc.Column.from_numpy(keys)
